@@ -1,0 +1,122 @@
+/* rindex_gpu.h — the drop-in boundary: C ABI of librindex_gpu.so (hand-written sm_100a CUDA).
+ *
+ * The reference (nicolaprezza/r-index @ 7009b53) has no FFI layer: its hot path is the public
+ * C++ surface of ri::r_index<>. Each entry point below names the reference interface it
+ * replaces (paths under /root/reference). INTEGRATION.md shows the binding a maintainer of the
+ * reference would add. Plain pointers and sizes only; no torch, no C++ types.
+ *
+ * Conventions (each checked against the reference source):
+ *   - positions, ranges, counts: uint64_t                        (internal/definitions.hpp:39)
+ *   - SA ranges are inclusive; the EMPTY range is the literal pair {1,0} (r_index.hpp:175,184)
+ *   - patterns: N * m contiguous bytes, fixed length m           (ri-count.cpp:104-110)
+ *   - locate order per pattern: SA[hi], SA[hi-1], ..., SA[lo]    (r_index.hpp:340-351)
+ *   - never exits or throws: returns RIG_OK (0) or a negative code; rig_strerror() names it.
+ */
+#ifndef RINDEX_GPU_H_
+#define RINDEX_GPU_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIG_OK 0
+#define RIG_ERR_ARG -1      /* null pointer / inconsistent sizes */
+#define RIG_ERR_CUDA -2     /* a CUDA runtime call failed; rig_last_cuda_error() has the text */
+#define RIG_ERR_NO_DEVICE -3
+#define RIG_ERR_CAPACITY -4 /* occurrence buffer too small; *occ_total holds the needed count */
+#define RIG_ERR_INDEX -5    /* logical arrays are not a valid r-index (unsorted pred, bad sums, ...) */
+#define RIG_ERR_NOMEM -6
+
+/* Layout-free content of an r-index — what the reference keeps in
+ *   F            internal/r_index.hpp:655   (here 257 entries, F[256] = n)
+ *   bwt          internal/r_index.hpp:657   rle_string: run heads + run lengths (rle_string.hpp:52-124)
+ *   samples_last internal/r_index.hpp:664   SA-1 (wrap to n-1) at the last position of every run
+ *   pred         internal/r_index.hpp:663   sorted SA-1 at the first position of every run
+ *   pred_to_run  internal/r_index.hpp:665
+ * All arrays are HOST pointers, read during rig_index_create only. */
+typedef struct rig_logical_view {
+    uint64_t n; /* BWT length = text length + 1 */
+    uint64_t r; /* number of BWT runs */
+    const uint64_t* F;            /* [257] */
+    const uint8_t* run_heads;     /* [r] */
+    const uint64_t* run_lens;     /* [r] */
+    const uint64_t* samples_last; /* [r] */
+    const uint64_t* pred_pos;     /* [r] ascending */
+    const uint64_t* pred_to_run;  /* [r] */
+} rig_logical_view;
+
+typedef struct rig_options {
+    uint32_t runs_per_block;   /* 0 = default; 4, 8 or 16: lanes cooperating on one rank query */
+    uint32_t lf_bucket_log2;   /* 0 = auto: log2 of (directory buckets per run block) */
+    uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
+    uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
+    uint32_t reserved[4];
+} rig_options;
+
+typedef struct rig_index_info {
+    uint64_t n, r, sigma;        /* sigma = distinct BWT symbols (terminator included) */
+    uint64_t device_bytes;       /* HBM footprint of the flattened index */
+    uint64_t lf_blocks, lf_buckets, phi_buckets;
+    uint32_t runs_per_block, lf_shift, phi_shift, device;
+    uint32_t sm_count, reserved;
+} rig_index_info;
+
+/* CUDA-event timings (ms) of the phases of the most recent batch call on this index. */
+typedef struct rig_timing {
+    float h2d_ms;     /* pattern upload (host-buffer entry points only) */
+    float search_ms;  /* backward-search kernel (count or count+toehold) */
+    float scan_ms;    /* exclusive scans of n_occ / chain counts (locate only) */
+    float expand_ms;  /* Phi expansion kernel (locate only) */
+    float d2h_ms;     /* result download (host-buffer entry points only) */
+    uint32_t launches;      /* kernels launched by the call */
+    uint32_t reserved;
+    uint64_t lf_steps;      /* executed LF steps (early exits excluded), r_index.hpp:297 */
+    uint64_t occ_total;     /* occurrences written */
+    uint64_t chains;        /* independent Phi chains the ranges were split into */
+} rig_timing;
+
+typedef struct rig_index rig_index;
+
+int rig_device_count(void);
+const char* rig_strerror(int code);
+const char* rig_last_cuda_error(void);
+const char* rig_version(void);
+
+/* Flatten the logical arrays into HBM-resident word arrays with interleaved rank directories
+ * and upload them to `device`. Replaces r_index<>::load (internal/r_index.hpp:407-422). */
+int rig_index_create(const rig_logical_view* view, int device, rig_index** out);
+int rig_index_create_ex(const rig_logical_view* view, int device, const rig_options* opt, rig_index** out);
+void rig_index_destroy(rig_index* idx);
+int rig_index_info_get(const rig_index* idx, rig_index_info* info);
+
+/* Replaces N calls of r_index<>::count (internal/r_index.hpp:292-302; LF :171-190;
+ * rle_string::rank rle_string.hpp:170-218). HOST buffers; copies are part of the call. */
+int rig_count_batch(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi);
+
+/* Replaces N calls of r_index<>::locate_all (internal/r_index.hpp:328-355; count_and_get_occ
+ * :482-545; Phi :195-221). HOST buffers. occ_offsets has N+1 entries; pattern p's occurrences
+ * are occ[occ_offsets[p] .. occ_offsets[p+1]). If occ == NULL or occ_capacity (in entries) is
+ * too small, lo/hi/occ_offsets/occ_total are still filled and RIG_ERR_CAPACITY is returned. */
+int rig_locate_batch(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                     uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total);
+
+/* Same operations on DEVICE buffers (pointers valid on the index's device); `stream` is a
+ * cudaStream_t (NULL = the index's own stream). Count is fully asynchronous; locate
+ * synchronises once after the scan to learn occ_total (returned on the host). */
+int rig_count_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
+                        uint64_t* d_hi, void* stream);
+int rig_locate_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
+                         uint64_t* d_hi, uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t occ_capacity,
+                         uint64_t* occ_total, void* stream);
+
+/* Order-independent + order-dependent digest of a device u64 array (for parity at sizes where
+ * copying every occurrence back is pointless): out[0] = sum, out[1] = sum of v*(i+1) (mod 2^64). */
+int rig_digest_dev(rig_index* idx, const uint64_t* d_values, uint64_t count, uint64_t out[2], void* stream);
+
+int rig_last_timing(const rig_index* idx, rig_timing* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

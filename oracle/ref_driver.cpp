@@ -1,0 +1,150 @@
+// ref_driver.cpp — C entry points over the UNMODIFIED reference headers (oracle/_ref/libri_ref.so).
+//
+// TEST INFRASTRUCTURE ONLY (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl
+// reference). Never linked or loaded by the product path.
+//
+// The reference sources are compiled where they lie (-I/root/reference -I/root/reference/internal,
+// see oracle/Makefile); sdsl-lite is replaced by oracle/sdsl_shim. What runs here
+// is therefore the reference's own r_index<>::count / locate_all / Phi / rle_string::rank code
+// (internal/r_index.hpp:171-221,292-355,482-545; internal/rle_string.hpp:126-256), over restated
+// SDSL primitives.
+#include <string>
+#include <vector>
+#include <set>
+#include <tuple>
+#include <sstream>
+#include <fstream>
+#include <iostream>
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+#include <chrono>
+#include <queue>
+#include <map>
+#include <memory>
+#include <thread>
+#include <atomic>
+#include <streambuf>
+#define private public  // read-only access to r_index<> members for ref_extract (test infra only)
+#include "internal/r_index.hpp"
+#undef private
+#include <thread>
+#include <atomic>
+#include <streambuf>
+
+using namespace ri;
+typedef r_index<> ref_index_t;
+
+namespace {
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+struct Quiet {  // the reference ctor prints progress to cout (r_index.hpp:53-57); silence it on request
+    std::streambuf* old = nullptr; NullBuf nb;
+    explicit Quiet(bool on) { if (on) old = std::cout.rdbuf(&nb); }
+    ~Quiet() { if (old) std::cout.rdbuf(old); }
+};
+template <class Fn>
+void shard(uint64_t N, int nthreads, Fn fn) {
+    if (nthreads <= 1) { fn(0, N, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        uint64_t a = N * (uint64_t)t / (uint64_t)nthreads, b = N * (uint64_t)(t + 1) / (uint64_t)nthreads;
+        th.emplace_back([=]() { fn(a, b, t); });
+    }
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+// Returns NULL if the text holds 0x00/0x01 (the reference would exit(1), r_index.hpp:46-51).
+void* ref_build(const uint8_t* text, uint64_t len, int quiet) {
+    for (uint64_t i = 0; i < len; ++i) if (text[i] == 0 || text[i] == 1) return nullptr;
+    Quiet q(quiet != 0);
+    std::string s((const char*)text, len);
+    return new ref_index_t(s, true);
+}
+void ref_free(void* h) { delete (ref_index_t*)h; }
+uint64_t ref_bwt_size(void* h) { return ((ref_index_t*)h)->bwt_size(); }
+uint64_t ref_number_of_runs(void* h) { return ((ref_index_t*)h)->number_of_runs(); }
+
+int ref_save(void* h, const char* path) {  // same framing as ri-build.cpp:129-144
+    std::ofstream out(path);
+    if (!out) return -1;
+    bool fast = false;
+    out.write((char*)&fast, sizeof(fast));
+    ((ref_index_t*)h)->serialize(out);
+    return out ? 0 : -1;
+}
+void* ref_load(const char* path) {  // same framing as ri-count.cpp:153-158
+    std::ifstream in(path);
+    if (!in) return nullptr;
+    bool fast;
+    in.read((char*)&fast, sizeof(fast));
+    ref_index_t* idx = new ref_index_t();
+    idx->load(in);
+    return idx;
+}
+
+// N calls of r_index<>::count. Returns seconds spent in the query loop.
+double ref_count_batch(void* h, const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi, int nthreads) {
+    ref_index_t* idx = (ref_index_t*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    shard(N, nthreads, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t p = a; p < b; ++p) {
+            std::string P((const char*)patt + p * m, m);
+            range_t rn = idx->count(P);
+            if (lo) lo[p] = rn.first;
+            if (hi) hi[p] = rn.second;
+        }
+    });
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// N calls of r_index<>::locate_all. occ_offsets[N+1] must already hold the exclusive prefix sums
+// of the per-pattern counts when occ != NULL (use ref_count_batch first); with occ == NULL the
+// vectors are dropped as ri-locate does (ri-locate.cpp:144). Returns seconds in the query loop;
+// *occ_total = number of occurrences produced.
+double ref_locate_batch(void* h, const uint8_t* patt, uint64_t N, uint64_t m, const uint64_t* occ_offsets,
+                        uint64_t* occ, uint64_t* occ_total, int nthreads) {
+    ref_index_t* idx = (ref_index_t*)h;
+    std::atomic<uint64_t> total(0);
+    auto t0 = std::chrono::steady_clock::now();
+    shard(N, nthreads, [&](uint64_t a, uint64_t b, int) {
+        uint64_t mine = 0;
+        for (uint64_t p = a; p < b; ++p) {
+            std::string P((const char*)patt + p * m, m);
+            std::vector<ulint> OCC = idx->locate_all(P);
+            mine += OCC.size();
+            if (occ) std::memcpy(occ + occ_offsets[p], OCC.data(), OCC.size() * sizeof(ulint));
+        }
+        total += mine;
+    });
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (occ_total) *occ_total = total.load();
+    return dt;
+}
+
+// Single-operation probes for unit parity of the device primitives.
+uint64_t ref_bwt_rank(void* h, uint64_t i, uint8_t c) { return ((ref_index_t*)h)->bwt.rank(i, c); }
+uint8_t ref_bwt_at(void* h, uint64_t i) { return ((ref_index_t*)h)->bwt[i]; }
+uint64_t ref_phi(void* h, uint64_t i) { return ((ref_index_t*)h)->Phi(i); }
+
+// The logical content of a reference-built/loaded index, read through the reference's own
+// accessors. This is also the extraction INTEGRATION.md proposes for feeding rig_index_create.
+// Arrays: F[257], heads[r], lens[r], samples_last[r], pred_pos[r], pred_to_run[r].
+void ref_extract(void* h, uint64_t* F, uint8_t* heads, uint64_t* lens, uint64_t* samples_last, uint64_t* pred_pos,
+                 uint64_t* pred_to_run) {
+    ref_index_t* idx = (ref_index_t*)h;
+    uint64_t r = idx->number_of_runs();
+    for (int c = 0; c < 256; ++c) F[c] = idx->F[c];
+    F[256] = idx->bwt_size();
+    for (uint64_t j = 0; j < r; ++j) {
+        heads[j] = idx->bwt.run_heads[j];        // rle_string.hpp:568
+        lens[j] = idx->bwt.run_at(j);            // rle_string.hpp:331-338
+        samples_last[j] = idx->samples_last[j];  // r_index.hpp:664
+        pred_pos[j] = idx->pred.select(j);       // r_index.hpp:663, sparse_sd_vector.hpp:178
+        pred_to_run[j] = idx->pred_to_run[j];    // r_index.hpp:665
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,395 @@
+// kernels.cuh — sm_100a device code of the count + locate hot path.
+//
+//   search_kernel<G,LOCATE>  backward search, one group PAIR per pattern: G lanes evaluate
+//                            rank(lo) and G lanes evaluate rank(hi+1) of the same LF step in
+//                            lockstep (32/(2G) patterns per warp). LOCATE also tracks the toehold.
+//                            Replaces r_index::count / count_and_get_occ / LF and
+//                            rle_string::rank / operator[] / select / run_of_position
+//                            (reference internal/r_index.hpp:171-190,292-302,482-545;
+//                             internal/rle_string.hpp:126-256).
+//   scan_*                   exclusive scans of n_occ and chain counts (output offsets).
+//   phi_expand_kernel        Phi walks, one independent chain per LANE, chains cut at BWT run
+//                            boundaries, lanes refill from a global queue (reference
+//                            r_index::Phi :195-221 and the locate_all loop :340-351).
+//   digest_kernel            checksum of a u64 array.
+//
+// No tensor cores: the path has no dense contraction; it is dependent integer loads.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rigk {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+struct FlatDev {
+    u64 n, r, nblk, toe0;
+    u32 K, S, lf_shift, phi_shift;
+    const u64* F;             // [257]
+    const uint16_t* sid;      // [256]
+    const u64* start;         // [nblk*K+1]
+    const uint8_t* head;      // [nblk*K]
+    const u64* bstart;        // [nblk+1]
+    const ulonglong2* cum;    // [nblk*S] (count before block, last run of symbol before block)
+    const u32* bdir;          // [lf_nbkt+1]
+    const u64* samples_last;  // [r]
+    const ulonglong2* phi_ent;  // [r] (pos, delta)
+    const u32* phi_dir;       // [phi_nbkt+1]
+};
+
+#define RIG_FULL 0xffffffffu
+
+template <int G>
+__device__ __forceinline__ u32 gballot(bool p, u32 gbase) {
+    u32 m = __ballot_sync(RIG_FULL, p);
+    return (G == 32) ? m : ((m >> gbase) & ((1u << G) - 1u));
+}
+
+template <int G>
+__device__ __forceinline__ u64 greduce_add(u64 v) {
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(RIG_FULL, v, off);
+    return v;
+}
+
+// One cooperative query by a group of G lanes (all 32 lanes of the warp execute this together,
+// each group with its own x / c): locate the run holding BWT position x (0 <= x < n) and return
+//   cnt        = #c in bwt[0..x]  (INCLUSIVE)   = rle_string::rank(x+1, c)   rle_string.hpp:170-218
+//   run        = run holding x                   = rle_string::run_of_position rle_string.hpp:223-256
+//   head_is_c  = bwt[x] == c                     = rle_string::operator[]     rle_string.hpp:126-131
+//   prev_c_run = last run with head c strictly before `run` (or ~0): the run holding the last c
+//                before x when bwt[x] != c — what rank/select/run_of_position compute together at
+//                r_index.hpp:516-531.
+// Dependent memory rounds: bdir -> (bstart, only when the bucket straddles blocks) -> block.
+template <int G, bool WANT_RUN>
+__device__ __forceinline__ void block_query(const FlatDev& ix, u64 x, uint8_t c, u32 sidc, int gl, u32 gbase,
+                                            u64& cnt, u64& run, bool& head_is_c, u64& prev_c_run) {
+    const u64 q = x >> ix.lf_shift;
+    u32 b0 = __ldg(ix.bdir + q);
+    u32 b1 = __ldg(ix.bdir + q + 1);
+    // G-ary search for the last block whose first position is <= x (blocks b0..b1 are candidates)
+    while (__any_sync(RIG_FULL, b1 > b0)) {
+        const u32 span = b1 - b0;
+        const u32 step = (span + G - 1) / G;
+        u64 probe = (u64)b0 + (u64)(gl + 1) * step;
+        if (probe > b1) probe = b1;
+        const bool le = __ldg(ix.bstart + probe) <= x;
+        const u32 k = __popc(gballot<G>(le, gbase));
+        if (span) {
+            if (k == 0) {
+                b1 = min(b1, b0 + step - 1);
+            } else {
+                const u64 nb0 = min((u64)b1, (u64)b0 + (u64)k * step);
+                b1 = (u32)min((u64)b1, nb0 + step - 1);
+                b0 = (u32)nb0;
+            }
+        }
+    }
+    const u64 base = (u64)b0 * G;
+    const u64 st = __ldg(ix.start + base + gl);
+    const uint8_t hd = __ldg(ix.head + base + gl);
+    const ulonglong2 cm = __ldg(ix.cum + (u64)b0 * ix.S + sidc);
+    const u64 nxt = __shfl_down_sync(RIG_FULL, st, 1, G);
+    const u32 mle = gballot<G>(st <= x, gbase);
+    const int t = __popc(mle) - 1;  // >= 0: the block's first run starts at or before x
+    const bool isc = (hd == c);
+    u64 contrib = 0;
+    if (isc) contrib = (gl < t) ? (nxt - st) : ((gl == t) ? (x - st + 1) : 0);
+    cnt = cm.x + greduce_add<G>(contrib);
+    if (WANT_RUN) {
+        const u32 mc = gballot<G>(isc, gbase);
+        head_is_c = (mc >> t) & 1u;
+        const u32 below = mc & ((1u << t) - 1u);
+        prev_c_run = below ? (base + (31 - __clz(below))) : cm.y;
+        run = base + t;
+    }
+}
+
+template <int G, bool LOCATE>
+__global__ void __launch_bounds__(256)
+search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
+              u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
+              u64* __restrict__ nch_out, u64* __restrict__ nocc_out, u64* __restrict__ lf_steps) {
+    __shared__ u64 sF[257];
+    __shared__ uint16_t sSid[256];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) sF[i] = ix.F[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sSid[i] = ix.sid[i];
+    __syncthreads();
+
+    constexpr int PPW = 32 / (2 * G);  // patterns per warp
+    const int lane = threadIdx.x & 31;
+    const u64 warp = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int which = (lane / G) & 1;  // 0: rank before lo, 1: rank up to hi
+    const int gl = lane % G;
+    const u32 gbase = lane & ~(G - 1);
+    const int pairbase = lane & ~(2 * G - 1);
+    const u64 p = warp * PPW + lane / (2 * G);
+    bool alive = p < N;
+    const uint8_t* P = patt + (alive ? p : 0) * m;
+
+    u64 lo = 0, hi = ix.n - 1;  // full_range, r_index.hpp:155-160
+    u64 k = ix.toe0;            // SA[n-1], r_index.hpp:489
+    u32 steps = 0;
+    for (u64 i = 0; i < m; ++i) {
+        if (!__any_sync(RIG_FULL, alive)) break;  // r_index.hpp:297 (early exit on empty range)
+        const uint8_t c = alive ? __ldg(P + (m - 1 - i)) : 0;
+        const u64 Fc = sF[c], Fc1 = sF[c + 1];
+        const bool act = alive && (Fc < Fc1);  // r_index.hpp:174 (absent symbol -> {1,0})
+        const bool valid = act && (which || lo > 0);
+        const u64 x = valid ? (which ? hi : lo - 1) : 0;
+        u64 cnt, run = 0, prevc = 0;
+        bool hic = false;
+        block_query<G, LOCATE>(ix, x, c, valid ? sSid[c] : 0, gl, gbase, cnt, run, hic, prevc);
+        if (!valid) cnt = 0;
+        const u64 A = __shfl_sync(RIG_FULL, cnt, pairbase);      // rank(lo, c)      r_index.hpp:178
+        const u64 B = __shfl_sync(RIG_FULL, cnt, pairbase + G);  // rank(hi+1, c)    r_index.hpp:181
+        if (LOCATE) {
+            hic = __shfl_sync(RIG_FULL, (int)hic, pairbase + G);
+            prevc = __shfl_sync(RIG_FULL, prevc, pairbase + G);
+        }
+        if (alive) {
+            steps += act ? 1u : 0u;
+            if (!act || B == A) {  // r_index.hpp:175,184
+                lo = 1; hi = 0; alive = false;
+            } else {
+                if (LOCATE) {
+                    if (hic) k -= 1;                           // r_index.hpp:505-509
+                    else k = __ldg(ix.samples_last + prevc);   // r_index.hpp:516-533
+                }
+                lo = Fc + A;        // r_index.hpp:186
+                hi = Fc + B - 1;    // r_index.hpp:188
+            }
+        }
+    }
+    const bool leader = (lane == pairbase) && (p < N);
+    if (LOCATE) {
+        // runs holding lo and hi: the range is cut into one Phi chain per overlapped run
+        const bool ne = (p < N) && hi >= lo;
+        u64 cnt, run = 0, prevc;
+        bool hic;
+        block_query<G, true>(ix, ne ? (which ? hi : lo) : 0, 0, 0, gl, gbase, cnt, run, hic, prevc);
+        const u64 jL = __shfl_sync(RIG_FULL, run, pairbase);
+        const u64 jR = __shfl_sync(RIG_FULL, run, pairbase + G);
+        if (leader) {
+            toe_out[p] = k;
+            jl_out[p] = jL;
+            nch_out[p] = ne ? (jR - jL + 1) : 0;
+            nocc_out[p] = ne ? (hi - lo + 1) : 0;  // r_index.hpp:338
+        }
+    }
+    if (leader) { lo_out[p] = lo; hi_out[p] = hi; }
+    // executed LF steps (for the algorithmic-bytes figure)
+    u32 s = leader ? steps : 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(RIG_FULL, s, off);
+    if (lane == 0 && s) atomicAdd(lf_steps, (u64)s);
+}
+
+// ------------------------------------------------------------------ scans
+#define RIG_SCAN_THREADS 256
+#define RIG_SCAN_ITEMS 8
+#define RIG_SCAN_TILE (RIG_SCAN_THREADS * RIG_SCAN_ITEMS)
+
+__device__ __forceinline__ u64 block_reduce_u64(u64 v, u64* smem) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(RIG_FULL, v, off);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smem[w] = v;
+    __syncthreads();
+    u64 t = 0;
+    if (w == 0) {
+        t = (l < (blockDim.x >> 5)) ? smem[l] : 0;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(RIG_FULL, t, off);
+    }
+    __syncthreads();
+    return t;  // valid in warp 0
+}
+
+// tile sums of two arrays: sums[0][b], sums[1][b]
+__global__ void __launch_bounds__(RIG_SCAN_THREADS)
+scan_tile_sums(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, u64* __restrict__ sums, u64 ntiles) {
+    __shared__ u64 sm[32];
+    const u64 base = (u64)blockIdx.x * RIG_SCAN_TILE;
+    u64 sa = 0, sb = 0;
+    for (int i = 0; i < RIG_SCAN_ITEMS; ++i) {
+        const u64 idx = base + (u64)i * RIG_SCAN_THREADS + threadIdx.x;
+        if (idx < N) { sa += a[idx]; sb += b[idx]; }
+    }
+    sa = block_reduce_u64(sa, sm);
+    sb = block_reduce_u64(sb, sm);
+    if (threadIdx.x == 0) { sums[blockIdx.x] = sa; sums[ntiles + blockIdx.x] = sb; }
+}
+
+// single block: exclusive scan of the tile sums in place; totals[0], totals[1]
+__global__ void __launch_bounds__(1024) scan_sums_inplace(u64* __restrict__ sums, u64 ntiles, u64* __restrict__ totals) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    for (int arr = 0; arr < 2; ++arr) {
+        u64* s = sums + (u64)arr * ntiles;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (u64 base = 0; base < ntiles; base += blockDim.x) {
+            const u64 idx = base + threadIdx.x;
+            const u64 v = idx < ntiles ? s[idx] : 0;
+            u64 inc = v;
+            const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const u64 t = __shfl_up_sync(RIG_FULL, inc, off);
+                if (l >= off) inc += t;
+            }
+            if (l == 31) wsum[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                u64 ws = wsum[l];
+                u64 wi = ws;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const u64 t = __shfl_up_sync(RIG_FULL, wi, off);
+                    if (l >= off) wi += t;
+                }
+                wsum[l] = wi - ws;  // exclusive prefix of warp sums
+            }
+            __syncthreads();
+            const u64 c0 = carry;
+            const u64 excl = c0 + wsum[w] + inc - v;
+            if (idx < ntiles) s[idx] = excl;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[arr] = carry;
+        __syncthreads();
+    }
+}
+
+// per tile: exclusive scan with the tile's offset; out arrays have N+1 entries
+__global__ void __launch_bounds__(RIG_SCAN_THREADS)
+scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u64* __restrict__ sums, u64 ntiles,
+           u64* __restrict__ out_a, u64* __restrict__ out_b, const u64* __restrict__ totals) {
+    __shared__ u64 wsum[2][RIG_SCAN_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * RIG_SCAN_TILE + (u64)threadIdx.x * RIG_SCAN_ITEMS;
+    u64 va[RIG_SCAN_ITEMS], vb[RIG_SCAN_ITEMS];
+    u64 ta = 0, tb = 0;
+#pragma unroll
+    for (int i = 0; i < RIG_SCAN_ITEMS; ++i) {
+        const u64 idx = base + i;
+        va[i] = idx < N ? a[idx] : 0;
+        vb[i] = idx < N ? b[idx] : 0;
+        ta += va[i]; tb += vb[i];
+    }
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u64 ia = ta, ib = tb;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 xa = __shfl_up_sync(RIG_FULL, ia, off), xb = __shfl_up_sync(RIG_FULL, ib, off);
+        if (l >= off) { ia += xa; ib += xb; }
+    }
+    if (l == 31) { wsum[0][w] = ia; wsum[1][w] = ib; }
+    __syncthreads();
+    u64 wa = 0, wb = 0;
+    for (int j = 0; j < w; ++j) { wa += wsum[0][j]; wb += wsum[1][j]; }
+    u64 ea = sums[blockIdx.x] + wa + ia - ta;
+    u64 eb = sums[ntiles + blockIdx.x] + wb + ib - tb;
+#pragma unroll
+    for (int i = 0; i < RIG_SCAN_ITEMS; ++i) {
+        const u64 idx = base + i;
+        if (idx < N) { out_a[idx] = ea; out_b[idx] = eb; }
+        ea += va[i]; eb += vb[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out_a[N] = totals[0]; out_b[N] = totals[1]; }
+}
+
+// ------------------------------------------------------------------ Phi
+// r_index::Phi (r_index.hpp:195-221). Predecessor over the sorted run-first samples strictly
+// below i (sparse_sd_vector::rank excludes i, :107-112), circular (:153-157).
+__device__ __forceinline__ u64 phi_step(const FlatDev& ix, u64 i) {
+    const u64 q = i >> ix.phi_shift;
+    const u32 a = __ldg(ix.phi_dir + q);
+    const u32 e = __ldg(ix.phi_dir + q + 1);
+    u32 lb = a;  // first entry in [a,e) with pos >= i
+    if (e - a > 8) {
+        u32 lo = a, hi = e;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (__ldg(&ix.phi_ent[mid].x) < i) lo = mid + 1; else hi = mid;
+        }
+        lb = lo;
+    } else {
+        while (lb < e && __ldg(&ix.phi_ent[lb].x) < i) ++lb;
+    }
+    const u64 kk = lb ? (u64)lb - 1 : ix.r - 1;  // wrap: no sample below i -> the last one (n-1)
+    const u64 d = __ldg(&ix.phi_ent[kk].y);
+    u64 v = i + d;
+    if (v >= ix.n) v -= ix.n;  // (prev + delta) % n, r_index.hpp:219
+    return v;
+}
+
+// One chain per lane. Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]),
+// min(hi,start[j+1]-1)], walked from the top down; SA at the top is the toehold (j = last run of
+// the range) or samples_last[j]+1 (a run end is a free toehold: same identity as r_index.hpp:489,533).
+// Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order SA[hi], SA[hi-1], ... (r_index.hpp:340-351).
+__global__ void __launch_bounds__(256)
+phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
+                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
+                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ counter, u64 total_chains) {
+    const int lane = threadIdx.x & 31;
+    u64 remaining = 0, k = 0;
+    u64* outp = nullptr;
+    bool exhausted = false;
+    for (;;) {
+        const bool need = (remaining == 0) && !exhausted;
+        const u32 nm = __ballot_sync(RIG_FULL, need);
+        if (nm) {
+            const int leader = __ffs(nm) - 1;
+            u64 base = 0;
+            if (lane == leader) base = atomicAdd(counter, (u64)__popc(nm));
+            base = __shfl_sync(RIG_FULL, base, leader);
+            if (need) {
+                const u64 w = base + __popc(nm & ((1u << lane) - 1u));
+                if (w >= total_chains) {
+                    exhausted = true;
+                } else {
+                    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
+                    while (b - a > 1) {
+                        const u64 mid = (a + b) >> 1;
+                        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+                    }
+                    const u64 p = a;
+                    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
+                    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
+                    const u64 sj = __ldg(ix.start + j), ej = __ldg(ix.start + j + 1) - 1;
+                    const u64 top = min(H, ej), bot = max(L, sj);
+                    if (top == H) k = __ldg(toe_in + p);
+                    else { k = __ldg(ix.samples_last + j) + 1; if (k >= ix.n) k -= ix.n; }
+                    outp = out + __ldg(occ_off + p) + (H - top);
+                    *outp++ = k;
+                    remaining = top - bot;
+                }
+            }
+        }
+        if (!__any_sync(RIG_FULL, remaining > 0 || !exhausted)) break;
+        if (remaining > 0) {
+            k = phi_step(ix, k);
+            *outp++ = k;
+            --remaining;
+        }
+    }
+}
+
+// out[0] += sum v, out[1] += sum v*(i+1)   (mod 2^64)
+__global__ void __launch_bounds__(256) digest_kernel(const u64* __restrict__ v, u64 count, u64* __restrict__ out) {
+    __shared__ u64 sm[32];
+    u64 s0 = 0, s1 = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64)gridDim.x * blockDim.x) {
+        const u64 x = v[i];
+        s0 += x; s1 += x * (i + 1);
+    }
+    s0 = block_reduce_u64(s0, sm);
+    s1 = block_reduce_u64(s1, sm);
+    if (threadIdx.x == 0) { atomicAdd(out, s0); atomicAdd(out + 1, s1); }
+}
+
+}  // namespace rigk

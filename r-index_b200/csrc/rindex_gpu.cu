@@ -1,0 +1,423 @@
+// rindex_gpu.cu — C ABI of librindex_gpu.so (include/rindex_gpu.h): index upload, batch
+// count / locate launches, timing. Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+// There is no CPU path in this library: every query entry point launches CUDA kernels.
+#include "../../include/rindex_gpu.h"
+#include "flat_layout.hpp"
+#include "kernels.cuh"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+using rigk::FlatDev;
+typedef unsigned long long ull;
+
+static thread_local std::string g_cuda_err;
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+            return RIG_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RIG_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); p = nullptr; return RIG_ERR_NOMEM; }
+        cap = want;
+        return RIG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct rig_index {
+    int device = 0;
+    int sm_count = 0;
+    FlatDev d{};
+    rig_index_info info{};
+    rig_options opt{};
+    void* arena = nullptr;  // one allocation holding every flat array
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // workspace (grow-only)
+    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ;
+    ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest
+    ull* h_counters = nullptr;  // pinned mirror
+    rig_timing timing{};
+    bool timing_pending = false;
+    bool ev_valid[6] = {false, false, false, false, false, false};
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+int rig_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* rig_strerror(int code) {
+    switch (code) {
+        case RIG_OK: return "ok";
+        case RIG_ERR_ARG: return "invalid argument";
+        case RIG_ERR_CUDA: return "CUDA runtime error";
+        case RIG_ERR_NO_DEVICE: return "no such CUDA device";
+        case RIG_ERR_CAPACITY: return "occurrence buffer too small";
+        case RIG_ERR_INDEX: return "logical arrays are not a valid r-index";
+        case RIG_ERR_NOMEM: return "out of device memory";
+        default: return "unknown error";
+    }
+}
+
+const char* rig_last_cuda_error(void) { return g_cuda_err.c_str(); }
+const char* rig_version(void) { return "rindex_b200 0.1 (sm_100a)"; }
+
+int rig_index_create(const rig_logical_view* view, int device, rig_index** out) {
+    rig_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    return rig_index_create_ex(view, device, &opt, out);
+}
+
+int rig_index_create_ex(const rig_logical_view* view, int device, const rig_options* optp, rig_index** out) {
+    if (!view || !out) return RIG_ERR_ARG;
+    *out = nullptr;
+    rig_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    if (optp) opt = *optp;
+    int ndev = rig_device_count();
+    if (device < 0 || device >= ndev) return RIG_ERR_NO_DEVICE;
+    CU_TRY(cudaSetDevice(device));
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+
+    rigf::FlatHost f;
+    int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
+    if (rc != RIG_OK) return rc;
+    if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
+
+    rig_index* ix = new (std::nothrow) rig_index();
+    if (!ix) return RIG_ERR_NOMEM;
+    ix->device = device;
+    ix->opt = opt;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+
+    // one arena, every array 256-byte aligned
+    struct Part { const void* src; size_t bytes; size_t off; };
+    Part parts[10] = {
+        {f.F.data(), f.F.size() * 8, 0},            {f.sid.data(), f.sid.size() * 2, 0},
+        {f.start.data(), f.start.size() * 8, 0},    {f.head.data(), f.head.size(), 0},
+        {f.bstart.data(), f.bstart.size() * 8, 0},  {f.cum.data(), f.cum.size() * 8, 0},
+        {f.bdir.data(), f.bdir.size() * 4, 0},      {f.samples_last.data(), f.samples_last.size() * 8, 0},
+        {f.phi_ent.data(), f.phi_ent.size() * 8, 0}, {f.phi_dir.data(), f.phi_dir.size() * 4, 0}};
+    size_t total = 0;
+    for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 16, 256); }
+    cudaError_t e = cudaMalloc(&ix->arena, total);
+    if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc(arena): ") + cudaGetErrorString(e); delete ix; return RIG_ERR_NOMEM; }
+    CU_TRY(cudaMemset(ix->arena, 0, total));
+    for (auto& p : parts) CU_TRY(cudaMemcpy((char*)ix->arena + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
+    char* A = (char*)ix->arena;
+    FlatDev& d = ix->d;
+    d.n = f.n; d.r = f.r; d.nblk = f.nblk; d.toe0 = f.toe0;
+    d.K = f.K; d.S = f.S; d.lf_shift = f.lf_shift; d.phi_shift = f.phi_shift;
+    d.F = (const ull*)(A + parts[0].off);
+    d.sid = (const uint16_t*)(A + parts[1].off);
+    d.start = (const ull*)(A + parts[2].off);
+    d.head = (const uint8_t*)(A + parts[3].off);
+    d.bstart = (const ull*)(A + parts[4].off);
+    d.cum = (const ulonglong2*)(A + parts[5].off);
+    d.bdir = (const uint32_t*)(A + parts[6].off);
+    d.samples_last = (const ull*)(A + parts[7].off);
+    d.phi_ent = (const ulonglong2*)(A + parts[8].off);
+    d.phi_dir = (const uint32_t*)(A + parts[9].off);
+
+    CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
+    CU_TRY(cudaMalloc((void**)&ix->d_counters, 8 * sizeof(ull)));
+    CU_TRY(cudaMemset(ix->d_counters, 0, 8 * sizeof(ull)));
+    CU_TRY(cudaMallocHost((void**)&ix->h_counters, 8 * sizeof(ull)));
+    std::memset(ix->h_counters, 0, 8 * sizeof(ull));
+
+    rig_index_info& I = ix->info;
+    std::memset(&I, 0, sizeof(I));
+    I.n = f.n; I.r = f.r; I.sigma = f.S; I.device_bytes = total;
+    I.lf_blocks = f.nblk; I.lf_buckets = f.lf_nbkt; I.phi_buckets = f.phi_nbkt;
+    I.runs_per_block = f.K; I.lf_shift = f.lf_shift; I.phi_shift = f.phi_shift;
+    I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
+    *out = ix;
+    return RIG_OK;
+}
+
+void rig_index_destroy(rig_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
+                      &ix->occoff, &ix->occ})
+        b->release();
+    if (ix->arena) cudaFree(ix->arena);
+    if (ix->d_counters) cudaFree(ix->d_counters);
+    if (ix->h_counters) cudaFreeHost(ix->h_counters);
+    for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+int rig_index_info_get(const rig_index* ix, rig_index_info* info) {
+    if (!ix || !info) return RIG_ERR_ARG;
+    *info = ix->info;
+    return RIG_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <bool LOCATE>
+int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi,
+                  cudaStream_t st) {
+    const int threads = 256;
+    const uint32_t G = ix->d.K;
+    const uint64_t ppw = 32 / (2 * G);
+    const uint64_t warps = (N + ppw - 1) / ppw;
+    const uint64_t blocks = (warps + (threads / 32) - 1) / (threads / 32);
+    if (blocks > 0x7fffffffull) return RIG_ERR_ARG;
+    ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
+    ull* steps = ix->d_counters + 0;
+#define RIG_LAUNCH(GG)                                                                                     \
+    rigk::search_kernel<GG, LOCATE><<<(unsigned)blocks, threads, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, \
+                                                                           toe, jl, nch, nocc, steps)
+    switch (G) {
+        case 4: RIG_LAUNCH(4); break;
+        case 8: RIG_LAUNCH(8); break;
+        case 16: RIG_LAUNCH(16); break;
+        default: return RIG_ERR_ARG;
+    }
+#undef RIG_LAUNCH
+    CU_TRY(cudaGetLastError());
+    return RIG_OK;
+}
+
+int finish_timing(rig_index* ix) {
+    if (!ix->timing_pending) return RIG_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    // the last recorded event closes the call
+    for (int i = 5; i >= 0; --i)
+        if (ix->ev_valid[i]) { CU_TRY(cudaEventSynchronize(ix->ev[i])); break; }
+    auto el = [&](int a, int b, float& dst) -> int {
+        dst = 0.f;
+        if (ix->ev_valid[a] && ix->ev_valid[b]) CU_TRY(cudaEventElapsedTime(&dst, ix->ev[a], ix->ev[b]));
+        return RIG_OK;
+    };
+    int rc;
+    if ((rc = el(0, 1, ix->timing.h2d_ms))) return rc;
+    if ((rc = el(1, 2, ix->timing.search_ms))) return rc;
+    if ((rc = el(2, 3, ix->timing.scan_ms))) return rc;
+    if ((rc = el(3, 4, ix->timing.expand_ms))) return rc;
+    if ((rc = el(4, 5, ix->timing.d2h_ms))) return rc;
+    ix->timing.lf_steps = ix->h_counters[0];
+    ix->timing_pending = false;
+    return RIG_OK;
+}
+
+void begin_call(rig_index* ix) {
+    std::memset(&ix->timing, 0, sizeof(ix->timing));
+    for (bool& b : ix->ev_valid) b = false;
+    ix->timing_pending = true;
+}
+
+int rec(rig_index* ix, int i, cudaStream_t st) {
+    CU_TRY(cudaEventRecord(ix->ev[i], st));
+    ix->ev_valid[i] = true;
+    return RIG_OK;
+}
+
+// count on device buffers; events 1..2 bracket the kernel
+int count_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, cudaStream_t st) {
+    int rc;
+    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
+    if ((rc = rec(ix, 1, st))) return rc;
+    if (N) {
+        if ((rc = launch_search<false>(ix, d_patt, N, m, d_lo, d_hi, st))) return rc;
+        ix->timing.launches += 1;
+    }
+    if ((rc = rec(ix, 2, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    return RIG_OK;
+}
+
+// search + scans (sync) + expansion; events 1..4
+int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
+               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
+    int rc;
+    const uint64_t ntiles = (N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE;
+    if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
+        (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 2) * 8)) ||
+        (rc = ix->sums.ensure((2 * ntiles + 2) * 8)))
+        return rc;
+    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
+    if ((rc = rec(ix, 1, st))) return rc;
+    if (N) {
+        if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, st))) return rc;
+        ix->timing.launches += 1;
+    }
+    if ((rc = rec(ix, 2, st))) return rc;
+    ull* totals = ix->d_counters + 2;
+    if (N) {
+        rigk::scan_tile_sums<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>((ull*)ix->nocc.p, (ull*)ix->nch.p, N,
+                                                                             (ull*)ix->sums.p, ntiles);
+        rigk::scan_sums_inplace<<<1, 1024, 0, st>>>((ull*)ix->sums.p, ntiles, totals);
+        rigk::scan_tiles<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>((ull*)ix->nocc.p, (ull*)ix->nch.p, N,
+                                                                         (ull*)ix->sums.p, ntiles, d_occoff,
+                                                                         (ull*)ix->choff.p, totals);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 3;
+    } else {
+        CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
+    }
+    CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 3, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    const uint64_t total = ix->h_counters[2], chains = ix->h_counters[3];
+    ix->timing.occ_total = total;
+    ix->timing.chains = chains;
+    if (occ_total) *occ_total = total;
+    if (total > cap || (total && !d_occ)) {
+        if ((rc = rec(ix, 4, st))) return rc;
+        return RIG_ERR_CAPACITY;
+    }
+    if (chains) {
+        const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 256;
+        uint64_t persist = (uint64_t)ix->sm_count * (2048 / threads);
+        uint64_t need = (chains + threads - 1) / threads;
+        unsigned blocks = (unsigned)(need < persist ? need : persist);
+        rigk::phi_expand_kernel<<<blocks, threads, 0, st>>>(ix->d, N, (ull*)ix->choff.p, d_occoff, d_lo, d_hi,
+                                                            (ull*)ix->toe.p, (ull*)ix->jl.p, d_occ,
+                                                            ix->d_counters + 1, chains);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 1;
+    }
+    if ((rc = rec(ix, 4, st))) return rc;
+    return RIG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rig_count_batch_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
+                        uint64_t* d_hi, void* stream) {
+    if (!ix || (N && (!d_patterns && m)) || (N && (!d_lo || !d_hi))) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    begin_call(ix);
+    return count_dev(ix, d_patterns, N, m, (ull*)d_lo, (ull*)d_hi, st);
+}
+
+int rig_locate_batch_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
+                         uint64_t* d_hi, uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t occ_capacity,
+                         uint64_t* occ_total, void* stream) {
+    if (!ix || !d_occ_offsets || (N && (!d_patterns && m)) || (N && (!d_lo || !d_hi))) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    begin_call(ix);
+    return locate_dev(ix, d_patterns, N, m, (ull*)d_lo, (ull*)d_hi, (ull*)d_occ_offsets, (ull*)d_occ, occ_capacity,
+                      occ_total, st);
+}
+
+int rig_count_batch(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi) {
+    if (!ix || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8))) return rc;
+    begin_call(ix);
+    if ((rc = rec(ix, 0, st))) return rc;
+    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
+    if ((rc = count_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, st))) return rc;
+    if ((rc = rec(ix, 3, st)) || (rc = rec(ix, 4, st))) return rc;
+    if (N) {
+        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = rec(ix, 5, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
+int rig_locate_batch(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                     uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total) {
+    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
+        (rc = ix->occoff.ensure((N + 2) * 8)))
+        return rc;
+    if (occ && occ_capacity && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
+    begin_call(ix);
+    if ((rc = rec(ix, 0, st))) return rc;
+    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
+                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
+    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
+    if (occ_total) *occ_total = total;
+    if (N) {
+        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ.p, total * 8, cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 5, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return lrc;
+}
+
+int rig_digest_dev(rig_index* ix, const uint64_t* d_values, uint64_t count, uint64_t out[2], void* stream) {
+    if (!ix || !out || (count && !d_values)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    ull* acc = ix->d_counters + 4;
+    CU_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(ull), st));
+    if (count) {
+        uint64_t blocks = (count + 255) / 256;
+        uint64_t maxb = (uint64_t)ix->sm_count * 8;
+        rigk::digest_kernel<<<(unsigned)(blocks < maxb ? blocks : maxb), 256, 0, st>>>((const ull*)d_values, count, acc);
+        CU_TRY(cudaGetLastError());
+    }
+    ull h[2];
+    CU_TRY(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    out[0] = h[0]; out[1] = h[1];
+    return RIG_OK;
+}
+
+int rig_last_timing(const rig_index* cix, rig_timing* t) {
+    if (!cix || !t) return RIG_ERR_ARG;
+    rig_index* ix = const_cast<rig_index*>(cix);
+    int rc = finish_timing(ix);
+    if (rc) return rc;
+    *t = ix->timing;
+    return RIG_OK;
+}
+
+}  // extern "C"

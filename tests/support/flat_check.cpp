@@ -1,0 +1,124 @@
+// flat_check.cpp — TEST DOUBLE, not shipped: walks the flattened arrays of
+// r-index_b200/csrc/flat_layout.hpp with scalar CPU code that mirrors, step by step, what the
+// CUDA kernels in kernels.cuh do (bdir -> bstart search -> block scan; toehold; chain cutting at
+// run boundaries; phi_dir -> phi_ent). It lets the CPU-only test tier validate the flatten step
+// and the index arithmetic against the oracle before any GPU time is spent. It is compiled into
+// tests/support/libflat_check.so by tests/conftest.py and is never loaded by the product.
+#include "../../r-index_b200/csrc/flat_layout.hpp"
+#include <cstring>
+
+using rigf::FlatHost;
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+namespace {
+
+struct Q { u64 cnt, run, prev_c_run; bool head_is_c; };
+
+// mirrors rigk::block_query
+Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
+    const u32 K = f.K;
+    u64 q = x >> f.lf_shift;
+    u64 b0 = f.bdir[q], b1 = f.bdir[q + 1];
+    while (b1 > b0) {  // same G-ary narrowing as the kernel, G = K probes per round
+        u64 span = b1 - b0, step = (span + K - 1) / K, k = 0;
+        for (u32 g = 0; g < K; ++g) {
+            u64 probe = b0 + (u64)(g + 1) * step;
+            if (probe > b1) probe = b1;
+            if (f.bstart[probe] <= x) ++k;
+        }
+        if (k == 0) b1 = std::min(b1, b0 + step - 1);
+        else { u64 nb0 = std::min(b1, b0 + k * step); b1 = std::min(b1, nb0 + step - 1); b0 = nb0; }
+    }
+    u64 base = b0 * K;
+    int t = -1;
+    for (u32 g = 0; g < K; ++g) if (f.start[base + g] <= x) ++t;
+    Q r;
+    u64 sum = 0; u32 mc = 0;
+    for (u32 g = 0; g < K; ++g) {
+        bool isc = f.head[base + g] == c;
+        if (isc) mc |= 1u << g;
+        if (isc) sum += ((int)g < t) ? (f.start[base + g + 1] - f.start[base + g]) : (((int)g == t) ? (x - f.start[base + g] + 1) : 0);
+    }
+    r.cnt = f.cum[(b0 * f.S + sidc) * 2] + sum;
+    r.head_is_c = (mc >> t) & 1u;
+    u32 below = mc & ((1u << t) - 1u);
+    r.prev_c_run = below ? base + (31 - __builtin_clz(below)) : f.cum[(b0 * f.S + sidc) * 2 + 1];
+    r.run = base + t;
+    return r;
+}
+
+// mirrors rigk::phi_step
+u64 phi_step(const FlatHost& f, u64 i) {
+    u64 q = i >> f.phi_shift;
+    u32 a = f.phi_dir[q], e = f.phi_dir[q + 1], lb = a;
+    while (lb < e && f.phi_ent[2 * (u64)lb] < i) ++lb;
+    u64 kk = lb ? (u64)lb - 1 : f.r - 1;
+    u64 v = i + f.phi_ent[2 * kk + 1];
+    if (v >= f.n) v -= f.n;
+    return v;
+}
+
+// mirrors rigk::search_kernel (one pattern)
+void search(const FlatHost& f, const uint8_t* P, u64 m, bool locate, u64& lo, u64& hi, u64& k) {
+    lo = 0; hi = f.n - 1; k = f.toe0;
+    for (u64 i = 0; i < m; ++i) {
+        uint8_t c = P[m - 1 - i];
+        u64 Fc = f.F[c], Fc1 = f.F[c + 1];
+        if (!(Fc < Fc1)) { lo = 1; hi = 0; return; }
+        u32 sidc = f.sid[c];
+        u64 A = lo > 0 ? block_query(f, lo - 1, c, sidc).cnt : 0;
+        Q qb = block_query(f, hi, c, sidc);
+        if (qb.cnt == A) { lo = 1; hi = 0; return; }
+        if (locate) { if (qb.head_is_c) k -= 1; else k = f.samples_last[qb.prev_c_run]; }
+        lo = Fc + A; hi = Fc + qb.cnt - 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, int* rc_out) {
+    rig_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2;
+    FlatHost* f = new FlatHost();
+    int rc = rigf::flatten(*v, opt, *f);
+    if (rc_out) *rc_out = rc;
+    if (rc != RIG_OK) { delete f; return nullptr; }
+    return f;
+}
+void fc_destroy(void* h) { delete (FlatHost*)h; }
+uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
+
+void fc_count(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi) {
+    const FlatHost& f = *(FlatHost*)h;
+    for (u64 p = 0; p < N; ++p) { u64 k; search(f, patt + p * m, m, false, lo[p], hi[p], k); }
+}
+
+// Same decomposition as the GPU: ranges cut into one chain per overlapped run.
+// occ_off must hold N+1 exclusive prefix sums; returns the number of chains.
+uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi, const u64* occ_off, u64* occ) {
+    const FlatHost& f = *(FlatHost*)h;
+    u64 chains = 0;
+    for (u64 p = 0; p < N; ++p) {
+        u64 k;
+        search(f, patt + p * m, m, true, lo[p], hi[p], k);
+        if (hi[p] < lo[p]) continue;
+        u64 L = lo[p], H = hi[p];
+        u64 jL = block_query(f, L, 0, 0).run, jR = block_query(f, H, 0, 0).run;
+        for (u64 j = jL; j <= jR; ++j) {
+            u64 sj = f.start[j], ej = f.start[j + 1] - 1;
+            u64 top = std::min(H, ej), bot = std::max(L, sj);
+            u64 v = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
+            u64* out = occ + occ_off[p] + (H - top);
+            *out++ = v;
+            for (u64 t = top; t > bot; --t) { v = phi_step(f, v); *out++ = v; }
+            ++chains;
+        }
+    }
+    return chains;
+}
+
+}  // extern "C"
