@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2s|...]
+
+A "step" = one pass of the locate hot path (backward search + toehold, scans, Phi expansion) over
+one batch of synthetic patterns. Default workload = BASELINE.json configs[1] (C2): ri-locate on
+100 MB synthetic repetitive DNA (sigma=4), 100k patterns of length 20, 1xB200.
+
+  value      occurrences/s, device-resident inputs, CUDA-event timed (whole job, all ranks)
+  e2e        occurrences/s through the host-buffer C-ABI call (rig_locate_batch) with pinned host
+             buffers: H2D of the patterns and D2H of ranges, offsets and every occurrence inside
+  roofline   dominant kernel (Phi expansion): algorithmic bytes (264 B/occurrence) /
+             CUDA-event duration vs the measured HBM copy bandwidth
+  cpu_baseline  the reference's own code (oracle/_ref) on the box's host cores, bounded sample
+
+N > 1: one process per GPU (torchrun), index replicated per GPU, patterns sharded (each rank its
+own batch: weak scaling), no collective on the data path; times are max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+CACHE = os.path.join(ROOT, ".cache")
+
+# SURVEY.md §8d configs, concretised. snps: tuned so that r ~ n/1000 for C2 (measured: see DESIGN.md).
+WORKLOADS = {
+    # name: (kind, n, p0, p1, text_seed, N, m, patt_seed, start_limit, description)
+    "c2": ("dna_drift", 100_000_000, 50_000, 3, 0xB2000002, 100_000, 20, 0xB2001002, 0,
+           "C2 ri-locate: 100MB synthetic DNA sigma=4 repetitive, 100k len-20 patterns"),
+    "c2s": ("dna_drift", 10_000_000, 50_000, 3, 0xB2000002, 20_000, 20, 0xB2001002, 0,
+            "C2 scaled down 10x (smoke/dev)"),
+    "c5s": ("dna_indep", 400_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
+            "C5 scaled to 400MB (1000 copies): Phi-chain stress, ~1k occ/pattern"),
+}
+B_PHI = 264          # algorithmic bytes per occurrence: 4 x 64 B blocks + 8 B store
+B_RANK = lambda ell: 64 * (3 + ell)  # noqa: E731  per rank query
+FALLBACK_HBM_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def prepare(workload, need_ref=False, rank=0):
+    """Generate text + patterns (deterministic), build or load the cached indexes."""
+    rib = ge.load_package()
+    kind, n, p0, p1, tseed, N, m, pseed, limit, desc = WORKLOADS[workload]
+    os.makedirs(CACHE, exist_ok=True)
+    t0 = time.time()
+    text = rib.gen_text(kind, n, p0, p1, tseed)
+    patt = rib.gen_patterns(text, N, m, pseed + rank, limit)
+    path = os.path.join(CACHE, "%s.rib" % workload)
+    if os.path.exists(path):
+        host = rib.HostIndex.load(path)
+    else:
+        log("[bench] building index for %s (n=%d) ..." % (workload, n))
+        host = rib.HostIndex.from_text(text)
+        if rank == 0:
+            tmp = path + ".tmp%d" % os.getpid()
+            host.save(tmp)
+            os.replace(tmp, path)
+    ref = None
+    if need_ref:
+        ob = ge.load_oracle()
+        rpath = os.path.join(CACHE, "%s.ref.ri" % workload)
+        if ob.have_ref():
+            if os.path.exists(rpath):
+                ref = ob.RefIndex.load(rpath)
+            else:
+                log("[bench] building REFERENCE index for %s ..." % workload)
+                ref = ob.RefIndex.from_text(text)
+                ref.save(rpath)
+        else:
+            if not ob.have_port():
+                ob.build()
+            log("[bench] oracle/_ref missing: CPU baseline falls back to the plain-C port")
+            ref = ob.PortIndex(text, sa=rib.suffix_array(text))
+    log("[bench] prepared %s in %.1fs: n=%d r=%d n/r=%.1f" % (workload, time.time() - t0, host.n, host.r, host.n / host.r))
+    return text, patt, N, m, host, ref, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # "under load" = samples in the upper half of the observed range
+            hi = [x for x in sm if x >= 0.5 * max(sm)]
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu summary (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(ref, patt, N, m, sample_patterns, threads):
+    """Reference CPU path (locate_all per pattern, results dropped as ri-locate does) on a bounded sample."""
+    S = min(N, sample_patterns)
+    sub = patt[: S * m]
+    _, _, _, occ_total, secs = ref.locate(sub, S, m, threads=threads, want=False)
+    return occ_total, secs, S
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=True)
+    S = min(N, args.ref_sample)
+    threads = cores if ref.kind == "reference" else 1
+    for _ in range(args.warmup):
+        cpu_baseline(ref, patt, N, m, max(1, S // 10), threads)
+    tot_occ, tot_s = 0, 0.0
+    for k in range(args.steps):
+        occ, secs, S = cpu_baseline(ref, patt, N, m, S, threads)
+        tot_occ += occ; tot_s += secs
+    val = tot_occ / tot_s
+    line = {
+        "impl": "reference", "metric": "locate_occurrences_per_s", "value": val, "unit": "occ/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "n": host.n, "r": host.r, "patterns_per_step": S, "pattern_length": m,
+                   "note": "reference CPU code (oracle/_ref: reference headers over SDSL-API shim), bounded sample of the same patterns"},
+        "cpu_baseline": {"value": val, "unit": "occ/s", "cores": threads, "kind": ref.kind,
+                         "sample": "first %d of %d patterns per step, locate_all, results dropped" % (S, N)},
+        "e2e": {"value": val, "unit": "occ/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rib = ge.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
+    t0 = time.time()
+    gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
+                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads)
+    load_s = time.time() - t0
+    info = gpu.info
+    stream = torch.cuda.current_stream().cuda_stream
+
+    d_patt = torch.from_numpy(patt).to(dev)
+    d_lo = torch.empty(N, dtype=torch.int64, device=dev)
+    d_hi = torch.empty(N, dtype=torch.int64, device=dev)
+    d_off = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    # size the occurrence buffer with the two-call protocol
+    try:
+        need = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), None, 0, stream)
+    except rib.RigError as e:
+        if e.code != -4:
+            raise
+        need = e.needed
+    d_occ = torch.empty(max(need, 1), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev():
+        return gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(),
+                              d_occ.data_ptr(), d_occ.numel(), stream)
+
+    def count_dev():
+        gpu.count_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    expand_ms, search_ms, scan_ms, launches = [], [], [], 0
+    occ_total = 0
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
+        ev[k][0].record()
+        occ_total = step_dev()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        t = gpu.timing()
+        expand_ms.append(t["expand_ms"]); search_ms.append(t["search_ms"]); scan_ms.append(t["scan_ms"])
+        launches += t["launches"]
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    lf_steps, chains = t["lf_steps"], t["chains"]
+
+    # count-only pass (patterns/s), same patterns, device resident
+    cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    count_dev(); barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        cev[k][0].record(); count_dev(); cev[k][1].record()
+    barrier()
+    count_ms = sum(a.elapsed_time(b) for a, b in cev)
+    launches_count = args.steps
+
+    # end to end through the host-buffer C-ABI call, pinned host memory
+    h_patt = torch.from_numpy(patt).pin_memory()
+    h_lo = torch.empty(N, dtype=torch.int64).pin_memory()
+    h_hi = torch.empty(N, dtype=torch.int64).pin_memory()
+    h_off = torch.empty(N + 1, dtype=torch.int64).pin_memory()
+    h_occ = torch.empty(max(need, 1), dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        return gpu.locate_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(),
+                              h_occ.data_ptr(), h_occ.numel())
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_t = 0.0
+    for k in range(e2e_steps):
+        flush.zero_(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        tot_e2e = step_e2e()
+        e2e_t += time.perf_counter() - t1
+    barrier()
+    assert tot_e2e == occ_total
+    # cheap self-check of the e2e result (not a parity test: those live in tests/)
+    assert int(h_off[-1]) == occ_total
+
+    # reduce over ranks: max time, sum work
+    red = torch.tensor([total_ms, count_ms, e2e_t * 1e3 / e2e_steps * args.steps], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(occ_total), float(N), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    total_ms_g, count_ms_g, e2e_ms_g = [float(x) for x in red.tolist()]
+    occ_g, N_g, launches_g = [float(x) for x in work.tolist()]
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        exp_ms = statistics.mean(expand_ms)
+        alg_bytes = occ_total * B_PHI
+        achieved = alg_bytes / (exp_ms * 1e-3) / 1e9
+        ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
+        srch_ms = statistics.mean(search_ms)
+        line = {
+            "metric": "locate_occurrences_per_s", "value": occ_g * args.steps / (total_ms_g * 1e-3), "unit": "occ/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_g / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n": int(info.n), "r": int(info.r), "sigma": int(info.sigma),
+                       "patterns_per_gpu": N, "pattern_length": m, "occurrences_per_step_per_gpu": occ_total,
+                       "phi_chains_per_step": int(chains), "lf_steps_per_step": int(lf_steps),
+                       "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
+                       "runs_per_block": int(info.runs_per_block), "parallelism": "patterns sharded x%d, index replicated" % world,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
+                       "timing": "CUDA events per step on the launch stream; max over ranks"},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "e2e": {"value": occ_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
+                    "h2d_bytes_per_step": int(N * m), "d2h_bytes_per_step": int(8 * (2 * N + N + 1 + occ_total)),
+                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
+            "gpu_launches": int(launches_g) + launches_count * world,
+            "count": {"metric": "count_patterns_per_s", "value": N_g * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
+                      "ms_per_step": count_ms_g / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "phi_expand_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic("phi_expand_kernel"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
+                         "regime": "A (index resident in L2: touched bytes are served by L2; DRAM traffic ~ output stream)",
+                         "search_kernel": {"launch_ms": srch_ms, "algorithmic_bytes": int(lf_steps) * 3 * B_RANK(ell),
+                                           "achieved": int(lf_steps) * 3 * B_RANK(ell) / (srch_ms * 1e-3) / 1e9 if srch_ms > 0 else None},
+                         "scan_ms": statistics.mean(scan_ms)},
+        }
+        if ref is not None:
+            cores = os.cpu_count() or 1
+            threads = cores if ref.kind == "reference" else 1
+            cpu_baseline(ref, patt, N, m, max(1, args.cpu_sample // 10), threads)  # warm-up
+            occ_c, secs_c, S = cpu_baseline(ref, patt, N, m, args.cpu_sample, threads)
+            line["cpu_baseline"] = {"value": occ_c / secs_c, "unit": "occ/s", "cores": threads, "kind": ref.kind,
+                                    "sample": "first %d of %d patterns (%d occurrences), locate_all loop, %.2fs" % (S, N, occ_c, secs_c)}
+            if ref.kind == "reference":
+                occ_1, secs_1, S1 = cpu_baseline(ref, patt, N, m, max(1, args.cpu_sample // 8), 1)
+                line["cpu_baseline"]["single_core_value"] = occ_1 / secs_1
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="patterns in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=10000, help="patterns per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--runs-per-block", type=int, default=0)
+    ap.add_argument("--lf-log2", type=int, default=0)
+    ap.add_argument("--phi-log2", type=int, default=0)
+    ap.add_argument("--expand-threads", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

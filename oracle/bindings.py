@@ -243,6 +243,8 @@ class PortIndex:
         np.cumsum(nocc, out=off[1:])
         occ = np.zeros(int(off[-1]), dtype=np.uint64)
         secs = self.lib.rio_locate_batch(self.h, _ptr(p), N, m, _ptr(off), _ptr(occ), None)
+        if not want:
+            return None, None, None, int(occ.size), secs
         return lo, hi, off, occ, secs
 
     def rank(self, i, c):

@@ -54,6 +54,10 @@ def _np_view(addr, count, dtype):
     return np.ctypeslib.as_array(ctypes.cast(addr, ctypes.POINTER(ct)), shape=(count,))
 
 
+class _Arrays(dict):
+    """dict of borrowed numpy views + a reference to the owning HostIndex."""
+
+
 class HostIndex:
     """Logical r-index on the host (what the reference keeps in F / bwt / pred / samples_last /
     pred_to_run, internal/r_index.hpp:655-665), built by this repo's own builder."""
@@ -94,9 +98,11 @@ class HostIndex:
     def arrays(self):
         """Borrowed numpy views of the logical arrays (valid while this object lives)."""
         v, r = self.view, self.r
-        return dict(n=self.n, r=r, F=_np_view(v.F, 257, np.uint64), run_heads=_np_view(v.run_heads, r, np.uint8),
+        d = _Arrays(n=self.n, r=r, F=_np_view(v.F, 257, np.uint64), run_heads=_np_view(v.run_heads, r, np.uint8),
                     run_lens=_np_view(v.run_lens, r, np.uint64), samples_last=_np_view(v.samples_last, r, np.uint64),
                     pred_pos=_np_view(v.pred_pos, r, np.uint64), pred_to_run=_np_view(v.pred_to_run, r, np.uint64))
+        d._owner = self  # the views borrow the C++ object's memory: the dict keeps it alive
+        return d
 
     def close(self):
         if self.h:

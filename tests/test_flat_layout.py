@@ -1,0 +1,76 @@
+"""CPU tier: the flatten-at-load step (r-index_b200/csrc/flat_layout.hpp) checked with the scalar
+test double (tests/support/flat_check.cpp), which mirrors the kernels' index arithmetic."""
+import numpy as np
+import pytest
+
+from conftest import rib, ob, FlatCheck, mixed_patterns, repetitive_text, GOLDEN
+import os
+
+
+@pytest.mark.parametrize("K", [4, 8, 16])
+def test_flat_walk_equals_oracle(K):
+    rng = np.random.default_rng(K)
+    for it in range(60):
+        n = int(rng.integers(1, 1500))
+        t = repetitive_text(n, int(rng.integers(1, 120)), int(rng.integers(0, 4)), 50 * K + it, sigma=int(rng.choice([1, 2, 4, 15])))
+        host = rib.HostIndex.from_text(t)
+        port = ob.PortIndex(t)
+        N, m = 40, int(rng.integers(1, 8))
+        patt = mixed_patterns(t, N, m, it)
+        elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+        fc = FlatCheck(host, K=K, lf_log2=int(rng.choice([0, 1, 3, 6])), phi_log2=int(rng.choice([0, 1, 3, 6])))
+        assert fc.rc == 0
+        lo, hi, off, occ, chains = fc.locate(patt, N, m)
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi)
+        assert np.array_equal(off, eoff) and np.array_equal(occ, eocc)
+        assert chains >= int((ehi >= elo).sum())
+
+
+def test_flat_walk_medium_texts():
+    for kind, args in (("dna_drift", (300_000, 3_000, 3, 5)), ("versioned_doc", (200_000, 2_000, 96, 6)),
+                       ("pangenome", (200_000, 4_000, 100, 7))):
+        t = rib.gen_text(kind, *args)
+        host = rib.HostIndex.from_text(t)
+        port = ob.PortIndex(t, sa=rib.suffix_array(t))
+        N, m = 400, 9
+        patt = mixed_patterns(t, N, m, 3)
+        elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+        lo, hi, off, occ, _ = FlatCheck(host, K=16).locate(patt, N, m)
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(occ, eocc)
+
+
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")))
+def test_flat_walk_golden(fname):
+    g = np.load(os.path.join(GOLDEN, fname))
+    host = rib.HostIndex.from_text(g["text"])
+    lo, hi, off, occ, _ = FlatCheck(host, K=8).locate(g["patterns"], int(g["N"]), int(g["m"]))
+    assert np.array_equal(lo, g["lo"]) and np.array_equal(hi, g["hi"]) and np.array_equal(off, g["occ_offsets"])
+    if "occ" in g.files:
+        assert np.array_equal(occ, g["occ"])
+
+
+def test_flatten_rejects_invalid_indexes():
+    t = repetitive_text(3000, 100, 2, 1)
+    host = rib.HostIndex.from_text(t)  # arrays() are borrowed views: keep the owner alive while copying
+    good = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in host.arrays().items()}
+    assert FlatCheck(good).rc == 0
+
+    def broken(**kw):
+        d = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in good.items()}
+        for k, f in kw.items():
+            f(d[k]) if callable(f) else d.__setitem__(k, f)
+        return FlatCheck(d).rc
+
+    def bump(i):
+        def f(a):
+            a[i] += 1
+        return f
+    assert broken(run_lens=bump(0)) == -5           # lengths no longer sum to n
+    assert broken(pred_pos=bump(-1)) == -5          # last sample must be n-1
+    assert broken(F=bump(70)) == -5                 # F disagrees with the runs
+    assert broken(n=good["n"] + 1) == -5
+
+    def swap(a):
+        a[[0, 1]] = a[[1, 0]]
+    assert broken(pred_pos=swap) == -5              # pred must be ascending
+    assert FlatCheck(good, K=5).rc == -1            # unsupported group size

@@ -1,0 +1,217 @@
+"""-m gpu: the CUDA path, called through the C ABI (include/rindex_gpu.h), against the oracle.
+
+Bar: bit-exact (u64 ranges, offsets and every occurrence position, in locate_all order
+SA[hi], SA[hi-1], ..., SA[lo] — reference internal/r_index.hpp:340-351)."""
+import numpy as np
+import pytest
+
+from conftest import rib, ob, mixed_patterns, repetitive_text, needs_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_all(gpu, oracle, patt, N, m, tag=""):
+    elo, ehi, eoff, eocc, _ = oracle.locate(patt, N, m)
+    lo, hi = gpu.count(patt, N, m)
+    assert np.array_equal(lo, elo), tag + " count lo"
+    assert np.array_equal(hi, ehi), tag + " count hi"
+    lo2, hi2, off, occ = gpu.locate(patt, N, m)
+    assert np.array_equal(lo2, elo) and np.array_equal(hi2, ehi), tag + " locate ranges"
+    assert np.array_equal(off, eoff), tag + " offsets"
+    assert np.array_equal(occ, eocc), tag + " occurrences"
+    return eocc.size
+
+
+@pytest.mark.parametrize("K", [4, 8, 16])
+def test_small_random_texts(K):
+    rng = np.random.default_rng(100 + K)
+    for it in range(40):
+        n = int(rng.integers(1, 400))
+        sigma = int(rng.choice([1, 2, 4, 15]))
+        base = int(rng.integers(1, max(2, n // 3)))
+        text = repetitive_text(n, base, int(rng.integers(0, 4)), 1000 * K + it, sigma=sigma)
+        m = int(rng.integers(1, 7))
+        N = 64
+        patt = mixed_patterns(text, N, m, it)
+        host = rib.HostIndex.from_text(text)
+        port = ob.PortIndex(text)
+        gpu = rib.GpuIndex(host, runs_per_block=K, lf_bucket_log2=int(rng.choice([0, 1, 5])),
+                           phi_bucket_log2=int(rng.choice([0, 1, 5])))
+        _check_all(gpu, port, patt, N, m, "K=%d it=%d" % (K, it))
+        gpu.close()
+
+
+@pytest.mark.parametrize("K", [4, 8, 16])
+def test_repetitive_dna_medium(K):
+    text = rib.gen_text("dna_drift", 400_000, 4_000, 3, 77)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host, runs_per_block=K)
+    for (N, m, seed) in [(1000, 8, 1), (777, 20, 2), (33, 1, 3), (500, 50, 4)]:
+        patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+        nocc = _check_all(gpu, port, patt, N, m, "dna N=%d m=%d" % (N, m))
+        assert nocc > 0
+    t = gpu.timing()
+    assert t["launches"] >= 1 and t["occ_total"] > 0 and t["chains"] > 0
+
+
+def test_large_alphabet_versioned_doc():
+    text = rib.gen_text("versioned_doc", 300_000, 3_000, 96, 5)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host)
+    assert gpu.info.sigma > 60
+    for (N, m, seed) in [(800, 30, 1), (400, 3, 2)]:
+        patt = mixed_patterns(text, N, m, seed)
+        _check_all(gpu, port, patt, N, m, "doc N=%d m=%d" % (N, m))
+
+
+def test_edge_cases():
+    text = np.frombuffer(b"abracadabra_abracadabra_\xff\xfe\xffabra" * 7, dtype=np.uint8)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text)
+    gpu = rib.GpuIndex(host)
+    # N = 0
+    lo, hi = gpu.count(np.zeros(0, dtype=np.uint8), 0, 5)
+    assert lo.size == 0 and hi.size == 0
+    lo, hi, off, occ = gpu.locate(np.zeros(0, dtype=np.uint8), 0, 5)
+    assert off.tolist() == [0] and occ.size == 0
+    # m = 0: the full range, occ = n (terminator row included) — r_index.hpp:292-302 with an empty loop
+    lo, hi, off, occ = gpu.locate(np.zeros(0, dtype=np.uint8), 3, 0)
+    elo, ehi, eoff, eocc, _ = port.locate(np.zeros(0, dtype=np.uint8), 3, 0)
+    assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(occ, eocc)
+    assert int(hi[0] - lo[0] + 1) == text.size + 1
+    # absent symbols, the terminator byte 0x01, 0x00 and 0xFF (F[256] sentinel)
+    pats = [b"\x00", b"\x01", b"\xff", b"\xfe", b"z", b"a"]
+    patt = np.frombuffer(b"".join(pats), dtype=np.uint8)
+    _check_all(gpu, port, patt, len(pats), 1, "single bytes")
+    lo, hi = gpu.count(patt, len(pats), 1)
+    assert (lo[0], hi[0]) == (1, 0)          # 0x00 never occurs: the empty range is {1,0}
+    assert hi[1] - lo[1] + 1 == 1            # 0x01 matches the terminator row only
+    pats2 = [b"abra", b"\xff\xfe\xff\x61", b"a\x01ra", b"zzzz", b"dabr", b"_abr", b"ra_a", b"bra\xff"]
+    patt2 = np.frombuffer(b"".join(pats2), dtype=np.uint8)
+    _check_all(gpu, port, patt2, len(pats2), 4, "mixed")
+    # pattern longer than the text
+    patt3 = np.frombuffer(bytes(text) + b"a", dtype=np.uint8)
+    _check_all(gpu, port, patt3, 1, patt3.size, "too long")
+    # the whole text as a pattern occurs exactly once, at position 0
+    lo, hi, off, occ = gpu.locate(text, 1, text.size)
+    assert occ.tolist() == [0]
+
+
+def test_single_run_and_tiny_texts():
+    for t in [b"a", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"ab", b"ba", b"abababababababababab", b"\xff" * 40]:
+        text = np.frombuffer(t, dtype=np.uint8)
+        host = rib.HostIndex.from_text(text)
+        port = ob.PortIndex(text)
+        for K in (4, 16):
+            gpu = rib.GpuIndex(host, runs_per_block=K)
+            for m in (1, 2, 3):
+                patt = mixed_patterns(text, 32, m, m)
+                _check_all(gpu, port, patt, 32, m, repr(t[:8]))
+            gpu.close()
+
+
+def test_capacity_protocol_and_errors():
+    text = rib.gen_text("dna_drift", 50_000, 1_000, 2, 9)
+    host = rib.HostIndex.from_text(text)
+    gpu = rib.GpuIndex(host)
+    N, m = 100, 6
+    patt = rib.gen_patterns(text, N, m, 4)
+    import ctypes
+    lo = np.zeros(N, dtype=np.uint64); hi = np.zeros(N, dtype=np.uint64); off = np.zeros(N + 1, dtype=np.uint64)
+    tot = ctypes.c_uint64(0)
+    small = np.zeros(3, dtype=np.uint64)
+    rc = gpu.lib.rig_locate_batch(gpu.h, patt.ctypes.data, N, m, lo.ctypes.data, hi.ctypes.data, off.ctypes.data,
+                                  small.ctypes.data, small.size, ctypes.byref(tot))
+    assert rc == -4 and tot.value == off[-1] and tot.value > 3      # RIG_ERR_CAPACITY, ranges still filled
+    assert np.array_equal(np.where(hi >= lo, hi - lo + 1, 0), np.diff(off))
+    rc = gpu.lib.rig_count_batch(gpu.h, patt.ctypes.data, N, m, None, hi.ctypes.data)
+    assert rc == -1                                                  # RIG_ERR_ARG
+    assert gpu.lib.rig_strerror(-4) == b"occurrence buffer too small"
+    # a corrupt index is rejected at create time
+    bad = dict(host.arrays())
+    bad["run_lens"] = bad["run_lens"].copy(); bad["run_lens"][0] += 1
+    with pytest.raises(rib.RigError) as e:
+        rib.GpuIndex(bad)
+    assert e.value.code == -5
+    with pytest.raises(rib.RigError) as e:
+        rib.GpuIndex(host, device=99)
+    assert e.value.code == -3
+
+
+def test_device_buffer_api_and_digest():
+    torch = pytest.importorskip("torch")
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 21)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host)
+    N, m = 2000, 10
+    patt = rib.gen_patterns(text, N, m, 8)
+    elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+    dev = torch.device("cuda:0")
+    d_patt = torch.from_numpy(patt).to(dev)
+    d_lo = torch.zeros(N, dtype=torch.int64, device=dev); d_hi = torch.zeros(N, dtype=torch.int64, device=dev)
+    d_off = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.count_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_lo.cpu().numpy().view(np.uint64), elo)
+    assert np.array_equal(d_hi.cpu().numpy().view(np.uint64), ehi)
+    with pytest.raises(rib.RigError) as e:
+        gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), None, 0, stream)
+    assert e.value.code == -4 and e.value.needed == eocc.size
+    d_occ = torch.zeros(eocc.size, dtype=torch.int64, device=dev)
+    tot = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(),
+                         d_occ.numel(), stream)
+    torch.cuda.synchronize()
+    assert tot == eocc.size
+    assert np.array_equal(d_occ.cpu().numpy().view(np.uint64), eocc)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), eoff)
+    from rindex_b200._gpu import digest_host
+    assert gpu.digest_dev(d_occ.data_ptr(), d_occ.numel(), stream) == digest_host(eocc)
+    t = gpu.timing()
+    assert t["occ_total"] == eocc.size and t["lf_steps"] > 0 and t["expand_ms"] > 0
+
+
+@needs_ref
+def test_against_reference_code_and_reference_built_index():
+    """The reference's own r_index<> (oracle/_ref): same answers, and an index BUILT BY THE
+    REFERENCE, extracted through its accessors (the INTEGRATION.md path), drives the GPU."""
+    text = rib.gen_text("dna_drift", 250_000, 2_500, 3, 31)
+    ref = ob.RefIndex.from_text(text)
+    N, m = 1500, 12
+    patt = mixed_patterns(text, N, m, 5, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    gpu = rib.GpuIndex(ref.extract())
+    _check_all(gpu, ref, patt, N, m, "ref-built")
+    gpu2 = rib.GpuIndex(rib.HostIndex.from_text(text))
+    _check_all(gpu2, ref, patt, N, m, "own-built")
+
+
+def test_full_size_properties_c2_like():
+    """At a size where the oracle would take minutes: size-independent properties.
+    n_occ == hi-lo+1; every reported position really holds the pattern (ri-locate -c idea,
+    reference ri-locate.cpp:156-190); positions per pattern are distinct; count == locate ranges."""
+    n = 20_000_000
+    text = rib.gen_text("dna_drift", n, 50_000, 3, 0xB2000002)
+    host = rib.HostIndex.from_text(text)
+    gpu = rib.GpuIndex(host)
+    N, m = 20_000, 20
+    patt = rib.gen_patterns(text, N, m, 0xB2001002)
+    lo, hi = gpu.count(patt, N, m)
+    lo2, hi2, off, occ = gpu.locate(patt, N, m)
+    assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+    nocc = np.where(hi >= lo, hi - lo + np.uint64(1), np.uint64(0))
+    assert np.array_equal(np.diff(off), nocc) and occ.size == int(nocc.sum())
+    assert (nocc > 0).all()  # patterns were sampled from the text
+    assert int(occ.max()) <= n - m
+    P = patt.reshape(N, m)
+    rng = np.random.default_rng(0)
+    for p in rng.integers(0, N, size=300):
+        o = occ[int(off[p]):int(off[p + 1])].astype(np.int64)
+        assert np.unique(o).size == o.size
+        win = text[o[:, None] + np.arange(m)[None, :]]
+        assert (win == P[p][None, :]).all()
+    # whole-output check for the first patterns: count by brute force
+    for p in range(5):
+        assert ob.brute_count(text, P[p]) == int(nocc[p])

@@ -1,0 +1,95 @@
+"""CPU tier: host-side builder, container I/O, generators, pattern-file parsing."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rib, ob, repetitive_text, needs_ref
+
+
+def test_builder_equals_oracle_content():
+    """This repo's builder produces exactly the logical arrays the reference's construction defines
+    (r_index.hpp:553-634 sufsort, :72-82 F, :108-146 pred/pred_to_run/samples_last)."""
+    rng = np.random.default_rng(3)
+    for it in range(40):
+        n = int(rng.integers(1, 3000))
+        t = repetitive_text(n, int(rng.integers(1, 200)), int(rng.integers(0, 5)), it, sigma=int(rng.choice([1, 2, 4, 15])))
+        a = rib.HostIndex.from_text(t).arrays()
+        b = ob.PortIndex(t).extract()
+        assert a["n"] == b["n"] == n + 1 and a["r"] == b["r"]
+        for k in ("F", "run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run"):
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+        assert int(a["run_lens"].sum()) == n + 1
+        assert int(a["pred_pos"][-1]) == n  # last text position always sampled, r_index.hpp:129
+
+
+@needs_ref
+def test_builder_equals_reference_built_index():
+    t = rib.gen_text("dna_drift", 120_000, 1_500, 3, 11)
+    a = rib.HostIndex.from_text(t).arrays()
+    b = ob.RefIndex.from_text(t).extract()
+    for k in ("F", "run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_reserved_characters_rejected():
+    for bad in (b"abc\x00def", b"abc\x01def"):
+        with pytest.raises(ValueError, match="reserved characters 0x0, 0x1"):
+            rib.HostIndex.from_text(bad)
+
+
+def test_save_load_roundtrip(tmp_path):
+    t = repetitive_text(5000, 100, 2, 1)
+    h = rib.HostIndex.from_text(t)
+    for flag in (True, False):
+        p = str(tmp_path / ("x%d.ri" % flag))
+        h.save(p, with_flag_byte=flag)
+        g = rib.HostIndex.load(p, with_flag_byte=flag)
+        a, b = h.arrays(), g.arrays()
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    with pytest.raises(IOError):
+        rib.HostIndex.load(str(tmp_path / "missing.ri"))
+    junk = tmp_path / "junk.ri"
+    junk.write_bytes(b"\x00not an index at all")
+    with pytest.raises(IOError):
+        rib.HostIndex.load(str(junk))
+    # the leading byte is the reference's `fast` flag (ri-build.cpp:133): file = 1 byte + container
+    assert open(str(tmp_path / "x1.ri"), "rb").read(9)[1:] == b"RIB200v1"
+
+
+def test_generators_deterministic_and_shaped():
+    a = rib.gen_text("dna_drift", 100_000, 1_000, 3, 42)
+    b = rib.gen_text("dna_drift", 100_000, 1_000, 3, 42)
+    c = rib.gen_text("dna_drift", 100_000, 1_000, 3, 43)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert set(np.unique(a).tolist()) == set(b"ACGT")
+    d = rib.gen_text("versioned_doc", 50_000, 1_000, 96, 1)
+    assert d.min() >= 0x0A and d.max() <= 0x7E and np.unique(d).size > 40
+    e = rib.gen_text("pangenome", 60_000, 2_000, 50, 1)
+    assert set(np.unique(e).tolist()) <= set(b"ACGTN") and (e == ord("N")).sum() >= 10
+    f = rib.gen_text("dna_indep", 80_000, 2_000, 1_000_000, 1)
+    assert f.size == 80_000
+    # repetitive: far fewer runs than symbols
+    h = rib.HostIndex.from_text(a)
+    assert h.r * 10 < h.n
+    p = rib.gen_patterns(a, 50, 7, 5)
+    s = bytes(a)
+    assert all(bytes(p[i * 7:(i + 1) * 7]) in s for i in range(50))
+    assert np.array_equal(p, rib.gen_patterns(a, 50, 7, 5))
+
+
+def test_pattern_file_format(tmp_path):
+    """Pizza&Chili shape read by the reference (utils.hpp:57-91, ri-count.cpp:86-110): header line,
+    then N*m raw bytes which may contain newlines and bytes >= 0x80."""
+    body = np.frombuffer(b"ab\ncd\xff\x80ef" * 3, dtype=np.uint8)
+    p = str(tmp_path / "p.patt")
+    rib.write_pattern_file(p, body, 9, 3)
+    N, m, got = rib.parse_pattern_file(open(p, "rb").read())
+    assert (N, m) == (9, 3) and np.array_equal(got, body)
+    N, m, _ = rib.parse_pattern_file(b"# number=7 length=10 file=genome.fasta forbidden=\n\t\n" + b"x" * 70)
+    assert (N, m) == (7, 10)
+    with pytest.raises(ValueError):
+        rib.parse_pattern_file(b"# nomber=7 length=10 file=x forbidden=\n")
+    with pytest.raises(ValueError):
+        rib.parse_pattern_file(b"# number=7 length=10\n")  # no space after the last field
