@@ -218,10 +218,14 @@ def run_ours(args):
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
-                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads)
+                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads, phi_jump=args.phi_jump)
     load_s = time.time() - t0
     info = gpu.info
-    stream = torch.cuda.current_stream().cuda_stream
+    # the library launches on the stream it is given (NULL would mean its own stream): use a real
+    # torch stream so that torch.cuda.Event sees the same stream the kernels run on
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     d_patt = torch.from_numpy(patt).to(dev)
     d_lo = torch.empty(N, dtype=torch.int64, device=dev)
@@ -334,7 +338,7 @@ def run_ours(args):
                        "patterns_per_gpu": N, "pattern_length": m, "occurrences_per_step_per_gpu": occ_total,
                        "phi_chains_per_step": int(chains), "lf_steps_per_step": int(lf_steps),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
-                       "runs_per_block": int(info.runs_per_block), "parallelism": "patterns sharded x%d, index replicated" % world,
+                       "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump), "parallelism": "patterns sharded x%d, index replicated" % world,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
                        "timing": "CUDA events per step on the launch stream; max over ranks"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
@@ -382,6 +386,7 @@ def main():
     ap.add_argument("--lf-log2", type=int, default=0)
     ap.add_argument("--phi-log2", type=int, default=0)
     ap.add_argument("--expand-threads", type=int, default=0)
+    ap.add_argument("--phi-jump", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -51,7 +51,7 @@ typedef struct rig_options {
     uint32_t lf_bucket_log2;   /* 0 = auto: log2 of (directory buckets per run block) */
     uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
     uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
-    uint32_t reserved[4];
+    uint32_t reserved[4];      /* reserved[0] = phi_jump: 0 = auto, 1 = none, 2/4/8 = build the Phi^D jump table */
 } rig_options;
 
 typedef struct rig_index_info {
@@ -59,7 +59,9 @@ typedef struct rig_index_info {
     uint64_t device_bytes;       /* HBM footprint of the flattened index */
     uint64_t lf_blocks, lf_buckets, phi_buckets;
     uint32_t runs_per_block, lf_shift, phi_shift, device;
-    uint32_t sm_count, reserved;
+    uint32_t sm_count, phi_jump;  /* phi_jump = D of the Phi^D jump table (1 = none) */
+    uint64_t phi_jump_pieces;     /* pieces of the Phi^D translation table (<= D*r) */
+    uint32_t words32, reserved;   /* words32 = 1: n < 2^32-1, Phi directory records are 32-bit */
 } rig_index_info;
 
 /* CUDA-event timings (ms) of the phases of the most recent batch call on this index. */

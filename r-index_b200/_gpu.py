@@ -30,7 +30,8 @@ class Options(ctypes.Structure):
 class IndexInfo(ctypes.Structure):
     _fields_ = [("n", _u64), ("r", _u64), ("sigma", _u64), ("device_bytes", _u64), ("lf_blocks", _u64),
                 ("lf_buckets", _u64), ("phi_buckets", _u64), ("runs_per_block", _u32), ("lf_shift", _u32),
-                ("phi_shift", _u32), ("device", _u32), ("sm_count", _u32), ("reserved", _u32)]
+                ("phi_shift", _u32), ("device", _u32), ("sm_count", _u32), ("phi_jump", _u32),
+                ("phi_jump_pieces", _u64), ("words32", _u32), ("reserved", _u32)]
 
 
 class Timing(ctypes.Structure):
@@ -115,7 +116,8 @@ def view_from_arrays(d):
 class GpuIndex:
     """A flattened r-index resident in one GPU's HBM (struct rig_index)."""
 
-    def __init__(self, source, device=0, runs_per_block=0, lf_bucket_log2=0, phi_bucket_log2=0, expand_threads=0):
+    def __init__(self, source, device=0, runs_per_block=0, lf_bucket_log2=0, phi_bucket_log2=0, expand_threads=0,
+                 phi_jump=0):
         lib = gpu_lib()
         if isinstance(source, HostIndex):
             view, self._keep = source.view, source
@@ -124,6 +126,7 @@ class GpuIndex:
         else:
             raise TypeError("GpuIndex needs a HostIndex or a dict of logical arrays")
         opt = Options(runs_per_block, lf_bucket_log2, phi_bucket_log2, expand_threads)
+        opt.reserved[0] = phi_jump
         h = _vp()
         rc = lib.rig_index_create_ex(ctypes.byref(view), device, ctypes.byref(opt), ctypes.byref(h))
         if rc != 0:
@@ -175,6 +178,8 @@ class GpuIndex:
                                            ctypes.byref(tot))
         if rc != 0:
             raise RigError(rc, "rig_locate_batch")
+        if occ is None:
+            occ = np.empty(0, dtype=np.uint64)
         return lo, hi, off, occ[: int(tot.value)]
 
     def locate_raw(self, p_ptr, N, m, lo_ptr, hi_ptr, off_ptr, occ_ptr, cap):

@@ -22,7 +22,15 @@
 //   r_index::pred (EF) + pred_to_run + samples_last      phi_ent[]: (text position, delta) pairs sorted
 //     r_index.hpp:663-665                                  by position, delta = samples_last[run-1] - pos
 //                                                         (mod n), so Phi(i) = (i + delta) mod n;
-//                                                       phi_dir[]: direct-addressed position>>s -> rank
+//                                                       Stored as a TRANSLATION TABLE (TransTable): sorted
+//                                                         piece starts + deltas, a direct-addressed
+//                                                         directory position>>s -> piece, and "fat" bucket
+//                                                         records (d0,s1,d1,s2) that answer a step in ONE
+//                                                         128/256-bit load in the common case.
+//                                                       A second table holds Phi^D = Phi applied D times
+//                                                         (composition of piecewise translations: <= D*r
+//                                                         pieces), so D lanes walk one chain D steps at a
+//                                                         time: critical path / D, same answers.
 //   r_index::samples_last                               samples_last[] : u64, run order (toeholds,
 //                                                         chain splitting at run boundaries)
 //   r_index::F                                          F[257], sid[256] (symbol -> dense id)
@@ -36,6 +44,74 @@ namespace rigf {
 
 typedef uint64_t u64;
 typedef uint32_t u32;
+
+// A piecewise translation of [0,n): piece k covers [start[k], start[k+1]) and maps i -> (i + delta[k]) mod n.
+struct TransTable {
+    std::vector<u64> start, delta;  // start[0] == 0, strictly ascending
+    u32 shift = 0;
+    u64 nbkt = 0;
+    std::vector<u32> dir;           // [nbkt+1] piece covering position q<<shift (dir[nbkt] = last piece)
+    std::vector<u64> fat;           // [4*nbkt] (d0, s1, d1, s2) per bucket, ~0 = none
+    u64 pieces() const { return start.size(); }
+    u64 bytes(bool w32) const { return start.size() * 16 + dir.size() * 4 + fat.size() * (w32 ? 4 : 8); }
+    u64 apply(u64 i, u64 n) const {  // scalar evaluation (host-side composition + tests)
+        u64 k = (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1;
+        u64 v = i + delta[k];
+        return v >= n ? v - n : v;
+    }
+    void build_directory(u64 n, u32 buckets_log2) {
+        shift = 0;
+        u64 target = pieces() << buckets_log2;
+        if (target < 1) target = 1;
+        while (((n - 1) >> shift) + 1 > target) ++shift;
+        nbkt = ((n - 1) >> shift) + 1;
+        dir.assign(nbkt + 1, 0);
+        fat.assign(4 * nbkt, 0);
+        const u64 P = pieces();
+        u64 a = 0;
+        for (u64 q = 0; q < nbkt; ++q) {
+            const u64 lo = q << shift, hi = (q + 1) << shift;
+            while (a + 1 < P && start[a + 1] <= lo) ++a;
+            dir[q] = (u32)a;
+            fat[4 * q + 0] = delta[a];
+            const bool h1 = a + 1 < P && start[a + 1] < hi, h2 = a + 2 < P && start[a + 2] < hi;
+            fat[4 * q + 1] = h1 ? start[a + 1] : ~(u64)0;
+            fat[4 * q + 2] = h1 ? delta[a + 1] : 0;
+            fat[4 * q + 3] = h2 ? start[a + 2] : ~(u64)0;
+        }
+        dir[nbkt] = (u32)(P - 1);
+    }
+};
+
+// C = B after A (apply A first): pieces of A cut where their image crosses a piece boundary of B.
+static inline TransTable compose(const TransTable& A, const TransTable& B, u64 n) {
+    TransTable C;
+    const u64 PA = A.pieces(), PB = B.pieces();
+    for (u64 k = 0; k < PA; ++k) {
+        const u64 s = A.start[k], e = (k + 1 < PA) ? A.start[k + 1] : n, a = A.delta[k];
+        // image of [s,e) under +a mod n: at most two linear ranges
+        u64 u = s + a, len = e - s;
+        if (u >= n) u -= n;
+        u64 done = 0;
+        while (done < len) {
+            const u64 pos = (u + done >= n) ? u + done - n : u + done;          // image position
+            const u64 lin_end = (u + done >= n) ? (u + len - n) : std::min(u + len, n);  // end of this linear range
+            u64 j = (u64)(std::upper_bound(B.start.begin(), B.start.end(), pos) - B.start.begin()) - 1;
+            u64 cur = pos;
+            while (cur < lin_end) {
+                const u64 pend = std::min(lin_end, (j + 1 < PB) ? B.start[j + 1] : n);
+                u64 d = a + B.delta[j];
+                if (d >= n) d -= n;
+                const u64 pre = s + done + (cur - pos);
+                if (!C.start.empty() && C.delta.back() == d) { /* merge with previous piece */ }
+                else { C.start.push_back(pre); C.delta.push_back(d); }
+                cur = pend; ++j;
+            }
+            done += lin_end - pos;
+        }
+    }
+    return C;
+}
 
 struct FlatHost {
     u64 n = 0, r = 0;
@@ -53,11 +129,12 @@ struct FlatHost {
     std::vector<u64> cum;          // [nblk*S*2] (count, last run id or ~0)
     std::vector<u32> bdir;         // [lf_nbkt + 1]
     std::vector<u64> samples_last; // [r]
-    std::vector<u64> phi_ent;      // [2r] (pos, delta)
-    std::vector<u32> phi_dir;      // [phi_nbkt + 1]
+    bool w32 = false;              // n < 2^32-1: fat records hold 32-bit words
+    u32 jump = 1;                  // D of the second translation table (1 = none)
+    TransTable phi[2];             // [0] = Phi, [1] = Phi^jump
     u64 bytes() const {
         return F.size() * 8 + sid.size() * 2 + start.size() * 8 + head.size() + bstart.size() * 8 + cum.size() * 8 +
-               bdir.size() * 4 + samples_last.size() * 8 + phi_ent.size() * 8 + phi_dir.size() * 4;
+               bdir.size() * 4 + samples_last.size() * 8 + phi[0].bytes(w32) + phi[1].bytes(w32);
     }
 };
 
@@ -72,9 +149,9 @@ static inline u32 pick_shift(u64 n, u64 target_buckets) {
 static inline int flatten(const rig_logical_view& v, const rig_options& opt, FlatHost& f, u64 max_bytes = 0) {
     if (!v.F || !v.run_heads || !v.run_lens || !v.samples_last || !v.pred_pos || !v.pred_to_run) return RIG_ERR_ARG;
     if (v.n < 1 || v.r < 1 || v.r > v.n || v.r >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
-    u32 K = opt.runs_per_block ? opt.runs_per_block : 16;
-    if (K != 4 && K != 8 && K != 16) return RIG_ERR_ARG;
-    f.n = v.n; f.r = v.r; f.K = K;
+    if (opt.runs_per_block != 0 && opt.runs_per_block != 4 && opt.runs_per_block != 8 && opt.runs_per_block != 16)
+        return RIG_ERR_ARG;
+    f.n = v.n; f.r = v.r;
     const u64 n = v.n, r = v.r;
 
     // symbols
@@ -90,6 +167,11 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         f.S = S;
     }
     const u32 S = f.S;
+    // Runs per block = lanes per rank query. Small groups put more patterns in a warp (the search
+    // kernel is issue-bound: measured 0.50 / 0.30 / 0.19 ms for K = 16 / 8 / 4 on config C2), but the
+    // per-block symbol directory costs S*16 bytes per K runs, so large alphabets get larger blocks.
+    const u32 K = opt.runs_per_block ? opt.runs_per_block : (S <= 16 ? 4u : (S <= 64 ? 8u : 16u));
+    f.K = K;
     f.nblk = (r + K - 1) / K;
     const u64 nblk = f.nblk, rpad = nblk * K;
     if (max_bytes && nblk * S * 16 > max_bytes) return RIG_ERR_NOMEM;
@@ -142,29 +224,47 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     f.samples_last.assign(v.samples_last, v.samples_last + r);
     for (u64 j = 0; j < r; ++j) if (f.samples_last[j] >= n) return RIG_ERR_INDEX;
     f.toe0 = (f.samples_last[r - 1] + 1) % n;
-    f.phi_ent.assign(2 * r, 0);
-    for (u64 k = 0; k < r; ++k) {
-        u64 p = v.pred_pos[k], run = v.pred_to_run[k];
-        if (p >= n || run >= r || (k > 0 && v.pred_pos[k - 1] >= p)) return RIG_ERR_INDEX;
-        f.phi_ent[2 * k] = p;
-        // Phi(i) = (samples_last[run-1] + (i - p)) mod n  (r_index.hpp:205-219; wrap case :210 is the
-        // same formula mod n because the circular predecessor is then n-1). run 0 is never reached
-        // (Phi(SA[0]) is undefined, r_index.hpp:197,213).
-        f.phi_ent[2 * k + 1] = run > 0 ? (f.samples_last[run - 1] + n - p) % n : 0;
-    }
-    if (v.pred_pos[r - 1] != n - 1) return RIG_ERR_INDEX;  // last text position is always sampled, r_index.hpp:129
-    u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 2;
-    f.phi_shift = pick_shift(n, r << fp);
-    f.phi_nbkt = ((n - 1) >> f.phi_shift) + 1;
-    f.phi_dir.assign(f.phi_nbkt + 1, 0);
+    // Phi as a translation table. Samples p_0 < ... < p_{r-1} = n-1 (r_index.hpp:129); for
+    // i in (p_k, p_{k+1}] the strict predecessor is p_k and Phi(i) = (samples_last[run_k - 1] + i - p_k) mod n
+    // (r_index.hpp:205-219); for i in [0, p_0] the circular predecessor is p_{r-1} (:153-157, :210).
+    // Pieces: [0, p_0] with the delta of sample r-1, then [p_k + 1, p_{k+1}] with the delta of sample k.
     {
-        u64 k = 0;
-        for (u64 q = 0; q < f.phi_nbkt; ++q) {
-            u64 p = q << f.phi_shift;
-            while (k < r && v.pred_pos[k] < p) ++k;
-            f.phi_dir[q] = (u32)k;
+        std::vector<u64> dl(r);
+        for (u64 k = 0; k < r; ++k) {
+            const u64 p = v.pred_pos[k], run = v.pred_to_run[k];
+            if (p >= n || run >= r || (k > 0 && v.pred_pos[k - 1] >= p)) return RIG_ERR_INDEX;
+            // run 0 is never reached by a valid query (Phi(SA[0]) is undefined, r_index.hpp:197,213)
+            dl[k] = run > 0 ? (f.samples_last[run - 1] + n - p) % n : 0;
         }
-        f.phi_dir[f.phi_nbkt] = (u32)r;
+        if (v.pred_pos[r - 1] != n - 1) return RIG_ERR_INDEX;  // last text position is always sampled
+        TransTable& T = f.phi[0];
+        T.start.clear(); T.delta.clear();
+        T.start.push_back(0); T.delta.push_back(dl[r - 1]);
+        for (u64 k = 0; k + 1 < r; ++k) { T.start.push_back(v.pred_pos[k] + 1); T.delta.push_back(dl[k]); }
+    }
+    const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 2;
+    f.phi[0].build_directory(n, fp);
+    f.w32 = n < 0xFFFFFFFEull;
+    // Jump table Phi^D: D = requested, or the largest of {4,2} whose table stays L2-friendly.
+    u32 D = opt.reserved[0];
+    if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
+    if (D == 0) {
+        const u64 budget = 40ull << 20;  // bytes of fat directory we are willing to keep hot in L2
+        const u64 per_piece = (u64)(f.w32 ? 16 : 32) << fp;
+        D = (4 * r * per_piece <= budget) ? 4 : ((2 * r * per_piece <= budget) ? 2 : 1);
+    }
+    f.jump = D;
+    if (D > 1) {
+        TransTable T2 = compose(f.phi[0], f.phi[0], n);
+        if (D == 2) f.phi[1] = std::move(T2);
+        else {
+            TransTable T4 = compose(T2, T2, n);
+            if (D == 4) f.phi[1] = std::move(T4);
+            else f.phi[1] = compose(T4, T4, n);
+        }
+        f.phi[1].build_directory(n, fp);
+    } else {
+        f.phi[1] = TransTable();
     }
     return RIG_OK;
 }

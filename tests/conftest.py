@@ -49,12 +49,18 @@ def _native_built():
 class FlatCheck:
     """ctypes wrapper of the scalar test double over the flattened arrays."""
 
-    def __init__(self, host_index, K=16, lf_log2=0, phi_log2=0):
+    def __init__(self, host_index, K=16, lf_log2=0, phi_log2=0, jump=0, force_wide=False):
         _build_flatcheck()
         self.lib = ctypes.CDLL(FLATCHECK_SO)
         self.lib.fc_create.restype = ctypes.c_void_p
         self.lib.fc_create.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                                       ctypes.POINTER(ctypes.c_int)]
+                                       ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+        self.lib.fc_jump.restype = ctypes.c_uint64
+        self.lib.fc_jump.argtypes = [ctypes.c_void_p]
+        self.lib.fc_pieces.restype = ctypes.c_uint64
+        self.lib.fc_pieces.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.lib.fc_force_wide.argtypes = [ctypes.c_void_p]
+        self.lib.fc_check_jump.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
         self.lib.fc_destroy.argtypes = [ctypes.c_void_p]
         self.lib.fc_count.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_uint64] * 2 + [ctypes.c_void_p] * 2
         self.lib.fc_locate.restype = ctypes.c_uint64
@@ -65,8 +71,11 @@ class FlatCheck:
             view, self._keep = view_from_arrays(host_index)
         else:
             view, self._keep = host_index.view, host_index
-        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, ctypes.byref(rc))
+        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, jump, ctypes.byref(rc))
         self.rc = rc.value
+        if self.h and force_wide:
+            self.lib.fc_force_wide(self.h)
+        self.jump = int(self.lib.fc_jump(self.h)) if self.h else 0
 
     def count(self, patt, N, m):
         p = np.ascontiguousarray(patt, dtype=np.uint8)

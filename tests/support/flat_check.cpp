@@ -48,13 +48,26 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
     return r;
 }
 
-// mirrors rigk::phi_step
-u64 phi_step(const FlatHost& f, u64 i) {
-    u64 q = i >> f.phi_shift;
-    u32 a = f.phi_dir[q], e = f.phi_dir[q + 1], lb = a;
-    while (lb < e && f.phi_ent[2 * (u64)lb] < i) ++lb;
-    u64 kk = lb ? (u64)lb - 1 : f.r - 1;
-    u64 v = i + f.phi_ent[2 * kk + 1];
+// mirrors rigk::trans_step (including the 32-bit truncation of the fat records when w32)
+u64 trans_step(const FlatHost& f, const rigf::TransTable& T, u64 i) {
+    u64 q = i >> T.shift;
+    u64 d0 = T.fat[4 * q], s1 = T.fat[4 * q + 1], d1 = T.fat[4 * q + 2], s2 = T.fat[4 * q + 3];
+    u64 d;
+    bool slow;
+    if (f.w32) {
+        u32 i32 = (u32)i;
+        slow = !(i32 < (u32)s2);
+        d = (i32 < (u32)s1) ? (u32)d0 : (u32)d1;
+    } else {
+        slow = !(i < s2);
+        d = (i < s1) ? d0 : d1;
+    }
+    if (slow) {
+        u32 lo = T.dir[q] + 2, hi = T.dir[q + 1];
+        while (lo < hi) { u32 mid = (lo + hi + 1) >> 1; if (T.start[mid] <= i) lo = mid; else hi = mid - 1; }
+        d = T.delta[lo];
+    }
+    u64 v = i + d;
     if (v >= f.n) v -= f.n;
     return v;
 }
@@ -79,10 +92,10 @@ void search(const FlatHost& f, const uint8_t* P, u64 m, bool locate, u64& lo, u6
 
 extern "C" {
 
-void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, int* rc_out) {
+void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, uint32_t jump, int* rc_out) {
     rig_options opt;
     std::memset(&opt, 0, sizeof(opt));
-    opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2;
+    opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2; opt.reserved[0] = jump;
     FlatHost* f = new FlatHost();
     int rc = rigf::flatten(*v, opt, *f);
     if (rc_out) *rc_out = rc;
@@ -91,6 +104,19 @@ void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_
 }
 void fc_destroy(void* h) { delete (FlatHost*)h; }
 uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
+uint64_t fc_jump(void* h) { return ((FlatHost*)h)->jump; }
+uint64_t fc_pieces(void* h, int t) { return ((FlatHost*)h)->phi[t].pieces(); }
+void fc_force_wide(void* h) { ((FlatHost*)h)->w32 = false; }  // exercise the 64-bit record path on small inputs
+// Phi^D(i) evaluated three ways must agree: D scalar applications of table 0, one scalar application
+// of table 1, one fat-directory step on table 1.
+int fc_check_jump(void* h, uint64_t i) {
+    const FlatHost& f = *(FlatHost*)h;
+    u64 a = i;
+    for (u32 s = 0; s < f.jump; ++s) a = f.phi[0].apply(a, f.n);
+    if (f.jump == 1) return trans_step(f, f.phi[0], i) == f.phi[0].apply(i, f.n) ? 0 : 1;
+    u64 b = f.phi[1].apply(i, f.n), c = trans_step(f, f.phi[1], i);
+    return (a == b && b == c) ? 0 : 1;
+}
 
 void fc_count(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi) {
     const FlatHost& f = *(FlatHost*)h;
@@ -111,10 +137,21 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
         for (u64 j = jL; j <= jR; ++j) {
             u64 sj = f.start[j], ej = f.start[j + 1] - 1;
             u64 top = std::min(H, ej), bot = std::max(L, sj);
-            u64 v = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
-            u64* out = occ + occ_off[p] + (H - top);
-            *out++ = v;
-            for (u64 t = top; t > bot; --t) { v = phi_step(f, v); *out++ = v; }
+            u64 v0 = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
+            u64 g0 = occ_off[p] + (H - top), len = top - bot + 1;
+            const u32 D = f.jump;
+            if (D == 1) {  // mirrors phi_expand_kernel
+                u64 v = v0;
+                occ[g0] = v;
+                for (u64 t = 1; t < len; ++t) { v = trans_step(f, f.phi[0], v); occ[g0 + t] = v; }
+            } else {       // mirrors phi_expand_group_kernel: D lanes, lane c owns slots == c (mod D)
+                for (u32 c = 0; c < D; ++c) {
+                    u64 v = v0;
+                    u64 t = (c + D - (u32)(g0 % D)) % D;
+                    for (u32 s = 0; s + 1 < D; ++s) if ((u64)s < t && t < len) v = trans_step(f, f.phi[0], v);
+                    while (t < len) { occ[g0 + t] = v; t += D; if (t < len) v = trans_step(f, f.phi[1], v); }
+                }
+            }
             ++chains;
         }
     }

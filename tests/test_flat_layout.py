@@ -26,6 +26,40 @@ def test_flat_walk_equals_oracle(K):
         assert chains >= int((ehi >= elo).sum())
 
 
+@pytest.mark.parametrize("jump", [1, 2, 4, 8])
+@pytest.mark.parametrize("wide", [False, True])
+def test_jump_tables_equal_repeated_phi(jump, wide):
+    """Phi^D (composition of piecewise translations) == D applications of Phi, for every SA value
+    it can legally be applied to, through the scalar table AND the fat-directory step (32- and
+    64-bit records); locate through the D-lane scheme reproduces the oracle."""
+    rng = np.random.default_rng(10 * jump + wide)
+    for it in range(25):
+        n = int(rng.integers(1, 2500))
+        t = repetitive_text(n, int(rng.integers(1, 150)), int(rng.integers(0, 4)), 7000 + 31 * jump + it, sigma=int(rng.choice([1, 2, 4, 15])))
+        host = rib.HostIndex.from_text(t)
+        fc = FlatCheck(host, K=4, phi_log2=int(rng.choice([0, 1, 4])), jump=jump, force_wide=wide)
+        assert fc.rc == 0 and fc.jump == jump
+        assert fc.lib.fc_pieces(fc.h, 0) == host.r
+        if jump > 1:
+            assert fc.lib.fc_pieces(fc.h, 1) <= jump * host.r
+        sa = rib.suffix_array(t)
+        for x in range(jump, n + 1):  # SA[x] with at least D predecessors in SA order
+            assert fc.lib.fc_check_jump(fc.h, int(sa[x])) == 0
+        port = ob.PortIndex(t)
+        N, m = 30, int(rng.integers(1, 5))
+        patt = mixed_patterns(t, N, m, it)
+        elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+        lo, hi, off, occ, _ = fc.locate(patt, N, m)
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(occ, eocc)
+
+
+def test_jump_table_auto_policy():
+    t = rib.gen_text("dna_drift", 300_000, 3_000, 3, 5)
+    fc = FlatCheck(rib.HostIndex.from_text(t))
+    assert fc.jump == 4          # small index: the Phi^4 table is L2-friendly
+    assert FlatCheck(rib.HostIndex.from_text(t), jump=3).rc == -1
+
+
 def test_flat_walk_medium_texts():
     for kind, args in (("dna_drift", (300_000, 3_000, 3, 5)), ("versioned_doc", (200_000, 2_000, 96, 6)),
                        ("pangenome", (200_000, 4_000, 100, 7))):

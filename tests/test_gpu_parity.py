@@ -215,3 +215,24 @@ def test_full_size_properties_c2_like():
     # whole-output check for the first patterns: count by brute force
     for p in range(5):
         assert ob.brute_count(text, P[p]) == int(nocc[p])
+
+
+@pytest.mark.parametrize("jump", [1, 2, 4, 8])
+@pytest.mark.parametrize("variant", ["3", "11", "1"])
+def test_phi_jump_tables_and_wide_paths(jump, variant, monkeypatch):
+    """Every expansion kernel variant gives the oracle's occurrences: D lanes per chain over the
+    Phi^D jump table (D = 2, 4, 8), the one-lane-per-chain kernel (D = 1, coalesced and plain
+    stores), and the 64-bit code paths used when n >= 2^32 (RIG_VARIANT bit 3)."""
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 99)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host, phi_jump=jump)
+    assert gpu.info.phi_jump == jump and gpu.info.words32 == (0 if variant == "11" else 1)
+    for (N, m, seed) in [(1500, 9, 1), (300, 3, 2)]:
+        patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+        _check_all(gpu, port, patt, N, m, "jump=%d variant=%s" % (jump, variant))
+    text2 = np.frombuffer(b"abracadabra" * 30, dtype=np.uint8)
+    gpu2 = rib.GpuIndex(rib.HostIndex.from_text(text2), phi_jump=jump)
+    patt = mixed_patterns(text2, 64, 2, 3)
+    _check_all(gpu2, ob.PortIndex(text2), patt, 64, 2, "tiny jump=%d" % jump)
