@@ -51,7 +51,7 @@ typedef struct rig_options {
     uint32_t lf_bucket_log2;   /* 0 = auto: log2 of (directory buckets per run block) */
     uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
     uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
-    uint32_t reserved[4];      /* reserved[0] = phi_jump: 0 = auto, 1 = none, 2/4/8 = build the Phi^D jump table */
+    uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup */
 } rig_options;
 
 typedef struct rig_index_info {
@@ -59,8 +59,8 @@ typedef struct rig_index_info {
     uint64_t device_bytes;       /* HBM footprint of the flattened index */
     uint64_t lf_blocks, lf_buckets, phi_buckets;
     uint32_t runs_per_block, lf_shift, phi_shift, device;
-    uint32_t sm_count, phi_jump;  /* phi_jump = D of the Phi^D jump table (1 = none) */
-    uint64_t phi_jump_pieces;     /* pieces of the Phi^D translation table (<= D*r) */
+    uint32_t sm_count, phi_jump;  /* phi_jump = D: each Phi record holds the deltas of Phi^1..Phi^D */
+    uint64_t phi_jump_pieces;     /* pieces of the refined Phi^1..Phi^D translation (<= D*r) */
     uint32_t words32, reserved;   /* words32 = 1: n < 2^32-1, Phi directory records are 32-bit */
 } rig_index_info;
 

@@ -2,9 +2,9 @@
 // kernels read. Plain C++ (no CUDA), so the layout can also be checked on a CPU-only box by
 // tests/support/flat_check.cpp (a test double that walks these same arrays with scalar code).
 //
-// What the reference keeps as SDSL objects, and what replaces each here:
+// What the reference keeps as SDSL objects, and what replaces each here (all O(r) words):
 //
-//   reference member (internal/…)                      flat arrays (all O(r) words)
+//   reference member (internal/…)                      flat arrays
 //   -------------------------------------------------  ---------------------------------------------
 //   rle_string::runs  (EF marks, every B=2nd run end)   start[]  : u64 start position of every run,
 //     rle_string.hpp:78,112                               grouped in BLOCKS of K runs (K = lanes that
@@ -19,18 +19,16 @@
 //                                                         DIRECTORY, interleaved at block granularity.
 //                                                         One level replaces the ℓ wavelet-tree levels
 //                                                         AND the per-letter Elias-Fano select.
-//   r_index::pred (EF) + pred_to_run + samples_last      phi_ent[]: (text position, delta) pairs sorted
-//     r_index.hpp:663-665                                  by position, delta = samples_last[run-1] - pos
-//                                                         (mod n), so Phi(i) = (i + delta) mod n;
-//                                                       Stored as a TRANSLATION TABLE (TransTable): sorted
-//                                                         piece starts + deltas, a direct-addressed
-//                                                         directory position>>s -> piece, and "fat" bucket
-//                                                         records (d0,s1,d1,s2) that answer a step in ONE
-//                                                         128/256-bit load in the common case.
-//                                                       A second table holds Phi^D = Phi applied D times
-//                                                         (composition of piecewise translations: <= D*r
-//                                                         pieces), so D lanes walk one chain D steps at a
-//                                                         time: critical path / D, same answers.
+//   r_index::pred (EF) + pred_to_run + samples_last      PhiTable: Phi is a piecewise translation of
+//     r_index.hpp:663-665                                  [0,n): for i in (p_k, p_{k+1}] it adds the
+//                                                         constant samples_last[run_k - 1] - p_k (mod n).
+//                                                         Composing it with itself D times refines the
+//                                                         pieces (<= D*r of them); each piece then holds
+//                                                         D deltas, so ONE record lookup yields
+//                                                         SA[x-1], ..., SA[x-D] from SA[x].
+//                                                         Bucket records (deltas of the piece covering
+//                                                         the bucket start, next piece start, next piece
+//                                                         id) are direct-addressed by position>>s.
 //   r_index::samples_last                               samples_last[] : u64, run order (toeholds,
 //                                                         chain splitting at run boundaries)
 //   r_index::F                                          F[257], sid[256] (symbol -> dense id)
@@ -45,67 +43,84 @@ namespace rigf {
 typedef uint64_t u64;
 typedef uint32_t u32;
 
-// A piecewise translation of [0,n): piece k covers [start[k], start[k+1]) and maps i -> (i + delta[k]) mod n.
-struct TransTable {
-    std::vector<u64> start, delta;  // start[0] == 0, strictly ascending
-    u32 shift = 0;
+// Phi, Phi^2, ..., Phi^D as one refined piecewise translation.
+//   piece k covers [start[k], start[k+1]);  Phi^j(i) = (i + delta[k*D + j-1]) mod n  for i in piece k.
+// Bucket q (positions [q<<shift, (q+1)<<shift)) has a record of RW words:
+//   [0..D)  deltas of the piece covering the bucket's first position
+//   [D]     s1  = start of the next piece if it begins inside the bucket, else ~0
+//   [D+1]   nxt = index of that next piece (valid when s1 != ~0)
+//   [D+2]   s2  = start of the piece after it if inside the bucket, else ~0
+//   rest    padding to RW = 4 (D=1), 8 (D=2,4) or 16 (D=8) words
+// query i: i < s1 -> record deltas; i < s2 -> deltas of piece nxt; else binary search in pieces (nxt, dir[q+1]].
+struct PhiTable {
+    u32 D = 1, RW = 4, shift = 0;
     u64 nbkt = 0;
-    std::vector<u32> dir;           // [nbkt+1] piece covering position q<<shift (dir[nbkt] = last piece)
-    std::vector<u64> fat;           // [4*nbkt] (d0, s1, d1, s2) per bucket, ~0 = none
+    std::vector<u64> start;   // [pieces], start[0] == 0, strictly ascending
+    std::vector<u64> delta;   // [pieces * D]
+    std::vector<u32> dir;     // [nbkt+1] piece covering the first position of the bucket
+    std::vector<u64> rec;     // [nbkt * RW]
     u64 pieces() const { return start.size(); }
-    u64 bytes(bool w32) const { return start.size() * 16 + dir.size() * 4 + fat.size() * (w32 ? 4 : 8); }
-    u64 apply(u64 i, u64 n) const {  // scalar evaluation (host-side composition + tests)
-        u64 k = (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1;
-        u64 v = i + delta[k];
+    u64 bytes(bool w32) const { return start.size() * 8 + delta.size() * (w32 ? 4 : 8) + dir.size() * 4 + rec.size() * (w32 ? 4 : 8); }
+    static u32 record_words(u32 D) { return D == 1 ? 4 : (D <= 4 ? 8 : 16); }
+    u64 piece_of(u64 i) const { return (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1; }
+    // scalar evaluation of Phi^j(i), 1 <= j <= D (host-side construction + tests)
+    u64 apply(u64 i, u32 j, u64 n) const {
+        u64 v = i + delta[piece_of(i) * D + (j - 1)];
         return v >= n ? v - n : v;
     }
     void build_directory(u64 n, u32 buckets_log2) {
+        RW = record_words(D);
         shift = 0;
         u64 target = pieces() << buckets_log2;
         if (target < 1) target = 1;
         while (((n - 1) >> shift) + 1 > target) ++shift;
         nbkt = ((n - 1) >> shift) + 1;
         dir.assign(nbkt + 1, 0);
-        fat.assign(4 * nbkt, 0);
+        rec.assign(nbkt * RW, 0);
         const u64 P = pieces();
         u64 a = 0;
         for (u64 q = 0; q < nbkt; ++q) {
             const u64 lo = q << shift, hi = (q + 1) << shift;
             while (a + 1 < P && start[a + 1] <= lo) ++a;
             dir[q] = (u32)a;
-            fat[4 * q + 0] = delta[a];
+            u64* R = &rec[q * RW];
+            for (u32 j = 0; j < D; ++j) R[j] = delta[a * D + j];
             const bool h1 = a + 1 < P && start[a + 1] < hi, h2 = a + 2 < P && start[a + 2] < hi;
-            fat[4 * q + 1] = h1 ? start[a + 1] : ~(u64)0;
-            fat[4 * q + 2] = h1 ? delta[a + 1] : 0;
-            fat[4 * q + 3] = h2 ? start[a + 2] : ~(u64)0;
+            R[D] = h1 ? start[a + 1] : ~(u64)0;
+            R[D + 1] = h1 ? a + 1 : 0;
+            R[D + 2] = h2 ? start[a + 2] : ~(u64)0;
         }
         dir[nbkt] = (u32)(P - 1);
     }
 };
 
-// C = B after A (apply A first): pieces of A cut where their image crosses a piece boundary of B.
-static inline TransTable compose(const TransTable& A, const TransTable& B, u64 n) {
-    TransTable C;
-    const u64 PA = A.pieces(), PB = B.pieces();
+// Extend a table holding Phi^1..Phi^j to Phi^1..Phi^(j+1): every piece is cut where its image under
+// Phi^j crosses a piece boundary of Phi (the single-step table), and gets delta_{j+1} = delta_j + delta_Phi.
+static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64 n) {
+    PhiTable C;
+    const u32 j = A.D;
+    C.D = j + 1;
+    const u64 PA = A.pieces(), PB = Phi.pieces();
     for (u64 k = 0; k < PA; ++k) {
-        const u64 s = A.start[k], e = (k + 1 < PA) ? A.start[k + 1] : n, a = A.delta[k];
-        // image of [s,e) under +a mod n: at most two linear ranges
-        u64 u = s + a, len = e - s;
+        const u64 s = A.start[k], e = (k + 1 < PA) ? A.start[k + 1] : n, a = A.delta[k * j + (j - 1)];
+        const u64 len = e - s;
+        u64 u = s + a;  // image of s under Phi^j
         if (u >= n) u -= n;
         u64 done = 0;
-        while (done < len) {
-            const u64 pos = (u + done >= n) ? u + done - n : u + done;          // image position
-            const u64 lin_end = (u + done >= n) ? (u + len - n) : std::min(u + len, n);  // end of this linear range
-            u64 j = (u64)(std::upper_bound(B.start.begin(), B.start.end(), pos) - B.start.begin()) - 1;
+        while (done < len) {  // at most two linear ranges (the image may wrap around n)
+            const bool wrapped = u + done >= n;
+            const u64 pos = wrapped ? u + done - n : u + done;
+            const u64 lin_end = wrapped ? (u + len - n) : std::min(u + len, n);
+            u64 b = Phi.piece_of(pos);
             u64 cur = pos;
             while (cur < lin_end) {
-                const u64 pend = std::min(lin_end, (j + 1 < PB) ? B.start[j + 1] : n);
-                u64 d = a + B.delta[j];
+                const u64 pend = std::min(lin_end, (b + 1 < PB) ? Phi.start[b + 1] : n);
+                u64 d = a + Phi.delta[b];
                 if (d >= n) d -= n;
-                const u64 pre = s + done + (cur - pos);
-                if (!C.start.empty() && C.delta.back() == d) { /* merge with previous piece */ }
-                else { C.start.push_back(pre); C.delta.push_back(d); }
-                cur = pend; ++j;
+                C.start.push_back(s + done + (cur - pos));
+                for (u32 t = 0; t < j; ++t) C.delta.push_back(A.delta[k * j + t]);
+                C.delta.push_back(d);
+                cur = pend; ++b;
             }
             done += lin_end - pos;
         }
@@ -119,7 +134,6 @@ struct FlatHost {
     u32 S = 0;           // distinct BWT symbols
     u64 nblk = 0;        // run blocks
     u32 lf_shift = 0;  u64 lf_nbkt = 0;
-    u32 phi_shift = 0; u64 phi_nbkt = 0;
     u64 toe0 = 0;        // SA[n-1] = (samples_last[r-1]+1) % n, r_index.hpp:489
     std::vector<u64> F;            // [257]
     std::vector<uint16_t> sid;     // [256] dense symbol id or 0xFFFF
@@ -129,12 +143,11 @@ struct FlatHost {
     std::vector<u64> cum;          // [nblk*S*2] (count, last run id or ~0)
     std::vector<u32> bdir;         // [lf_nbkt + 1]
     std::vector<u64> samples_last; // [r]
-    bool w32 = false;              // n < 2^32-1: fat records hold 32-bit words
-    u32 jump = 1;                  // D of the second translation table (1 = none)
-    TransTable phi[2];             // [0] = Phi, [1] = Phi^jump
+    bool w32 = false;              // n < 2^32-1: Phi records and deltas are stored as 32-bit words
+    PhiTable phi;                  // Phi^1..Phi^D refined
     u64 bytes() const {
         return F.size() * 8 + sid.size() * 2 + start.size() * 8 + head.size() + bstart.size() * 8 + cum.size() * 8 +
-               bdir.size() * 4 + samples_last.size() * 8 + phi[0].bytes(w32) + phi[1].bytes(w32);
+               bdir.size() * 4 + samples_last.size() * 8 + phi.bytes(w32);
     }
 };
 
@@ -220,14 +233,16 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         f.bdir[f.lf_nbkt] = (u32)(nblk - 1);
     }
 
-    // samples + Phi
+    // samples
     f.samples_last.assign(v.samples_last, v.samples_last + r);
     for (u64 j = 0; j < r; ++j) if (f.samples_last[j] >= n) return RIG_ERR_INDEX;
     f.toe0 = (f.samples_last[r - 1] + 1) % n;
+
     // Phi as a translation table. Samples p_0 < ... < p_{r-1} = n-1 (r_index.hpp:129); for
     // i in (p_k, p_{k+1}] the strict predecessor is p_k and Phi(i) = (samples_last[run_k - 1] + i - p_k) mod n
     // (r_index.hpp:205-219); for i in [0, p_0] the circular predecessor is p_{r-1} (:153-157, :210).
     // Pieces: [0, p_0] with the delta of sample r-1, then [p_k + 1, p_{k+1}] with the delta of sample k.
+    PhiTable P1;
     {
         std::vector<u64> dl(r);
         for (u64 k = 0; k < r; ++k) {
@@ -237,35 +252,26 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
             dl[k] = run > 0 ? (f.samples_last[run - 1] + n - p) % n : 0;
         }
         if (v.pred_pos[r - 1] != n - 1) return RIG_ERR_INDEX;  // last text position is always sampled
-        TransTable& T = f.phi[0];
-        T.start.clear(); T.delta.clear();
-        T.start.push_back(0); T.delta.push_back(dl[r - 1]);
-        for (u64 k = 0; k + 1 < r; ++k) { T.start.push_back(v.pred_pos[k] + 1); T.delta.push_back(dl[k]); }
+        P1.D = 1;
+        P1.start.push_back(0); P1.delta.push_back(dl[r - 1]);
+        for (u64 k = 0; k + 1 < r; ++k) { P1.start.push_back(v.pred_pos[k] + 1); P1.delta.push_back(dl[k]); }
     }
     const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 2;
-    f.phi[0].build_directory(n, fp);
     f.w32 = n < 0xFFFFFFFEull;
-    // Jump table Phi^D: D = requested, or the largest of {4,2} whose table stays L2-friendly.
+    // D = occurrences produced per record lookup: requested, or the largest of {4,2} whose bucket
+    // records stay L2-friendly (they compete with the streamed occurrence output for the 126 MB L2).
     u32 D = opt.reserved[0];
     if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
     if (D == 0) {
-        const u64 budget = 40ull << 20;  // bytes of fat directory we are willing to keep hot in L2
-        const u64 per_piece = (u64)(f.w32 ? 16 : 32) << fp;
-        D = (4 * r * per_piece <= budget) ? 4 : ((2 * r * per_piece <= budget) ? 2 : 1);
+        const u64 budget = 48ull << 20;
+        const u64 wb = f.w32 ? 4 : 8;
+        auto cost = [&](u32 d) { return (u64)d * r * ((PhiTable::record_words(d) * wb) << fp); };
+        D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);
     }
-    f.jump = D;
-    if (D > 1) {
-        TransTable T2 = compose(f.phi[0], f.phi[0], n);
-        if (D == 2) f.phi[1] = std::move(T2);
-        else {
-            TransTable T4 = compose(T2, T2, n);
-            if (D == 4) f.phi[1] = std::move(T4);
-            else f.phi[1] = compose(T4, T4, n);
-        }
-        f.phi[1].build_directory(n, fp);
-    } else {
-        f.phi[1] = TransTable();
-    }
+    f.phi = P1;
+    for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
+    f.phi.build_directory(n, fp);
+    if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
     return RIG_OK;
 }
 

@@ -3,7 +3,8 @@
 // There is no CPU path in this library: every query entry point launches CUDA kernels.
 #include "../../include/rindex_gpu.h"
 #include "flat_layout.hpp"
-#include "kernels.cuh"
+#include "search_kernels.cuh"
+#include "phi_kernels.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,7 +60,7 @@ struct rig_index {
     ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
-    int variant = 3;  // see rig_index_create_ex
+    int variant = 0;  // see rig_index_create_ex
     bool timing_pending = false;
     bool ev_valid[6] = {false, false, false, false, false, false};
 };
@@ -112,8 +113,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
     if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
-    int variant = 3;  // tuning/testing switches (env RIG_VARIANT): bit1 coalesced stores in the D=1 kernel,
-                      // bit2 ignore the jump table, bit3 force the 64-bit code paths (as for n >= 2^32)
+    int variant = 0;  // testing switch (env RIG_VARIANT): bit3 forces the 64-bit code paths (as for n >= 2^32)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) f.w32 = false;
 
@@ -127,28 +127,30 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
-    std::vector<uint32_t> fat32[2];
-    for (int t = 0; t < 2; ++t)
-        if (f.w32) {  // 32-bit fat records: ~0 sentinels truncate to 0xFFFFFFFF, everything else is < n < 2^32-1
-            fat32[t].resize(f.phi[t].fat.size());
-            for (size_t i = 0; i < fat32[t].size(); ++i) fat32[t][i] = (uint32_t)f.phi[t].fat[i];
-        }
+    std::vector<uint32_t> rec32, delta32;
+    if (f.w32) {  // 32-bit words: ~0 sentinels truncate to 0xFFFFFFFF, everything else is < n < 2^32-1
+        rec32.resize(f.phi.rec.size());
+        for (size_t i = 0; i < rec32.size(); ++i) rec32[i] = (uint32_t)f.phi.rec[i];
+        delta32.resize(f.phi.delta.size());
+        for (size_t i = 0; i < delta32.size(); ++i) delta32[i] = (uint32_t)f.phi.delta[i];
+    }
     struct Part { const void* src; size_t bytes; size_t off; };
     std::vector<Part> parts = {
         {f.F.data(), f.F.size() * 8, 0},            {f.sid.data(), f.sid.size() * 2, 0},
         {f.start.data(), f.start.size() * 8, 0},    {f.head.data(), f.head.size(), 0},
         {f.bstart.data(), f.bstart.size() * 8, 0},  {f.cum.data(), f.cum.size() * 8, 0},
         {f.bdir.data(), f.bdir.size() * 4, 0},      {f.samples_last.data(), f.samples_last.size() * 8, 0}};
-    for (int t = 0; t < 2; ++t) {
-        const rigf::TransTable& T = f.phi[t];
-        if (f.w32) parts.push_back({fat32[t].data(), fat32[t].size() * 4, 0});
-        else parts.push_back({T.fat.data(), T.fat.size() * 8, 0});
-        parts.push_back({T.dir.data(), T.dir.size() * 4, 0});
-        parts.push_back({T.start.data(), T.start.size() * 8, 0});
-        parts.push_back({T.delta.data(), T.delta.size() * 8, 0});
+    if (f.w32) {
+        parts.push_back({rec32.data(), rec32.size() * 4, 0});
+        parts.push_back({delta32.data(), delta32.size() * 4, 0});
+    } else {
+        parts.push_back({f.phi.rec.data(), f.phi.rec.size() * 8, 0});
+        parts.push_back({f.phi.delta.data(), f.phi.delta.size() * 8, 0});
     }
+    parts.push_back({f.phi.start.data(), f.phi.start.size() * 8, 0});
+    parts.push_back({f.phi.dir.data(), f.phi.dir.size() * 4, 0});
     size_t total = 0;
-    for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 32, 256); }
+    for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 128, 256); }
     cudaError_t e = cudaMalloc(&ix->arena, total);
     if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc(arena): ") + cudaGetErrorString(e); delete ix; return RIG_ERR_NOMEM; }
     CU_TRY(cudaMemset(ix->arena, 0, total));
@@ -157,7 +159,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     char* A = (char*)ix->arena;
     FlatDev& d = ix->d;
     d.n = f.n; d.r = f.r; d.nblk = f.nblk; d.toe0 = f.toe0;
-    d.K = f.K; d.S = f.S; d.lf_shift = f.lf_shift; d.phi_shift = f.phi[0].shift;
+    d.K = f.K; d.S = f.S; d.lf_shift = f.lf_shift; d.pad0 = 0;
     d.F = (const ull*)(A + parts[0].off);
     d.sid = (const uint16_t*)(A + parts[1].off);
     d.start = (const ull*)(A + parts[2].off);
@@ -166,15 +168,12 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.cum = (const ulonglong2*)(A + parts[5].off);
     d.bdir = (const uint32_t*)(A + parts[6].off);
     d.samples_last = (const ull*)(A + parts[7].off);
-    for (int t = 0; t < 2; ++t) {
-        rigk::PhiTabDev& P = d.phi[t];
-        P.fat = (const void*)(A + parts[8 + 4 * t].off);
-        P.dir = (const uint32_t*)(A + parts[9 + 4 * t].off);
-        P.start = (const ull*)(A + parts[10 + 4 * t].off);
-        P.delta = (const ull*)(A + parts[11 + 4 * t].off);
-        P.shift = f.phi[t].shift; P.pad = 0;
-    }
-    d.jump = f.jump; d.w32 = f.w32 ? 1u : 0u;
+    d.phi.rec = (const void*)(A + parts[8].off);
+    d.phi.delta = (const void*)(A + parts[9].off);
+    d.phi.start = (const ull*)(A + parts[10].off);
+    d.phi.dir = (const uint32_t*)(A + parts[11].off);
+    d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
+    d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
 
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
@@ -186,9 +185,9 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     rig_index_info& I = ix->info;
     std::memset(&I, 0, sizeof(I));
     I.n = f.n; I.r = f.r; I.sigma = f.S; I.device_bytes = total;
-    I.lf_blocks = f.nblk; I.lf_buckets = f.lf_nbkt; I.phi_buckets = f.phi[0].nbkt;
-    I.runs_per_block = f.K; I.lf_shift = f.lf_shift; I.phi_shift = f.phi[0].shift;
-    I.phi_jump = f.jump; I.phi_jump_pieces = f.phi[1].pieces(); I.words32 = f.w32 ? 1u : 0u;
+    I.lf_blocks = f.nblk; I.lf_buckets = f.lf_nbkt; I.phi_buckets = f.phi.nbkt;
+    I.runs_per_block = f.K; I.lf_shift = f.lf_shift; I.phi_shift = f.phi.shift;
+    I.phi_jump = f.phi.D; I.phi_jump_pieces = f.phi.pieces(); I.words32 = f.w32 ? 1u : 0u;
     I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
     *out = ix;
     return RIG_OK;
@@ -340,31 +339,25 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
     }
     if (chains) {
         const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 256;
-        uint64_t persist = (uint64_t)ix->sm_count * (2048 / threads);
-        uint64_t need = (chains + threads - 1) / threads;
-        unsigned blocks = (unsigned)(need < persist ? need : persist);
         const bool w32 = ix->d.w32 != 0;
-        if (ix->d.jump > 1 && !(ix->variant & 4)) {
-            const uint64_t D = ix->d.jump;
-            const uint64_t nb = (chains * D + threads - 1) / threads;
-            if (nb > 0x7fffffffull) return RIG_ERR_ARG;
-#define RIG_GROUP(W, DD)                                                                                          \
-    rigk::phi_expand_group_kernel<W, DD><<<(unsigned)nb, threads, 0, st>>>(ix->d, N, (ull*)ix->choff.p, d_occoff,  \
-                                                                           d_lo, d_hi, (ull*)ix->toe.p,            \
-                                                                           (ull*)ix->jl.p, d_occ, chains)
-            if (w32) { if (D == 2) RIG_GROUP(true, 2); else if (D == 4) RIG_GROUP(true, 4); else RIG_GROUP(true, 8); }
-            else { if (D == 2) RIG_GROUP(false, 2); else if (D == 4) RIG_GROUP(false, 4); else RIG_GROUP(false, 8); }
-#undef RIG_GROUP
-        } else {
-#define RIG_EXPAND(W, C)                                                                                         \
-    rigk::phi_expand_kernel<W, C><<<blocks, threads, 0, st>>>(ix->d, N, (ull*)ix->choff.p, d_occoff, d_lo, d_hi, \
-                                                              (ull*)ix->toe.p, (ull*)ix->jl.p, d_occ,            \
-                                                              ix->d_counters + 1, chains)
-            const bool co = (ix->variant & 2) != 0;
-            if (w32) { if (co) RIG_EXPAND(true, true); else RIG_EXPAND(true, false); }
-            else { if (co) RIG_EXPAND(false, true); else RIG_EXPAND(false, false); }
-#undef RIG_EXPAND
+        const uint64_t nb = (chains + threads - 1) / threads;
+        if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+#define RIG_EXPAND(W, DD)                                                                                  \
+    rigk::phi_expand_kernel<W, DD><<<(unsigned)nb, threads, 0, st>>>(ix->d, N, (ull*)ix->choff.p, d_occoff, \
+                                                                     d_lo, d_hi, (ull*)ix->toe.p,           \
+                                                                     (ull*)ix->jl.p, d_occ, chains)
+        switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
+            case 2: RIG_EXPAND(false, 1); break;
+            case 3: RIG_EXPAND(true, 1); break;
+            case 4: RIG_EXPAND(false, 2); break;
+            case 5: RIG_EXPAND(true, 2); break;
+            case 8: RIG_EXPAND(false, 4); break;
+            case 9: RIG_EXPAND(true, 4); break;
+            case 16: RIG_EXPAND(false, 8); break;
+            case 17: RIG_EXPAND(true, 8); break;
+            default: return RIG_ERR_ARG;
         }
+#undef RIG_EXPAND
         CU_TRY(cudaGetLastError());
         ix->timing.launches += 1;
     }

@@ -1,4 +1,5 @@
-// kernels.cuh — sm_100a device code of the count + locate hot path.
+// search_kernels.cuh — sm_100a device code of the count + locate hot path (backward search, scans,
+// digest). The Phi expansion kernel lives in phi_kernels.cuh.
 //
 //   search_kernel<G,LOCATE>  backward search, one group PAIR per pattern: G lanes evaluate
 //                            rank(lo) and G lanes evaluate rank(hi+1) of the same LF step in
@@ -23,17 +24,19 @@ namespace rigk {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+// Phi^1..Phi^D as one refined piecewise translation (flat_layout.hpp: PhiTable). Words are u32 when
+// FlatDev::w32 (n < 2^32-1), else u64.
 struct PhiTabDev {
-    const void* fat;   // [4*nbkt] (d0, s1, d1, s2) as u32 (w32) or u64; one 16/32-byte record per bucket
-    const u32* dir;    // [nbkt+1] piece covering the first position of the bucket
-    const u64* start;  // [pieces]
-    const u64* delta;  // [pieces]
-    u32 shift, pad;
+    const void* rec;    // [nbkt * RW] bucket records: D deltas, s1, nxt, s2, padding
+    const void* delta;  // [pieces * D]
+    const u64* start;   // [pieces]
+    const u32* dir;     // [nbkt+1] piece covering the first position of the bucket
+    u32 shift, D;
 };
 
 struct FlatDev {
     u64 n, r, nblk, toe0;
-    u32 K, S, lf_shift, phi_shift;
+    u32 K, S, lf_shift, pad0;
     const u64* F;             // [257]
     const uint16_t* sid;      // [256]
     const u64* start;         // [nblk*K+1]
@@ -42,8 +45,8 @@ struct FlatDev {
     const ulonglong2* cum;    // [nblk*S] (count before block, last run of symbol before block)
     const u32* bdir;          // [lf_nbkt+1]
     const u64* samples_last;  // [r]
-    PhiTabDev phi[2];         // [0] = Phi, [1] = Phi^jump (piecewise translations, see flat_layout.hpp)
-    u32 jump, w32;            // jump = D (1: no second table); w32: fat records are 4 x u32
+    PhiTabDev phi;
+    u32 w32, pad;             // w32: Phi records / deltas are 32-bit words
 };
 
 #define RIG_FULL 0xffffffffu
@@ -315,180 +318,6 @@ scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u6
         ea += va[i]; eb += vb[i];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { out_a[N] = totals[0]; out_b[N] = totals[1]; }
-}
-
-// ------------------------------------------------------------------ Phi
-// One application of a piecewise translation (Phi or Phi^D): find the piece holding i, add its
-// delta mod n. For Phi this is r_index::Phi (r_index.hpp:195-221): strict predecessor over the
-// sorted run-first samples (sparse_sd_vector::rank excludes i, :107-112), circular (:153-157),
-// then (prev_sample + delta) % n (:219). Common case: ONE 16-byte (W32) or 32-byte record.
-template <bool W32>
-__device__ __forceinline__ u64 trans_step(const PhiTabDev& T, u64 i, u64 n) {
-    const u64 q = i >> T.shift;
-    u64 d;
-    bool slow;
-    if (W32) {
-        const uint4 e = __ldg(reinterpret_cast<const uint4*>(T.fat) + q);  // (d0, s1, d1, s2), 0xFFFFFFFF = none
-        const u32 i32 = (u32)i;
-        slow = !(i32 < e.w);
-        d = (i32 < e.y) ? e.x : e.z;
-    } else {
-        u64 d0, s1, d1, s2;  // one 32-byte sector, one LDG.E.256
-        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(d0), "=l"(s1), "=l"(d1), "=l"(s2)
-                     : "l"(reinterpret_cast<const u64*>(T.fat) + 4 * q));
-        slow = !(i < s2);
-        d = (i < s1) ? d0 : d1;
-    }
-    if (slow) {  // rare: three or more pieces start inside this bucket at or below i
-        u32 lo = __ldg(T.dir + q) + 2, hi = __ldg(T.dir + q + 1);
-        while (lo < hi) {  // last piece in [lo,hi] whose start is <= i
-            const u32 mid = (lo + hi + 1) >> 1;
-            if (__ldg(T.start + mid) <= i) lo = mid; else hi = mid - 1;
-        }
-        d = __ldg(T.delta + lo);
-    }
-    u64 v = i + d;
-    if (v >= n) v -= n;
-    return v;
-}
-
-// Per-lane output stage: occurrences of one chain go to consecutive u64 slots. COALESCE gathers
-// the four values of a 32-byte sector in registers and writes them with one 256-bit streaming
-// store (one L2 transaction instead of four partial-sector writes); chain heads/tails that do
-// not fill a sector fall back to 8-byte stores.
-template <bool HINTS, bool COALESCE>
-struct OutStage {
-    u64* p;            // address of the NEXT value to be appended
-    u64 b0, b1, b2, b3;  // shift register: b3 = newest
-    u32 cnt;
-    __device__ __forceinline__ void reset(u64* dst) { p = dst; cnt = 0; }
-    __device__ __forceinline__ static void st1(u64* a, u64 v) {
-        if (HINTS) __stcs(a, v); else *a = v;
-    }
-    __device__ __forceinline__ void push(u64 v) {
-        if (!COALESCE) { st1(p, v); ++p; return; }
-        b0 = b1; b1 = b2; b2 = b3; b3 = v;
-        ++cnt; ++p;
-        if ((reinterpret_cast<unsigned long long>(p) & 31ull) == 0) {  // a sector just closed
-            if (cnt == 4) {
-                if (HINTS)
-                    asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.u64 [%0], {%1,%2,%3,%4};"
-                                 :: "l"(p - 4), "l"(b0), "l"(b1), "l"(b2), "l"(b3) : "memory");
-                else
-                    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};"
-                                 :: "l"(p - 4), "l"(b0), "l"(b1), "l"(b2), "l"(b3) : "memory");
-            } else {
-                flush_partial();
-            }
-            cnt = 0;
-        }
-    }
-    __device__ __forceinline__ void flush_partial() {  // the newest cnt (<4) values end at p
-        if (cnt >= 3) st1(p - 3, b1);
-        if (cnt >= 2) st1(p - 2, b2);
-        if (cnt >= 1) st1(p - 1, b3);
-    }
-    __device__ __forceinline__ void finish() {
-        if (COALESCE) { flush_partial(); cnt = 0; }
-    }
-};
-
-// One chain per lane. Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]),
-// min(hi,start[j+1]-1)], walked from the top down; SA at the top is the toehold (j = last run of
-// the range) or samples_last[j]+1 (a run end is a free toehold: same identity as r_index.hpp:489,533).
-// Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order SA[hi], SA[hi-1], ... (r_index.hpp:340-351).
-template <bool W32, bool COALESCE>
-__global__ void __launch_bounds__(256)
-phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
-                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ counter, u64 total_chains) {
-    const int lane = threadIdx.x & 31;
-    u64 remaining = 0, k = 0;
-    OutStage<true, COALESCE> os;
-    os.reset(nullptr);
-    bool exhausted = false;
-    for (;;) {
-        const bool need = (remaining == 0) && !exhausted;
-        const u32 nm = __ballot_sync(RIG_FULL, need);
-        if (nm) {
-            const int leader = __ffs(nm) - 1;
-            u64 base = 0;
-            if (lane == leader) base = atomicAdd(counter, (u64)__popc(nm));
-            base = __shfl_sync(RIG_FULL, base, leader);
-            if (need) {
-                os.finish();
-                const u64 w = base + __popc(nm & ((1u << lane) - 1u));
-                if (w >= total_chains) {
-                    exhausted = true;
-                } else {
-                    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
-                    while (b - a > 1) {
-                        const u64 mid = (a + b) >> 1;
-                        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
-                    }
-                    const u64 p = a;
-                    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-                    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-                    const u64 sj = __ldg(ix.start + j), ej = __ldg(ix.start + j + 1) - 1;
-                    const u64 top = min(H, ej), bot = max(L, sj);
-                    if (top == H) k = __ldg(toe_in + p);
-                    else { k = __ldg(ix.samples_last + j) + 1; if (k >= ix.n) k -= ix.n; }
-                    os.reset(out + __ldg(occ_off + p) + (H - top));
-                    os.push(k);
-                    remaining = top - bot;
-                }
-            }
-        }
-        if (!__any_sync(RIG_FULL, remaining > 0 || !exhausted)) break;
-        if (remaining > 0) {
-            k = trans_step<W32>(ix.phi[0], k, ix.n);
-            os.push(k);
-            --remaining;
-        }
-    }
-    os.finish();
-}
-
-// D lanes per chain, stepping with the jump table Phi^D. Lane c owns the output slots whose global
-// index is congruent to c mod D, so the D lanes of a group always store D consecutive, D*8-byte
-// aligned slots in one instruction (hardware-coalesced full sectors for D = 4). Lane c first walks
-// t_c < D single Phi steps from the chain's toehold, then jumps D occurrences per load.
-// Same chain decomposition, toeholds and output slots as phi_expand_kernel.
-template <bool W32, int D>
-__global__ void __launch_bounds__(256)
-phi_expand_group_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
-                        const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                        const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains) {
-    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 w = tid / D;
-    const u32 c = (u32)(tid % D);
-    if (w >= total_chains) return;  // no warp collectives below: whole groups may leave
-    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
-    while (b - a > 1) {
-        const u64 mid = (a + b) >> 1;
-        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
-    }
-    const u64 p = a;
-    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-    const u64 sj = __ldg(ix.start + j), ej = __ldg(ix.start + j + 1) - 1;
-    const u64 top = min(H, ej), bot = max(L, sj);
-    u64 v;
-    if (top == H) v = __ldg(toe_in + p);
-    else { v = __ldg(ix.samples_last + j) + 1; if (v >= ix.n) v -= ix.n; }
-    const u64 g0 = __ldg(occ_off + p) + (H - top);  // global slot of SA[top]
-    const u64 len = top - bot + 1;
-    u64 t = (c + D - (u32)(g0 % D)) % D;            // first chain offset owned by this lane
-#pragma unroll
-    for (int s = 0; s < D - 1; ++s)
-        if ((u64)s < t && t < len) v = trans_step<W32>(ix.phi[0], v, ix.n);
-    u64* o = out + g0;
-    while (t < len) {
-        __stcs(o + t, v);
-        t += D;
-        if (t < len) v = trans_step<W32>(ix.phi[1], v, ix.n);
-    }
 }
 
 // out[0] += sum v, out[1] += sum v*(i+1)   (mod 2^64)

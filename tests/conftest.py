@@ -58,7 +58,7 @@ class FlatCheck:
         self.lib.fc_jump.restype = ctypes.c_uint64
         self.lib.fc_jump.argtypes = [ctypes.c_void_p]
         self.lib.fc_pieces.restype = ctypes.c_uint64
-        self.lib.fc_pieces.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.lib.fc_pieces.argtypes = [ctypes.c_void_p]
         self.lib.fc_force_wide.argtypes = [ctypes.c_void_p]
         self.lib.fc_check_jump.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
         self.lib.fc_destroy.argtypes = [ctypes.c_void_p]

@@ -48,28 +48,25 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
     return r;
 }
 
-// mirrors rigk::trans_step (including the 32-bit truncation of the fat records when w32)
-u64 trans_step(const FlatHost& f, const rigf::TransTable& T, u64 i) {
+// mirrors rigk::phi_lookup (including the 32-bit truncation of records and deltas when w32)
+void phi_lookup(const FlatHost& f, u64 i, u64* e) {
+    const rigf::PhiTable& T = f.phi;
+    const u32 D = T.D, RW = T.RW;
+    const u64 mask = f.w32 ? 0xFFFFFFFFull : ~(u64)0;
     u64 q = i >> T.shift;
-    u64 d0 = T.fat[4 * q], s1 = T.fat[4 * q + 1], d1 = T.fat[4 * q + 2], s2 = T.fat[4 * q + 3];
-    u64 d;
-    bool slow;
-    if (f.w32) {
-        u32 i32 = (u32)i;
-        slow = !(i32 < (u32)s2);
-        d = (i32 < (u32)s1) ? (u32)d0 : (u32)d1;
-    } else {
-        slow = !(i < s2);
-        d = (i < s1) ? d0 : d1;
+    const u64* w = &T.rec[q * RW];
+    u64 d[8];
+    for (u32 j = 0; j < D; ++j) d[j] = w[j] & mask;
+    if (i >= (w[D] & mask)) {
+        u64 piece = w[D + 1] & mask;
+        if (i >= (w[D + 2] & mask)) {
+            u64 lo = piece + 1, hi = T.dir[q + 1];
+            while (lo < hi) { u64 mid = (lo + hi + 1) >> 1; if (T.start[mid] <= i) lo = mid; else hi = mid - 1; }
+            piece = lo;
+        }
+        for (u32 j = 0; j < D; ++j) d[j] = T.delta[piece * D + j] & mask;
     }
-    if (slow) {
-        u32 lo = T.dir[q] + 2, hi = T.dir[q + 1];
-        while (lo < hi) { u32 mid = (lo + hi + 1) >> 1; if (T.start[mid] <= i) lo = mid; else hi = mid - 1; }
-        d = T.delta[lo];
-    }
-    u64 v = i + d;
-    if (v >= f.n) v -= f.n;
-    return v;
+    for (u32 j = 0; j < D; ++j) { u64 v = i + d[j]; if (v >= f.n) v -= f.n; e[j] = v; }
 }
 
 // mirrors rigk::search_kernel (one pattern)
@@ -104,18 +101,21 @@ void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_
 }
 void fc_destroy(void* h) { delete (FlatHost*)h; }
 uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
-uint64_t fc_jump(void* h) { return ((FlatHost*)h)->jump; }
-uint64_t fc_pieces(void* h, int t) { return ((FlatHost*)h)->phi[t].pieces(); }
-void fc_force_wide(void* h) { ((FlatHost*)h)->w32 = false; }  // exercise the 64-bit record path on small inputs
-// Phi^D(i) evaluated three ways must agree: D scalar applications of table 0, one scalar application
-// of table 1, one fat-directory step on table 1.
+uint64_t fc_jump(void* h) { return ((FlatHost*)h)->phi.D; }
+uint64_t fc_pieces(void* h) { return ((FlatHost*)h)->phi.pieces(); }
+void fc_force_wide(void* h) { ((FlatHost*)h)->w32 = false; }  // exercise the 64-bit word path on small inputs
+// Phi^j(i), j = 1..D, evaluated three ways must agree: j applications of Phi^1 through the scalar
+// table, one scalar application of delta_j, and the bucket-record lookup the kernel performs.
 int fc_check_jump(void* h, uint64_t i) {
     const FlatHost& f = *(FlatHost*)h;
+    u64 e[8];
+    phi_lookup(f, i, e);
     u64 a = i;
-    for (u32 s = 0; s < f.jump; ++s) a = f.phi[0].apply(a, f.n);
-    if (f.jump == 1) return trans_step(f, f.phi[0], i) == f.phi[0].apply(i, f.n) ? 0 : 1;
-    u64 b = f.phi[1].apply(i, f.n), c = trans_step(f, f.phi[1], i);
-    return (a == b && b == c) ? 0 : 1;
+    for (u32 j = 1; j <= f.phi.D; ++j) {
+        a = f.phi.apply(a, 1, f.n);
+        if (a != f.phi.apply(i, j, f.n) || a != e[j - 1]) return (int)j;
+    }
+    return 0;
 }
 
 void fc_count(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi) {
@@ -137,20 +137,29 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
         for (u64 j = jL; j <= jR; ++j) {
             u64 sj = f.start[j], ej = f.start[j + 1] - 1;
             u64 top = std::min(H, ej), bot = std::max(L, sj);
-            u64 v0 = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
-            u64 g0 = occ_off[p] + (H - top), len = top - bot + 1;
-            const u32 D = f.jump;
-            if (D == 1) {  // mirrors phi_expand_kernel
-                u64 v = v0;
-                occ[g0] = v;
-                for (u64 t = 1; t < len; ++t) { v = trans_step(f, f.phi[0], v); occ[g0 + t] = v; }
-            } else {       // mirrors phi_expand_group_kernel: D lanes, lane c owns slots == c (mod D)
-                for (u32 c = 0; c < D; ++c) {
-                    u64 v = v0;
-                    u64 t = (c + D - (u32)(g0 % D)) % D;
-                    for (u32 s = 0; s + 1 < D; ++s) if ((u64)s < t && t < len) v = trans_step(f, f.phi[0], v);
-                    while (t < len) { occ[g0 + t] = v; t += D; if (t < len) v = trans_step(f, f.phi[1], v); }
-                }
+            // mirrors rigk::phi_expand_kernel: head singles up to alignment, D per lookup, tail
+            u64 v = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
+            const u64 g0 = occ_off[p] + (H - top);
+            const u32 D = f.phi.D;
+            u64* o = occ + g0;
+            *o++ = v;
+            u64 remaining = top - bot, e[8];
+            const u32 mis = (u32)((g0 + 1) % D);
+            if (D > 1 && mis != 0 && remaining > 0) {
+                const u32 cnt = (u32)std::min<u64>(D - mis, remaining);
+                phi_lookup(f, v, e);
+                for (u32 t = 0; t < cnt; ++t) { o[t] = e[t]; v = e[t]; }
+                o += cnt; remaining -= cnt;
+            }
+            while (remaining >= D) {
+                phi_lookup(f, v, e);
+                if (((u64)(o - occ)) % D != 0) return ~(u64)0;  // vector stores must be aligned
+                for (u32 t = 0; t < D; ++t) o[t] = e[t];
+                v = e[D - 1]; o += D; remaining -= D;
+            }
+            if (D > 1 && remaining > 0) {
+                phi_lookup(f, v, e);
+                for (u32 t = 0; t < remaining; ++t) o[t] = e[t];
             }
             ++chains;
         }
