@@ -45,22 +45,25 @@ typedef uint32_t u32;
 
 // Phi, Phi^2, ..., Phi^D as one refined piecewise translation.
 //   piece k covers [start[k], start[k+1]);  Phi^j(i) = (i + delta[k*D + j-1]) mod n  for i in piece k.
-// Bucket q (positions [q<<shift, (q+1)<<shift)) has a record of RW words:
-//   [0..D)  deltas of the piece covering the bucket's first position
-//   [D]     s1  = start of the next piece if it begins inside the bucket, else ~0
-//   [D+1]   nxt = index of that next piece (valid when s1 != ~0)
-//   [D+2]   s2  = start of the piece after it if inside the bucket, else ~0
-//   rest    padding to RW = 4 (D=1), 8 (D=2,4) or 16 (D=8) words
-// query i: i < s1 -> record deltas; i < s2 -> deltas of piece nxt; else binary search in pieces (nxt, dir[q+1]].
+// Device form: two arrays of RW-word entries (RW = 4 for D=1, 8 for D=2,4, 16 for D=8), so that a
+// lane needs ONE load instruction per step whatever it is doing:
+//   rec[q]  bucket q = positions [q<<shift, (q+1)<<shift):
+//           [0..D) deltas of the piece covering the bucket's first position
+//           [D]    s1  = start of the first piece that begins inside the bucket (after its first position), else ~0
+//           [D+1]  nxt = index of that piece
+//           [D+2]  cnt = number of pieces that begin inside the bucket
+//   pent[k] piece k:  [0..D) its deltas, [D] its start
+// query i: i < s1 -> record deltas; else the answer is the last piece in [nxt, nxt+cnt) with start <= i
+// (cnt == 1: piece nxt; otherwise a binary search whose every probe is one pent[] load).
 struct PhiTable {
     u32 D = 1, RW = 4, shift = 0;
     u64 nbkt = 0;
     std::vector<u64> start;   // [pieces], start[0] == 0, strictly ascending
     std::vector<u64> delta;   // [pieces * D]
-    std::vector<u32> dir;     // [nbkt+1] piece covering the first position of the bucket
     std::vector<u64> rec;     // [nbkt * RW]
+    std::vector<u64> pent;    // [pieces * RW]
     u64 pieces() const { return start.size(); }
-    u64 bytes(bool w32) const { return start.size() * 8 + delta.size() * (w32 ? 4 : 8) + dir.size() * 4 + rec.size() * (w32 ? 4 : 8); }
+    u64 bytes(bool w32) const { return (rec.size() + pent.size()) * (w32 ? 4 : 8); }
     static u32 record_words(u32 D) { return D == 1 ? 4 : (D <= 4 ? 8 : 16); }
     u64 piece_of(u64 i) const { return (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1; }
     // scalar evaluation of Phi^j(i), 1 <= j <= D (host-side construction + tests)
@@ -75,22 +78,25 @@ struct PhiTable {
         if (target < 1) target = 1;
         while (((n - 1) >> shift) + 1 > target) ++shift;
         nbkt = ((n - 1) >> shift) + 1;
-        dir.assign(nbkt + 1, 0);
         rec.assign(nbkt * RW, 0);
         const u64 P = pieces();
+        pent.assign(P * RW, 0);
+        for (u64 k = 0; k < P; ++k) {
+            for (u32 j = 0; j < D; ++j) pent[k * RW + j] = delta[k * D + j];
+            pent[k * RW + D] = start[k];
+        }
         u64 a = 0;
         for (u64 q = 0; q < nbkt; ++q) {
             const u64 lo = q << shift, hi = (q + 1) << shift;
             while (a + 1 < P && start[a + 1] <= lo) ++a;
-            dir[q] = (u32)a;
+            u64 e = a + 1;
+            while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
             u64* R = &rec[q * RW];
             for (u32 j = 0; j < D; ++j) R[j] = delta[a * D + j];
-            const bool h1 = a + 1 < P && start[a + 1] < hi, h2 = a + 2 < P && start[a + 2] < hi;
-            R[D] = h1 ? start[a + 1] : ~(u64)0;
-            R[D + 1] = h1 ? a + 1 : 0;
-            R[D + 2] = h2 ? start[a + 2] : ~(u64)0;
+            R[D] = (e > a + 1) ? start[a + 1] : ~(u64)0;
+            R[D + 1] = (e > a + 1) ? a + 1 : 0;
+            R[D + 2] = e - (a + 1);
         }
-        dir[nbkt] = (u32)(P - 1);
     }
 };
 
@@ -256,14 +262,15 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         P1.start.push_back(0); P1.delta.push_back(dl[r - 1]);
         for (u64 k = 0; k + 1 < r; ++k) { P1.start.push_back(v.pred_pos[k] + 1); P1.delta.push_back(dl[k]); }
     }
-    const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 2;
+    // buckets per piece: 2 (measured on C2: 0.51 ms vs 0.57 ms with 4 — the smaller table stays in L2)
+    const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 1;
     f.w32 = n < 0xFFFFFFFEull;
     // D = occurrences produced per record lookup: requested, or the largest of {4,2} whose bucket
     // records stay L2-friendly (they compete with the streamed occurrence output for the 126 MB L2).
     u32 D = opt.reserved[0];
     if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
     if (D == 0) {
-        const u64 budget = 48ull << 20;
+        const u64 budget = 56ull << 20;
         const u64 wb = f.w32 ? 4 : 8;
         auto cost = [&](u32 d) { return (u64)d * r * ((PhiTable::record_words(d) * wb) << fp); };
         D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);

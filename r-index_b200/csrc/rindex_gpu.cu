@@ -61,6 +61,8 @@ struct rig_index {
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
+    size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
+    float l2_hit_ratio = 1.f;
     bool timing_pending = false;
     bool ev_valid[6] = {false, false, false, false, false, false};
 };
@@ -113,7 +115,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
     if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
-    int variant = 0;  // testing switch (env RIG_VARIANT): bit3 forces the 64-bit code paths (as for n >= 2^32)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit3 forces the 64-bit code paths (as for n >= 2^32)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) f.w32 = false;
 
@@ -127,12 +129,12 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
-    std::vector<uint32_t> rec32, delta32;
+    std::vector<uint32_t> rec32, pent32;
     if (f.w32) {  // 32-bit words: ~0 sentinels truncate to 0xFFFFFFFF, everything else is < n < 2^32-1
         rec32.resize(f.phi.rec.size());
         for (size_t i = 0; i < rec32.size(); ++i) rec32[i] = (uint32_t)f.phi.rec[i];
-        delta32.resize(f.phi.delta.size());
-        for (size_t i = 0; i < delta32.size(); ++i) delta32[i] = (uint32_t)f.phi.delta[i];
+        pent32.resize(f.phi.pent.size());
+        for (size_t i = 0; i < pent32.size(); ++i) pent32[i] = (uint32_t)f.phi.pent[i];
     }
     struct Part { const void* src; size_t bytes; size_t off; };
     std::vector<Part> parts = {
@@ -142,13 +144,11 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
         {f.bdir.data(), f.bdir.size() * 4, 0},      {f.samples_last.data(), f.samples_last.size() * 8, 0}};
     if (f.w32) {
         parts.push_back({rec32.data(), rec32.size() * 4, 0});
-        parts.push_back({delta32.data(), delta32.size() * 4, 0});
+        parts.push_back({pent32.data(), pent32.size() * 4, 0});
     } else {
         parts.push_back({f.phi.rec.data(), f.phi.rec.size() * 8, 0});
-        parts.push_back({f.phi.delta.data(), f.phi.delta.size() * 8, 0});
+        parts.push_back({f.phi.pent.data(), f.phi.pent.size() * 8, 0});
     }
-    parts.push_back({f.phi.start.data(), f.phi.start.size() * 8, 0});
-    parts.push_back({f.phi.dir.data(), f.phi.dir.size() * 4, 0});
     size_t total = 0;
     for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 128, 256); }
     cudaError_t e = cudaMalloc(&ix->arena, total);
@@ -169,12 +169,27 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.bdir = (const uint32_t*)(A + parts[6].off);
     d.samples_last = (const ull*)(A + parts[7].off);
     d.phi.rec = (const void*)(A + parts[8].off);
-    d.phi.delta = (const void*)(A + parts[9].off);
-    d.phi.start = (const ull*)(A + parts[10].off);
-    d.phi.dir = (const uint32_t*)(A + parts[11].off);
+    d.phi.pent = (const void*)(A + parts[9].off);
     d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
     d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
 
+    // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
+    // limit; harmless for other users of the context) and size the window / hit ratio to it.
+    {
+        const size_t rec_bytes = f.phi.rec.size() * (f.w32 ? 4 : 8);
+        // Measured on C2 (B200, 79 MiB max carve-out): reserving persisting L2 made the expansion kernel
+        // SLOWER (0.51 -> 0.91 ms; the carve-out shrinks the L2 left for the output stream and the other
+        // arrays), so it is off unless RIG_VARIANT bit0 asks for the experiment.
+        if ((variant & 1) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 && rec_bytes > 0) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+                ix->l2_window_bytes = rec_bytes < (size_t)prop.accessPolicyMaxWindowSize ? rec_bytes : (size_t)prop.accessPolicyMaxWindowSize;
+                const double ratio = (double)prop.persistingL2CacheMaxSize / (double)ix->l2_window_bytes;
+                ix->l2_hit_ratio = ratio >= 1.0 ? 1.f : (float)ratio;
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
     CU_TRY(cudaMalloc((void**)&ix->d_counters, 8 * sizeof(ull)));
@@ -189,6 +204,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     I.runs_per_block = f.K; I.lf_shift = f.lf_shift; I.phi_shift = f.phi.shift;
     I.phi_jump = f.phi.D; I.phi_jump_pieces = f.phi.pieces(); I.words32 = f.w32 ? 1u : 0u;
     I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
+    I.reserved = ix->l2_window_bytes ? (uint32_t)(prop.persistingL2CacheMaxSize >> 20) : 0;  // MiB of persisting L2 in use
     *out = ix;
     return RIG_OK;
 }
@@ -342,10 +358,28 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         const bool w32 = ix->d.w32 != 0;
         const uint64_t nb = (chains + threads - 1) / threads;
         if (nb > 0x7fffffffull) return RIG_ERR_ARG;
-#define RIG_EXPAND(W, DD)                                                                                  \
-    rigk::phi_expand_kernel<W, DD><<<(unsigned)nb, threads, 0, st>>>(ix->d, N, (ull*)ix->choff.p, d_occoff, \
-                                                                     d_lo, d_hi, (ull*)ix->toe.p,           \
-                                                                     (ull*)ix->jl.p, d_occ, chains)
+        // Keep the Phi bucket records resident in L2 while ~10-100x more occurrence bytes stream past
+        // them: persisting access-policy window on the record array for this launch.
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)nb); cfg.blockDim = dim3((unsigned)threads); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        if (ix->l2_window_bytes) {
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(ix->d.phi.rec);
+            attr[0].val.accessPolicyWindow.num_bytes = ix->l2_window_bytes;
+            attr[0].val.accessPolicyWindow.hitRatio = ix->l2_hit_ratio;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+        }
+        const ull* a_choff = (const ull*)ix->choff.p; const ull* a_occoff = d_occoff;
+        const ull* a_lo = d_lo; const ull* a_hi = d_hi;
+        const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
+        ull a_N = N, a_chains = chains;
+#define RIG_EXPAND(W, DD)                                                                                     \
+    CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD>, ix->d, a_N, a_choff, a_occoff, a_lo, a_hi, \
+                              a_toe, a_jl, d_occ, a_chains))
         switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
             case 2: RIG_EXPAND(false, 1); break;
             case 3: RIG_EXPAND(true, 1); break;

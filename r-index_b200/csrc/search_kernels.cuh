@@ -9,9 +9,6 @@
 //                            (reference internal/r_index.hpp:171-190,292-302,482-545;
 //                             internal/rle_string.hpp:126-256).
 //   scan_*                   exclusive scans of n_occ and chain counts (output offsets).
-//   phi_expand_kernel        Phi walks, one independent chain per LANE, chains cut at BWT run
-//                            boundaries, lanes refill from a global queue (reference
-//                            r_index::Phi :195-221 and the locate_all loop :340-351).
 //   digest_kernel            checksum of a u64 array.
 //
 // No tensor cores: the path has no dense contraction; it is dependent integer loads.
@@ -24,13 +21,11 @@ namespace rigk {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-// Phi^1..Phi^D as one refined piecewise translation (flat_layout.hpp: PhiTable). Words are u32 when
-// FlatDev::w32 (n < 2^32-1), else u64.
+// Phi^1..Phi^D as one refined piecewise translation (flat_layout.hpp: PhiTable). Entries are RW words
+// of u32 (FlatDev::w32, n < 2^32-1) or u64; RW = 4 (D=1), 8 (D=2,4), 16 (D=8).
 struct PhiTabDev {
-    const void* rec;    // [nbkt * RW] bucket records: D deltas, s1, nxt, s2, padding
-    const void* delta;  // [pieces * D]
-    const u64* start;   // [pieces]
-    const u32* dir;     // [nbkt+1] piece covering the first position of the bucket
+    const void* rec;    // [nbkt]   bucket records: D deltas, s1, nxt, cnt
+    const void* pent;   // [pieces] piece entries:  D deltas, start
     u32 shift, D;
 };
 

@@ -48,25 +48,32 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
     return r;
 }
 
-// mirrors rigk::phi_lookup (including the 32-bit truncation of records and deltas when w32)
-void phi_lookup(const FlatHost& f, u64 i, u64* e) {
+// mirrors the per-lane state machine of rigk::phi_expand_kernel for ONE lookup: returns
+// e[t] = Phi^(t+1)(i), reading only rec[] / pent[] entries (with the 32-bit truncation when w32).
+// *loads counts the entry loads the lane needed.
+void phi_lookup(const FlatHost& f, u64 i, u64* e, u64* loads = nullptr) {
     const rigf::PhiTable& T = f.phi;
     const u32 D = T.D, RW = T.RW;
     const u64 mask = f.w32 ? 0xFFFFFFFFull : ~(u64)0;
-    u64 q = i >> T.shift;
-    const u64* w = &T.rec[q * RW];
-    u64 d[8];
-    for (u32 j = 0; j < D; ++j) d[j] = w[j] & mask;
-    if (i >= (w[D] & mask)) {
-        u64 piece = w[D + 1] & mask;
-        if (i >= (w[D + 2] & mask)) {
-            u64 lo = piece + 1, hi = T.dir[q + 1];
-            while (lo < hi) { u64 mid = (lo + hi + 1) >> 1; if (T.start[mid] <= i) lo = mid; else hi = mid - 1; }
-            piece = lo;
+    bool searching = false;
+    u64 slo = 0, shi = 0, nload = 0;
+    for (;;) {
+        const u64 probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+        const u64* w = searching ? &T.pent[probe * RW] : &T.rec[(i >> T.shift) * RW];
+        ++nload;
+        bool emit;
+        if (!searching) {
+            emit = i < (w[D] & mask);
+            if (!emit) { slo = w[D + 1] & mask; shi = slo + (w[D + 2] & mask) - 1; searching = true; }
+        } else if (slo == shi) emit = true;
+        else if ((w[D] & mask) <= i) { slo = probe; emit = (slo == shi); }
+        else { shi = probe - 1; emit = false; }
+        if (emit) {
+            for (u32 j = 0; j < D; ++j) { u64 v = i + (w[j] & mask); if (v >= f.n) v -= f.n; e[j] = v; }
+            if (loads) *loads += nload;
+            return;
         }
-        for (u32 j = 0; j < D; ++j) d[j] = T.delta[piece * D + j] & mask;
     }
-    for (u32 j = 0; j < D; ++j) { u64 v = i + d[j]; if (v >= f.n) v -= f.n; e[j] = v; }
 }
 
 // mirrors rigk::search_kernel (one pattern)
