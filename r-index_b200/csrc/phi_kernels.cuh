@@ -12,26 +12,30 @@
 //
 // The walk is a per-lane STATE MACHINE with exactly one RW-word load per loop iteration, whatever the
 // lane is doing (reading the bucket record of its current position, or probing a piece entry while it
-// searches a crowded bucket). Measured reason: with an if/else "slow path", one lane
-// of 32 taking it stalls the whole warp for 2-6 extra dependent L2 round trips on almost every
-// iteration; with the state machine a lane's slow path costs that lane extra iterations only.
+// searches a crowded bucket): a lane's slow path costs that lane extra iterations, not the warp.
+// All value arithmetic is done in the table's word type (u32 when n < 2^32-1): the kernel was
+// measured issue-bound at 113 instructions per iteration with 64-bit arithmetic.
 #pragma once
 #include "search_kernels.cuh"
 
 namespace rigk {
 
+template <bool KEEP>
 __device__ __forceinline__ void ldg256(const void* p, u64& a, u64& b, u64& c, u64& d) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    if (KEEP)  // ask L2 to evict these lines last: the streamed occurrence output competes for the same sets
+        asm volatile("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    else
+        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 __device__ __forceinline__ void stg256_stream(void* p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.u64 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-// Load the RW-word entry at `p` (RW*wordsize aligned) into w[] (zero-extended to u64).
-template <bool W32, int RW>
-__device__ __forceinline__ void load_entry(const void* p, u64 (&w)[RW]) {
-    if (W32) {
+// Load the RW-word entry at `p` (RW*sizeof(WT) aligned).
+template <typename WT, int RW, bool KEEP>
+__device__ __forceinline__ void load_entry(const void* p, WT (&w)[RW]) {
+    if constexpr (sizeof(WT) == 4) {
         if constexpr (RW == 4) {
             const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
             w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
@@ -39,25 +43,26 @@ __device__ __forceinline__ void load_entry(const void* p, u64 (&w)[RW]) {
 #pragma unroll
             for (int k = 0; k < RW / 8; ++k) {
                 u64 a, b, c, d;
-                ldg256(reinterpret_cast<const u32*>(p) + 8 * k, a, b, c, d);
-                w[8 * k + 0] = (u32)a; w[8 * k + 1] = a >> 32; w[8 * k + 2] = (u32)b; w[8 * k + 3] = b >> 32;
-                w[8 * k + 4] = (u32)c; w[8 * k + 5] = c >> 32; w[8 * k + 6] = (u32)d; w[8 * k + 7] = d >> 32;
+                ldg256<KEEP>(reinterpret_cast<const u32*>(p) + 8 * k, a, b, c, d);
+                w[8 * k + 0] = (u32)a; w[8 * k + 1] = (u32)(a >> 32); w[8 * k + 2] = (u32)b; w[8 * k + 3] = (u32)(b >> 32);
+                w[8 * k + 4] = (u32)c; w[8 * k + 5] = (u32)(c >> 32); w[8 * k + 6] = (u32)d; w[8 * k + 7] = (u32)(d >> 32);
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < RW / 4; ++k)
-            ldg256(reinterpret_cast<const u64*>(p) + 4 * k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            ldg256<KEEP>(reinterpret_cast<const u64*>(p) + 4 * k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
 }
 
-template <int D>
-__device__ __forceinline__ void store_group(u64* p, const u64 (&e)[D]) {  // p is D*8-byte aligned
-    if constexpr (D == 1) __stcs(p, e[0]);
-    else if constexpr (D == 2) __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2(e[0], e[1]));
+template <typename WT, int D>
+__device__ __forceinline__ void store_group(u64* p, const WT (&e)[D]) {  // p is D*8-byte aligned
+    if constexpr (D == 1) __stcs(p, (u64)e[0]);
+    else if constexpr (D == 2) __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2((u64)e[0], (u64)e[1]));
     else {
 #pragma unroll
-        for (int k = 0; k < D / 4; ++k) stg256_stream(p + 4 * k, e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+        for (int k = 0; k < D / 4; ++k)
+            stg256_stream(p + 4 * k, (u64)e[4 * k], (u64)e[4 * k + 1], (u64)e[4 * k + 2], (u64)e[4 * k + 3]);
     }
 }
 
@@ -68,13 +73,14 @@ __device__ __forceinline__ void store_group(u64* p, const u64 (&e)[D]) {  // p i
 // deltas are those of the piece holding v. For t = 0 this is r_index::Phi (r_index.hpp:195-221):
 // strict circular predecessor over the sorted run-first samples (sparse_sd_vector.hpp:107-112,153-157)
 // and (prev_sample + delta) % n (:219), folded into one delta per piece.
-template <bool W32, int D>
+template <typename WT, int D, bool KEEP>
 __global__ void __launch_bounds__(256)
 phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
                   const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
                   const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
-    constexpr u64 ESZ = (u64)RW * (W32 ? 4 : 8);  // entry size in bytes
+    constexpr u32 ESZ = RW * (u32)sizeof(WT);  // entry size in bytes
+    constexpr bool W32 = sizeof(WT) == 4;
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= total_chains) return;  // no warp collectives below
     u64 a = 0, b = N;  // largest p with ch_off[p] <= w
@@ -87,28 +93,32 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
     const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
     const u64 sj = __ldg(ix.start + j), ej = __ldg(ix.start + j + 1) - 1;
     const u64 top = min(H, ej), bot = max(L, sj);
-    u64 v;
-    if (top == H) v = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
-    else { v = __ldg(ix.samples_last + j) + 1; if (v >= ix.n) v -= ix.n; }  // run end: SA = sample + 1
+    u64 v0;
+    if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
+    else { v0 = __ldg(ix.samples_last + j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
     u64* o = out + __ldg(occ_off + p) + (H - top);  // next slot to write
-    __stcs(o, v);
+    __stcs(o, v0);
     ++o;
-    u64 remaining = top - bot;  // occurrences still to produce
-    const u64 n = ix.n;
+    WT v = (WT)v0;
+    WT remaining = (WT)(top - bot);  // occurrences still to produce (a chain never exceeds n)
+    const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
+    // slots up to the next D*8-byte boundary go out singly; afterwards every emit is one aligned group
+    u32 take = D - (u32)((reinterpret_cast<unsigned long long>(o) >> 3) % D);
     bool searching = false;   // false: next load = bucket record of v; true: next load = piece entry `probe`
-    u64 slo = 0, shi = 0;     // search interval of piece indices, invariant start[slo] <= v
+    u32 slo = 0, shi = 0;     // search interval of piece indices, invariant start[slo] <= v
     while (remaining > 0) {
-        const u64 probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
-        const char* addr = searching ? (pent + probe * ESZ) : (rec + (v >> shift) * ESZ);
-        u64 e[RW];
-        load_entry<W32, RW>(addr, e);  // the ONE load of this iteration
+        const u32 probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+        const char* addr = searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(v >> shift) * ESZ);
+        WT e[RW];
+        load_entry<WT, RW, KEEP>(addr, e);  // the ONE load of this iteration
         bool emit;
         if (!searching) {
             emit = v < e[D];              // no piece begins inside the bucket at or below v
-            if (!emit) { slo = e[D + 1]; shi = slo + e[D + 2] - 1; searching = true; }
+            slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+            searching = !emit;
         } else if (slo == shi) {
             emit = true;                  // the entry just loaded is the answer
         } else if (e[D] <= v) {
@@ -118,28 +128,27 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
         }
         if (emit) {
             searching = false;
+            slo = shi = 0;
+            WT x[D];
 #pragma unroll
             for (int t = 0; t < D; ++t) {
-                u64 x = v + e[t];
-                if (x >= n) x -= n;
-                e[t] = x;
+                x[t] = v + e[t];
+                if ((W32 && x[t] < v) || x[t] >= n) x[t] -= n;  // (v + delta) mod n; 32-bit: detect the carry
             }
-            // slots until the next D*8-byte boundary; full aligned groups leave as one vector store
-            const u32 mis = (u32)((reinterpret_cast<unsigned long long>(o) >> 3) % D);
-            const u64 cnt = min((u64)(D - mis), remaining);
-            if (cnt == D) {
-                u64 g[D];
-#pragma unroll
-                for (int t = 0; t < D; ++t) g[t] = e[t];
-                store_group<D>(o, g);
-                v = e[D - 1];
+            if (take == D && remaining >= (WT)D) {
+                store_group<WT, D>(o, x);
+                v = x[D - 1];
+                o += D;
+                remaining -= (WT)D;
             } else {
+                const u32 cnt = (u32)min((u64)take, (u64)remaining);
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)
-                    if ((u64)t < cnt) { __stcs(o + t, e[t]); v = e[t]; }
+                    if ((u32)t < cnt) { __stcs(o + t, (u64)x[t]); v = x[t]; }
+                o += cnt;
+                remaining -= (WT)cnt;
+                take = D;
             }
-            o += cnt;
-            remaining -= cnt;
         }
     }
 }

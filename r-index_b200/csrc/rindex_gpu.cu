@@ -115,7 +115,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
     if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit3 forces the 64-bit code paths (as for n >= 2^32)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit3 forces the 64-bit code paths (as for n >= 2^32)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) f.w32 = false;
 
@@ -377,18 +377,23 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         const ull* a_lo = d_lo; const ull* a_hi = d_hi;
         const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
         ull a_N = N, a_chains = chains;
+        const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
 #define RIG_EXPAND(W, DD)                                                                                     \
-    CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD>, ix->d, a_N, a_choff, a_occoff, a_lo, a_hi, \
-                              a_toe, a_jl, d_occ, a_chains))
+    do {                                                                                                      \
+        if (keep) CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, true>, ix->d, a_N, a_choff,  \
+                                            a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains));            \
+        else CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, false>, ix->d, a_N, a_choff,      \
+                                       a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains));                 \
+    } while (0)
         switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
-            case 2: RIG_EXPAND(false, 1); break;
-            case 3: RIG_EXPAND(true, 1); break;
-            case 4: RIG_EXPAND(false, 2); break;
-            case 5: RIG_EXPAND(true, 2); break;
-            case 8: RIG_EXPAND(false, 4); break;
-            case 9: RIG_EXPAND(true, 4); break;
-            case 16: RIG_EXPAND(false, 8); break;
-            case 17: RIG_EXPAND(true, 8); break;
+            case 2: RIG_EXPAND(ull, 1); break;
+            case 3: RIG_EXPAND(uint32_t, 1); break;
+            case 4: RIG_EXPAND(ull, 2); break;
+            case 5: RIG_EXPAND(uint32_t, 2); break;
+            case 8: RIG_EXPAND(ull, 4); break;
+            case 9: RIG_EXPAND(uint32_t, 4); break;
+            case 16: RIG_EXPAND(ull, 8); break;
+            case 17: RIG_EXPAND(uint32_t, 8); break;
             default: return RIG_ERR_ARG;
         }
 #undef RIG_EXPAND
