@@ -1,0 +1,144 @@
+// ri-locate — locate all occurrences of the input patterns (reference ri-locate.cpp: same usage text,
+// options -c / -o, argument handling and stdout lines). The per-pattern loop (:126-192) becomes one
+// batch call per GPU shard. -o keeps the reference's format: per pattern, positions sorted ascending,
+// printed through an (int) cast (:146-152; positions >= 2^31 therefore wrap exactly as upstream).
+#include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include "cli_common.hpp"
+
+using namespace ri;
+using namespace std;
+
+static string check_text_file, ofile;
+static int gpus = 1;
+
+static void help() {
+    cout << "ri-locate: locate all occurrences of the input patterns." << endl << endl;
+    cout << "Usage: ri-locate [options] <index> <patterns>" << endl;
+    cout << "   -c <text>    check correctness of each pattern occurrence on this text file (must be the same indexed)" << endl;
+    cout << "   -o <ofile>   write pattern occurrences to this file (ASCII)" << endl;
+    cout << "   <index>      index file (with extension .ri)" << endl;
+    cout << "   <patterns>   file in pizza&chili format containing the patterns." << endl;
+    exit(0);
+}
+
+static void parse_args(char** argv, int argc, int& ptr) {
+    string s(argv[ptr]);
+    ptr++;
+    if (s.compare("-c") == 0) {
+        if (ptr >= argc - 1) {
+            cout << "Error: missing parameter after -c option." << endl;
+            help();
+        }
+        check_text_file = string(argv[ptr]);
+        ptr++;
+    } else if (s.compare("-o") == 0) {
+        if (ptr >= argc - 1) {
+            cout << "Error: missing parameter after -o option." << endl;
+            help();
+        }
+        ofile = string(argv[ptr]);
+        ptr++;
+    } else if (s.compare("--gpus") == 0 && ptr < argc - 2) {  // addition
+        gpus = atoi(argv[ptr]);
+        ptr++;
+    } else {
+        cout << "Error: unknown option " << s << endl;
+        help();
+    }
+}
+
+int main(int argc, char** argv) {
+    using std::chrono::high_resolution_clock;
+    if (argc < 3) help();
+    int ptr = 1;
+    while (ptr < argc - 2) parse_args(argv, argc, ptr);
+    string idx_file(argv[ptr]);
+    string patt_file(argv[ptr + 1]);
+    std::ifstream in(idx_file, std::ios::binary);
+    bool fast;
+    in.read((char*)&fast, sizeof(fast));
+    cout << "Loading r-index" << endl;
+
+    string text;
+    bool c = false;
+    ofstream out;
+    if (ofile.compare(string()) != 0) out = ofstream(ofile);
+    if (check_text_file.compare(string()) != 0) {
+        c = true;
+        ifstream ifs1(check_text_file, std::ios::binary);
+        stringstream ss;
+        ss << ifs1.rdbuf();
+        text = ss.str();
+    }
+
+    auto t1 = high_resolution_clock::now();
+    rib::LogicalIndex L;
+    if (!rib::load(L, in)) {
+        cout << "Error: index file is not an r-index built by this ri-build" << endl;
+        exit(1);
+    }
+    auto t2 = high_resolution_clock::now();
+    cout << "searching patterns ... " << endl;
+    PatternFile pf = read_patterns(patt_file);  // a malformed header exits(0) here, as upstream (utils.hpp:51-55)
+    auto u1 = high_resolution_clock::now();
+    GpuFleet fleet(L, gpus);                    // flatten + upload: accounted as load time, not search time
+    auto u2 = high_resolution_clock::now();
+    const uint64_t n = pf.n, m = pf.m;
+    std::vector<uint64_t> lo(n), hi(n);
+    std::vector<std::vector<uint64_t>> off, occ;
+    uint64_t occ_tot = fleet.locate(pf.body.data(), n, m, lo.data(), hi.data(), off, occ);
+
+    const int G = fleet.size();
+    if (ofile.compare(string()) != 0 || c) {
+        for (int g = 0; g < G; ++g) {
+            const uint64_t a = n * g / G, b = n * (g + 1) / G;
+            for (uint64_t i = a; i < b; ++i) {
+                uint64_t* first = occ[g].data() + off[g][i - a];
+                uint64_t* last = occ[g].data() + off[g][i - a + 1];
+                std::sort(first, last);  // reference sorts per pattern for -o and -c (:147,:159)
+                if (ofile.compare(string()) != 0)
+                    for (uint64_t* x = first; x != last; ++x) out << (int)*x << endl;
+                if (c) {  // check occurrences (reference :156-190)
+                    uint64_t* it = std::unique(first, last);
+                    uint64_t distinct = (uint64_t)(it - first);
+                    uint64_t want = hi[i] >= lo[i] ? (hi[i] - lo[i]) + 1 : 0;
+                    if (distinct != want) {
+                        cout << "Error: wrong number of located occurrences: " << distinct << "/" << want << endl;
+                        exit(0);
+                    }
+                    const char* p = (const char*)pf.body.data() + i * m;
+                    for (uint64_t* x = first; x != it; ++x) {
+                        if (*x + m > text.size() || memcmp(text.data() + *x, p, m) != 0) {
+                            cout << "Error: wrong occurrence: " << *x << " (" << occ_tot << " occurrences" << ") " << endl;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    print_progress_lines(n);
+    double occ_avg = (double)occ_tot / n;
+    cout << endl << occ_avg << " average occurrences per pattern" << endl;
+    auto t3 = high_resolution_clock::now();
+
+    uint64_t upload = std::chrono::duration_cast<std::chrono::milliseconds>(u2 - u1).count();
+    uint64_t load = std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count() + upload;
+    cout << "Load time : " << load << " milliseconds" << endl;
+    uint64_t search = std::chrono::duration_cast<std::chrono::milliseconds>(t3 - t2).count() - upload;
+    cout << "number of patterns n = " << n << endl;
+    cout << "pattern length m = " << m << endl;
+    cout << "total number of occurrences  occ_t = " << occ_tot << endl;
+    cout << "Total time : " << search << " milliseconds" << endl;
+    cout << "Search time : " << (double)search / n << " milliseconds/pattern (total: " << n << " patterns)" << endl;
+    cout << "Search time : " << (double)search / occ_tot << " milliseconds/occurrence (total: " << occ_tot << " occurrences)" << endl;
+    rig_timing t;
+    if (rig_last_timing(fleet.handle(0), &t) == RIG_OK)
+        cout << "[gpu] devices = " << G << ", device 0: search = " << t.search_ms << " ms, scan = " << t.scan_ms
+             << " ms, phi expansion = " << t.expand_ms << " ms, chains = " << t.chains << endl;
+    in.close();
+}

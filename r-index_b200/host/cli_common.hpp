@@ -1,0 +1,120 @@
+// cli_common.hpp — shared by ri-count / ri-locate: pattern-file reading, the reference's progress
+// lines, and the multi-GPU fan-out (index replicated on every GPU, patterns cut into contiguous
+// shards, one host thread per device, no collective on the search path — SURVEY.md §8e).
+#pragma once
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+#include "logical_index.hpp"
+#include "utils.hpp"
+#include "../../include/rindex_gpu.h"
+
+namespace ri {
+
+struct PatternFile {
+    uint64_t n = 0, m = 0;
+    std::vector<uint8_t> body;  // n*m bytes
+};
+
+// Reference reader: one header line, then n*m raw bytes read with ifs.get (binary-safe: patterns may
+// contain '\n' and bytes >= 0x80) — ri-count.cpp:86-110. A short file leaves the missing bytes 0.
+inline PatternFile read_patterns(const std::string& path) {
+    PatternFile pf;
+    std::ifstream ifs(path, std::ios::binary);
+    std::string header;
+    std::getline(ifs, header);
+    pf.n = get_number_of_patterns(header);
+    pf.m = get_patterns_length(header);
+    pf.body.assign(pf.n * pf.m, 0);
+    ifs.read((char*)pf.body.data(), (std::streamsize)pf.body.size());
+    return pf;
+}
+
+// The "% done ..." lines of the reference's loop (ri-count.cpp:96-102), in the same order.
+inline void print_progress_lines(uint64_t n) {
+    unsigned last_perc = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        unsigned perc = (unsigned)((100 * i) / n);
+        if (perc > last_perc) {
+            std::cout << perc << "% done ..." << std::endl;
+            last_perc = perc;
+        }
+    }
+}
+
+inline void die(int rc, const char* where) {
+    std::cout << "Error: " << where << ": " << rig_strerror(rc);
+    const char* ce = rig_last_cuda_error();
+    if (ce && *ce) std::cout << " [" << ce << "]";
+    std::cout << std::endl;
+    exit(1);
+}
+
+// One rig_index per device; shard p covers patterns [N*p/G, N*(p+1)/G).
+class GpuFleet {
+public:
+    explicit GpuFleet(const rib::LogicalIndex& L, int gpus) {
+        int have = rig_device_count();
+        if (have < 1) { std::cout << "Error: no CUDA device available (this build has no CPU query path)" << std::endl; exit(1); }
+        G = gpus <= 0 ? 1 : (gpus > have ? have : gpus);
+        idx.assign(G, nullptr);
+        rig_logical_view v;
+        v.n = L.n; v.r = L.r; v.F = L.F;
+        v.run_heads = L.run_heads.data(); v.run_lens = L.run_lens.data(); v.samples_last = L.samples_last.data();
+        v.pred_pos = L.pred_pos.data(); v.pred_to_run = L.pred_to_run.data();
+        std::vector<int> rcs(G, 0);
+        run([&](int g) { rcs[g] = rig_index_create(&v, g, &idx[g]); });
+        for (int g = 0; g < G; ++g) if (rcs[g] != RIG_OK) die(rcs[g], "rig_index_create");
+    }
+    ~GpuFleet() { for (auto* p : idx) rig_index_destroy(p); }
+    int size() const { return G; }
+    rig_index* handle(int g) { return idx[g]; }
+
+    void count(const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi) {
+        std::vector<int> rcs(G, 0);
+        run([&](int g) {
+            uint64_t a = N * g / G, b = N * (g + 1) / G;
+            rcs[g] = rig_count_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a);
+        });
+        for (int g = 0; g < G; ++g) if (rcs[g] != RIG_OK) die(rcs[g], "rig_count_batch");
+    }
+    // Per-shard results: occ[g] holds the occurrences of shard g's patterns back to back;
+    // off[g] (shard-local, size = shard patterns + 1) indexes into it.
+    uint64_t locate(const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                    std::vector<std::vector<uint64_t>>& off, std::vector<std::vector<uint64_t>>& occ) {
+        off.assign(G, {}); occ.assign(G, {});
+        std::vector<int> rcs(G, 0);
+        std::vector<uint64_t> totals(G, 0);
+        run([&](int g) {
+            uint64_t a = N * g / G, b = N * (g + 1) / G;
+            off[g].assign(b - a + 1, 0);
+            int rc = rig_locate_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), nullptr, 0, &totals[g]);
+            if (rc == RIG_ERR_CAPACITY) {
+                occ[g].resize(totals[g]);
+                rc = rig_locate_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), occ[g].data(),
+                                      occ[g].size(), &totals[g]);
+            }
+            rcs[g] = rc;
+        });
+        uint64_t total = 0;
+        for (int g = 0; g < G; ++g) { if (rcs[g] != RIG_OK) die(rcs[g], "rig_locate_batch"); total += totals[g]; }
+        return total;
+    }
+
+private:
+    template <class Fn>
+    void run(Fn fn) {
+        if (G == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back([&, g]() { fn(g); });
+        for (auto& t : th) t.join();
+    }
+    int G = 1;
+    std::vector<rig_index*> idx;
+};
+
+}  // namespace ri

@@ -1,0 +1,157 @@
+// r_index.hpp — host-side mirror of the reference's public index surface, backed by the CUDA library.
+//
+// Same names, argument meaning and error behaviour as ri::r_index<> (reference
+// internal/r_index.hpp:28-667) for the members the count/locate path and the three CLIs use:
+//   r_index()                      :37     r_index(string&, bool sais) :42   (build; same stdout lines)
+//   range_t count(string&)         :292    ulint occ(string&)          :307
+//   vector<ulint> locate_all(string&) :328 ulint serialize(ostream&)   :382  void load(istream&) :407
+//   number_of_runs() :361  text_size() :450  bwt_size() :454  get_terminator_position() :368
+// plus the batch surface this repo adds (one FFI call per batch instead of one call per pattern):
+//   count_batch(), locate_batch().
+// Every query — single-pattern calls included — runs on the GPU through include/rindex_gpu.h.
+// There is no CPU query path: if no device is available the query members print the error and exit(1).
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cmath>
+#include <iostream>
+#include <string>
+#include <vector>
+#include <utility>
+#include "logical_index.hpp"
+#include "../../include/rindex_gpu.h"
+
+namespace ri {
+
+typedef uint64_t ulint;
+typedef unsigned char uchar;
+typedef std::pair<ulint, ulint> range_t;
+
+inline uint8_t bitsize(uint64_t x) {  // reference internal/utils.hpp:43-48
+    if (x == 0) return 1;
+    return 64 - __builtin_clzll(x);
+}
+
+template <class sparse_bv_type = void, class rle_string_t = void>  // template kept so that `r_index<>` compiles
+class r_index {
+public:
+    r_index() {}
+    ~r_index() { release_device(); }
+    r_index(const r_index&) = delete;
+    r_index& operator=(const r_index&) = delete;
+
+    // Build index (reference r_index.hpp:42-150: same progress lines on stdout, exit(1) on reserved bytes).
+    r_index(std::string& input, bool sais = true) {
+        using std::cout; using std::endl; using std::flush;
+        if (rib::contains_reserved_chars((const uint8_t*)input.data(), input.size())) {
+            cout << "Error: input string contains one of the reserved characters 0x0, 0x1" << endl;
+            exit(1);
+        }
+        cout << "Text length = " << input.size() << endl << endl;
+        cout << "(1/3) Building BWT and computing SA samples";
+        if (sais) cout << " (SE-SAIS) ... " << flush;
+        else cout << "(DIVSUFSORT) ... " << flush;  // both flags use this repo's own in-memory SA-IS
+        L = rib::build_logical_index((const uint8_t*)input.data(), input.size());
+        cout << "done.\n(2/3) RLE encoding BWT ... " << flush;
+        cout << "done. " << endl << endl;
+        cout << "Number of BWT equal-letter runs: r = " << L.r << endl;
+        cout << "Rate n/r = " << double(L.n) / L.r << endl;
+        cout << "log2(r) = " << log2(double(L.r)) << endl;
+        cout << "log2(n/r) = " << log2(double(L.n) / L.r) << endl << endl;
+        cout << "(3/3) Building phi function ..." << flush;
+        cout << " done. " << endl << endl;
+    }
+
+    range_t full_range() { return {0, bwt_size() - 1}; }
+
+    // Return BWT range of pattern P (reference :292-302). Empty range = {1,0}.
+    range_t count(std::string& P) {
+        ulint lo = 0, hi = 0;
+        count_batch((const uint8_t*)P.data(), 1, P.size(), &lo, &hi);
+        return {lo, hi};
+    }
+    // Number of occurrences of P (reference :307-313).
+    ulint occ(std::string& P) {
+        auto rn = count(P);
+        return rn.second >= rn.first ? (rn.second - rn.first) + 1 : 0;
+    }
+    // All occurrences of P, in the reference's order SA[hi], SA[hi-1], ..., SA[lo] (reference :328-355).
+    std::vector<ulint> locate_all(std::string& P) {
+        ulint lo = 0, hi = 0;
+        std::vector<ulint> off, occv;
+        locate_batch((const uint8_t*)P.data(), 1, P.size(), &lo, &hi, off, occv);
+        return occv;
+    }
+
+    // ---- batch surface: N patterns of fixed length m, contiguous (the Pizza&Chili body) ----
+    void count_batch(const uint8_t* patt, ulint N, ulint m, ulint* lo, ulint* hi) {
+        ensure_device();
+        check(rig_count_batch(dev, patt, N, m, lo, hi), "rig_count_batch");
+    }
+    // occ_offsets gets N+1 entries; returns the total number of occurrences.
+    ulint locate_batch(const uint8_t* patt, ulint N, ulint m, ulint* lo, ulint* hi, std::vector<ulint>& occ_offsets,
+                       std::vector<ulint>& occ) {
+        ensure_device();
+        occ_offsets.assign(N + 1, 0);
+        uint64_t total = 0;
+        int rc = rig_locate_batch(dev, patt, N, m, lo, hi, occ_offsets.data(), occ.data(), occ.size(), &total);
+        if (rc == RIG_ERR_CAPACITY) {  // two-call protocol: first call sized the result
+            occ.resize(total);
+            rc = rig_locate_batch(dev, patt, N, m, lo, hi, occ_offsets.data(), occ.data(), occ.size(), &total);
+        }
+        check(rc, "rig_locate_batch");
+        occ.resize(total);
+        return total;
+    }
+
+    ulint number_of_runs() { return L.r; }
+    ulint get_terminator_position() { return L.terminator_position; }
+    ulint text_size() { return L.n - 1; }
+    ulint bwt_size() { return L.n; }
+    uchar get_terminator() { return rib::kTerminator; }
+
+    // serialize / load (reference :382-422). Container = this repo's own (logical_index.hpp); byte
+    // compatibility with SDSL-serialized .ri files is out of scope.
+    ulint serialize(std::ostream& out) { return rib::serialize(L, out); }
+    void load(std::istream& in) {
+        release_device();
+        if (!rib::load(L, in)) {
+            std::cout << "Error: index file is not an r-index built by this ri-build" << std::endl;
+            exit(1);
+        }
+    }
+
+    // ---- device control (additions) ----
+    void set_device(int d) { if (d != device) { release_device(); device = d; } }
+    const rig_index_info& device_info() { ensure_device(); return info; }
+    rig_timing last_timing() { rig_timing t; ensure_device(); rig_last_timing(dev, &t); return t; }
+    rig_index* device_handle() { ensure_device(); return dev; }
+    const rib::LogicalIndex& logical() const { return L; }
+
+private:
+    void ensure_device() {
+        if (dev) return;
+        rig_logical_view v;
+        v.n = L.n; v.r = L.r; v.F = L.F;
+        v.run_heads = L.run_heads.data(); v.run_lens = L.run_lens.data(); v.samples_last = L.samples_last.data();
+        v.pred_pos = L.pred_pos.data(); v.pred_to_run = L.pred_to_run.data();
+        check(rig_index_create(&v, device, &dev), "rig_index_create");
+        rig_index_info_get(dev, &info);
+    }
+    void release_device() { if (dev) { rig_index_destroy(dev); dev = nullptr; } }
+    void check(int rc, const char* where) {
+        if (rc == RIG_OK) return;
+        std::cout << "Error: " << where << ": " << rig_strerror(rc);
+        const char* ce = rig_last_cuda_error();
+        if (ce && *ce) std::cout << " [" << ce << "]";
+        std::cout << std::endl;
+        exit(1);
+    }
+
+    rib::LogicalIndex L;
+    rig_index* dev = nullptr;
+    rig_index_info info{};
+    int device = 0;
+};
+
+}  // namespace ri
