@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing for the pattern-parallel path: the index is replicated on
+every GPU, patterns are cut into contiguous shards, and there is NO collective on the search path.
+The optional collation below (all-gather of the fixed-size range records, all-gather-v of the
+occurrence buffers) runs over torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU
+tests. Same shard formula as the C++ fan-out (host/cli_common.hpp: GpuFleet)."""
+import numpy as np
+
+
+def shard_bounds(N, world, rank):
+    """Contiguous shard [a, b) of rank `rank`: concatenating shard outputs in rank order reproduces
+    the single-GPU output order."""
+    return N * rank // world, N * (rank + 1) // world
+
+
+def _torch():
+    import torch
+    import torch.distributed as dist
+    return torch, dist
+
+
+def collate_ranges(lo, hi, N, device=None):
+    """all-gather of the per-pattern (lo, hi) records. lo/hi: this rank's shard (numpy u64).
+    Returns full-length numpy arrays on every rank."""
+    torch, dist = _torch()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = max(shard_bounds(N, world, r)[1] - shard_bounds(N, world, r)[0] for r in range(world))
+    buf = torch.zeros(2 * per, dtype=torch.int64, device=device)
+    a, b = shard_bounds(N, world, rank)
+    buf[: b - a] = torch.from_numpy(lo.view(np.int64)).to(buf.device)
+    buf[per: per + b - a] = torch.from_numpy(hi.view(np.int64)).to(buf.device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    glo = np.zeros(N, dtype=np.uint64)
+    ghi = np.zeros(N, dtype=np.uint64)
+    for r in range(world):
+        ra, rb = shard_bounds(N, world, r)
+        t = out[r].cpu().numpy().view(np.uint64)
+        glo[ra:rb] = t[: rb - ra]
+        ghi[ra:rb] = t[per: per + rb - ra]
+    return glo, ghi
+
+
+def collate_occurrences(off_local, occ_local, device=None):
+    """all-gather-v of the occurrence buffers (padded all_gather). off_local: shard-local offsets
+    (shard patterns + 1), occ_local: this shard's occurrences. Returns (global offsets, global occ)."""
+    torch, dist = _torch()
+    world = dist.get_world_size()
+    sizes = torch.tensor([occ_local.size, off_local.size - 1], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [tuple(int(x) for x in s.cpu().tolist()) for s in all_sizes]
+    max_occ = max(s[0] for s in all_sizes)
+    max_pat = max(s[1] for s in all_sizes)
+    buf = torch.zeros(max_occ + max_pat + 1, dtype=torch.int64, device=device)
+    buf[: occ_local.size] = torch.from_numpy(occ_local.view(np.int64)).to(buf.device)
+    buf[max_occ: max_occ + off_local.size] = torch.from_numpy(off_local.view(np.int64)).to(buf.device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    occs, offs, base = [], [np.zeros(1, dtype=np.uint64)], 0
+    for r in range(world):
+        t = out[r].cpu().numpy().view(np.uint64)
+        n_occ, n_pat = all_sizes[r]
+        occs.append(t[:n_occ])
+        offs.append(t[max_occ + 1: max_occ + 1 + n_pat] + np.uint64(base))
+        base += n_occ
+    return np.concatenate(offs), np.concatenate(occs)
