@@ -326,8 +326,15 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         exp_ms = statistics.mean(expand_ms)
-        alg_bytes = occ_total * B_PHI
+        # Roofline of the dominant kernel (Phi expansion), HBM-bound. ALGORITHMIC bytes = what must cross
+        # HBM for this launch: 8 B per occurrence written + one pass over the Phi tables (they are L2
+        # resident afterwards: regime A). SURVEY §8d's per-occurrence figure (264 B = 4 x 64 B blocks + 8 B,
+        # the reference structure's TOUCHED bytes) is reported next to it as `survey_touched`: this layout
+        # touches 32 B per 4 occurrences instead, and those bytes are served by L2.
+        phi_table_bytes = int(info.device_bytes)
+        alg_bytes = occ_total * 8 + phi_table_bytes
         achieved = alg_bytes / (exp_ms * 1e-3) / 1e9
+        touched = occ_total * B_PHI
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
         srch_ms = statistics.mean(search_ms)
         line = {
@@ -351,7 +358,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "phi_expand_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("phi_expand_kernel"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
+                         "algorithmic_bytes": "8 B/occurrence output + one pass over the flattened index",
                          "regime": "A (index resident in L2: touched bytes are served by L2; DRAM traffic ~ output stream)",
+                         "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": touched / (exp_ms * 1e-3) / 1e9,
+                                            "note": "SURVEY 8d touched-bytes figure / launch time; L2-served, not an HBM fraction"},
                          "search_kernel": {"launch_ms": srch_ms, "algorithmic_bytes": int(lf_steps) * 3 * B_RANK(ell),
                                            "achieved": int(lf_steps) * 3 * B_RANK(ell) / (srch_ms * 1e-3) / 1e9 if srch_ms > 0 else None},
                          "scan_ms": statistics.mean(scan_ms)},
@@ -359,12 +369,15 @@ def run_ours(args):
         if ref is not None:
             cores = os.cpu_count() or 1
             threads = cores if ref.kind == "reference" else 1
-            cpu_baseline(ref, patt, N, m, max(1, args.cpu_sample // 10), threads)  # warm-up
-            occ_c, secs_c, S = cpu_baseline(ref, patt, N, m, args.cpu_sample, threads)
-            line["cpu_baseline"] = {"value": occ_c / secs_c, "unit": "occ/s", "cores": threads, "kind": ref.kind,
-                                    "sample": "first %d of %d patterns (%d occurrences), locate_all loop, %.2fs" % (S, N, occ_c, secs_c)}
-            if ref.kind == "reference":
-                occ_1, secs_1, S1 = cpu_baseline(ref, patt, N, m, max(1, args.cpu_sample // 8), 1)
+            cpu_baseline(ref, patt, N, m, max(1, min(N, args.cpu_sample) // 10), threads)  # warm-up
+            best = None
+            for _ in range(3):  # best of 3, all host threads
+                occ_c, secs_c, S = cpu_baseline(ref, patt, N, m, args.cpu_sample, threads)
+                best = secs_c if best is None else min(best, secs_c)
+            line["cpu_baseline"] = {"value": occ_c / best, "unit": "occ/s", "cores": threads, "kind": ref.kind,
+                                    "sample": "%d of %d patterns (%d occurrences), reference locate_all loop, results dropped as ri-locate does, best of 3: %.2fs" % (S, N, occ_c, best)}
+            if ref.kind == "reference":  # the reference as shipped is single-threaded: 1-core figure on 1/8 of the sample
+                occ_1, secs_1, S1 = cpu_baseline(ref, patt, N, m, max(1, min(N, args.cpu_sample) // 8), 1)
                 line["cpu_baseline"]["single_core_value"] = occ_1 / secs_1
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -379,8 +392,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=20000, help="patterns in the cpu_baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=10000, help="patterns per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="patterns in the cpu_baseline sample (default: all)")
+    ap.add_argument("--ref-sample", type=int, default=1 << 30, help="patterns per step of --impl reference (default: all)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--runs-per-block", type=int, default=0)
     ap.add_argument("--lf-log2", type=int, default=0)
