@@ -91,11 +91,11 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
     const u64 p = a;
     const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
     const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-    const u64 sj = __ldg(ix.start + j), ej = __ldg(ix.start + j + 1) - 1;
+    const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
     const u64 top = min(H, ej), bot = max(L, sj);
     u64 v0;
     if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
-    else { v0 = __ldg(ix.samples_last + j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
+    else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
     u64* o = out + __ldg(occ_off + p) + (H - top);  // next slot to write
     __stcs(o, v0);
     ++o;

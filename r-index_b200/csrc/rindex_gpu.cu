@@ -129,8 +129,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
-    std::vector<uint32_t> rec32, pent32;
-    if (f.w32) {  // 32-bit words: ~0 sentinels truncate to 0xFFFFFFFF, everything else is < n < 2^32-1
+    std::vector<uint32_t> rec32, pent32, start32, bstart32, cum32, sl32;
+    auto narrow = [](const std::vector<uint64_t>& src, std::vector<uint32_t>& dst) {
+        dst.resize(src.size());
+        for (size_t i = 0; i < src.size(); ++i) dst[i] = (uint32_t)src[i];
+    };
+    if (f.w32) {  // 32-bit words: ~0 sentinels truncate to 0xFFFFFFFF, everything else is <= n < 2^32-1
+        narrow(f.start, start32); narrow(f.bstart, bstart32); narrow(f.cum, cum32); narrow(f.samples_last, sl32);
         rec32.resize(f.phi.rec.size());
         for (size_t i = 0; i < rec32.size(); ++i) rec32[i] = (uint32_t)f.phi.rec[i];
         pent32.resize(f.phi.pent.size());
@@ -142,6 +147,12 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
         {f.start.data(), f.start.size() * 8, 0},    {f.head.data(), f.head.size(), 0},
         {f.bstart.data(), f.bstart.size() * 8, 0},  {f.cum.data(), f.cum.size() * 8, 0},
         {f.bdir.data(), f.bdir.size() * 4, 0},      {f.samples_last.data(), f.samples_last.size() * 8, 0}};
+    if (f.w32) {
+        parts[2] = {start32.data(), start32.size() * 4, 0};
+        parts[4] = {bstart32.data(), bstart32.size() * 4, 0};
+        parts[5] = {cum32.data(), cum32.size() * 4, 0};
+        parts[7] = {sl32.data(), sl32.size() * 4, 0};
+    }
     if (f.w32) {
         parts.push_back({rec32.data(), rec32.size() * 4, 0});
         parts.push_back({pent32.data(), pent32.size() * 4, 0});
@@ -162,12 +173,12 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.K = f.K; d.S = f.S; d.lf_shift = f.lf_shift; d.pad0 = 0;
     d.F = (const ull*)(A + parts[0].off);
     d.sid = (const uint16_t*)(A + parts[1].off);
-    d.start = (const ull*)(A + parts[2].off);
+    d.start = (const void*)(A + parts[2].off);
     d.head = (const uint8_t*)(A + parts[3].off);
-    d.bstart = (const ull*)(A + parts[4].off);
-    d.cum = (const ulonglong2*)(A + parts[5].off);
+    d.bstart = (const void*)(A + parts[4].off);
+    d.cum = (const void*)(A + parts[5].off);
     d.bdir = (const uint32_t*)(A + parts[6].off);
-    d.samples_last = (const ull*)(A + parts[7].off);
+    d.samples_last = (const void*)(A + parts[7].off);
     d.phi.rec = (const void*)(A + parts[8].off);
     d.phi.pent = (const void*)(A + parts[9].off);
     d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
@@ -246,12 +257,12 @@ int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, 
     if (blocks > 0x7fffffffull) return RIG_ERR_ARG;
     ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
     ull* steps = ix->d_counters + 0;
-    const bool n32 = ix->d.n <= 0xFFFFFFFFull && !(ix->variant & 8);
+    const bool n32 = ix->d.w32 != 0;
 #define RIG_LAUNCH(GG)                                                                                          \
     do {                                                                                                        \
-        if (n32) rigk::search_kernel<GG, LOCATE, true><<<(unsigned)blocks, threads, 0, st>>>(                   \
+        if (n32) rigk::search_kernel<GG, LOCATE, uint32_t><<<(unsigned)blocks, threads, 0, st>>>(               \
             ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);                                        \
-        else rigk::search_kernel<GG, LOCATE, false><<<(unsigned)blocks, threads, 0, st>>>(                      \
+        else rigk::search_kernel<GG, LOCATE, ull><<<(unsigned)blocks, threads, 0, st>>>(                        \
             ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);                                        \
     } while (0)
     switch (G) {

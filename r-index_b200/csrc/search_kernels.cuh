@@ -34,14 +34,14 @@ struct FlatDev {
     u32 K, S, lf_shift, pad0;
     const u64* F;             // [257]
     const uint16_t* sid;      // [256]
-    const u64* start;         // [nblk*K+1]
+    const void* start;        // [nblk*K+1]  PT (u32 when w32, else u64)
     const uint8_t* head;      // [nblk*K]
-    const u64* bstart;        // [nblk+1]
-    const ulonglong2* cum;    // [nblk*S] (count before block, last run of symbol before block)
+    const void* bstart;       // [nblk+1]    PT
+    const void* cum;          // [nblk*S]    (PT count before block, PT last run of symbol before block)
     const u32* bdir;          // [lf_nbkt+1]
-    const u64* samples_last;  // [r]
+    const void* samples_last; // [r]         PT
     PhiTabDev phi;
-    u32 w32, pad;             // w32: Phi records / deltas are 32-bit words
+    u32 w32, pad;             // w32: every position-holding array (and the Phi tables) uses 32-bit words
 };
 
 #define RIG_FULL 0xffffffffu
@@ -59,6 +59,15 @@ __device__ __forceinline__ u64 greduce_add(u64 v) {
     return v;
 }
 
+// Position-typed access to the flat arrays: PT = u32 when n < 2^32-1 (all arrays holding positions
+// are then stored as 32-bit words: half the bytes per block, 32-bit compares/adds), u64 otherwise.
+template <typename PT> struct CumPair;
+template <> struct CumPair<u32> { typedef uint2 type; };
+template <> struct CumPair<u64> { typedef ulonglong2 type; };
+
+template <typename PT>
+__device__ __forceinline__ PT ld_pos(const void* base, u64 idx) { return __ldg(reinterpret_cast<const PT*>(base) + idx); }
+
 // One cooperative query by a group of G lanes (all 32 lanes of the warp execute this together,
 // each group with its own x / c): locate the run holding BWT position x (0 <= x < n) and return
 //   cnt        = #c in bwt[0..x]  (INCLUSIVE)   = rle_string::rank(x+1, c)   rle_string.hpp:170-218
@@ -68,65 +77,66 @@ __device__ __forceinline__ u64 greduce_add(u64 v) {
 //                before x when bwt[x] != c — what rank/select/run_of_position compute together at
 //                r_index.hpp:516-531.
 // Dependent memory rounds: bdir -> (bstart, only when the bucket straddles blocks) -> block.
-template <int G, bool WANT_RUN, bool N32>
-__device__ __forceinline__ void block_query(const FlatDev& ix, u64 x, uint8_t c, u32 sidc, int gl, u32 gbase,
-                                            u64& cnt, u64& run, bool& head_is_c, u64& prev_c_run) {
-    const u64 q = x >> ix.lf_shift;
+template <int G, bool WANT_RUN, typename PT>
+__device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, u32 sidc, int gl, u32 gbase,
+                                            PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run) {
+    const u32 q = (u32)(x >> ix.lf_shift);
     u32 b0 = __ldg(ix.bdir + q);
     u32 b1 = __ldg(ix.bdir + q + 1);
     // G-ary search for the last block whose first position is <= x (blocks b0..b1 are candidates)
     while (__any_sync(RIG_FULL, b1 > b0)) {
         const u32 span = b1 - b0;
         const u32 step = (span + G - 1) / G;
-        u64 probe = (u64)b0 + (u64)(gl + 1) * step;
-        if (probe > b1) probe = b1;
-        const bool le = __ldg(ix.bstart + probe) <= x;
+        u32 probe = b0 + (u32)(gl + 1) * step;  // blocks < 2^32 / K: no overflow
+        if (probe > b1 || probe < b0) probe = b1;
+        const bool le = ld_pos<PT>(ix.bstart, probe) <= x;
         const u32 k = __popc(gballot<G>(le, gbase));
         if (span) {
             if (k == 0) {
                 b1 = min(b1, b0 + step - 1);
             } else {
-                const u64 nb0 = min((u64)b1, (u64)b0 + (u64)k * step);
-                b1 = (u32)min((u64)b1, nb0 + step - 1);
-                b0 = (u32)nb0;
+                const u32 nb0 = min(b1, b0 + k * step);
+                b1 = min(b1, nb0 + step - 1);
+                b0 = nb0;
             }
         }
     }
-    const u64 base = (u64)b0 * G;
-    const u64 st = __ldg(ix.start + base + gl);
+    const u32 base = b0 * G;
+    const PT st = ld_pos<PT>(ix.start, (u64)base + gl);
     const uint8_t hd = __ldg(ix.head + base + gl);
-    const ulonglong2 cm = __ldg(ix.cum + (u64)b0 * ix.S + sidc);
-    const u64 nxt = __shfl_down_sync(RIG_FULL, st, 1, G);
+    const typename CumPair<PT>::type cm =
+        __ldg(reinterpret_cast<const typename CumPair<PT>::type*>(ix.cum) + ((u64)b0 * ix.S + sidc));
+    const PT nxt = __shfl_down_sync(RIG_FULL, st, 1, G);
     const u32 mle = gballot<G>(st <= x, gbase);
     const int t = __popc(mle) - 1;  // >= 0: the block's first run starts at or before x
     const bool isc = (hd == c);
-    u64 contrib = 0;
-    if (isc) contrib = (gl < t) ? (nxt - st) : ((gl == t) ? (x - st + 1) : 0);
-    if (N32) {
-        // n <= 2^32: the per-lane pieces are disjoint BWT intervals, so their sum fits 32 bits and
-        // one REDUX over the group's lanes replaces the 64-bit shuffle tree
+    PT contrib = 0;
+    if (isc) contrib = (gl < t) ? (PT)(nxt - st) : ((gl == t) ? (PT)(x - st + 1) : (PT)0);
+    if constexpr (sizeof(PT) == 4) {
+        // n < 2^32: the per-lane pieces are disjoint BWT intervals, so their sum fits 32 bits and one
+        // REDUX over the group's lanes replaces the shuffle tree
         const u32 gm = (G == 32) ? RIG_FULL : (((1u << G) - 1u) << gbase);
-        cnt = cm.x + (u64)__reduce_add_sync(gm, (u32)contrib);
+        cnt = (PT)cm.x + __reduce_add_sync(gm, contrib);
     } else {
-        cnt = cm.x + greduce_add<G>(contrib);
+        cnt = (PT)cm.x + greduce_add<G>(contrib);
     }
     if (WANT_RUN) {
         const u32 mc = gballot<G>(isc, gbase);
         head_is_c = (mc >> t) & 1u;
         const u32 below = mc & ((1u << t) - 1u);
-        prev_c_run = below ? (base + (31 - __clz(below))) : cm.y;
+        prev_c_run = below ? (base + (31 - __clz(below))) : (u32)cm.y;
         run = base + t;
     }
 }
 
-template <int G, bool LOCATE, bool N32>
+template <int G, bool LOCATE, typename PT>
 __global__ void __launch_bounds__(256)
 search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
               u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
               u64* __restrict__ nch_out, u64* __restrict__ nocc_out, u64* __restrict__ lf_steps) {
-    __shared__ u64 sF[257];
+    __shared__ PT sF[257];
     __shared__ uint16_t sSid[256];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) sF[i] = ix.F[i];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) sF[i] = (PT)ix.F[i];  // F[256] = n fits: n < 2^32-1 when PT = u32
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sSid[i] = ix.sid[i];
     __syncthreads();
 
@@ -141,22 +151,23 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
     bool alive = p < N;
     const uint8_t* P = patt + (alive ? p : 0) * m;
 
-    u64 lo = 0, hi = ix.n - 1;  // full_range, r_index.hpp:155-160
-    u64 k = ix.toe0;            // SA[n-1], r_index.hpp:489
+    PT lo = 0, hi = (PT)(ix.n - 1);  // full_range, r_index.hpp:155-160
+    PT k = (PT)ix.toe0;              // SA[n-1], r_index.hpp:489
     u32 steps = 0;
     for (u64 i = 0; i < m; ++i) {
         if (!__any_sync(RIG_FULL, alive)) break;  // r_index.hpp:297 (early exit on empty range)
         const uint8_t c = alive ? __ldg(P + (m - 1 - i)) : 0;
-        const u64 Fc = sF[c], Fc1 = sF[c + 1];
+        const PT Fc = sF[c], Fc1 = sF[c + 1];
         const bool act = alive && (Fc < Fc1);  // r_index.hpp:174 (absent symbol -> {1,0})
         const bool valid = act && (which || lo > 0);
-        const u64 x = valid ? (which ? hi : lo - 1) : 0;
-        u64 cnt, run = 0, prevc = 0;
+        const PT x = valid ? (which ? hi : (PT)(lo - 1)) : (PT)0;
+        PT cnt;
+        u32 run = 0, prevc = 0;
         bool hic = false;
-        block_query<G, LOCATE, N32>(ix, x, c, valid ? sSid[c] : 0, gl, gbase, cnt, run, hic, prevc);
+        block_query<G, LOCATE, PT>(ix, x, c, valid ? sSid[c] : 0, gl, gbase, cnt, run, hic, prevc);
         if (!valid) cnt = 0;
-        const u64 A = __shfl_sync(RIG_FULL, cnt, pairbase);      // rank(lo, c)      r_index.hpp:178
-        const u64 B = __shfl_sync(RIG_FULL, cnt, pairbase + G);  // rank(hi+1, c)    r_index.hpp:181
+        const PT A = __shfl_sync(RIG_FULL, cnt, pairbase);      // rank(lo, c)      r_index.hpp:178
+        const PT B = __shfl_sync(RIG_FULL, cnt, pairbase + G);  // rank(hi+1, c)    r_index.hpp:181
         if (LOCATE) {
             hic = __shfl_sync(RIG_FULL, (int)hic, pairbase + G);
             prevc = __shfl_sync(RIG_FULL, prevc, pairbase + G);
@@ -167,8 +178,8 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
                 lo = 1; hi = 0; alive = false;
             } else {
                 if (LOCATE) {
-                    if (hic) k -= 1;                           // r_index.hpp:505-509
-                    else k = __ldg(ix.samples_last + prevc);   // r_index.hpp:516-533
+                    if (hic) k -= 1;                                  // r_index.hpp:505-509
+                    else k = ld_pos<PT>(ix.samples_last, prevc);      // r_index.hpp:516-533
                 }
                 lo = Fc + A;        // r_index.hpp:186
                 hi = Fc + B - 1;    // r_index.hpp:188
@@ -179,16 +190,17 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
     if (LOCATE) {
         // runs holding lo and hi: the range is cut into one Phi chain per overlapped run
         const bool ne = (p < N) && hi >= lo;
-        u64 cnt, run = 0, prevc;
+        PT cnt;
+        u32 run = 0, prevc;
         bool hic;
-        block_query<G, true, N32>(ix, ne ? (which ? hi : lo) : 0, 0, 0, gl, gbase, cnt, run, hic, prevc);
-        const u64 jL = __shfl_sync(RIG_FULL, run, pairbase);
-        const u64 jR = __shfl_sync(RIG_FULL, run, pairbase + G);
+        block_query<G, true, PT>(ix, ne ? (which ? hi : lo) : (PT)0, 0, 0, gl, gbase, cnt, run, hic, prevc);
+        const u32 jL = __shfl_sync(RIG_FULL, run, pairbase);
+        const u32 jR = __shfl_sync(RIG_FULL, run, pairbase + G);
         if (leader) {
             toe_out[p] = k;
             jl_out[p] = jL;
-            nch_out[p] = ne ? (jR - jL + 1) : 0;
-            nocc_out[p] = ne ? (hi - lo + 1) : 0;  // r_index.hpp:338
+            nch_out[p] = ne ? (u64)(jR - jL + 1) : 0;
+            nocc_out[p] = ne ? (u64)(hi - lo) + 1 : 0;  // r_index.hpp:338
         }
     }
     if (leader) { lo_out[p] = lo; hi_out[p] = hi; }
