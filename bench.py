@@ -44,6 +44,10 @@ WORKLOADS = {
             "C2 scaled down 10x (smoke/dev)"),
     "c5s": ("dna_indep", 400_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
             "C5 scaled to 400MB (1000 copies): Phi-chain stress, ~1k occ/pattern"),
+    "c3s": ("versioned_doc", 200_000_000, 25_000, 96, 0xB2000003, 200_000, 30, 0xB2001003, 0,
+            "C3 scaled to 200MB: einstein-like sigma=96 versioned document, 200k len-30 patterns"),
+    "c4s": ("pangenome", 1_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_000_000, 100, 0xB2001004, 0,
+            "C4 scaled to 1GB: synthetic pan-genome sigma=5 (100 haplotypes), 1M len-100 reads (count; index >> L2)"),
 }
 B_PHI = 264          # algorithmic bytes per occurrence: 4 x 64 B blocks + 8 B store
 B_RANK = lambda ell: 64 * (3 + ell)  # noqa: E731  per rank query

@@ -188,8 +188,15 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     const u32 S = f.S;
     // Runs per block = lanes per rank query. Small groups put more patterns in a warp (the search
     // kernel is issue-bound: measured 0.50 / 0.30 / 0.19 ms for K = 16 / 8 / 4 on config C2), but the
-    // per-block symbol directory costs S*16 bytes per K runs, so large alphabets get larger blocks.
-    const u32 K = opt.runs_per_block ? opt.runs_per_block : (S <= 16 ? 4u : (S <= 64 ? 8u : 16u));
+    // per-block symbol directory costs S words pairs per K runs: take the smallest K whose directory
+    // stays within ~64 MB (C3-like sigma = 97 with r = 5e4 gets K = 4; sigma = 194 with r = 3e5 gets K = 8).
+    const bool w32_pos = n < 0xFFFFFFFEull;
+    u32 K = opt.runs_per_block;
+    if (K == 0) {
+        const u64 pair_bytes = w32_pos ? 8 : 16, budget = 64ull << 20;
+        K = 16;
+        for (u32 k : {4u, 8u}) if (((r + k - 1) / k) * (u64)S * pair_bytes <= budget) { K = k; break; }
+    }
     f.K = K;
     f.nblk = (r + K - 1) / K;
     const u64 nblk = f.nblk, rpad = nblk * K;
@@ -270,7 +277,7 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     u32 D = opt.reserved[0];
     if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
     if (D == 0) {
-        const u64 budget = 56ull << 20;
+        const u64 budget = 192ull << 20;  // measured: C5s (r = 3.4e5) D=4 at 93 MB: 0.44 ms vs D=2 at 50 MB: 0.94 ms
         const u64 wb = f.w32 ? 4 : 8;
         auto cost = [&](u32 d) { return (u64)d * r * ((PhiTable::record_words(d) * wb) << fp); };
         D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);

@@ -66,6 +66,14 @@ __device__ __forceinline__ void store_group(u64* p, const WT (&e)[D]) {  // p is
     }
 }
 
+// Pull the Phi tables into L2 with one streaming pass (evict_last) before the walk: a cold table costs
+// every chain a DRAM round trip per first touch, and with 32 lanes in lockstep almost every iteration
+// of every warp would contain one. ~40 MB at HBM speed is a few microseconds.
+__global__ void __launch_bounds__(256) l2_warm_kernel(const char* base, u64 bytes) {
+    const u64 line = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 128;
+    if (line < bytes) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(base + line));
+}
+
 // Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]), min(hi,start[j+1]-1)], walked
 // from the top down. Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order (r_index.hpp:340-351).
 //
@@ -109,11 +117,15 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
     u32 take = D - (u32)((reinterpret_cast<unsigned long long>(o) >> 3) % D);
     bool searching = false;   // false: next load = bucket record of v; true: next load = piece entry `probe`
     u32 slo = 0, shi = 0;     // search interval of piece indices, invariant start[slo] <= v
+    // Software-pipelined: the entry for the CURRENT state is already in flight / in registers when an
+    // iteration starts; the iteration first decides (emit or narrow the search), computes the next
+    // address and ISSUES THE NEXT LOAD, and only then writes this iteration's occurrences — so the
+    // loop-carried chain between two loads is ~10 ALU ops and the stores overlap the load latency
+    // (measured: 55% of the stall samples sat on the first use of the loaded entry).
+    u32 probe = 0;
+    WT e[RW];
+    if (remaining > 0) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
     while (remaining > 0) {
-        const u32 probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
-        const char* addr = searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(v >> shift) * ESZ);
-        WT e[RW];
-        load_entry<WT, RW, KEEP>(addr, e);  // the ONE load of this iteration
         bool emit;
         if (!searching) {
             emit = v < e[D];              // no piece begins inside the bucket at or below v
@@ -126,30 +138,45 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
         } else {
             shi = probe - 1; emit = false;
         }
+        WT x[D];
+        u32 cnt = 0;
+        WT vn = v;
         if (emit) {
             searching = false;
             slo = shi = 0;
-            WT x[D];
 #pragma unroll
             for (int t = 0; t < D; ++t) {
                 x[t] = v + e[t];
                 if ((W32 && x[t] < v) || x[t] >= n) x[t] -= n;  // (v + delta) mod n; 32-bit: detect the carry
             }
-            if (take == D && remaining >= (WT)D) {
+            cnt = (take == D && remaining >= (WT)D) ? (u32)D : (u32)min((u64)take, (u64)remaining);
+            vn = x[D - 1];
+#pragma unroll
+            for (int t = 0; t < D - 1; ++t)
+                if ((u32)(t + 1) == cnt) vn = x[t];
+        }
+        const WT rem_next = remaining - (WT)cnt;
+        // ---- next load (critical path) ----
+        probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+        WT e2[RW];
+        if (rem_next > 0)
+            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
+        // ---- this iteration's occurrences (off the critical path) ----
+        if (emit) {
+            if (cnt == (u32)D) {
                 store_group<WT, D>(o, x);
-                v = x[D - 1];
-                o += D;
-                remaining -= (WT)D;
             } else {
-                const u32 cnt = (u32)min((u64)take, (u64)remaining);
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)
-                    if ((u32)t < cnt) { __stcs(o + t, (u64)x[t]); v = x[t]; }
-                o += cnt;
-                remaining -= (WT)cnt;
+                    if ((u32)t < cnt) __stcs(o + t, (u64)x[t]);
                 take = D;
             }
+            o += cnt;
         }
+        v = vn;
+        remaining = rem_next;
+#pragma unroll
+        for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
 }
 

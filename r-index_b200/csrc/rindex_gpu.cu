@@ -61,6 +61,7 @@ struct rig_index {
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
+    size_t phi_bytes = 0;        // rec + pent span in the arena (warmed into L2 before each expansion)
     size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
     float l2_hit_ratio = 1.f;
     bool timing_pending = false;
@@ -115,7 +116,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
     if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit3 forces the 64-bit code paths (as for n >= 2^32)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) f.w32 = false;
 
@@ -182,6 +183,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.phi.rec = (const void*)(A + parts[8].off);
     d.phi.pent = (const void*)(A + parts[9].off);
     d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
+    ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
     d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
 
     // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
@@ -389,6 +391,11 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
         ull a_N = N, a_chains = chains;
         const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
+        if (!(ix->variant & 4) && ix->phi_bytes) {  // warm the Phi tables into L2 (bit2 disables: A/B switch)
+            const uint64_t lines = (ix->phi_bytes + 127) / 128;
+            rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
+            ix->timing.launches += 1;
+        }
 #define RIG_EXPAND(W, DD)                                                                                     \
     do {                                                                                                      \
         if (keep) CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, true>, ix->d, a_N, a_choff,  \
