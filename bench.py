@@ -185,6 +185,20 @@ def run_reference(args):
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=True)
     S = min(N, args.ref_sample)
     threads = cores if ref.kind == "reference" else 1
+    if args.mode == "count":
+        for _ in range(args.warmup):
+            ref.count(patt[: max(1, S // 10) * m], max(1, S // 10), m, threads=threads, want=False)
+        tot_s = sum(ref.count(patt[: S * m], S, m, threads=threads, want=False)[2] for _ in range(args.steps))
+        val = S * args.steps / tot_s
+        print(json.dumps({
+            "impl": "reference", "metric": "count_patterns_per_s", "value": val, "unit": "patterns/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n": host.n, "r": host.r, "patterns_per_step": S, "pattern_length": m},
+            "cpu_baseline": {"value": val, "unit": "patterns/s", "cores": threads, "kind": ref.kind,
+                             "sample": "first %d of %d patterns per step, count()" % (S, N)},
+            "e2e": {"value": val, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return 0
     for _ in range(args.warmup):
         cpu_baseline(ref, patt, N, m, max(1, S // 10), threads)
     tot_occ, tot_s = 0, 0.0
@@ -204,6 +218,130 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours_count(args):
+    """--mode count: the ri-count configs (C4). A step = one backward-search pass (rig_count_batch_dev)
+    over the batch; value = patterns/s; roofline = the search kernel against HBM (regime B when the
+    flattened index is larger than L2)."""
+    import torch
+    import torch.distributed as dist
+    rib = ge.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
+    t0 = time.time()
+    gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
+                       phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1)
+    load_s = time.time() - t0
+    info = gpu.info
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    d_patt = torch.from_numpy(patt).to(dev)
+    d_lo = torch.empty(N, dtype=torch.int64, device=dev)
+    d_hi = torch.empty(N, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        gpu.count_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(); step(); ev[k][1].record()
+        torch.cuda.synchronize()
+        t = gpu.timing()
+        kern_ms.append(t["search_ms"])
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    lf_steps = t["lf_steps"]
+    # end to end: host buffers (pinned) through rig_count_batch
+    h_patt = torch.from_numpy(patt).pin_memory()
+    h_lo = torch.empty(N, dtype=torch.int64).pin_memory()
+    h_hi = torch.empty(N, dtype=torch.int64).pin_memory()
+    for _ in range(2):
+        gpu.count_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr())
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_t = 0.0
+    for k in range(e2e_steps):
+        flush.zero_(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        gpu.count_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr())
+        e2e_t += time.perf_counter() - t1
+    barrier()
+    nocc = (h_hi - h_lo + 1).clamp(min=0)
+    occ_t = int(nocc[(h_hi >= h_lo)].sum())
+    red = torch.tensor([total_ms, e2e_t * 1e3 / e2e_steps * args.steps], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(N), float(lf_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    total_ms_g, e2e_ms_g = [float(x) for x in red.tolist()]
+    N_g, lf_g = [float(x) for x in work.tolist()]
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        k_ms = statistics.mean(kern_ms)
+        # per rank query this layout touches 4 sectors (bdir, start[], head[], cum[]) = 128 B; 2 queries per LF step
+        alg_bytes = int(lf_steps) * 2 * 128 + N * (m + 16)
+        ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
+        regime = "B (flattened index %d MB > L2: every touched sector is a DRAM fetch)" % (info.device_bytes >> 20) \
+            if info.device_bytes > (100 << 20) else "A (index resident in L2)"
+        line = {
+            "metric": "count_patterns_per_s", "value": N_g * args.steps / (total_ms_g * 1e-3), "unit": "patterns/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_g / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n": int(info.n), "r": int(info.r), "sigma": int(info.sigma), "patterns_per_gpu": N,
+                       "pattern_length": m, "lf_steps_per_step": int(lf_steps), "total_occurrences": occ_t,
+                       "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
+                       "runs_per_block": int(info.runs_per_block), "parallelism": "patterns sharded x%d, index replicated" % world,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                       "timing": "CUDA events per step on the launch stream; max over ranks"},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "e2e": {"value": N_g * args.steps / (e2e_ms_g * 1e-3), "unit": "patterns/s", "h2d_bytes_per_step": int(N * m),
+                    "d2h_bytes_per_step": int(16 * N), "api": "rig_count_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
+            "gpu_launches": args.steps * world,
+            "lf_steps_per_s": lf_g * args.steps / (total_ms_g * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("search_kernel_" + args.workload),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_ms,
+                         "algorithmic_bytes": "per LF step 2 rank queries x 4 sectors x 32 B (bdir, run starts, run heads, symbol directory) + m + 16 B per pattern",
+                         "regime": regime,
+                         "survey_touched": {"bytes_per_lf_step": 2 * B_RANK(ell),
+                                            "achieved": int(lf_steps) * 2 * B_RANK(ell) / (k_ms * 1e-3) / 1e9}},
+        }
+        if ref is not None:
+            cores = os.cpu_count() or 1
+            threads = cores if ref.kind == "reference" else 1
+            S = min(N, args.cpu_sample)
+            ref.count(patt[: max(1, S // 10) * m], max(1, S // 10), m, threads=threads, want=False)
+            best = min(ref.count(patt[: S * m], S, m, threads=threads, want=False)[2] for _ in range(3))
+            line["cpu_baseline"] = {"value": S / best, "unit": "patterns/s", "cores": threads, "kind": ref.kind,
+                                    "sample": "%d of %d patterns, reference count() loop, best of 3: %.2fs" % (S, N, best)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 
@@ -404,11 +542,12 @@ def main():
     ap.add_argument("--phi-log2", type=int, default=0)
     ap.add_argument("--expand-threads", type=int, default=0)
     ap.add_argument("--phi-jump", type=int, default=0)
+    ap.add_argument("--mode", default="locate", choices=["locate", "count"], help="locate (default, C2) or count (ri-count configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    return run_ours_count(args) if args.mode == "count" else run_ours(args)
 
 
 if __name__ == "__main__":

@@ -51,7 +51,8 @@ typedef struct rig_options {
     uint32_t lf_bucket_log2;   /* 0 = auto: log2 of (directory buckets per run block) */
     uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
     uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
-    uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup */
+    uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup;
+                                  reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths) */
 } rig_options;
 
 typedef struct rig_index_info {

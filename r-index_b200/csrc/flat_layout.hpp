@@ -36,6 +36,7 @@
 #include <cstdint>
 #include <vector>
 #include <algorithm>
+#include <cstring>
 #include "../../include/rindex_gpu.h"
 
 namespace rigf {
@@ -146,14 +147,22 @@ struct FlatHost {
     std::vector<u64> start;        // [nblk*K + 1], padding = n
     std::vector<uint8_t> head;     // [nblk*K], padding = 0
     std::vector<u64> bstart;       // [nblk + 1], bstart[nblk] = n
-    std::vector<u64> cum;          // [nblk*S*2] (count, last run id or ~0)
+    std::vector<u64> cum;          // [nblk*S*2] (count, last run id or ~0) — host-side staging only
+    // Device form of the three arrays above, interleaved per block ("block record", one per K runs):
+    //   [start x K : W-byte words][head x K : bytes][pad to W][count-before-block x S : W-byte words][pad to 32]
+    // so that one rank query touches the directory sector (bdir) + ONE record (1-2 adjacent sectors)
+    // instead of three separate arrays. W = 4 when w32 else 8.
+    std::vector<uint8_t> blk;      // [nblk * blk_stride]
+    u32 blk_stride = 0, off_head = 0, off_cum = 0;
+    std::vector<u64> last;         // [nblk*S] id of the last run of each symbol before the block (locate toehold misses)
     std::vector<u32> bdir;         // [lf_nbkt + 1]
     std::vector<u64> samples_last; // [r]
     bool w32 = false;              // n < 2^32-1: Phi records and deltas are stored as 32-bit words
     PhiTable phi;                  // Phi^1..Phi^D refined
     u64 bytes() const {
-        return F.size() * 8 + sid.size() * 2 + start.size() * 8 + head.size() + bstart.size() * 8 + cum.size() * 8 +
-               bdir.size() * 4 + samples_last.size() * 8 + phi.bytes(w32);
+        const u64 W = w32 ? 4 : 8;
+        return F.size() * 8 + sid.size() * 2 + start.size() * W + blk.size() + bstart.size() * W + last.size() * W +
+               bdir.size() * 4 + samples_last.size() * W + phi.bytes(w32);
     }
 };
 
@@ -190,7 +199,8 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     // kernel is issue-bound: measured 0.50 / 0.30 / 0.19 ms for K = 16 / 8 / 4 on config C2), but the
     // per-block symbol directory costs S words pairs per K runs: take the smallest K whose directory
     // stays within ~64 MB (C3-like sigma = 97 with r = 5e4 gets K = 4; sigma = 194 with r = 3e5 gets K = 8).
-    const bool w32_pos = n < 0xFFFFFFFEull;
+    f.w32 = n < 0xFFFFFFFEull && !(opt.reserved[1] & 1);  // reserved[1] bit0: force 64-bit words (tests)
+    const bool w32_pos = f.w32;
     u32 K = opt.runs_per_block;
     if (K == 0) {
         const u64 pair_bytes = w32_pos ? 8 : 16, budget = 64ull << 20;
@@ -229,6 +239,25 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     for (int c = 0; c < 256; ++c) {  // F must agree with the runs
         u64 have = f.sid[c] == 0xFFFF ? 0 : cnt[f.sid[c]];
         if (f.F[c + 1] - f.F[c] != have) return RIG_ERR_INDEX;
+    }
+
+    // interleaved block records
+    {
+        const u32 W = f.w32 ? 4 : 8;
+        f.off_head = K * W;
+        f.off_cum = (K * W + K + W - 1) / W * W;
+        f.blk_stride = (f.off_cum + S * W + 31) / 32 * 32;
+        f.blk.assign(nblk * (u64)f.blk_stride, 0);
+        f.last.assign(nblk * (u64)S, 0);
+        auto put = [&](uint8_t* dst, u64 v) { if (W == 4) { uint32_t x = (uint32_t)v; memcpy(dst, &x, 4); } else memcpy(dst, &v, 8); };
+        for (u64 b = 0; b < nblk; ++b) {
+            uint8_t* R = &f.blk[b * f.blk_stride];
+            for (u32 t = 0; t < K; ++t) { put(R + t * W, f.start[b * K + t]); R[f.off_head + t] = f.head[b * K + t]; }
+            for (u32 sy = 0; sy < S; ++sy) {
+                put(R + f.off_cum + sy * W, f.cum[(b * S + sy) * 2]);
+                f.last[b * S + sy] = f.cum[(b * S + sy) * 2 + 1];
+            }
+        }
     }
 
     // position -> block directory
@@ -271,7 +300,6 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     }
     // buckets per piece: 2 (measured on C2: 0.51 ms vs 0.57 ms with 4 — the smaller table stays in L2)
     const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 1;
-    f.w32 = n < 0xFFFFFFFEull;
     // D = occurrences produced per record lookup: requested, or the largest of {4,2} whose bucket
     // records stay L2-friendly (they compete with the streamed occurrence output for the 126 MB L2).
     u32 D = opt.reserved[0];

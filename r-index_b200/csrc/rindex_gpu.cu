@@ -112,13 +112,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32)
+    if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
+    if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
     if (f.bytes() + (64u << 20) > free_b) return RIG_ERR_NOMEM;
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32)
-    if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
-    if (variant & 8) f.w32 = false;
 
     rig_index* ix = new (std::nothrow) rig_index();
     if (!ix) return RIG_ERR_NOMEM;
@@ -130,13 +130,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
-    std::vector<uint32_t> rec32, pent32, start32, bstart32, cum32, sl32;
+    std::vector<uint32_t> rec32, pent32, start32, bstart32, last32, sl32;
     auto narrow = [](const std::vector<uint64_t>& src, std::vector<uint32_t>& dst) {
         dst.resize(src.size());
         for (size_t i = 0; i < src.size(); ++i) dst[i] = (uint32_t)src[i];
     };
     if (f.w32) {  // 32-bit words: ~0 sentinels truncate to 0xFFFFFFFF, everything else is <= n < 2^32-1
-        narrow(f.start, start32); narrow(f.bstart, bstart32); narrow(f.cum, cum32); narrow(f.samples_last, sl32);
+        narrow(f.start, start32); narrow(f.bstart, bstart32); narrow(f.last, last32); narrow(f.samples_last, sl32);
         rec32.resize(f.phi.rec.size());
         for (size_t i = 0; i < rec32.size(); ++i) rec32[i] = (uint32_t)f.phi.rec[i];
         pent32.resize(f.phi.pent.size());
@@ -145,13 +145,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     struct Part { const void* src; size_t bytes; size_t off; };
     std::vector<Part> parts = {
         {f.F.data(), f.F.size() * 8, 0},            {f.sid.data(), f.sid.size() * 2, 0},
-        {f.start.data(), f.start.size() * 8, 0},    {f.head.data(), f.head.size(), 0},
-        {f.bstart.data(), f.bstart.size() * 8, 0},  {f.cum.data(), f.cum.size() * 8, 0},
+        {f.start.data(), f.start.size() * 8, 0},    {f.blk.data(), f.blk.size(), 0},
+        {f.bstart.data(), f.bstart.size() * 8, 0},  {f.last.data(), f.last.size() * 8, 0},
         {f.bdir.data(), f.bdir.size() * 4, 0},      {f.samples_last.data(), f.samples_last.size() * 8, 0}};
     if (f.w32) {
         parts[2] = {start32.data(), start32.size() * 4, 0};
         parts[4] = {bstart32.data(), bstart32.size() * 4, 0};
-        parts[5] = {cum32.data(), cum32.size() * 4, 0};
+        parts[5] = {last32.data(), last32.size() * 4, 0};
         parts[7] = {sl32.data(), sl32.size() * 4, 0};
     }
     if (f.w32) {
@@ -175,9 +175,10 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.F = (const ull*)(A + parts[0].off);
     d.sid = (const uint16_t*)(A + parts[1].off);
     d.start = (const void*)(A + parts[2].off);
-    d.head = (const uint8_t*)(A + parts[3].off);
+    d.blk = (const char*)(A + parts[3].off);
+    d.blk_stride = f.blk_stride; d.off_head = f.off_head; d.off_cum = f.off_cum; d.pad1 = 0;
     d.bstart = (const void*)(A + parts[4].off);
-    d.cum = (const void*)(A + parts[5].off);
+    d.last = (const void*)(A + parts[5].off);
     d.bdir = (const uint32_t*)(A + parts[6].off);
     d.samples_last = (const void*)(A + parts[7].off);
     d.phi.rec = (const void*)(A + parts[8].off);

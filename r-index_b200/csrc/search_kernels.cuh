@@ -35,9 +35,10 @@ struct FlatDev {
     const u64* F;             // [257]
     const uint16_t* sid;      // [256]
     const void* start;        // [nblk*K+1]  PT (u32 when w32, else u64)
-    const uint8_t* head;      // [nblk*K]
+    const char* blk;          // [nblk] interleaved block records: K starts (PT), K heads (u8), S counts (PT)
+    const void* last;         // [nblk*S]    PT: last run of each symbol before the block
+    u32 blk_stride, off_head, off_cum, pad1;
     const void* bstart;       // [nblk+1]    PT
-    const void* cum;          // [nblk*S]    (PT count before block, PT last run of symbol before block)
     const u32* bdir;          // [lf_nbkt+1]
     const void* samples_last; // [r]         PT
     PhiTabDev phi;
@@ -61,10 +62,6 @@ __device__ __forceinline__ u64 greduce_add(u64 v) {
 
 // Position-typed access to the flat arrays: PT = u32 when n < 2^32-1 (all arrays holding positions
 // are then stored as 32-bit words: half the bytes per block, 32-bit compares/adds), u64 otherwise.
-template <typename PT> struct CumPair;
-template <> struct CumPair<u32> { typedef uint2 type; };
-template <> struct CumPair<u64> { typedef ulonglong2 type; };
-
 template <typename PT>
 __device__ __forceinline__ PT ld_pos(const void* base, u64 idx) { return __ldg(reinterpret_cast<const PT*>(base) + idx); }
 
@@ -102,10 +99,10 @@ __device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, 
         }
     }
     const u32 base = b0 * G;
-    const PT st = ld_pos<PT>(ix.start, (u64)base + gl);
-    const uint8_t hd = __ldg(ix.head + base + gl);
-    const typename CumPair<PT>::type cm =
-        __ldg(reinterpret_cast<const typename CumPair<PT>::type*>(ix.cum) + ((u64)b0 * ix.S + sidc));
+    const char* rp = ix.blk + (u64)b0 * ix.blk_stride;  // the block record: starts | heads | counts
+    const PT st = __ldg(reinterpret_cast<const PT*>(rp) + gl);
+    const uint8_t hd = __ldg(reinterpret_cast<const uint8_t*>(rp + ix.off_head) + gl);
+    const PT cm = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
     const PT nxt = __shfl_down_sync(RIG_FULL, st, 1, G);
     const u32 mle = gballot<G>(st <= x, gbase);
     const int t = __popc(mle) - 1;  // >= 0: the block's first run starts at or before x
@@ -116,15 +113,18 @@ __device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, 
         // n < 2^32: the per-lane pieces are disjoint BWT intervals, so their sum fits 32 bits and one
         // REDUX over the group's lanes replaces the shuffle tree
         const u32 gm = (G == 32) ? RIG_FULL : (((1u << G) - 1u) << gbase);
-        cnt = (PT)cm.x + __reduce_add_sync(gm, contrib);
+        cnt = cm + __reduce_add_sync(gm, contrib);
     } else {
-        cnt = (PT)cm.x + greduce_add<G>(contrib);
+        cnt = cm + greduce_add<G>(contrib);
     }
     if (WANT_RUN) {
         const u32 mc = gballot<G>(isc, gbase);
         head_is_c = (mc >> t) & 1u;
         const u32 below = mc & ((1u << t) - 1u);
-        prev_c_run = below ? (base + (31 - __clz(below))) : (u32)cm.y;
+        // no c-run before `run` inside this block: the per-block side table has the last one before it
+        // (only consumed on a toehold miss, r_index.hpp:516-533)
+        prev_c_run = below ? (base + (31 - __clz(below)))
+                           : (head_is_c ? 0u : (u32)ld_pos<PT>(ix.last, (u64)b0 * ix.S + sidc));
         run = base + t;
     }
 }

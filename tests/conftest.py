@@ -54,12 +54,12 @@ class FlatCheck:
         self.lib = ctypes.CDLL(FLATCHECK_SO)
         self.lib.fc_create.restype = ctypes.c_void_p
         self.lib.fc_create.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                                       ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
         self.lib.fc_jump.restype = ctypes.c_uint64
         self.lib.fc_jump.argtypes = [ctypes.c_void_p]
         self.lib.fc_pieces.restype = ctypes.c_uint64
         self.lib.fc_pieces.argtypes = [ctypes.c_void_p]
-        self.lib.fc_force_wide.argtypes = [ctypes.c_void_p]
+        self.lib.fc_w32.argtypes = [ctypes.c_void_p]
         self.lib.fc_check_jump.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
         self.lib.fc_destroy.argtypes = [ctypes.c_void_p]
         self.lib.fc_count.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_uint64] * 2 + [ctypes.c_void_p] * 2
@@ -71,10 +71,9 @@ class FlatCheck:
             view, self._keep = view_from_arrays(host_index)
         else:
             view, self._keep = host_index.view, host_index
-        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, jump, ctypes.byref(rc))
+        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, jump, int(force_wide), ctypes.byref(rc))
         self.rc = rc.value
-        if self.h and force_wide:
-            self.lib.fc_force_wide(self.h)
+        self.w32 = bool(self.lib.fc_w32(self.h)) if self.h else None
         self.jump = int(self.lib.fc_jump(self.h)) if self.h else 0
 
     def count(self, patt, N, m):

@@ -15,9 +15,10 @@ namespace {
 
 struct Q { u64 cnt, run, prev_c_run; bool head_is_c; };
 
-// mirrors rigk::block_query
+// mirrors rigk::block_query, reading the interleaved block records exactly as the device does
+u64 rd(const uint8_t* p, bool w32) { if (w32) { uint32_t x; memcpy(&x, p, 4); return x; } u64 x; memcpy(&x, p, 8); return x; }
 Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
-    const u32 K = f.K;
+    const u32 K = f.K, W = f.w32 ? 4 : 8;
     u64 q = x >> f.lf_shift;
     u64 b0 = f.bdir[q], b1 = f.bdir[q + 1];
     while (b1 > b0) {  // same G-ary narrowing as the kernel, G = K probes per round
@@ -30,20 +31,23 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
         if (k == 0) b1 = std::min(b1, b0 + step - 1);
         else { u64 nb0 = std::min(b1, b0 + k * step); b1 = std::min(b1, nb0 + step - 1); b0 = nb0; }
     }
+    const uint8_t* R = &f.blk[b0 * f.blk_stride];
     u64 base = b0 * K;
+    u64 st[16];
+    for (u32 g = 0; g < K; ++g) st[g] = rd(R + g * W, f.w32);
     int t = -1;
-    for (u32 g = 0; g < K; ++g) if (f.start[base + g] <= x) ++t;
+    for (u32 g = 0; g < K; ++g) if (st[g] <= x) ++t;
     Q r;
     u64 sum = 0; u32 mc = 0;
     for (u32 g = 0; g < K; ++g) {
-        bool isc = f.head[base + g] == c;
+        bool isc = R[f.off_head + g] == c;
         if (isc) mc |= 1u << g;
-        if (isc) sum += ((int)g < t) ? (f.start[base + g + 1] - f.start[base + g]) : (((int)g == t) ? (x - f.start[base + g] + 1) : 0);
+        if (isc) sum += ((int)g < t) ? (st[g + 1] - st[g]) : (((int)g == t) ? (x - st[g] + 1) : 0);
     }
-    r.cnt = f.cum[(b0 * f.S + sidc) * 2] + sum;
+    r.cnt = rd(R + f.off_cum + sidc * W, f.w32) + sum;
     r.head_is_c = (mc >> t) & 1u;
     u32 below = mc & ((1u << t) - 1u);
-    r.prev_c_run = below ? base + (31 - __builtin_clz(below)) : f.cum[(b0 * f.S + sidc) * 2 + 1];
+    r.prev_c_run = below ? base + (31 - __builtin_clz(below)) : f.last[b0 * f.S + sidc];
     r.run = base + t;
     return r;
 }
@@ -96,10 +100,11 @@ void search(const FlatHost& f, const uint8_t* P, u64 m, bool locate, u64& lo, u6
 
 extern "C" {
 
-void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, uint32_t jump, int* rc_out) {
+void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, uint32_t jump, uint32_t force_wide, int* rc_out) {
     rig_options opt;
     std::memset(&opt, 0, sizeof(opt));
     opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2; opt.reserved[0] = jump;
+    opt.reserved[1] = force_wide ? 1 : 0;
     FlatHost* f = new FlatHost();
     int rc = rigf::flatten(*v, opt, *f);
     if (rc_out) *rc_out = rc;
@@ -110,7 +115,7 @@ void fc_destroy(void* h) { delete (FlatHost*)h; }
 uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
 uint64_t fc_jump(void* h) { return ((FlatHost*)h)->phi.D; }
 uint64_t fc_pieces(void* h) { return ((FlatHost*)h)->phi.pieces(); }
-void fc_force_wide(void* h) { ((FlatHost*)h)->w32 = false; }  // exercise the 64-bit word path on small inputs
+int fc_w32(void* h) { return ((FlatHost*)h)->w32 ? 1 : 0; }
 // Phi^j(i), j = 1..D, evaluated three ways must agree: j applications of Phi^1 through the scalar
 // table, one scalar application of delta_j, and the bucket-record lookup the kernel performs.
 int fc_check_jump(void* h, uint64_t i) {
