@@ -164,7 +164,7 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
         // ---- this iteration's occurrences (off the critical path) ----
         if (emit) {
             if (cnt == (u32)D) {
-                store_group<WT, D>(o, x);
+                if (!(ix.pad & 1)) store_group<WT, D>(o, x);  // pad bit0: diagnostic "no stores" run (RIG_VARIANT bit4)
             } else {
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)

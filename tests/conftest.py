@@ -42,6 +42,7 @@ def _build_flatcheck():
 @pytest.fixture(scope="session", autouse=True)
 def _native_built():
     rib.build_host()
+    rib.build_gpu()   # nvcc cross-compiles without a GPU; no-op when librindex_gpu.so is up to date
     ob.build()
     _build_flatcheck()
 
