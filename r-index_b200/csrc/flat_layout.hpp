@@ -197,15 +197,18 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     const u32 S = f.S;
     // Runs per block = lanes per rank query. Small groups put more patterns in a warp (the search
     // kernel is issue-bound: measured 0.50 / 0.30 / 0.19 ms for K = 16 / 8 / 4 on config C2), but the
-    // per-block symbol directory costs S words pairs per K runs: take the smallest K whose directory
-    // stays within ~64 MB (C3-like sigma = 97 with r = 5e4 gets K = 4; sigma = 194 with r = 3e5 gets K = 8).
+    // per-block symbol directory costs S words per K runs (measured on the 1 GB pan-genome C4s, index
+    // beyond L2: 6.1 / 8.5 / 14.5 ms for K = 4 / 8 / 16 — the kernel stays issue-bound even there).
     f.w32 = n < 0xFFFFFFFEull && !(opt.reserved[1] & 1);  // reserved[1] bit0: force 64-bit words (tests)
     const bool w32_pos = f.w32;
     u32 K = opt.runs_per_block;
-    if (K == 0) {
-        const u64 pair_bytes = w32_pos ? 8 : 16, budget = 64ull << 20;
+    if (K == 0) {  // smallest K whose block records (K starts + K heads + S counts, 32-byte padded) stay within ~2 GB
+        const u64 W = w32_pos ? 4 : 8, budget = 2ull << 30;
         K = 16;
-        for (u32 k : {4u, 8u}) if (((r + k - 1) / k) * (u64)S * pair_bytes <= budget) { K = k; break; }
+        for (u32 k : {4u, 8u}) {
+            const u64 stride = ((k * W + k + W - 1) / W * W + S * W + 31) / 32 * 32;
+            if (((r + k - 1) / k) * stride <= budget) { K = k; break; }
+        }
     }
     f.K = K;
     f.nblk = (r + K - 1) / K;

@@ -53,8 +53,8 @@ __device__ __forceinline__ u32 gballot(bool p, u32 gbase) {
     return (G == 32) ? m : ((m >> gbase) & ((1u << G) - 1u));
 }
 
-template <int G>
-__device__ __forceinline__ u64 greduce_add(u64 v) {
+template <int G, typename T>
+__device__ __forceinline__ T greduce_add(T v) {
 #pragma unroll
     for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(RIG_FULL, v, off);
     return v;
@@ -109,14 +109,9 @@ __device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, 
     const bool isc = (hd == c);
     PT contrib = 0;
     if (isc) contrib = (gl < t) ? (PT)(nxt - st) : ((gl == t) ? (PT)(x - st + 1) : (PT)0);
-    if constexpr (sizeof(PT) == 4) {
-        // n < 2^32: the per-lane pieces are disjoint BWT intervals, so their sum fits 32 bits and one
-        // REDUX over the group's lanes replaces the shuffle tree
-        const u32 gm = (G == 32) ? RIG_FULL : (((1u << G) - 1u) << gbase);
-        cnt = cm + __reduce_add_sync(gm, contrib);
-    } else {
-        cnt = cm + greduce_add<G>(contrib);
-    }
+    // group-wide sum: log2(G) shuffle steps inside the group (a REDUX with a different lane mask per
+    // group is serialised by the hardware, one pass per distinct mask — 8 passes per warp at G = 4)
+    cnt = cm + greduce_add<G, PT>(contrib);
     if (WANT_RUN) {
         const u32 mc = gballot<G>(isc, gbase);
         head_is_c = (mc >> t) & 1u;
@@ -134,10 +129,13 @@ __global__ void __launch_bounds__(256)
 search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
               u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
               u64* __restrict__ nch_out, u64* __restrict__ nocc_out, u64* __restrict__ lf_steps) {
-    __shared__ PT sF[257];
-    __shared__ uint16_t sSid[256];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) sF[i] = (PT)ix.F[i];  // F[256] = n fits: n < 2^32-1 when PT = u32
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sSid[i] = ix.sid[i];
+    // per symbol: F[c], F[c+1], dense id — one shared-memory read per LF step
+    struct SymEnt { PT f0, f1; u32 sid, pad; };
+    __shared__ SymEnt sSym[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sSym[i].f0 = (PT)ix.F[i]; sSym[i].f1 = (PT)ix.F[i + 1];  // F[256] = n fits: n < 2^32-1 when PT = u32
+        sSym[i].sid = ix.sid[i]; sSym[i].pad = 0;
+    }
     __syncthreads();
 
     constexpr int PPW = 32 / (2 * G);  // patterns per warp
@@ -157,14 +155,15 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
     for (u64 i = 0; i < m; ++i) {
         if (!__any_sync(RIG_FULL, alive)) break;  // r_index.hpp:297 (early exit on empty range)
         const uint8_t c = alive ? __ldg(P + (m - 1 - i)) : 0;
-        const PT Fc = sF[c], Fc1 = sF[c + 1];
+        const SymEnt se = sSym[c];
+        const PT Fc = se.f0, Fc1 = se.f1;
         const bool act = alive && (Fc < Fc1);  // r_index.hpp:174 (absent symbol -> {1,0})
         const bool valid = act && (which || lo > 0);
         const PT x = valid ? (which ? hi : (PT)(lo - 1)) : (PT)0;
         PT cnt;
         u32 run = 0, prevc = 0;
         bool hic = false;
-        block_query<G, LOCATE, PT>(ix, x, c, valid ? sSid[c] : 0, gl, gbase, cnt, run, hic, prevc);
+        block_query<G, LOCATE, PT>(ix, x, c, valid ? se.sid : 0, gl, gbase, cnt, run, hic, prevc);
         if (!valid) cnt = 0;
         const PT A = __shfl_sync(RIG_FULL, cnt, pairbase);      // rank(lo, c)      r_index.hpp:178
         const PT B = __shfl_sync(RIG_FULL, cnt, pairbase + G);  // rank(hi+1, c)    r_index.hpp:181
