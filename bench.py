@@ -40,6 +40,8 @@ WORKLOADS = {
     # name: (kind, n, p0, p1, text_seed, N, m, patt_seed, start_limit, description)
     "c2": ("dna_drift", 100_000_000, 50_000, 3, 0xB2000002, 100_000, 20, 0xB2001002, 0,
            "C2 ri-locate: 100MB synthetic DNA sigma=4 repetitive, 100k len-20 patterns"),
+    "c2x4": ("dna_drift", 100_000_000, 50_000, 3, 0xB2000002, 400_000, 20, 0xB2001002, 0,
+             "C2 text with a 4x larger batch (400k len-20 patterns): parallelism sensitivity"),
     "c2s": ("dna_drift", 10_000_000, 50_000, 3, 0xB2000002, 20_000, 20, 0xB2001002, 0,
             "C2 scaled down 10x (smoke/dev)"),
     "c5s": ("dna_indep", 400_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
@@ -66,7 +68,8 @@ def prepare(workload, need_ref=False, rank=0):
     t0 = time.time()
     text = rib.gen_text(kind, n, p0, p1, tseed)
     patt = rib.gen_patterns(text, N, m, pseed + rank, limit)
-    path = os.path.join(CACHE, "%s.rib" % workload)
+    base = {"c2x4": "c2"}.get(workload, workload)  # workloads that share a text share its index
+    path = os.path.join(CACHE, "%s.rib" % base)
     if os.path.exists(path):
         host = rib.HostIndex.load(path)
     else:
@@ -79,7 +82,7 @@ def prepare(workload, need_ref=False, rank=0):
     ref = None
     if need_ref:
         ob = ge.load_oracle()
-        rpath = os.path.join(CACHE, "%s.ref.ri" % workload)
+        rpath = os.path.join(CACHE, "%s.ref.ri" % base)
         if ob.have_ref():
             if os.path.exists(rpath):
                 ref = ob.RefIndex.load(rpath)
