@@ -363,7 +363,8 @@ def run_ours(args):
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
-                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads, phi_jump=args.phi_jump)
+                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads, phi_jump=args.phi_jump,
+                       seed_jump=args.seed_jump)
     load_s = time.time() - t0
     info = gpu.info
     # the library launches on the stream it is given (NULL would mean its own stream): use a real
@@ -405,7 +406,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    expand_ms, search_ms, scan_ms, launches = [], [], [], 0
+    expand_ms, search_ms, scan_ms, seed_ms, window_ms, launches = [], [], [], [], [], 0
     occ_total = 0
     barrier()
     for k in range(args.steps):
@@ -416,6 +417,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         t = gpu.timing()
         expand_ms.append(t["expand_ms"]); search_ms.append(t["search_ms"]); scan_ms.append(t["scan_ms"])
+        seed_ms.append(t["seed_ms"]); window_ms.append(t["window_ms"])
         launches += t["launches"]
     barrier()
     clocks = sampler.stop()
@@ -476,9 +478,23 @@ def run_ours(args):
         # resident afterwards: regime A). SURVEY §8d's per-occurrence figure (264 B = 4 x 64 B blocks + 8 B,
         # the reference structure's TOUCHED bytes) is reported next to it as `survey_touched`: this layout
         # touches 32 B per 4 occurrences instead, and those bytes are served by L2.
-        phi_table_bytes = int(info.device_bytes)
-        alg_bytes = occ_total * 8 + phi_table_bytes
-        achieved = alg_bytes / (exp_ms * 1e-3) / 1e9
+        # Two-pass expansion: the dominant kernel is pass 2 (phi_window_kernel): it writes every occurrence,
+        # reads the Phi^1..D table once (the seed table is touched by pass 1 only), one seed + one count byte
+        # per window.
+        two_pass = int(info.seed_jump) > 1 and statistics.mean(window_ms) > 0
+        if two_pass:
+            win_ms = statistics.mean(window_ms)
+            windows = (occ_total + int(info.seed_jump) - 1) // int(info.seed_jump)
+            phi_table_bytes = int(info.device_bytes) - int(info.seed_bytes)
+            alg_bytes = occ_total * 8 + phi_table_bytes + windows * 9
+            dom_kernel, dom_ms = "phi_window_kernel", win_ms
+            alg_note = "8 B/occurrence output + one pass over the flattened index without the seed table + 9 B per window (seed, count)"
+        else:
+            phi_table_bytes = int(info.device_bytes)
+            alg_bytes = occ_total * 8 + phi_table_bytes
+            dom_kernel, dom_ms = "phi_expand_kernel", exp_ms
+            alg_note = "8 B/occurrence output + one pass over the flattened index"
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         touched = occ_total * B_PHI
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
         srch_ms = statistics.mean(search_ms)
@@ -490,7 +506,8 @@ def run_ours(args):
                        "patterns_per_gpu": N, "pattern_length": m, "occurrences_per_step_per_gpu": occ_total,
                        "phi_chains_per_step": int(chains), "lf_steps_per_step": int(lf_steps),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
-                       "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump), "parallelism": "patterns sharded x%d, index replicated" % world,
+                       "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump),
+                       "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes), "parallelism": "patterns sharded x%d, index replicated" % world,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
                        "timing": "CUDA events per step on the launch stream; max over ranks"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
@@ -500,10 +517,12 @@ def run_ours(args):
             "gpu_launches": int(launches_g) + launches_count * world,
             "count": {"metric": "count_patterns_per_s", "value": N_g * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
                       "ms_per_step": count_ms_g / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "phi_expand_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic("phi_expand_kernel"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
-                         "algorithmic_bytes": "8 B/occurrence output + one pass over the flattened index",
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
+                         "algorithmic_bytes": alg_note,
+                         "expansion": {"expand_ms": exp_ms, "seed_pass_ms": statistics.mean(seed_ms), "window_pass_ms": statistics.mean(window_ms),
+                                       "achieved_both_passes": (occ_total * 8 + int(info.device_bytes)) / (exp_ms * 1e-3) / 1e9},
                          "regime": "A (index resident in L2: touched bytes are served by L2; DRAM traffic ~ output stream)",
                          "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": touched / (exp_ms * 1e-3) / 1e9,
                                             "note": "SURVEY 8d touched-bytes figure / launch time; L2-served, not an HBM fraction"},
@@ -545,6 +564,7 @@ def main():
     ap.add_argument("--phi-log2", type=int, default=0)
     ap.add_argument("--expand-threads", type=int, default=0)
     ap.add_argument("--phi-jump", type=int, default=0)
+    ap.add_argument("--seed-jump", type=int, default=0, help="two-pass expansion window SEG: 0 auto, 1 off (single pass), 16..256")
     ap.add_argument("--mode", default="locate", choices=["locate", "count"], help="locate (default, C2) or count (ri-count configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

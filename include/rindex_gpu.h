@@ -52,7 +52,9 @@ typedef struct rig_options {
     uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
     uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
     uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup;
-                                  reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths) */
+                                  reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths);
+                                  reserved[2] = SEG of the two-pass Phi expansion: 0 = auto, 1 = off (single pass),
+                                  16/32/64/128/256 = occurrences per seed-table hop (window size in output slots) */
 } rig_options;
 
 typedef struct rig_index_info {
@@ -63,6 +65,8 @@ typedef struct rig_index_info {
     uint32_t sm_count, phi_jump;  /* phi_jump = D: each Phi record holds the deltas of Phi^1..Phi^D */
     uint64_t phi_jump_pieces;     /* pieces of the refined Phi^1..Phi^D translation (<= D*r) */
     uint32_t words32, reserved;   /* words32 = 1: n < 2^32-1, Phi directory records are 32-bit */
+    uint32_t seed_jump, seed_shift; /* seed table Phi^SEG of the two-pass expansion (0 = none) and its bucket shift */
+    uint64_t seed_pieces, seed_bytes;
 } rig_index_info;
 
 /* CUDA-event timings (ms) of the phases of the most recent batch call on this index. */
@@ -77,6 +81,8 @@ typedef struct rig_timing {
     uint64_t lf_steps;      /* executed LF steps (early exits excluded), r_index.hpp:297 */
     uint64_t occ_total;     /* occurrences written */
     uint64_t chains;        /* independent Phi chains the ranges were split into */
+    float seed_ms;          /* two-pass expansion: pass 1 (toeholds, chain heads, one seed per output window) */
+    float window_ms;        /* two-pass expansion: pass 2 (one lane per output window); both inside expand_ms */
 } rig_timing;
 
 typedef struct rig_index rig_index;

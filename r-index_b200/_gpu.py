@@ -31,13 +31,15 @@ class IndexInfo(ctypes.Structure):
     _fields_ = [("n", _u64), ("r", _u64), ("sigma", _u64), ("device_bytes", _u64), ("lf_blocks", _u64),
                 ("lf_buckets", _u64), ("phi_buckets", _u64), ("runs_per_block", _u32), ("lf_shift", _u32),
                 ("phi_shift", _u32), ("device", _u32), ("sm_count", _u32), ("phi_jump", _u32),
-                ("phi_jump_pieces", _u64), ("words32", _u32), ("reserved", _u32)]
+                ("phi_jump_pieces", _u64), ("words32", _u32), ("reserved", _u32), ("seed_jump", _u32),
+                ("seed_shift", _u32), ("seed_pieces", _u64), ("seed_bytes", _u64)]
 
 
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("search_ms", ctypes.c_float), ("scan_ms", ctypes.c_float),
                 ("expand_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float), ("launches", _u32), ("reserved", _u32),
-                ("lf_steps", _u64), ("occ_total", _u64), ("chains", _u64)]
+                ("lf_steps", _u64), ("occ_total", _u64), ("chains", _u64), ("seed_ms", ctypes.c_float),
+                ("window_ms", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -117,7 +119,7 @@ class GpuIndex:
     """A flattened r-index resident in one GPU's HBM (struct rig_index)."""
 
     def __init__(self, source, device=0, runs_per_block=0, lf_bucket_log2=0, phi_bucket_log2=0, expand_threads=0,
-                 phi_jump=0):
+                 phi_jump=0, seed_jump=0):
         lib = gpu_lib()
         if isinstance(source, HostIndex):
             view, self._keep = source.view, source
@@ -127,6 +129,7 @@ class GpuIndex:
             raise TypeError("GpuIndex needs a HostIndex or a dict of logical arrays")
         opt = Options(runs_per_block, lf_bucket_log2, phi_bucket_log2, expand_threads)
         opt.reserved[0] = phi_jump
+        opt.reserved[2] = seed_jump
         h = _vp()
         rc = lib.rig_index_create_ex(ctypes.byref(view), device, ctypes.byref(opt), ctypes.byref(h))
         if rc != 0:

@@ -135,6 +135,91 @@ static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64
     return C;
 }
 
+// Phi^J as ONE piecewise translation (final delta only): the seed table of the two-pass expansion.
+//   piece k covers [start[k], start[k+1]);  Phi^J(i) = (i + delta[k]) mod n  for i in piece k.
+// Built by doubling (Phi^2 = Phi o Phi, Phi^4 = Phi^2 o Phi^2, ...): J is a power of two and the
+// number of pieces is sum over runs of min(J, run length) <= min(J*r, n).
+// Device form: one 8-word bucket record per direct-addressed bucket, resolving up to TWO pieces that
+// begin inside the bucket without a second load, + a 2-word entry per piece for crowded buckets:
+//   rec[q]   [0] delta of the piece covering the bucket's first position
+//            [1] s1 = start of the first piece beginning inside the bucket (else ~0)   [2] its delta
+//            [3] s2 = start of the second piece beginning inside (else ~0)
+//            [4] nxt = index of the piece starting at s1   [5] cnt = pieces beginning inside   [6,7] 0
+//   pent[k]  [0] delta  [1] start
+// query i: i < s1 -> rec[0];  i < s2 -> rec[2];  else the last piece in [nxt+1, nxt+cnt) with start <= i.
+struct JumpTable {
+    u32 J = 0, shift = 0;
+    u64 nbkt = 0;
+    std::vector<u64> start, delta;
+    std::vector<u64> rec;   // [nbkt * 8]
+    std::vector<u64> pent;  // [pieces * 2]
+    u64 pieces() const { return start.size(); }
+    u64 bytes(bool w32) const { return (rec.size() + pent.size()) * (w32 ? 4 : 8); }
+    u64 piece_of(u64 i) const { return (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1; }
+    u64 apply(u64 i, u64 n) const {
+        u64 v = i + delta[piece_of(i)];
+        return v >= n ? v - n : v;
+    }
+    void build_directory(u64 n, u32 buckets_log2) {
+        shift = 0;
+        u64 target = pieces() << buckets_log2;
+        if (target < 1) target = 1;
+        while (((n - 1) >> shift) + 1 > target) ++shift;
+        nbkt = ((n - 1) >> shift) + 1;
+        const u64 P = pieces();
+        rec.assign(nbkt * 8, 0);
+        pent.resize(P * 2);
+        for (u64 k = 0; k < P; ++k) { pent[2 * k] = delta[k]; pent[2 * k + 1] = start[k]; }
+        u64 a = 0;
+        for (u64 q = 0; q < nbkt; ++q) {
+            const u64 lo = q << shift, hi = (q + 1) << shift;
+            while (a + 1 < P && start[a + 1] <= lo) ++a;
+            u64 e = a + 1;
+            while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
+            u64* R = &rec[q * 8];
+            const u64 cnt = e - (a + 1);
+            R[0] = delta[a];
+            R[1] = cnt >= 1 ? start[a + 1] : ~(u64)0;
+            R[2] = cnt >= 1 ? delta[a + 1] : 0;
+            R[3] = cnt >= 2 ? start[a + 2] : ~(u64)0;
+            R[4] = cnt >= 1 ? a + 1 : 0;
+            R[5] = cnt;
+        }
+    }
+};
+
+// C = B o A (apply A, then B) for two piecewise translations of [0,n) given as (start, delta) lists:
+// every piece of A is cut where its image crosses a piece boundary of B; delta_C = delta_A + delta_B.
+static inline void compose_translations(const std::vector<u64>& As, const std::vector<u64>& Ad,
+                                        const std::vector<u64>& Bs, const std::vector<u64>& Bd, u64 n,
+                                        std::vector<u64>& Cs, std::vector<u64>& Cd) {
+    Cs.clear(); Cd.clear();
+    const u64 PA = As.size(), PB = Bs.size();
+    Cs.reserve(PA * 2); Cd.reserve(PA * 2);
+    for (u64 k = 0; k < PA; ++k) {
+        const u64 s = As[k], e = (k + 1 < PA) ? As[k + 1] : n, a = Ad[k], len = e - s;
+        u64 u = s + a;  // image of s
+        if (u >= n) u -= n;
+        u64 done = 0;
+        while (done < len) {  // at most two linear ranges (the image may wrap around n)
+            const bool wrapped = u + done >= n;
+            const u64 pos = wrapped ? u + done - n : u + done;
+            const u64 lin_end = wrapped ? (u + len - n) : std::min(u + len, n);
+            u64 b = (u64)(std::upper_bound(Bs.begin(), Bs.end(), pos) - Bs.begin()) - 1;
+            u64 cur = pos;
+            while (cur < lin_end) {
+                const u64 pend = std::min(lin_end, (b + 1 < PB) ? Bs[b + 1] : n);
+                u64 d = a + Bd[b];
+                if (d >= n) d -= n;
+                Cs.push_back(s + done + (cur - pos));
+                Cd.push_back(d);
+                cur = pend; ++b;
+            }
+            done += lin_end - pos;
+        }
+    }
+}
+
 struct FlatHost {
     u64 n = 0, r = 0;
     u32 K = 16;          // runs per block
@@ -159,10 +244,11 @@ struct FlatHost {
     std::vector<u64> samples_last; // [r]
     bool w32 = false;              // n < 2^32-1: Phi records and deltas are stored as 32-bit words
     PhiTable phi;                  // Phi^1..Phi^D refined
+    JumpTable seed;                // Phi^SEG (seed.J = SEG; 0 = single-pass expansion only)
     u64 bytes() const {
         const u64 W = w32 ? 4 : 8;
         return F.size() * 8 + sid.size() * 2 + start.size() * W + blk.size() + bstart.size() * W + last.size() * W +
-               bdir.size() * 4 + samples_last.size() * W + phi.bytes(w32);
+               bdir.size() * 4 + samples_last.size() * W + phi.bytes(w32) + seed.bytes(w32);
     }
 };
 
@@ -317,6 +403,36 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
     f.phi.build_directory(n, fp);
     if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
+
+    // Seed table Phi^SEG for the two-pass expansion (phi_kernels.cuh): requested (reserved[2] = 16..256,
+    // 1 = off), or the largest of {64, 32, 16} whose table (40 B per piece with 32-bit words: one
+    // 32-byte bucket record per piece + an 8-byte piece entry) stays within ~2 GB / a quarter of the
+    // caller's byte limit. pieces(Phi^J) = sum over runs of min(J, run length), known before building.
+    u32 SEG = opt.reserved[2];
+    if (SEG != 0 && SEG != 1 && SEG != 16 && SEG != 32 && SEG != 64 && SEG != 128 && SEG != 256) return RIG_ERR_ARG;
+    if (SEG == 0) {
+        u64 budget = 2ull << 30;
+        if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
+        const u64 per_piece = f.w32 ? 40 : 80;
+        SEG = 1;
+        for (u32 cand : {64u, 32u, 16u}) {
+            u64 pieces = 0;
+            for (u64 j = 0; j < r; ++j) pieces += std::min<u64>(cand, v.run_lens[j]);
+            if (pieces * per_piece <= budget) { SEG = cand; break; }
+        }
+    }
+    f.seed = JumpTable();
+    if (SEG > 1) {
+        std::vector<u64> s0 = P1.start, d0 = P1.delta, s1, d1;
+        for (u32 J = 1; J < SEG; J *= 2) {
+            compose_translations(s0, d0, s0, d0, n, s1, d1);
+            s0.swap(s1); d0.swap(d1);
+        }
+        f.seed.J = SEG;
+        f.seed.start.swap(s0); f.seed.delta.swap(d0);
+        if (f.seed.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
+        f.seed.build_directory(n, 0);
+    }
     return RIG_OK;
 }
 

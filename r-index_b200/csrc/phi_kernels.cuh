@@ -1,6 +1,19 @@
 // phi_kernels.cuh — sm_100a Phi expansion: the locate_all loop of the reference
 // (internal/r_index.hpp:340-351: OCC = SA[hi], Phi(SA[hi]), Phi^2(SA[hi]), ...) for a whole batch.
 //
+// TWO PASSES when the index carries a seed table (Phi^SEG, flat_layout.hpp: JumpTable), one otherwise:
+//
+//   phi_expand_kernel<.., SEEDED=true>   one lane per chain: writes the toehold, walks the chain up to the
+//        next SEG-aligned slot of the OUTPUT array, then hops along the chain SEG occurrences at a time
+//        (one seed-table lookup per hop), writing only the occurrence that falls on each aligned slot
+//        (the window's SEED) and the number of further occurrences of that window (winfo[]).
+//   phi_window_kernel                    one lane per SEG-slot window of the output array: reads its seed,
+//        produces the window's occurrences with D per lookup, every store one aligned 32-byte sector.
+//
+// The single-pass form's time is (longest chain) x (load latency) with half-empty warps (chain lengths
+// differ by orders of magnitude inside a warp); the two-pass form turns the batch into uniform
+// 16-lookup work items, 1.6 M of them on config C2 instead of 143 k chains.
+//
 // One LANE per chain. A chain is the part of a pattern's SA range that lies inside one BWT run
 // (ranges are cut at run boundaries: every run end is a free toehold, SA = samples_last[run]+1, the
 // identity behind r_index.hpp:489,533), so a batch exposes (#patterns x #runs overlapped) independent
@@ -74,41 +87,19 @@ __global__ void __launch_bounds__(256) l2_warm_kernel(const char* base, u64 byte
     if (line < bytes) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(base + line));
 }
 
-// Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]), min(hi,start[j+1]-1)], walked
-// from the top down. Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order (r_index.hpp:340-351).
+// ---- walking a chain with the Phi^1..Phi^D table ---------------------------------------------------
+// From v = SA[x] (already written at o[-1]) produce `remaining` further occurrences SA[x-1], SA[x-2], ...
+// at o[0], o[1], ...; returns the last value produced (v itself when remaining == 0).
 //
 // Per step, from the current value v = SA[x]: e[t] = Phi^(t+1)(v) = (v + delta_t) mod n, where the
 // deltas are those of the piece holding v. For t = 0 this is r_index::Phi (r_index.hpp:195-221):
 // strict circular predecessor over the sorted run-first samples (sparse_sd_vector.hpp:107-112,153-157)
 // and (prev_sample + delta) % n (:219), folded into one delta per piece.
 template <typename WT, int D, bool KEEP>
-__global__ void __launch_bounds__(256)
-phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
-                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains) {
+__device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT remaining) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
     constexpr u32 ESZ = RW * (u32)sizeof(WT);  // entry size in bytes
     constexpr bool W32 = sizeof(WT) == 4;
-    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= total_chains) return;  // no warp collectives below
-    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
-    while (b - a > 1) {
-        const u64 mid = (a + b) >> 1;
-        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
-    }
-    const u64 p = a;
-    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-    const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
-    const u64 top = min(H, ej), bot = max(L, sj);
-    u64 v0;
-    if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
-    else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
-    u64* o = out + __ldg(occ_off + p) + (H - top);  // next slot to write
-    __stcs(o, v0);
-    ++o;
-    WT v = (WT)v0;
-    WT remaining = (WT)(top - bot);  // occurrences still to produce (a chain never exceeds n)
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
@@ -178,6 +169,159 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
 #pragma unroll
         for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
+    return v;
+}
+
+// One hop of SEG occurrences: Phi^SEG(v) through the seed table (8-word bucket record resolving up to
+// two pieces that begin inside the bucket; binary search over 2-word piece entries beyond that).
+template <typename WT>
+__device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
+    constexpr bool W32 = sizeof(WT) == 4;
+    WT w[8];
+    load_entry<WT, 8, false>(reinterpret_cast<const char*>(ix.seed.rec) + (u64)(v >> ix.seed.shift) * (8 * sizeof(WT)), w);
+    WT d;
+    if (v < w[1]) d = w[0];
+    else if (v < w[3]) d = w[2];
+    else {  // piece nxt+1 starts at s2 <= v: last piece of [nxt+1, nxt+cnt) with start <= v
+        const WT* pe = reinterpret_cast<const WT*>(ix.seed.pent);
+        u32 lo = (u32)w[4] + 1, hi = (u32)w[4] + (u32)w[5] - 1;
+        while (lo < hi) {
+            const u32 mid = (lo + hi + 1) >> 1;
+            if (__ldg(pe + 2 * (u64)mid + 1) <= v) lo = mid; else hi = mid - 1;
+        }
+        d = __ldg(pe + 2 * (u64)lo);
+    }
+    WT x = v + d;
+    if ((W32 && x < v) || x >= (WT)ix.n) x -= (WT)ix.n;
+    return x;
+}
+
+// Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]), min(hi,start[j+1]-1)], walked
+// from the top down. Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order (r_index.hpp:340-351).
+//
+// SEEDED = false: the lane produces its whole chain.
+// SEEDED = true : the lane produces the chain up to the first slot that is a multiple of SEG = 1 << seg_shift
+//                 (<= SEG occurrences), then only the occurrences on SEG-aligned slots (one seed_hop each)
+//                 and winfo[slot / SEG] = number of the chain's occurrences that follow the seed inside
+//                 its window (0 .. SEG-1). Every SEG-aligned slot below occ_total lies in exactly one chain,
+//                 so every window gets its seed and its count; phi_window_kernel fills in the rest.
+template <typename WT, int D, bool KEEP, bool SEEDED>
+__global__ void __launch_bounds__(256)
+phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
+                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
+                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains,
+                  uint8_t* __restrict__ winfo, u32 seg_shift) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= total_chains) return;  // no warp collectives below
+    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
+    while (b - a > 1) {
+        const u64 mid = (a + b) >> 1;
+        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+    }
+    const u64 p = a;
+    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
+    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
+    const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
+    const u64 top = min(H, ej), bot = max(L, sj);
+    u64 v0;
+    if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
+    else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
+    const u64 g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
+    __stcs(out + g0, v0);
+    if (!SEEDED) {
+        walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(top - bot));  // a chain never exceeds n
+    } else {
+        const u64 SEG = 1ull << seg_shift;
+        const u64 glast = g0 + (top - bot);                 // slot of the chain's last occurrence
+        const u64 b1 = (g0 + SEG - 1) & ~(SEG - 1);         // first aligned slot at or after g0
+        const u64 pre_last = min(b1, glast);
+        WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
+        if (b1 <= glast) {
+            u64 s = b1;
+            for (;;) {
+                winfo[s >> seg_shift] = (uint8_t)min(SEG - 1, glast - s);
+                s += SEG;
+                if (s > glast) break;
+                v = seed_hop<WT>(ix, v);
+                __stcs(out + s, (u64)v);
+            }
+        }
+    }
+}
+
+// One lane per SEG-slot window of the occurrence array: v = out[w*SEG] is the window's seed, winfo[w] the
+// number of further occurrences of the same chain inside the window. Each lookup yields Phi^1..Phi^D(v);
+// the lane stores the aligned group [v, Phi(v), .., Phi^(D-1)(v)] (one 32-byte sector for D = 4) and
+// continues from Phi^D(v). Same per-lane state machine and software pipelining as walk_chain.
+template <typename WT, int D, bool KEEP>
+__global__ void __launch_bounds__(256)
+phi_window_kernel(const FlatDev ix, const uint8_t* __restrict__ winfo, u64* __restrict__ out, u64 windows, u32 seg_shift) {
+    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
+    constexpr u32 ESZ = RW * (u32)sizeof(WT);
+    constexpr bool W32 = sizeof(WT) == 4;
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= windows) return;
+    u32 left = (u32)__ldg(winfo + w) + 1;  // slots of this window still to be written, the seed's included
+    if (left < 2) return;                  // the seed alone: already in place
+    u64* o = out + (w << seg_shift);
+    WT v = (WT)__ldcg(o);
+    const WT n = (WT)ix.n;
+    const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
+    const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
+    const u32 shift = ix.phi.shift;
+    bool searching = false;
+    u32 slo = 0, shi = 0, probe = 0;
+    WT e[RW];
+    load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
+    while (left > 1) {
+        bool emit;
+        if (!searching) {
+            emit = v < e[D];
+            slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+            searching = !emit;
+        } else if (slo == shi) {
+            emit = true;
+        } else if (e[D] <= v) {
+            slo = probe; emit = (slo == shi);
+        } else {
+            shi = probe - 1; emit = false;
+        }
+        WT g[D];          // the group to store: [v, Phi(v), ..]
+        u32 cnt = 0;
+        WT vn = v;
+        if (emit) {
+            searching = false;
+            slo = shi = 0;
+            g[0] = v;
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                WT x = v + e[t];
+                if ((W32 && x < v) || x >= n) x -= n;
+                if (t < D - 1) g[t + 1] = x; else vn = x;
+            }
+            cnt = min(left, (u32)D);
+        }
+        const u32 left_next = left - cnt;
+        probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+        WT e2[RW];
+        if (left_next > 1)
+            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
+        if (emit) {
+            if (cnt == (u32)D) {
+                if (!(ix.pad & 1)) store_group<WT, D>(o, g);
+            } else {
+#pragma unroll
+                for (int t = 0; t < D - 1; ++t)
+                    if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+            }
+            o += cnt;
+        }
+        v = vn;
+        left = left_next;
+#pragma unroll
+        for (int t = 0; t < RW; ++t) e[t] = e2[t];
+    }
+    if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
 }
 
 }  // namespace rigk

@@ -54,9 +54,9 @@ struct rig_index {
     rig_options opt{};
     void* arena = nullptr;  // one allocation holding every flat array
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes
     // workspace (grow-only)
-    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ;
+    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, winfo;
     ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
@@ -65,7 +65,7 @@ struct rig_index {
     size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
     float l2_hit_ratio = 1.f;
     bool timing_pending = false;
-    bool ev_valid[6] = {false, false, false, false, false, false};
+    bool ev_valid[7] = {false, false, false, false, false, false, false};
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -130,7 +130,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
-    std::vector<uint32_t> rec32, pent32, start32, bstart32, last32, sl32;
+    std::vector<uint32_t> rec32, pent32, start32, bstart32, last32, sl32, srec32, spent32;
     auto narrow = [](const std::vector<uint64_t>& src, std::vector<uint32_t>& dst) {
         dst.resize(src.size());
         for (size_t i = 0; i < src.size(); ++i) dst[i] = (uint32_t)src[i];
@@ -141,6 +141,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
         for (size_t i = 0; i < rec32.size(); ++i) rec32[i] = (uint32_t)f.phi.rec[i];
         pent32.resize(f.phi.pent.size());
         for (size_t i = 0; i < pent32.size(); ++i) pent32[i] = (uint32_t)f.phi.pent[i];
+        narrow(f.seed.rec, srec32); narrow(f.seed.pent, spent32);
     }
     struct Part { const void* src; size_t bytes; size_t off; };
     std::vector<Part> parts = {
@@ -157,9 +158,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     if (f.w32) {
         parts.push_back({rec32.data(), rec32.size() * 4, 0});
         parts.push_back({pent32.data(), pent32.size() * 4, 0});
+        parts.push_back({srec32.data(), srec32.size() * 4, 0});
+        parts.push_back({spent32.data(), spent32.size() * 4, 0});
     } else {
         parts.push_back({f.phi.rec.data(), f.phi.rec.size() * 8, 0});
         parts.push_back({f.phi.pent.data(), f.phi.pent.size() * 8, 0});
+        parts.push_back({f.seed.rec.data(), f.seed.rec.size() * 8, 0});
+        parts.push_back({f.seed.pent.data(), f.seed.pent.size() * 8, 0});
     }
     size_t total = 0;
     for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 128, 256); }
@@ -184,6 +189,9 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.phi.rec = (const void*)(A + parts[8].off);
     d.phi.pent = (const void*)(A + parts[9].off);
     d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
+    d.seed.rec = (const void*)(A + parts[10].off);
+    d.seed.pent = (const void*)(A + parts[11].off);
+    d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
     d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 16) ? 1u : 0u;  // diagnostic: expansion without its vector stores
 
@@ -219,6 +227,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     I.phi_jump = f.phi.D; I.phi_jump_pieces = f.phi.pieces(); I.words32 = f.w32 ? 1u : 0u;
     I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
     I.reserved = ix->l2_window_bytes ? (uint32_t)(prop.persistingL2CacheMaxSize >> 20) : 0;  // MiB of persisting L2 in use
+    I.seed_jump = d.seed.J; I.seed_shift = f.seed.shift; I.seed_pieces = f.seed.pieces(); I.seed_bytes = f.seed.bytes(f.w32);
     *out = ix;
     return RIG_OK;
 }
@@ -228,7 +237,7 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ})
+                      &ix->occoff, &ix->occ, &ix->winfo})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
@@ -283,7 +292,7 @@ int finish_timing(rig_index* ix) {
     if (!ix->timing_pending) return RIG_OK;
     CU_TRY(cudaSetDevice(ix->device));
     // the last recorded event closes the call
-    for (int i = 5; i >= 0; --i)
+    for (int i = 5; i >= 0; --i)  // ev[6] sits between ev[3] and ev[4] in stream order
         if (ix->ev_valid[i]) { CU_TRY(cudaEventSynchronize(ix->ev[i])); break; }
     auto el = [&](int a, int b, float& dst) -> int {
         dst = 0.f;
@@ -296,6 +305,8 @@ int finish_timing(rig_index* ix) {
     if ((rc = el(2, 3, ix->timing.scan_ms))) return rc;
     if ((rc = el(3, 4, ix->timing.expand_ms))) return rc;
     if ((rc = el(4, 5, ix->timing.d2h_ms))) return rc;
+    if ((rc = el(3, 6, ix->timing.seed_ms))) return rc;
+    if ((rc = el(6, 4, ix->timing.window_ms))) return rc;
     ix->timing.lf_steps = ix->h_counters[0];
     ix->timing_pending = false;
     return RIG_OK;
@@ -397,12 +408,36 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
             rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
             ix->timing.launches += 1;
         }
+        // Two passes when the index has a seed table and the output array is sector-aligned (the window
+        // kernel's vector stores need it); otherwise the single-pass walk.
+        const uint32_t SEG = ix->d.seed.J;
+        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 63) == 0);
+        uint32_t seg_shift = 0;
+        while ((1u << seg_shift) < SEG) ++seg_shift;
+        const uint64_t windows = two_pass ? (total + SEG - 1) / SEG : 0;
+        if (two_pass && (rc = ix->winfo.ensure(windows + 16))) return rc;
+        uint8_t* a_winfo = (uint8_t*)ix->winfo.p;
+        const int wthreads = 256;
+        const uint64_t wnb = (windows + wthreads - 1) / wthreads;
+        if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
+#define RIG_EXPAND2(W, DD, KP)                                                                                  \
+    do {                                                                                                        \
+        if (two_pass) {                                                                                         \
+            CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, true>, ix->d, a_N, a_choff,      \
+                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_winfo, seg_shift)); \
+            if ((rc = rec(ix, 6, st))) return rc;                                                               \
+            rigk::phi_window_kernel<W, DD, KP><<<(unsigned)wnb, wthreads, 0, st>>>(ix->d, a_winfo, d_occ,       \
+                                                                                  windows, seg_shift);        \
+            ix->timing.launches += 1;                                                                           \
+        } else {                                                                                                \
+            CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, false>, ix->d, a_N, a_choff,     \
+                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_winfo, seg_shift)); \
+        }                                                                                                       \
+    } while (0)
 #define RIG_EXPAND(W, DD)                                                                                     \
     do {                                                                                                      \
-        if (keep) CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, true>, ix->d, a_N, a_choff,  \
-                                            a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains));            \
-        else CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, false>, ix->d, a_N, a_choff,      \
-                                       a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains));                 \
+        if (keep) RIG_EXPAND2(W, DD, true);                                                                   \
+        else RIG_EXPAND2(W, DD, false);                                                                       \
     } while (0)
         switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
             case 2: RIG_EXPAND(ull, 1); break;
@@ -415,6 +450,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
             case 17: RIG_EXPAND(uint32_t, 8); break;
             default: return RIG_ERR_ARG;
         }
+#undef RIG_EXPAND2
 #undef RIG_EXPAND
         CU_TRY(cudaGetLastError());
         ix->timing.launches += 1;

@@ -29,6 +29,14 @@ struct PhiTabDev {
     u32 shift, D;
 };
 
+// Phi^J as one piecewise translation (flat_layout.hpp: JumpTable), the seed table of the two-pass
+// expansion. 8-word bucket records (delta0, s1, delta1, s2, nxt, cnt, 0, 0), 2-word piece entries.
+struct SeedTabDev {
+    const void* rec;
+    const void* pent;
+    u32 shift, J;       // J = 0: no seed table (single-pass expansion)
+};
+
 struct FlatDev {
     u64 n, r, nblk, toe0;
     u32 K, S, lf_shift, pad0;
@@ -42,6 +50,7 @@ struct FlatDev {
     const u32* bdir;          // [lf_nbkt+1]
     const void* samples_last; // [r]         PT
     PhiTabDev phi;
+    SeedTabDev seed;
     u32 w32, pad;             // w32: every position-holding array (and the Phi tables) uses 32-bit words
 };
 

@@ -50,17 +50,21 @@ def _native_built():
 class FlatCheck:
     """ctypes wrapper of the scalar test double over the flattened arrays."""
 
-    def __init__(self, host_index, K=16, lf_log2=0, phi_log2=0, jump=0, force_wide=False):
+    def __init__(self, host_index, K=16, lf_log2=0, phi_log2=0, jump=0, force_wide=False, seed_jump=0):
         _build_flatcheck()
         self.lib = ctypes.CDLL(FLATCHECK_SO)
         self.lib.fc_create.restype = ctypes.c_void_p
         self.lib.fc_create.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int), ctypes.c_uint32]
         self.lib.fc_jump.restype = ctypes.c_uint64
         self.lib.fc_jump.argtypes = [ctypes.c_void_p]
         self.lib.fc_pieces.restype = ctypes.c_uint64
         self.lib.fc_pieces.argtypes = [ctypes.c_void_p]
         self.lib.fc_w32.argtypes = [ctypes.c_void_p]
+        for fn in ("fc_seed_jump", "fc_seed_pieces"):
+            getattr(self.lib, fn).restype = ctypes.c_uint64
+            getattr(self.lib, fn).argtypes = [ctypes.c_void_p]
+        self.lib.fc_check_seed.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
         self.lib.fc_check_jump.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
         self.lib.fc_destroy.argtypes = [ctypes.c_void_p]
         self.lib.fc_count.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_uint64] * 2 + [ctypes.c_void_p] * 2
@@ -72,10 +76,11 @@ class FlatCheck:
             view, self._keep = view_from_arrays(host_index)
         else:
             view, self._keep = host_index.view, host_index
-        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, jump, int(force_wide), ctypes.byref(rc))
+        self.h = self.lib.fc_create(ctypes.byref(view), K, lf_log2, phi_log2, jump, int(force_wide), ctypes.byref(rc), seed_jump)
         self.rc = rc.value
         self.w32 = bool(self.lib.fc_w32(self.h)) if self.h else None
         self.jump = int(self.lib.fc_jump(self.h)) if self.h else 0
+        self.seed_jump = int(self.lib.fc_seed_jump(self.h)) if self.h else 0
 
     def count(self, patt, N, m):
         p = np.ascontiguousarray(patt, dtype=np.uint8)

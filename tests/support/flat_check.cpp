@@ -80,6 +80,69 @@ void phi_lookup(const FlatHost& f, u64 i, u64* e, u64* loads = nullptr) {
     }
 }
 
+// mirrors rigk::seed_hop: Phi^SEG(i) reading only seed.rec[] / seed.pent[] (32-bit truncation when w32)
+u64 seed_hop(const FlatHost& f, u64 i) {
+    const rigf::JumpTable& T = f.seed;
+    const u64 mask = f.w32 ? 0xFFFFFFFFull : ~(u64)0;
+    const u64* w = &T.rec[(i >> T.shift) * 8];
+    u64 d;
+    if (i < (w[1] & mask)) d = w[0] & mask;
+    else if (i < (w[3] & mask)) d = w[2] & mask;
+    else {
+        u64 lo = (w[4] & mask) + 1, hi = (w[4] & mask) + (w[5] & mask) - 1;
+        while (lo < hi) {
+            const u64 mid = (lo + hi + 1) >> 1;
+            if ((T.pent[2 * mid + 1] & mask) <= i) lo = mid; else hi = mid - 1;
+        }
+        d = T.pent[2 * lo] & mask;
+    }
+    u64 v = i + d;
+    if (v >= f.n) v -= f.n;
+    return v;
+}
+
+// mirrors rigk::walk_chain: `remaining` occurrences after v, written from o on; returns the last value
+u64 walk_chain(const FlatHost& f, u64 v, u64* occ, u64 slot, u64 remaining, bool& misaligned) {
+    const u32 D = f.phi.D;
+    u64 e[8];
+    u64* o = occ + slot;
+    const u32 mis = (u32)(slot % D);
+    if (D > 1 && mis != 0 && remaining > 0) {
+        const u32 cnt = (u32)std::min<u64>(D - mis, remaining);
+        phi_lookup(f, v, e);
+        for (u32 t = 0; t < cnt; ++t) { o[t] = e[t]; v = e[t]; }
+        o += cnt; remaining -= cnt;
+    }
+    while (remaining >= D) {
+        phi_lookup(f, v, e);
+        if (((u64)(o - occ)) % D != 0) misaligned = true;  // vector stores must be aligned
+        for (u32 t = 0; t < D; ++t) o[t] = e[t];
+        v = e[D - 1]; o += D; remaining -= D;
+    }
+    if (D > 1 && remaining > 0) {
+        phi_lookup(f, v, e);
+        for (u32 t = 0; t < remaining; ++t) { o[t] = e[t]; v = e[t]; }
+    }
+    return v;
+}
+
+// mirrors rigk::phi_window_kernel for window w
+void window_fill(const FlatHost& f, u64* occ, const uint8_t* winfo, u64 w) {
+    const u32 D = f.phi.D;
+    u64 left = (u64)winfo[w] + 1;
+    if (left < 2) return;
+    u64* o = occ + w * f.seed.J;
+    u64 v = *o, e[8];
+    while (left > 1) {
+        phi_lookup(f, v, e);
+        const u64 cnt = std::min<u64>(left, D);
+        o[0] = v;
+        for (u32 t = 1; t < cnt; ++t) o[t] = e[t - 1];
+        v = e[D - 1]; o += cnt; left -= cnt;
+    }
+    if (left == 1) *o = v;
+}
+
 // mirrors rigk::search_kernel (one pattern)
 void search(const FlatHost& f, const uint8_t* P, u64 m, bool locate, u64& lo, u64& hi, u64& k) {
     lo = 0; hi = f.n - 1; k = f.toe0;
@@ -100,11 +163,12 @@ void search(const FlatHost& f, const uint8_t* P, u64 m, bool locate, u64& lo, u6
 
 extern "C" {
 
-void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, uint32_t jump, uint32_t force_wide, int* rc_out) {
+void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_t phi_log2, uint32_t jump, uint32_t force_wide, int* rc_out, uint32_t seed_jump) {
     rig_options opt;
     std::memset(&opt, 0, sizeof(opt));
     opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2; opt.reserved[0] = jump;
     opt.reserved[1] = force_wide ? 1 : 0;
+    opt.reserved[2] = seed_jump;
     FlatHost* f = new FlatHost();
     int rc = rigf::flatten(*v, opt, *f);
     if (rc_out) *rc_out = rc;
@@ -114,6 +178,18 @@ void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_
 void fc_destroy(void* h) { delete (FlatHost*)h; }
 uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
 uint64_t fc_jump(void* h) { return ((FlatHost*)h)->phi.D; }
+uint64_t fc_seed_jump(void* h) { return ((FlatHost*)h)->seed.J; }
+uint64_t fc_seed_pieces(void* h) { return ((FlatHost*)h)->seed.pieces(); }
+// Phi^SEG through the seed table (scalar and bucket-record lookup) == SEG applications of Phi
+int fc_check_seed(void* h, uint64_t i) {
+    const FlatHost& f = *(FlatHost*)h;
+    if (f.seed.J < 2) return -1;
+    u64 a = i;
+    for (u32 j = 0; j < f.seed.J; ++j) a = f.phi.apply(a, 1, f.n);
+    if (a != f.seed.apply(i, f.n)) return 1;
+    if (a != seed_hop(f, i)) return 2;
+    return 0;
+}
 uint64_t fc_pieces(void* h) { return ((FlatHost*)h)->phi.pieces(); }
 int fc_w32(void* h) { return ((FlatHost*)h)->w32 ? 1 : 0; }
 // Phi^j(i), j = 1..D, evaluated three ways must agree: j applications of Phi^1 through the scalar
@@ -139,7 +215,9 @@ void fc_count(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi) {
 // occ_off must hold N+1 exclusive prefix sums; returns the number of chains.
 uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi, const u64* occ_off, u64* occ) {
     const FlatHost& f = *(FlatHost*)h;
-    u64 chains = 0;
+    u64 chains = 0, seeded = 0;
+    const u64 total = occ_off[N], windows = f.seed.J >= 2 ? (total + f.seed.J - 1) / f.seed.J : 0;
+    std::vector<uint8_t> winfo(windows + 1, 0xEE);
     for (u64 p = 0; p < N; ++p) {
         u64 k;
         search(f, patt + p * m, m, true, lo[p], hi[p], k);
@@ -149,33 +227,35 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
         for (u64 j = jL; j <= jR; ++j) {
             u64 sj = f.start[j], ej = f.start[j + 1] - 1;
             u64 top = std::min(H, ej), bot = std::max(L, sj);
-            // mirrors rigk::phi_expand_kernel: head singles up to alignment, D per lookup, tail
+            // mirrors rigk::phi_expand_kernel: toehold, then the whole chain (single pass) or the chain head
+            // up to the next SEG-aligned output slot followed by one seed per window (two passes)
             u64 v = (top == H) ? k : (f.samples_last[j] + 1) % f.n;
             const u64 g0 = occ_off[p] + (H - top);
-            const u32 D = f.phi.D;
-            u64* o = occ + g0;
-            *o++ = v;
-            u64 remaining = top - bot, e[8];
-            const u32 mis = (u32)((g0 + 1) % D);
-            if (D > 1 && mis != 0 && remaining > 0) {
-                const u32 cnt = (u32)std::min<u64>(D - mis, remaining);
-                phi_lookup(f, v, e);
-                for (u32 t = 0; t < cnt; ++t) { o[t] = e[t]; v = e[t]; }
-                o += cnt; remaining -= cnt;
+            occ[g0] = v;
+            bool mis = false;
+            if (f.seed.J < 2) {
+                walk_chain(f, v, occ, g0 + 1, top - bot, mis);
+            } else {
+                const u64 SEG = f.seed.J, glast = g0 + (top - bot), b1 = (g0 + SEG - 1) / SEG * SEG;
+                v = walk_chain(f, v, occ, g0 + 1, std::min(b1, glast) - g0, mis);
+                if (b1 <= glast) {
+                    u64 sl = b1;
+                    for (;;) {
+                        winfo[sl / SEG] = (uint8_t)std::min<u64>(SEG - 1, glast - sl);
+                        ++seeded;
+                        sl += SEG;
+                        if (sl > glast) break;
+                        v = seed_hop(f, v);
+                        occ[sl] = v;
+                    }
+                }
             }
-            while (remaining >= D) {
-                phi_lookup(f, v, e);
-                if (((u64)(o - occ)) % D != 0) return ~(u64)0;  // vector stores must be aligned
-                for (u32 t = 0; t < D; ++t) o[t] = e[t];
-                v = e[D - 1]; o += D; remaining -= D;
-            }
-            if (D > 1 && remaining > 0) {
-                phi_lookup(f, v, e);
-                for (u32 t = 0; t < remaining; ++t) o[t] = e[t];
-            }
+            if (mis) return ~(u64)0;
             ++chains;
         }
     }
+    if (seeded != windows) return ~(u64)0 - 1;  // every window must receive exactly one seed
+    for (u64 w = 0; w < windows; ++w) window_fill(f, occ, winfo.data(), w);
     return chains;
 }
 

@@ -51,6 +51,44 @@ def test_jump_tables_equal_repeated_phi(jump, wide):
         assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(occ, eocc)
 
 
+@pytest.mark.parametrize("seg", [1, 16, 32, 64, 256])
+@pytest.mark.parametrize("wide", [False, True])
+def test_seed_table_and_two_pass_expansion(seg, wide):
+    """Seed table Phi^SEG (built by doubling) == SEG applications of Phi for every SA value it can legally
+    be applied to, through the scalar table AND the 8-word bucket-record lookup; the two-pass expansion
+    (chain heads + one seed per SEG-slot output window, then one work item per window) reproduces the
+    oracle, gives every window exactly one seed and keeps every vector store aligned."""
+    rng = np.random.default_rng(100 * seg + wide)
+    for it in range(20):
+        n = int(rng.integers(1, 4000))
+        t = repetitive_text(n, int(rng.integers(1, 200)), int(rng.integers(0, 4)), 9000 + 17 * seg + it, sigma=int(rng.choice([1, 2, 4, 15])))
+        host = rib.HostIndex.from_text(t)
+        jump = int(rng.choice([1, 2, 4, 8]))
+        fc = FlatCheck(host, K=4, phi_log2=int(rng.choice([0, 1, 4])), jump=jump, force_wide=wide, seed_jump=seg)
+        assert fc.rc == 0 and fc.seed_jump == (seg if seg > 1 else 0)
+        if seg > 1:
+            assert host.r <= fc.lib.fc_seed_pieces(fc.h) <= min(seg * host.r + 1, n + 1)
+            sa = rib.suffix_array(t)
+            for x in range(seg, n + 1):
+                assert fc.lib.fc_check_seed(fc.h, int(sa[x])) == 0
+        port = ob.PortIndex(t)
+        for m in (1, 2, int(rng.integers(1, 6))):  # short patterns: long ranges, chains spanning many windows
+            N = 30
+            patt = mixed_patterns(t, N, m, it)
+            elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+            lo, hi, off, occ, chains = fc.locate(patt, N, m)
+            assert chains < 2**63
+            assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(occ, eocc)
+
+
+def test_seed_table_auto_policy():
+    t = rib.gen_text("dna_drift", 300_000, 3_000, 3, 5)
+    host = rib.HostIndex.from_text(t)
+    assert FlatCheck(host).seed_jump == 64       # small index: the largest window size fits the budget
+    assert FlatCheck(host, seed_jump=1).seed_jump == 0
+    assert FlatCheck(host, seed_jump=48).rc == -1
+
+
 def test_jump_table_auto_policy():
     t = rib.gen_text("dna_drift", 300_000, 3_000, 3, 5)
     fc = FlatCheck(rib.HostIndex.from_text(t))

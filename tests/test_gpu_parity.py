@@ -236,3 +236,52 @@ def test_phi_jump_tables_and_wide_paths(jump, variant, monkeypatch):
     gpu2 = rib.GpuIndex(rib.HostIndex.from_text(text2), phi_jump=jump)
     patt = mixed_patterns(text2, 64, 2, 3)
     _check_all(gpu2, ob.PortIndex(text2), patt, 64, 2, "tiny jump=%d" % jump)
+
+
+@pytest.mark.parametrize("seg", [1, 16, 64, 256])
+@pytest.mark.parametrize("variant", ["0", "8", "32"])
+def test_two_pass_expansion(seg, variant, monkeypatch):
+    """Two-pass expansion (seed table Phi^SEG + one work item per SEG-slot output window) for every window
+    size, 32- and 64-bit words, against the single-pass walk (SEG = 1, or RIG_VARIANT bit 5) and the oracle.
+    Short patterns give ranges of 10^4..10^5 occurrences: chains that span hundreds of windows."""
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 123)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    for jump in (4, 1):
+        gpu = rib.GpuIndex(host, phi_jump=jump, seed_jump=seg)
+        assert gpu.info.seed_jump == (seg if seg > 1 else 0)
+        for (N, m, seed) in [(1200, 9, 1), (200, 2, 2), (40, 1, 3), (500, 30, 4)]:
+            patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+            _check_all(gpu, port, patt, N, m, "seg=%d jump=%d variant=%s" % (seg, jump, variant))
+        t = gpu.timing()
+        if seg > 1 and variant != "32":
+            assert t["window_ms"] > 0 and t["seed_ms"] > 0
+        gpu.close()
+
+
+def test_two_pass_unaligned_output_falls_back_to_single_pass():
+    """The window kernel's vector stores need a sector-aligned occurrence array; a caller-supplied device
+    pointer that is only 8-byte aligned takes the single-pass walk and still gives the oracle's output."""
+    torch = pytest.importorskip("torch")
+    text = rib.gen_text("dna_drift", 200_000, 2_000, 3, 5)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host)
+    N, m = 800, 6
+    patt = rib.gen_patterns(text, N, m, 8)
+    elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+    dev = torch.device("cuda:0")
+    d_patt = torch.from_numpy(patt).to(dev)
+    d_lo = torch.zeros(N, dtype=torch.int64, device=dev); d_hi = torch.zeros(N, dtype=torch.int64, device=dev)
+    d_off = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    buf = torch.zeros(eocc.size + 8, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for shift in (0, 1, 3):
+        d_occ = buf[shift: shift + eocc.size]
+        tot = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(),
+                             d_occ.data_ptr(), eocc.size, stream)
+        torch.cuda.synchronize()
+        assert tot == eocc.size and np.array_equal(d_occ.cpu().numpy().view(np.uint64), eocc)
+        t = gpu.timing()
+        assert (t["window_ms"] > 0) == (shift == 0)
