@@ -139,19 +139,23 @@ static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64
 //   piece k covers [start[k], start[k+1]);  Phi^J(i) = (i + delta[k]) mod n  for i in piece k.
 // Built by doubling (Phi^2 = Phi o Phi, Phi^4 = Phi^2 o Phi^2, ...): J is a power of two and the
 // number of pieces is sum over runs of min(J, run length) <= min(J*r, n).
-// Device form: one 8-word bucket record per direct-addressed bucket, resolving up to TWO pieces that
-// begin inside the bucket without a second load, + a 2-word entry per piece for crowded buckets:
+// Device form: one 16-word bucket record per direct-addressed bucket (one bucket per piece on average),
+// resolving up to SEED_INLINE pieces that begin inside the bucket without a second load — a hop of the
+// seed pass is a chain of dependent DRAM-latency loads, so the record is sized to make it ONE load —
+// + a 2-word entry per piece for more crowded buckets:
 //   rec[q]   [0] delta of the piece covering the bucket's first position
-//            [1] s1 = start of the first piece beginning inside the bucket (else ~0)   [2] its delta
-//            [3] s2 = start of the second piece beginning inside (else ~0)
-//            [4] nxt = index of the piece starting at s1   [5] cnt = pieces beginning inside   [6,7] 0
+//            [1+2i] s_i = start of the i-th piece beginning inside the bucket (else ~0)   [2+2i] its delta   (i < 6)
+//            [13] nxt = index of the piece starting at s_0   [14] cnt = pieces beginning inside   [15] 0
 //   pent[k]  [0] delta  [1] start
-// query i: i < s1 -> rec[0];  i < s2 -> rec[2];  else the last piece in [nxt+1, nxt+cnt) with start <= i.
+// query v: the last inline piece with s_i <= v (else rec[0]); if cnt > 6 and v >= s_5, the last piece in
+// [nxt+5, nxt+cnt) with start <= v (binary search over pent).
+static const uint32_t SEED_INLINE = 6;
+static const uint32_t SEED_RW = 16;
 struct JumpTable {
     u32 J = 0, shift = 0;
     u64 nbkt = 0;
     std::vector<u64> start, delta;
-    std::vector<u64> rec;   // [nbkt * 8]
+    std::vector<u64> rec;   // [nbkt * SEED_RW]
     std::vector<u64> pent;  // [pieces * 2]
     u64 pieces() const { return start.size(); }
     u64 bytes(bool w32) const { return (rec.size() + pent.size()) * (w32 ? 4 : 8); }
@@ -167,7 +171,7 @@ struct JumpTable {
         while (((n - 1) >> shift) + 1 > target) ++shift;
         nbkt = ((n - 1) >> shift) + 1;
         const u64 P = pieces();
-        rec.assign(nbkt * 8, 0);
+        rec.assign(nbkt * SEED_RW, 0);
         pent.resize(P * 2);
         for (u64 k = 0; k < P; ++k) { pent[2 * k] = delta[k]; pent[2 * k + 1] = start[k]; }
         u64 a = 0;
@@ -176,14 +180,15 @@ struct JumpTable {
             while (a + 1 < P && start[a + 1] <= lo) ++a;
             u64 e = a + 1;
             while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
-            u64* R = &rec[q * 8];
+            u64* R = &rec[q * SEED_RW];
             const u64 cnt = e - (a + 1);
             R[0] = delta[a];
-            R[1] = cnt >= 1 ? start[a + 1] : ~(u64)0;
-            R[2] = cnt >= 1 ? delta[a + 1] : 0;
-            R[3] = cnt >= 2 ? start[a + 2] : ~(u64)0;
-            R[4] = cnt >= 1 ? a + 1 : 0;
-            R[5] = cnt;
+            for (u32 i = 0; i < SEED_INLINE; ++i) {
+                R[1 + 2 * i] = i < cnt ? start[a + 1 + i] : ~(u64)0;
+                R[2 + 2 * i] = i < cnt ? delta[a + 1 + i] : 0;
+            }
+            R[13] = cnt >= 1 ? a + 1 : 0;
+            R[14] = cnt;
         }
     }
 };
@@ -405,15 +410,15 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
 
     // Seed table Phi^SEG for the two-pass expansion (phi_kernels.cuh): requested (reserved[2] = 16..256,
-    // 1 = off), or the largest of {64, 32, 16} whose table (40 B per piece with 32-bit words: one
-    // 32-byte bucket record per piece + an 8-byte piece entry) stays within ~2 GB / a quarter of the
+    // 1 = off), or the largest of {64, 32, 16} whose table (72 B per piece with 32-bit words: one
+    // 64-byte bucket record per piece + an 8-byte piece entry) stays within ~2 GB / a quarter of the
     // caller's byte limit. pieces(Phi^J) = sum over runs of min(J, run length), known before building.
     u32 SEG = opt.reserved[2];
     if (SEG != 0 && SEG != 1 && SEG != 16 && SEG != 32 && SEG != 64 && SEG != 128 && SEG != 256) return RIG_ERR_ARG;
     if (SEG == 0) {
         u64 budget = 2ull << 30;
         if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
-        const u64 per_piece = f.w32 ? 40 : 80;
+        const u64 per_piece = f.w32 ? 72 : 144;
         SEG = 1;
         for (u32 cand : {64u, 32u, 16u}) {
             u64 pieces = 0;

@@ -172,19 +172,22 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
     return v;
 }
 
-// One hop of SEG occurrences: Phi^SEG(v) through the seed table (8-word bucket record resolving up to
-// two pieces that begin inside the bucket; binary search over 2-word piece entries beyond that).
+// One hop of SEG occurrences: Phi^SEG(v) through the seed table (flat_layout.hpp: JumpTable): a 16-word
+// bucket record resolving up to 6 pieces that begin inside the bucket; binary search over 2-word piece
+// entries only in more crowded buckets. The hops of a chain are dependent DRAM-latency loads (the seed
+// table is far larger than L2), so one hop must be one load.
 template <typename WT>
 __device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
     constexpr bool W32 = sizeof(WT) == 4;
-    WT w[8];
-    load_entry<WT, 8, false>(reinterpret_cast<const char*>(ix.seed.rec) + (u64)(v >> ix.seed.shift) * (8 * sizeof(WT)), w);
-    WT d;
-    if (v < w[1]) d = w[0];
-    else if (v < w[3]) d = w[2];
-    else {  // piece nxt+1 starts at s2 <= v: last piece of [nxt+1, nxt+cnt) with start <= v
+    WT w[16];
+    load_entry<WT, 16, false>(reinterpret_cast<const char*>(ix.seed.rec) + (u64)(v >> ix.seed.shift) * (16 * sizeof(WT)), w);
+    WT d = w[0];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (v >= w[1 + 2 * i]) d = w[2 + 2 * i];   // starts ascend; unused slots hold ~0 > v
+    if ((u32)w[14] > 6u && v >= w[11]) {  // piece nxt+5 starts at s_5 <= v: last piece of [nxt+5, nxt+cnt) with start <= v
         const WT* pe = reinterpret_cast<const WT*>(ix.seed.pent);
-        u32 lo = (u32)w[4] + 1, hi = (u32)w[4] + (u32)w[5] - 1;
+        u32 lo = (u32)w[13] + 5, hi = (u32)w[13] + (u32)w[14] - 1;
         while (lo < hi) {
             const u32 mid = (lo + hi + 1) >> 1;
             if (__ldg(pe + 2 * (u64)mid + 1) <= v) lo = mid; else hi = mid - 1;
@@ -196,50 +199,70 @@ __device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
     return x;
 }
 
+#define RIG_LINE 16  // output slots per 128-byte line
+
 // Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]), min(hi,start[j+1]-1)], walked
 // from the top down. Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order (r_index.hpp:340-351).
 //
 // SEEDED = false: the lane produces its whole chain.
-// SEEDED = true : the lane produces the chain up to the first slot that is a multiple of SEG = 1 << seg_shift
-//                 (<= SEG occurrences), then only the occurrences on SEG-aligned slots (one seed_hop each)
-//                 and winfo[slot / SEG] = number of the chain's occurrences that follow the seed inside
-//                 its window (0 .. SEG-1). Every SEG-aligned slot below occ_total lies in exactly one chain,
-//                 so every window gets its seed and its count; phi_window_kernel fills in the rest.
+// SEEDED = true : the lane produces the chain's head up to the next 128-byte line of the output array
+//                 (<= 16 occurrences), then cuts the rest of the chain into ITEMS of SEG = 1 << seg_shift
+//                 slots: per item one seed_hop, the occurrence on the item's first slot (its SEED) and one
+//                 entry (first slot << 8 | occurrences after the seed) in items[]. The chain's K entries are
+//                 reserved up front with ONE atomic per warp (shuffle scan of K), so the reservation's
+//                 latency hides behind the head walk. phi_window_kernel fills in the items.
 template <typename WT, int D, bool KEEP, bool SEEDED>
 __global__ void __launch_bounds__(256)
 phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
                   const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
                   const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains,
-                  uint8_t* __restrict__ winfo, u32 seg_shift) {
+                  u64* __restrict__ items, u64* __restrict__ item_count, u32 seg_shift) {
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= total_chains) return;  // no warp collectives below
-    u64 a = 0, b = N;  // largest p with ch_off[p] <= w
-    while (b - a > 1) {
-        const u64 mid = (a + b) >> 1;
-        if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+    const bool active = w < total_chains;
+    if (!SEEDED && !active) return;
+    u64 g0 = 0, glast = 0, v0 = 0;
+    if (active) {
+        u64 a = 0, b = N;  // largest p with ch_off[p] <= w
+        while (b - a > 1) {
+            const u64 mid = (a + b) >> 1;
+            if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+        }
+        const u64 p = a;
+        const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
+        const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
+        const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
+        const u64 top = min(H, ej), bot = max(L, sj);
+        if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
+        else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
+        g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
+        glast = g0 + (top - bot);             // slot of its last (a chain never exceeds n)
+        __stcs(out + g0, v0);
     }
-    const u64 p = a;
-    const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-    const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-    const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
-    const u64 top = min(H, ej), bot = max(L, sj);
-    u64 v0;
-    if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
-    else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
-    const u64 g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
-    __stcs(out + g0, v0);
     if (!SEEDED) {
-        walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(top - bot));  // a chain never exceeds n
+        walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(glast - g0));
     } else {
         const u64 SEG = 1ull << seg_shift;
-        const u64 glast = g0 + (top - bot);                 // slot of the chain's last occurrence
-        const u64 b1 = (g0 + SEG - 1) & ~(SEG - 1);         // first aligned slot at or after g0
-        const u64 pre_last = min(b1, glast);
+        const u64 a1 = (g0 + RIG_LINE - 1) & ~(u64)(RIG_LINE - 1);  // first line-aligned slot at or after g0
+        const u32 K = (active && a1 <= glast) ? (u32)((glast - a1) >> seg_shift) + 1u : 0u;  // items of this chain
+        // reserve K entries of items[]: inclusive warp scan, one atomic by the last lane
+        const int lane = threadIdx.x & 31;
+        u32 incl = K;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(RIG_FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        u64 wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(item_count, (u64)incl);
+        wbase = __shfl_sync(RIG_FULL, wbase, 31);
+        if (!active) return;
+        const u64 pre_last = min(a1, glast);
         WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
-        if (b1 <= glast) {
-            u64 s = b1;
+        if (K) {
+            u64* it = items + wbase + (incl - K);
+            u64 s = a1;
             for (;;) {
-                winfo[s >> seg_shift] = (uint8_t)min(SEG - 1, glast - s);
+                *it++ = (s << 8) | min(SEG - 1, glast - s);
                 s += SEG;
                 if (s > glast) break;
                 v = seed_hop<WT>(ix, v);
@@ -249,72 +272,142 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
     }
 }
 
-// One lane per SEG-slot window of the occurrence array: v = out[w*SEG] is the window's seed, winfo[w] the
-// number of further occurrences of the same chain inside the window. Each lookup yields Phi^1..Phi^D(v);
-// the lane stores the aligned group [v, Phi(v), .., Phi^(D-1)(v)] (one 32-byte sector for D = 4) and
-// continues from Phi^D(v). Same per-lane state machine and software pipelining as walk_chain.
+// pair access to a staging row (8-byte pairs of u32, 16-byte pairs of u64)
+__device__ __forceinline__ void st_pair(u32* row, u32 pair, u32 a, u32 b) { reinterpret_cast<uint2*>(row)[pair] = make_uint2(a, b); }
+__device__ __forceinline__ void st_pair(u64* row, u32 pair, u64 a, u64 b) { reinterpret_cast<ulonglong2*>(row)[pair] = make_ulonglong2(a, b); }
+__device__ __forceinline__ void ld_pair(const u32* row, u32 pair, u64& a, u64& b) { const uint2 x = reinterpret_cast<const uint2*>(row)[pair]; a = x.x; b = x.y; }
+__device__ __forceinline__ void ld_pair(const u64* row, u32 pair, u64& a, u64& b) { const ulonglong2 x = reinterpret_cast<const ulonglong2*>(row)[pair]; a = x.x; b = x.y; }
+
+__device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
+    // (the .L2::evict_first qualifier is only accepted on 256-bit stores; .cs is the 128-bit streaming form)
+    asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// One lane per item: items[i] = (first slot << 8 | cnt), v = out[first slot] is the item's seed, cnt the number
+// of further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v);
+// the lane emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] and continues from Phi^D(v). Same per-lane
+// state machine and software pipelining as walk_chain.
+//
+// STORES. A lane's groups are 32-byte sectors of its own 128-byte lines, so storing them directly costs one
+// L2 request per sector from 32 different lines per warp instruction — measured: the kernel ran into the
+// L2 tag-lookup rate (lts__t_tag_requests 80%) and the SM's request port (l1tex2xbar 71%), not into bytes.
+// Instead every line that will be complete is STAGED in shared memory (one row per lane, pair-swizzled);
+// at the end of each iteration the warp writes out the rows that became complete, 8 lanes x 16 bytes per
+// line, 4 whole lines per store instruction: one request per 128 bytes. Item heads are line-aligned, so
+// only the last partial line of an item is stored group by group.
 template <typename WT, int D, bool KEEP>
 __global__ void __launch_bounds__(256)
-phi_window_kernel(const FlatDev ix, const uint8_t* __restrict__ winfo, u64* __restrict__ out, u64 windows, u32 seg_shift) {
+phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ item_count,
+                  u64* __restrict__ out) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
     constexpr u32 ESZ = RW * (u32)sizeof(WT);
     constexpr bool W32 = sizeof(WT) == 4;
-    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= windows) return;
-    u32 left = (u32)__ldg(winfo + w) + 1;  // slots of this window still to be written, the seed's included
-    if (left < 2) return;                  // the seed alone: already in place
-    u64* o = out + (w << seg_shift);
-    WT v = (WT)__ldcg(o);
+    constexpr int GPL = RIG_LINE / D;  // groups per line
+    __shared__ __align__(16) WT stage[8][32][RIG_LINE];
+    __shared__ uint8_t sidx[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 sw = lane & 7;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n_items = __ldcg(item_count);
+    u32 left = 0;  // slots of this item still to be written, the seed's included
+    u64* o = out;
+    WT v = 0;
+    if (i < n_items) {
+        const u64 it = __ldcg(items + i);
+        left = (u32)(it & 255u) + 1;
+        o = out + (it >> 8);
+        if (left >= 2) v = (WT)__ldcg(o); else left = 0;  // a seed alone is already in place
+    }
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
-    bool searching = false;
-    u32 slo = 0, shi = 0, probe = 0;
+    bool searching = false, staging = false;
+    u32 slo = 0, shi = 0, probe = 0, fill = 0;  // fill: groups of the current line already staged
     WT e[RW];
-    load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
-    while (left > 1) {
-        bool emit;
-        if (!searching) {
-            emit = v < e[D];
-            slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
-            searching = !emit;
-        } else if (slo == shi) {
-            emit = true;
-        } else if (e[D] <= v) {
-            slo = probe; emit = (slo == shi);
-        } else {
-            shi = probe - 1; emit = false;
-        }
+    if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
+    while (__any_sync(RIG_FULL, left > 1)) {
+        bool emit = false;
         WT g[D];          // the group to store: [v, Phi(v), ..]
         u32 cnt = 0;
         WT vn = v;
-        if (emit) {
-            searching = false;
-            slo = shi = 0;
-            g[0] = v;
-#pragma unroll
-            for (int t = 0; t < D; ++t) {
-                WT x = v + e[t];
-                if ((W32 && x < v) || x >= n) x -= n;
-                if (t < D - 1) g[t + 1] = x; else vn = x;
+        if (left > 1) {
+            if (!searching) {
+                emit = v < e[D];
+                slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+                searching = !emit;
+            } else if (slo == shi) {
+                emit = true;
+            } else if (e[D] <= v) {
+                slo = probe; emit = (slo == shi);
+            } else {
+                shi = probe - 1; emit = false;
             }
-            cnt = min(left, (u32)D);
+            if (emit) {
+                searching = false;
+                slo = shi = 0;
+                g[0] = v;
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    WT x = v + e[t];
+                    if ((W32 && x < v) || x >= n) x -= n;
+                    if (t < D - 1) g[t + 1] = x; else vn = x;
+                }
+                cnt = min(left, (u32)D);
+            }
         }
         const u32 left_next = left - cnt;
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
         if (left_next > 1)
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
+        bool line_full = false;
         if (emit) {
+            if (fill == 0) staging = left >= (u32)RIG_LINE;  // this line will be complete: stage it
             if (cnt == (u32)D) {
-                if (!(ix.pad & 1)) store_group<WT, D>(o, g);
+                if (staging) {
+                    WT* row = &stage[wid][lane][0];
+                    if constexpr (D == 1) {
+                        row[(((fill >> 1) ^ sw) << 1) | (fill & 1)] = g[0];
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < D; t += 2) {
+                            st_pair(row, ((fill * D + t) >> 1) ^ sw, g[t], g[t + 1]);
+                        }
+                    }
+                    ++fill;
+                    line_full = (fill == (u32)GPL);
+                } else if (!(ix.pad & 1)) {
+                    store_group<WT, D>(o, g);
+                }
             } else {
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)
                     if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
             }
             o += cnt;
+        }
+        // ---- write out the lines that became complete in this iteration (warp-cooperative) ----
+        const u32 ready = __ballot_sync(RIG_FULL, line_full);
+        if (ready) {
+            if (line_full) sidx[wid][__popc(ready & ((1u << lane) - 1u))] = (uint8_t)lane;
+            __syncwarp();
+            const u32 nready = __popc(ready);
+            const u64 my_line = (u64)(o - RIG_LINE);  // start of the line this lane just completed (if it did)
+            for (u32 t = 0; t < nready; t += 4) {
+                const u32 k = t + (lane >> 3);
+                const bool act = k < nready;
+                const u32 src = act ? sidx[wid][k] : 0;
+                const u64 dst = __shfl_sync(RIG_FULL, (unsigned long long)my_line, src);
+                if (act && !(ix.pad & 1)) {
+                    const WT* srow = &stage[wid][src][0];
+                    u64 x0, x1;
+                    ld_pair(srow, sw ^ (src & 7), x0, x1);  // this lane writes slots 2*sw, 2*sw+1 of the line
+                    stg128_stream(reinterpret_cast<u64*>(dst) + 2 * sw, x0, x1);
+                }
+            }
+            __syncwarp();
+            if (line_full) fill = 0;
         }
         v = vn;
         left = left_next;

@@ -56,8 +56,8 @@ struct rig_index {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes
     // workspace (grow-only)
-    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, winfo;
-    ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest
+    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items;
+    ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest [6] expansion items
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
@@ -237,7 +237,7 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ, &ix->winfo})
+                      &ix->occoff, &ix->occ, &ix->items})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
@@ -408,30 +408,34 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
             rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
             ix->timing.launches += 1;
         }
-        // Two passes when the index has a seed table and the output array is sector-aligned (the window
-        // kernel's vector stores need it); otherwise the single-pass walk.
+        // Two passes when the index has a seed table and the output array is line-aligned (the window
+        // kernel writes whole 128-byte lines); otherwise the single-pass walk.
         const uint32_t SEG = ix->d.seed.J;
-        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 63) == 0);
+        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
         uint32_t seg_shift = 0;
         while ((1u << seg_shift) < SEG) ++seg_shift;
-        const uint64_t windows = two_pass ? (total + SEG - 1) / SEG : 0;
-        if (two_pass && (rc = ix->winfo.ensure(windows + 16))) return rc;
-        uint8_t* a_winfo = (uint8_t*)ix->winfo.p;
+        // a chain of L occurrences is cut into at most (L - 1) / SEG + 1 items
+        const uint64_t items_max = two_pass ? total / SEG + chains : 0;
+        if (two_pass && (rc = ix->items.ensure((items_max + 32) * 8))) return rc;
+        ull* a_items = (ull*)ix->items.p;
+        ull* a_icount = ix->d_counters + 6;  // zeroed with the other counters at the start of the call
         const int wthreads = 256;
-        const uint64_t wnb = (windows + wthreads - 1) / wthreads;
+        const uint64_t wnb = (items_max + wthreads - 1) / wthreads;
         if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
 #define RIG_EXPAND2(W, DD, KP)                                                                                  \
     do {                                                                                                        \
         if (two_pass) {                                                                                         \
             CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, true>, ix->d, a_N, a_choff,      \
-                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_winfo, seg_shift)); \
+                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
+                                      seg_shift));                                                              \
             if ((rc = rec(ix, 6, st))) return rc;                                                               \
-            rigk::phi_window_kernel<W, DD, KP><<<(unsigned)wnb, wthreads, 0, st>>>(ix->d, a_winfo, d_occ,       \
-                                                                                  windows, seg_shift);        \
+            rigk::phi_window_kernel<W, DD, KP><<<(unsigned)wnb, wthreads, 0, st>>>(ix->d, a_items, a_icount,    \
+                                                                                  d_occ);                     \
             ix->timing.launches += 1;                                                                           \
         } else {                                                                                                \
             CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, false>, ix->d, a_N, a_choff,     \
-                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_winfo, seg_shift)); \
+                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
+                                      seg_shift));                                                              \
         }                                                                                                       \
     } while (0)
 #define RIG_EXPAND(W, DD)                                                                                     \

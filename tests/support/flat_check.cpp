@@ -84,12 +84,12 @@ void phi_lookup(const FlatHost& f, u64 i, u64* e, u64* loads = nullptr) {
 u64 seed_hop(const FlatHost& f, u64 i) {
     const rigf::JumpTable& T = f.seed;
     const u64 mask = f.w32 ? 0xFFFFFFFFull : ~(u64)0;
-    const u64* w = &T.rec[(i >> T.shift) * 8];
-    u64 d;
-    if (i < (w[1] & mask)) d = w[0] & mask;
-    else if (i < (w[3] & mask)) d = w[2] & mask;
-    else {
-        u64 lo = (w[4] & mask) + 1, hi = (w[4] & mask) + (w[5] & mask) - 1;
+    const u64* w = &T.rec[(i >> T.shift) * rigf::SEED_RW];
+    u64 d = w[0] & mask;
+    for (u32 k = 0; k < rigf::SEED_INLINE; ++k)
+        if (i >= (w[1 + 2 * k] & mask)) d = w[2 + 2 * k] & mask;
+    if ((w[14] & mask) > rigf::SEED_INLINE && i >= (w[11] & mask)) {
+        u64 lo = (w[13] & mask) + 5, hi = (w[13] & mask) + (w[14] & mask) - 1;
         while (lo < hi) {
             const u64 mid = (lo + hi + 1) >> 1;
             if ((T.pent[2 * mid + 1] & mask) <= i) lo = mid; else hi = mid - 1;
@@ -126,21 +126,24 @@ u64 walk_chain(const FlatHost& f, u64 v, u64* occ, u64 slot, u64 remaining, bool
     return v;
 }
 
-// mirrors rigk::phi_window_kernel for window w
-void window_fill(const FlatHost& f, u64* occ, const uint8_t* winfo, u64 w) {
+// mirrors rigk::phi_window_kernel for one item (first slot << 8 | occurrences after the seed): groups
+// [v, Phi(v), .., Phi^(D-1)(v)]; whole 16-slot lines are written as lines, the rest group by group
+int item_fill(const FlatHost& f, u64* occ, u64 item) {
     const u32 D = f.phi.D;
-    u64 left = (u64)winfo[w] + 1;
-    if (left < 2) return;
-    u64* o = occ + w * f.seed.J;
-    u64 v = *o, e[8];
+    u64 left = (item & 255) + 1;
+    if (left < 2) return 0;
+    u64 slot = item >> 8;
+    if (slot % 16 != 0) return 1;  // items start on a 128-byte line of the output
+    u64 v = occ[slot], e[8];
     while (left > 1) {
         phi_lookup(f, v, e);
         const u64 cnt = std::min<u64>(left, D);
-        o[0] = v;
-        for (u32 t = 1; t < cnt; ++t) o[t] = e[t - 1];
-        v = e[D - 1]; o += cnt; left -= cnt;
+        occ[slot] = v;
+        for (u32 t = 1; t < cnt; ++t) occ[slot + t] = e[t - 1];
+        v = e[D - 1]; slot += cnt; left -= cnt;
     }
-    if (left == 1) *o = v;
+    if (left == 1) occ[slot] = v;
+    return 0;
 }
 
 // mirrors rigk::search_kernel (one pattern)
@@ -215,9 +218,8 @@ void fc_count(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi) {
 // occ_off must hold N+1 exclusive prefix sums; returns the number of chains.
 uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi, const u64* occ_off, u64* occ) {
     const FlatHost& f = *(FlatHost*)h;
-    u64 chains = 0, seeded = 0;
-    const u64 total = occ_off[N], windows = f.seed.J >= 2 ? (total + f.seed.J - 1) / f.seed.J : 0;
-    std::vector<uint8_t> winfo(windows + 1, 0xEE);
+    u64 chains = 0;
+    std::vector<u64> items;
     for (u64 p = 0; p < N; ++p) {
         u64 k;
         search(f, patt + p * m, m, true, lo[p], hi[p], k);
@@ -236,13 +238,12 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
             if (f.seed.J < 2) {
                 walk_chain(f, v, occ, g0 + 1, top - bot, mis);
             } else {
-                const u64 SEG = f.seed.J, glast = g0 + (top - bot), b1 = (g0 + SEG - 1) / SEG * SEG;
-                v = walk_chain(f, v, occ, g0 + 1, std::min(b1, glast) - g0, mis);
-                if (b1 <= glast) {
-                    u64 sl = b1;
+                const u64 SEG = f.seed.J, glast = g0 + (top - bot), a1 = (g0 + 15) / 16 * 16;
+                v = walk_chain(f, v, occ, g0 + 1, std::min(a1, glast) - g0, mis);
+                if (a1 <= glast) {
+                    u64 sl = a1;
                     for (;;) {
-                        winfo[sl / SEG] = (uint8_t)std::min<u64>(SEG - 1, glast - sl);
-                        ++seeded;
+                        items.push_back((sl << 8) | std::min<u64>(SEG - 1, glast - sl));
                         sl += SEG;
                         if (sl > glast) break;
                         v = seed_hop(f, v);
@@ -254,8 +255,9 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
             ++chains;
         }
     }
-    if (seeded != windows) return ~(u64)0 - 1;  // every window must receive exactly one seed
-    for (u64 w = 0; w < windows; ++w) window_fill(f, occ, winfo.data(), w);
+    if (f.seed.J >= 2 && items.size() > occ_off[N] / f.seed.J + chains) return ~(u64)0 - 1;  // the kernel's buffer bound
+    for (size_t k = items.size(); k-- > 0;)  // any order: items are independent
+        if (item_fill(f, occ, items[k])) return ~(u64)0 - 2;
     return chains;
 }
 
