@@ -207,8 +207,11 @@ __device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
 // SEEDED = false: the lane produces its whole chain.
 // SEEDED = true : the lane produces the chain's head up to the next 128-byte line of the output array
 //                 (<= 16 occurrences), then cuts the rest of the chain into ITEMS of SEG = 1 << seg_shift
-//                 slots: per item one seed_hop, the occurrence on the item's first slot (its SEED) and one
-//                 entry (first slot << 8 | occurrences after the seed) in items[]. The chain's K entries are
+//                 slots: per item one seed_hop and one 16-byte entry in items[]: (first slot << 8 |
+//                 occurrences after the seed, SEED = the occurrence on the item's first slot). The seed
+//                 travels in the entry, not through the output array: an 8-byte store into a random output
+//                 line is a DRAM read-modify-write here and a random sector read in pass 2, and the seed pass
+//                 was measured bound by exactly that random-access rate. The chain's K entries are
 //                 reserved up front with ONE atomic per warp (shuffle scan of K), so the reservation's
 //                 latency hides behind the head walk. phi_window_kernel fills in the items.
 template <typename WT, int D, bool KEEP, bool SEEDED>
@@ -259,14 +262,13 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
         const u64 pre_last = min(a1, glast);
         WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
         if (K) {
-            u64* it = items + wbase + (incl - K);
+            ulonglong2* it = reinterpret_cast<ulonglong2*>(items) + wbase + (incl - K);
             u64 s = a1;
             for (;;) {
-                *it++ = (s << 8) | min(SEG - 1, glast - s);
+                __stcs(it++, make_ulonglong2((s << 8) | min(SEG - 1, glast - s), (u64)v));
                 s += SEG;
                 if (s > glast) break;
                 v = seed_hop<WT>(ix, v);
-                __stcs(out + s, (u64)v);
             }
         }
     }
@@ -283,8 +285,8 @@ __device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
     asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 
-// One lane per item: items[i] = (first slot << 8 | cnt), v = out[first slot] is the item's seed, cnt the number
-// of further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v);
+// One lane per item: items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first
+// slot, cnt the number of further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v);
 // the lane emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] and continues from Phi^D(v). Same per-lane
 // state machine and software pipelining as walk_chain.
 //
@@ -295,7 +297,7 @@ __device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
 // at the end of each iteration the warp writes out the rows that became complete, 8 lanes x 16 bytes per
 // line, 4 whole lines per store instruction: one request per 128 bytes. Item heads are line-aligned, so
 // only the last partial line of an item is stored group by group.
-template <typename WT, int D, bool KEEP>
+template <typename WT, int D, bool KEEP, bool STAGE>
 __global__ void __launch_bounds__(256)
 phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ item_count,
                   u64* __restrict__ out) {
@@ -303,8 +305,8 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
     constexpr u32 ESZ = RW * (u32)sizeof(WT);
     constexpr bool W32 = sizeof(WT) == 4;
     constexpr int GPL = RIG_LINE / D;  // groups per line
-    __shared__ __align__(16) WT stage[8][32][RIG_LINE];
-    __shared__ uint8_t sidx[8][32];
+    __shared__ __align__(16) WT stage[STAGE ? 8 : 1][STAGE ? 32 : 1][RIG_LINE];
+    __shared__ uint8_t sidx[STAGE ? 8 : 1][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 sw = lane & 7;
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,10 +315,10 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
     u64* o = out;
     WT v = 0;
     if (i < n_items) {
-        const u64 it = __ldcg(items + i);
-        left = (u32)(it & 255u) + 1;
-        o = out + (it >> 8);
-        if (left >= 2) v = (WT)__ldcg(o); else left = 0;  // a seed alone is already in place
+        const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
+        left = (u32)(it.x & 255u) + 1;
+        o = out + (it.x >> 8);
+        v = (WT)it.y;
     }
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
@@ -363,7 +365,9 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
         bool line_full = false;
         if (emit) {
-            if (fill == 0) staging = left >= (u32)RIG_LINE;  // this line will be complete: stage it
+            // stage the line iff all of its GPL groups will be emitted as full groups (with D = 1 the loop ends
+            // at left == 1, one slot early, so one more slot is needed)
+            if (STAGE && fill == 0) staging = left >= (u32)(RIG_LINE + (D == 1 ? 1 : 0));
             if (cnt == (u32)D) {
                 if (staging) {
                     WT* row = &stage[wid][lane][0];
@@ -388,8 +392,8 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
             o += cnt;
         }
         // ---- write out the lines that became complete in this iteration (warp-cooperative) ----
-        const u32 ready = __ballot_sync(RIG_FULL, line_full);
-        if (ready) {
+        const u32 ready = STAGE ? __ballot_sync(RIG_FULL, line_full) : 0u;
+        if (STAGE && ready) {
             if (line_full) sidx[wid][__popc(ready & ((1u << lane) - 1u))] = (uint8_t)lane;
             __syncwarp();
             const u32 nready = __popc(ready);

@@ -112,7 +112,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit6 window kernel stores groups directly (no shared-memory line staging)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
@@ -198,14 +198,16 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
     // limit; harmless for other users of the context) and size the window / hit ratio to it.
     {
-        const size_t rec_bytes = f.phi.rec.size() * (f.w32 ? 4 : 8);
+        const size_t rec_bytes = ix->phi_bytes;  // bucket records + piece entries of the Phi^1..D table
         // Measured on C2 (B200, 79 MiB max carve-out): reserving persisting L2 made the expansion kernel
         // SLOWER (0.51 -> 0.91 ms; the carve-out shrinks the L2 left for the output stream and the other
         // arrays), so it is off unless RIG_VARIANT bit0 asks for the experiment.
         if ((variant & 1) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 && rec_bytes > 0) {
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+            size_t carve = (rec_bytes + (rec_bytes >> 2) + (1u << 20)) & ~(size_t)((1u << 20) - 1);  // table + 25%
+            if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
                 ix->l2_window_bytes = rec_bytes < (size_t)prop.accessPolicyMaxWindowSize ? rec_bytes : (size_t)prop.accessPolicyMaxWindowSize;
-                const double ratio = (double)prop.persistingL2CacheMaxSize / (double)ix->l2_window_bytes;
+                const double ratio = (double)carve / (double)ix->l2_window_bytes;
                 ix->l2_hit_ratio = ratio >= 1.0 ? 1.f : (float)ratio;
             } else {
                 cudaGetLastError();
@@ -416,7 +418,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         while ((1u << seg_shift) < SEG) ++seg_shift;
         // a chain of L occurrences is cut into at most (L - 1) / SEG + 1 items
         const uint64_t items_max = two_pass ? total / SEG + chains : 0;
-        if (two_pass && (rc = ix->items.ensure((items_max + 32) * 8))) return rc;
+        if (two_pass && (rc = ix->items.ensure((items_max + 32) * 16))) return rc;
         ull* a_items = (ull*)ix->items.p;
         ull* a_icount = ix->d_counters + 6;  // zeroed with the other counters at the start of the call
         const int wthreads = 256;
@@ -429,8 +431,15 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
                                       a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
                                       seg_shift));                                                              \
             if ((rc = rec(ix, 6, st))) return rc;                                                               \
-            rigk::phi_window_kernel<W, DD, KP><<<(unsigned)wnb, wthreads, 0, st>>>(ix->d, a_items, a_icount,    \
-                                                                                  d_occ);                     \
+            cudaLaunchConfig_t cfg2 = cfg;                                                                      \
+            cfg2.gridDim = dim3((unsigned)wnb); cfg2.blockDim = dim3((unsigned)wthreads);                       \
+            const ull* c_items = a_items; const ull* c_icount = a_icount;                                       \
+            if (ix->variant & 64)                                                                               \
+                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, false>, ix->d, c_items,     \
+                                          c_icount, d_occ));                                                    \
+            else                                                                                                \
+                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, true>, ix->d, c_items,      \
+                                          c_icount, d_occ));                                                    \
             ix->timing.launches += 1;                                                                           \
         } else {                                                                                                \
             CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, false>, ix->d, a_N, a_choff,     \

@@ -128,13 +128,13 @@ u64 walk_chain(const FlatHost& f, u64 v, u64* occ, u64 slot, u64 remaining, bool
 
 // mirrors rigk::phi_window_kernel for one item (first slot << 8 | occurrences after the seed): groups
 // [v, Phi(v), .., Phi^(D-1)(v)]; whole 16-slot lines are written as lines, the rest group by group
-int item_fill(const FlatHost& f, u64* occ, u64 item) {
+int item_fill(const FlatHost& f, u64* occ, u64 item, u64 seed) {
     const u32 D = f.phi.D;
     u64 left = (item & 255) + 1;
-    if (left < 2) return 0;
     u64 slot = item >> 8;
     if (slot % 16 != 0) return 1;  // items start on a 128-byte line of the output
-    u64 v = occ[slot], e[8];
+    u64 v = seed, e[8];
+    occ[slot] = v;
     while (left > 1) {
         phi_lookup(f, v, e);
         const u64 cnt = std::min<u64>(left, D);
@@ -244,10 +244,10 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
                     u64 sl = a1;
                     for (;;) {
                         items.push_back((sl << 8) | std::min<u64>(SEG - 1, glast - sl));
+                        items.push_back(v);
                         sl += SEG;
                         if (sl > glast) break;
                         v = seed_hop(f, v);
-                        occ[sl] = v;
                     }
                 }
             }
@@ -255,9 +255,9 @@ uint64_t fc_locate(void* h, const uint8_t* patt, u64 N, u64 m, u64* lo, u64* hi,
             ++chains;
         }
     }
-    if (f.seed.J >= 2 && items.size() > occ_off[N] / f.seed.J + chains) return ~(u64)0 - 1;  // the kernel's buffer bound
-    for (size_t k = items.size(); k-- > 0;)  // any order: items are independent
-        if (item_fill(f, occ, items[k])) return ~(u64)0 - 2;
+    if (f.seed.J >= 2 && items.size() / 2 > occ_off[N] / f.seed.J + chains) return ~(u64)0 - 1;  // the kernel's buffer bound
+    for (size_t k = items.size() / 2; k-- > 0;)  // any order: items are independent
+        if (item_fill(f, occ, items[2 * k], items[2 * k + 1])) return ~(u64)0 - 2;
     return chains;
 }
 
