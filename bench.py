@@ -48,6 +48,10 @@ WORKLOADS = {
             "C5 scaled to 400MB (1000 copies): Phi-chain stress, ~1k occ/pattern"),
     "c3s": ("versioned_doc", 200_000_000, 25_000, 96, 0xB2000003, 200_000, 30, 0xB2001003, 0,
             "C3 scaled to 200MB: einstein-like sigma=96 versioned document, 200k len-30 patterns"),
+    "c3": ("versioned_doc", 1_000_000_000, 25_000, 96, 0xB2000003, 125_000, 30, 0xB2001003, 0,
+           "C3 ri-locate at FULL size: 1 GB einstein-like sigma=96 versioned document; 125k len-30 patterns per GPU (the 1M patterns of the config sharded 8x)"),
+    "c5": ("dna_indep", 4_000_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
+           "C5 ri-locate at FULL size: 4 GB synthetic DNA sigma=4, 10k copies, ~10k occ/pattern, 100k len-15 patterns (n > 2^32: 64-bit words)"),
     "c4s": ("pangenome", 1_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_000_000, 100, 0xB2001004, 0,
             "C4 scaled to 1GB: synthetic pan-genome sigma=5 (100 haplotypes), 1M len-100 reads (count; index >> L2)"),
 }

@@ -286,27 +286,34 @@ __device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
 }
 
 // One lane per item: items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first
-// slot, cnt the number of further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v);
-// the lane emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] and continues from Phi^D(v). Same per-lane
-// state machine and software pipelining as walk_chain.
+// slot, cnt the number of further occurrences of the same chain that the item covers (< SEG). Each lookup
+// yields Phi^1..Phi^D(v); the lane emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] and continues from
+// Phi^D(v). Same per-lane state machine and software pipelining as walk_chain.
 //
-// STORES. A lane's groups are 32-byte sectors of its own 128-byte lines, so storing them directly costs one
-// L2 request per sector from 32 different lines per warp instruction — measured: the kernel ran into the
-// L2 tag-lookup rate (lts__t_tag_requests 80%) and the SM's request port (l1tex2xbar 71%), not into bytes.
-// Instead every line that will be complete is STAGED in shared memory (one row per lane, pair-swizzled);
-// at the end of each iteration the warp writes out the rows that became complete, 8 lanes x 16 bytes per
-// line, 4 whole lines per store instruction: one request per 128 bytes. Item heads are line-aligned, so
-// only the last partial line of an item is stored group by group.
-template <typename WT, int D, bool KEEP, bool STAGE>
-__global__ void __launch_bounds__(256)
+// STORES. A lane's groups are 32-byte sectors of its own 128-byte lines; stored directly (STAGE = false, the
+// default) they cost one L2 request per sector, and the kernel runs at the L2 tag-lookup rate
+// (lts__t_tag_requests 80%) and the SM's request port (l1tex2xbar 72%: one load request or one 32-byte store
+// payload per cycle), not at a byte rate. STAGE = true is the measured alternative (RIG_VARIANT bit 6): every
+// line that will be complete is staged in shared memory (two rows per lane, pair-swizzled; a lane emits at
+// most one group per trip, so between two flushes it completes at most one row and starts the other) and
+// every FLUSH_TRIPS trips the warp writes out the completed rows, 8 lanes x 16 bytes per line, 4 whole
+// lines per store instruction. That halves the tag requests (80% -> 37%) but the store payload through the
+// request port is unchanged and the extra instructions (+70%) make it issue-bound: 0.33 ms vs 0.27 ms on C2,
+// 1.93 vs 1.79 ms on C3s. Kept for the record, off by default.
+template <typename WT, int D, bool KEEP, bool STAGE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ item_count,
                   u64* __restrict__ out) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
     constexpr u32 ESZ = RW * (u32)sizeof(WT);
     constexpr bool W32 = sizeof(WT) == 4;
     constexpr int GPL = RIG_LINE / D;  // groups per line
-    __shared__ __align__(16) WT stage[STAGE ? 8 : 1][STAGE ? 32 : 1][RIG_LINE];
-    __shared__ uint8_t sidx[STAGE ? 8 : 1][32];
+    // a lane emits at most one group per trip: with a flush every <= GPL trips it cannot complete a second row
+    // while one is pending (4 trips = one row per lane in lockstep for D = 4)
+    constexpr u32 FLUSH_TRIPS = GPL < 4 ? GPL : 4;
+    static_assert(FLUSH_TRIPS <= GPL && (FLUSH_TRIPS & (FLUSH_TRIPS - 1)) == 0, "flush period");
+    __shared__ __align__(16) WT stage[STAGE ? WARPS : 1][STAGE ? 2 : 1][STAGE ? 32 : 1][RIG_LINE];
+    __shared__ uint8_t sidx[STAGE ? WARPS : 1][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 sw = lane & 7;
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,11 +331,38 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
-    bool searching = false, staging = false;
-    u32 slo = 0, shi = 0, probe = 0, fill = 0;  // fill: groups of the current line already staged
+    bool searching = false, staging = false, pending = false;  // pending: row cur^1 is complete, not yet written out
+    u32 slo = 0, shi = 0, probe = 0, fill = 0, cur = 0, trip = 0;  // fill: groups staged in row cur
+    u64* pend_line = out;
     WT e[RW];
     if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
-    while (__any_sync(RIG_FULL, left > 1)) {
+    for (;;) {
+        const bool more = __any_sync(RIG_FULL, left > 1);
+        // ---- write out completed rows: every FLUSH_TRIPS trips and once at the end (warp-uniform) ----
+        if (STAGE && (!more || (trip & (FLUSH_TRIPS - 1)) == FLUSH_TRIPS - 1)) {
+            const u32 ready = __ballot_sync(RIG_FULL, pending);
+            if (ready) {
+                if (pending) sidx[wid][__popc(ready & ((1u << lane) - 1u))] = (uint8_t)(lane | ((cur ^ 1u) << 5));
+                __syncwarp();
+                const u32 nready = __popc(ready);
+                for (u32 t = 0; t < nready; t += 4) {
+                    const u32 k = t + (lane >> 3);
+                    const bool act = k < nready;
+                    const u32 sx = act ? sidx[wid][k] : 0u;
+                    const u32 src = sx & 31u;
+                    const u64 dst = __shfl_sync(RIG_FULL, (unsigned long long)pend_line, src);
+                    if (act && !(ix.pad & 1)) {
+                        u64 x0, x1;
+                        ld_pair(&stage[wid][sx >> 5][src][0], sw ^ (src & 7), x0, x1);  // slots 2*sw, 2*sw+1 of the line
+                        stg128_stream(reinterpret_cast<u64*>(dst) + 2 * sw, x0, x1);
+                    }
+                }
+                __syncwarp();
+                pending = false;
+            }
+        }
+        if (!more) break;
+        ++trip;
         bool emit = false;
         WT g[D];          // the group to store: [v, Phi(v), ..]
         u32 cnt = 0;
@@ -363,24 +397,24 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
         WT e2[RW];
         if (left_next > 1)
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
-        bool line_full = false;
         if (emit) {
             // stage the line iff all of its GPL groups will be emitted as full groups (with D = 1 the loop ends
             // at left == 1, one slot early, so one more slot is needed)
             if (STAGE && fill == 0) staging = left >= (u32)(RIG_LINE + (D == 1 ? 1 : 0));
             if (cnt == (u32)D) {
-                if (staging) {
-                    WT* row = &stage[wid][lane][0];
+                if (STAGE && staging) {
+                    WT* row = &stage[wid][cur][lane][0];
                     if constexpr (D == 1) {
                         row[(((fill >> 1) ^ sw) << 1) | (fill & 1)] = g[0];
                     } else {
 #pragma unroll
-                        for (int t = 0; t < D; t += 2) {
+                        for (int t = 0; t < D; t += 2)
                             st_pair(row, ((fill * D + t) >> 1) ^ sw, g[t], g[t + 1]);
-                        }
                     }
-                    ++fill;
-                    line_full = (fill == (u32)GPL);
+                    if (++fill == (u32)GPL) {  // row complete: hand it to the next flush, continue in the other row
+                        fill = 0; cur ^= 1u; pending = true;
+                        pend_line = o + D - RIG_LINE;
+                    }
                 } else if (!(ix.pad & 1)) {
                     store_group<WT, D>(o, g);
                 }
@@ -390,28 +424,6 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
                     if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
             }
             o += cnt;
-        }
-        // ---- write out the lines that became complete in this iteration (warp-cooperative) ----
-        const u32 ready = STAGE ? __ballot_sync(RIG_FULL, line_full) : 0u;
-        if (STAGE && ready) {
-            if (line_full) sidx[wid][__popc(ready & ((1u << lane) - 1u))] = (uint8_t)lane;
-            __syncwarp();
-            const u32 nready = __popc(ready);
-            const u64 my_line = (u64)(o - RIG_LINE);  // start of the line this lane just completed (if it did)
-            for (u32 t = 0; t < nready; t += 4) {
-                const u32 k = t + (lane >> 3);
-                const bool act = k < nready;
-                const u32 src = act ? sidx[wid][k] : 0;
-                const u64 dst = __shfl_sync(RIG_FULL, (unsigned long long)my_line, src);
-                if (act && !(ix.pad & 1)) {
-                    const WT* srow = &stage[wid][src][0];
-                    u64 x0, x1;
-                    ld_pair(srow, sw ^ (src & 7), x0, x1);  // this lane writes slots 2*sw, 2*sw+1 of the line
-                    stg128_stream(reinterpret_cast<u64*>(dst) + 2 * sw, x0, x1);
-                }
-            }
-            __syncwarp();
-            if (line_full) fill = 0;
         }
         v = vn;
         left = left_next;

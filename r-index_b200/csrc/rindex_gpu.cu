@@ -112,7 +112,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit6 window kernel stores groups directly (no shared-memory line staging)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
@@ -421,7 +421,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         if (two_pass && (rc = ix->items.ensure((items_max + 32) * 16))) return rc;
         ull* a_items = (ull*)ix->items.p;
         ull* a_icount = ix->d_counters + 6;  // zeroed with the other counters at the start of the call
-        const int wthreads = 256;
+        const int wthreads = w32 ? 256 : 128;  // 32 KB of staging rows per block either way
         const uint64_t wnb = (items_max + wthreads - 1) / wthreads;
         if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
 #define RIG_EXPAND2(W, DD, KP)                                                                                  \
@@ -434,11 +434,12 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
             cudaLaunchConfig_t cfg2 = cfg;                                                                      \
             cfg2.gridDim = dim3((unsigned)wnb); cfg2.blockDim = dim3((unsigned)wthreads);                       \
             const ull* c_items = a_items; const ull* c_icount = a_icount;                                       \
-            if (ix->variant & 64)                                                                               \
-                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, false>, ix->d, c_items,     \
+            constexpr int WW = sizeof(W) == 4 ? 8 : 4;                                                          \
+            if (!(ix->variant & 64))                                                                            \
+                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, false, WW>, ix->d, c_items, \
                                           c_icount, d_occ));                                                    \
             else                                                                                                \
-                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, true>, ix->d, c_items,      \
+                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, true, WW>, ix->d, c_items,  \
                                           c_icount, d_occ));                                                    \
             ix->timing.launches += 1;                                                                           \
         } else {                                                                                                \
