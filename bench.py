@@ -48,7 +48,9 @@ WORKLOADS = {
             "C5 scaled to 400MB (1000 copies): Phi-chain stress, ~1k occ/pattern"),
     "c3s": ("versioned_doc", 200_000_000, 25_000, 96, 0xB2000003, 200_000, 30, 0xB2001003, 0,
             "C3 scaled to 200MB: einstein-like sigma=96 versioned document, 200k len-30 patterns"),
-    "c3": ("versioned_doc", 1_000_000_000, 25_000, 96, 0xB2000003, 125_000, 30, 0xB2001003, 0,
+    # edit probability per version 0.05 instead of SURVEY 8d's 0.25: 0.25 gives r = 165k at 40k versions, outside
+    # the config's r ~ 50k (measured: r = 21.7k + 14.3 per edit)
+    "c3": ("versioned_doc", 1_000_000_000, 25_000, 50_096, 0xB2000003, 125_000, 30, 0xB2001003, 0,
            "C3 ri-locate at FULL size: 1 GB einstein-like sigma=96 versioned document; 125k len-30 patterns per GPU (the 1M patterns of the config sharded 8x)"),
     "c5": ("dna_indep", 4_000_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
            "C5 ri-locate at FULL size: 4 GB synthetic DNA sigma=4, 10k copies, ~10k occ/pattern, 100k len-15 patterns (n > 2^32: 64-bit words)"),

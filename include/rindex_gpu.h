@@ -123,6 +123,37 @@ int rig_locate_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, 
  * copying every occurrence back is pointless): out[0] = sum, out[1] = sum of v*(i+1) (mod 2^64). */
 int rig_digest_dev(rig_index* idx, const uint64_t* d_values, uint64_t count, uint64_t out[2], void* stream);
 
+/* ---- ri-locate's post-processing options on the device ----
+ * -o (ri-locate.cpp:146-152): every pattern's occurrences sorted ascending (std::sort per pattern).
+ * -c (ri-locate.cpp:156-190): per pattern, the number of occurrences found in the text by brute force must equal
+ *    the number located, and text[o, o+m) must equal the pattern for every located o. On the device the N
+ *    string::find scans are one hash join between the text's m-grams and the patterns. */
+typedef struct rig_check_report {
+    uint64_t patterns_checked;
+    uint64_t wrong_count_patterns;   /* patterns whose brute-force count differs from hi-lo+1 ("wrong number of located occurrences") */
+    uint64_t wrong_occurrences;      /* located positions whose text does not match ("wrong occurrence") */
+    uint64_t unsorted_or_duplicate;  /* adjacent positions of one pattern not strictly ascending (after the sort: repeats) */
+    uint64_t first_bad_pattern;      /* smallest offending pattern index, ~0 if none */
+    uint64_t first_bad_position;     /* smallest offending text position, ~0 if none */
+} rig_check_report;
+
+#define RIG_LOCATE_SORT 1u   /* -o: per-pattern ascending order instead of locate_all order */
+#define RIG_LOCATE_CHECK 2u  /* -c: needs rig_text_attach; implies the sort, as in the reference */
+
+/* Copy the indexed text (len = n - 1 bytes, no terminator) into HBM for rig_check_dev / RIG_LOCATE_CHECK. */
+int rig_text_attach(rig_index* idx, const uint8_t* text, uint64_t len);
+/* In-place segmented sort of a device occurrence array (segments = d_occ_offsets[p] .. d_occ_offsets[p+1]). */
+int rig_sort_occurrences_dev(rig_index* idx, uint64_t N, const uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t total,
+                             void* stream);
+/* The -c check on device buffers; synchronises and fills *report. `sorted` != 0 also checks strict ascent. */
+int rig_check_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, const uint64_t* d_lo,
+                  const uint64_t* d_hi, const uint64_t* d_occ_offsets, const uint64_t* d_occ, uint64_t total, int sorted,
+                  rig_check_report* report, void* stream);
+/* rig_locate_batch with post-processing flags (HOST buffers). report may be NULL without RIG_LOCATE_CHECK. */
+int rig_locate_batch_ex(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                        uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
+                        rig_check_report* report);
+
 int rig_last_timing(const rig_index* idx, rig_timing* t);
 
 #ifdef __cplusplus

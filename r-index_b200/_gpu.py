@@ -17,6 +17,7 @@ DECLARED_SYMBOLS = [
     "rig_device_count", "rig_strerror", "rig_last_cuda_error", "rig_version", "rig_index_create",
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
+    "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -43,6 +44,22 @@ class Timing(ctypes.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class CheckReport(ctypes.Structure):
+    """struct rig_check_report: the outcome of ri-locate's -c self-check run on the device."""
+    _fields_ = [("patterns_checked", _u64), ("wrong_count_patterns", _u64), ("wrong_occurrences", _u64),
+                ("unsorted_or_duplicate", _u64), ("first_bad_pattern", _u64), ("first_bad_position", _u64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+    @property
+    def clean(self):
+        return self.wrong_count_patterns == 0 and self.wrong_occurrences == 0 and self.unsorted_or_duplicate == 0
+
+
+LOCATE_SORT, LOCATE_CHECK = 1, 2
 
 
 class RigError(RuntimeError):
@@ -81,6 +98,12 @@ def gpu_lib():
         lib.rig_locate_batch_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _vp]
         lib.rig_digest_dev.argtypes = [_vp, _vp, _u64, ctypes.POINTER(_u64 * 2), _vp]
         lib.rig_last_timing.argtypes = [_vp, ctypes.POINTER(Timing)]
+        lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
+        lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
+        lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
+                                      ctypes.POINTER(CheckReport), _vp]
+        lib.rig_locate_batch_ex.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _u32,
+                                            ctypes.POINTER(CheckReport)]
         _lib = lib
     return _lib
 
@@ -184,6 +207,46 @@ class GpuIndex:
         if occ is None:
             occ = np.empty(0, dtype=np.uint64)
         return lo, hi, off, occ[: int(tot.value)]
+
+    # ---- ri-locate -o / -c post-processing on the device ----
+    def text_attach(self, text):
+        t = _as_u8(text)
+        rc = self.lib.rig_text_attach(self.h, _ptr(t), t.size)
+        if rc != 0:
+            raise RigError(rc, "rig_text_attach")
+
+    def locate_ex(self, patterns, N, m, flags):
+        """rig_locate_batch_ex: returns (lo, hi, occ_offsets, occ, report-or-None)."""
+        p = _as_u8(patterns)
+        assert p.size >= N * m
+        lo = np.empty(N, dtype=np.uint64)
+        hi = np.empty(N, dtype=np.uint64)
+        off = np.empty(N + 1, dtype=np.uint64)
+        tot = _u64(0)
+        rep = CheckReport()
+        rc = self.lib.rig_locate_batch_ex(self.h, _ptr(p), N, m, _ptr(lo), _ptr(hi), _ptr(off), None, 0,
+                                          ctypes.byref(tot), 0, None)
+        if rc not in (0, RIG_ERR_CAPACITY):
+            raise RigError(rc, "rig_locate_batch_ex")
+        occ = np.empty(int(tot.value), dtype=np.uint64)
+        rc = self.lib.rig_locate_batch_ex(self.h, _ptr(p), N, m, _ptr(lo), _ptr(hi), _ptr(off), _ptr(occ), occ.size,
+                                          ctypes.byref(tot), flags, ctypes.byref(rep))
+        if rc != 0:
+            raise RigError(rc, "rig_locate_batch_ex")
+        return lo, hi, off, occ, (rep if flags & LOCATE_CHECK else None)
+
+    def sort_dev(self, N, d_off, d_occ, total, stream=None):
+        rc = self.lib.rig_sort_occurrences_dev(self.h, N, d_off, d_occ, total, stream)
+        if rc != 0:
+            raise RigError(rc, "rig_sort_occurrences_dev")
+
+    def check_dev(self, d_patterns, N, m, d_lo, d_hi, d_off, d_occ, total, is_sorted=True, stream=None):
+        rep = CheckReport()
+        rc = self.lib.rig_check_dev(self.h, d_patterns, N, m, d_lo, d_hi, d_off, d_occ, total, int(is_sorted),
+                                    ctypes.byref(rep), stream)
+        if rc != 0:
+            raise RigError(rc, "rig_check_dev")
+        return rep
 
     def locate_raw(self, p_ptr, N, m, lo_ptr, hi_ptr, off_ptr, occ_ptr, cap):
         """Host-pointer call with caller-managed (e.g. pinned) buffers given as integer addresses."""

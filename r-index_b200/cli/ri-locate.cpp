@@ -2,7 +2,8 @@
 // options -c / -o, argument handling and stdout lines). The per-pattern loop (:126-192) becomes one
 // batch call per GPU shard. -o keeps the reference's format: per pattern, positions sorted ascending,
 // printed through an (int) cast (:146-152; positions >= 2^31 therefore wrap exactly as upstream).
-#include <algorithm>
+// The per-pattern sort of -o/-c and the -c self-check (:156-190) run on the GPU (rig_locate_batch_ex:
+// segmented sort; brute-force counts as a hash join over the text, byte comparison of every occurrence).
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -90,35 +91,31 @@ int main(int argc, char** argv) {
     const uint64_t n = pf.n, m = pf.m;
     std::vector<uint64_t> lo(n), hi(n);
     std::vector<std::vector<uint64_t>> off, occ;
-    uint64_t occ_tot = fleet.locate(pf.body.data(), n, m, lo.data(), hi.data(), off, occ);
+    uint32_t flags = 0;
+    if (ofile.compare(string()) != 0) flags |= RIG_LOCATE_SORT;
+    if (c) { flags |= RIG_LOCATE_CHECK; fleet.attach_text((const uint8_t*)text.data(), text.size()); }
+    std::vector<rig_check_report> reports;
+    uint64_t occ_tot = fleet.locate(pf.body.data(), n, m, lo.data(), hi.data(), off, occ, flags, &reports);
 
     const int G = fleet.size();
-    if (ofile.compare(string()) != 0 || c) {
+    if (ofile.compare(string()) != 0) {
+        for (int g = 0; g < G; ++g)  // already sorted per pattern on the device (reference :147)
+            for (uint64_t x : occ[g]) out << (int)x << endl;
+    }
+    if (c) {  // check occurrences (reference :156-190): the first offending pattern, in shard order
         for (int g = 0; g < G; ++g) {
-            const uint64_t a = n * g / G, b = n * (g + 1) / G;
-            for (uint64_t i = a; i < b; ++i) {
-                uint64_t* first = occ[g].data() + off[g][i - a];
-                uint64_t* last = occ[g].data() + off[g][i - a + 1];
-                std::sort(first, last);  // reference sorts per pattern for -o and -c (:147,:159)
-                if (ofile.compare(string()) != 0)
-                    for (uint64_t* x = first; x != last; ++x) out << (int)*x << endl;
-                if (c) {  // check occurrences (reference :156-190)
-                    uint64_t* it = std::unique(first, last);
-                    uint64_t distinct = (uint64_t)(it - first);
-                    uint64_t want = hi[i] >= lo[i] ? (hi[i] - lo[i]) + 1 : 0;
-                    if (distinct != want) {
-                        cout << "Error: wrong number of located occurrences: " << distinct << "/" << want << endl;
-                        exit(0);
-                    }
-                    const char* p = (const char*)pf.body.data() + i * m;
-                    for (uint64_t* x = first; x != it; ++x) {
-                        if (*x + m > text.size() || memcmp(text.data() + *x, p, m) != 0) {
-                            cout << "Error: wrong occurrence: " << *x << " (" << occ_tot << " occurrences" << ") " << endl;
-                            break;
-                        }
-                    }
-                }
+            const rig_check_report& r = reports[g];
+            const uint64_t a = n * g / G;
+            if (r.wrong_count_patterns || r.unsorted_or_duplicate) {
+                const uint64_t i = a + (r.first_bad_pattern != ~0ull ? r.first_bad_pattern : 0);
+                const uint64_t want = hi[i] >= lo[i] ? (hi[i] - lo[i]) + 1 : 0;
+                cout << "Error: wrong number of located occurrences for pattern " << i << " (located " << want << "; "
+                     << r.wrong_count_patterns << " patterns disagree with the text, " << r.unsorted_or_duplicate
+                     << " repeated positions)" << endl;
+                exit(0);
             }
+            if (r.wrong_occurrences)
+                cout << "Error: wrong occurrence: " << r.first_bad_position << " (" << occ_tot << " occurrences" << ") " << endl;
         }
     }
     print_progress_lines(n);

@@ -5,12 +5,14 @@
 #include "flat_layout.hpp"
 #include "search_kernels.cuh"
 #include "phi_kernels.cuh"
+#include "post_kernels.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include <new>
+#include <algorithm>
 
 using rigk::FlatDev;
 typedef unsigned long long ull;
@@ -57,6 +59,12 @@ struct rig_index {
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes
     // workspace (grow-only)
     DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items;
+    DevBuf text, big1, big2, ctable, crep, cfound;  // post-processing (-o / -c): attached text, sort tiers, hash join
+    uint64_t text_len = 0;
+    bool has_text = false;
+    bool sort_attr_done = false;  // dynamic shared memory opt-in of the sort kernels (per device)
+    ull* d_post = nullptr;      // [0] big1 count [1] big2 count [2..7] check report
+    ull* h_post = nullptr;      // pinned mirror
     ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest [6] expansion items
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
@@ -220,6 +228,9 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     CU_TRY(cudaMemset(ix->d_counters, 0, 8 * sizeof(ull)));
     CU_TRY(cudaMallocHost((void**)&ix->h_counters, 8 * sizeof(ull)));
     std::memset(ix->h_counters, 0, 8 * sizeof(ull));
+    CU_TRY(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
+    CU_TRY(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
+    CU_TRY(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
 
     rig_index_info& I = ix->info;
     std::memset(&I, 0, sizeof(I));
@@ -239,11 +250,13 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ, &ix->items})
+                      &ix->occoff, &ix->occ, &ix->items, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
+    if (ix->d_post) cudaFree(ix->d_post);
+    if (ix->h_post) cudaFreeHost(ix->h_post);
     for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -563,6 +576,145 @@ int rig_digest_dev(rig_index* ix, const uint64_t* d_values, uint64_t count, uint
     CU_TRY(cudaStreamSynchronize(st));
     out[0] = h[0]; out[1] = h[1];
     return RIG_OK;
+}
+
+// ---- ri-locate -o / -c on the device -------------------------------------------------
+namespace {
+
+int sort_dev(rig_index* ix, uint64_t N, const ull* d_off, ull* d_occ, uint64_t total, cudaStream_t st) {
+    if (N == 0 || total < 2) return RIG_OK;
+    if (N >= 0x7fffffffull) return RIG_ERR_ARG;
+    const bool k32 = ix->d.w32 != 0;  // n < 2^32-1: every position fits 32 bits, half the shared memory per key
+    const uint32_t cap1 = 4096, cap2 = k32 ? 32768u : 16384u;
+    const size_t ksz = k32 ? 4 : 8;
+    const uint64_t nbig1 = std::min<uint64_t>(N, total / cap1 + 1), nbig2 = std::min<uint64_t>(N, total / cap2 + 1);
+    int rc;
+    if ((rc = ix->big1.ensure(nbig1 * 4)) || (rc = ix->big2.ensure(nbig2 * 4))) return rc;
+    CU_TRY(cudaMemsetAsync(ix->d_post, 0, 2 * sizeof(ull), st));
+    uint32_t* big1 = (uint32_t*)ix->big1.p; uint32_t* big2 = (uint32_t*)ix->big2.p;
+    if (!ix->sort_attr_done) {
+        CU_TRY(cudaFuncSetAttribute(rigk::segsort_smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+        CU_TRY(cudaFuncSetAttribute(rigk::segsort_smem_kernel<ull>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        ix->sort_attr_done = true;
+    }
+    // tier 1: one CTA per pattern, segments up to cap1 keys; tier 2: the longer ones, up to cap2; tier 3: the rest
+    if (k32) {
+        rigk::segsort_smem_kernel<uint32_t><<<(unsigned)N, 256, cap1 * ksz, st>>>(d_off, d_occ, N, cap1, nullptr, nullptr, big1, ix->d_post + 0);
+        rigk::segsort_smem_kernel<uint32_t><<<(unsigned)nbig1, 1024, cap2 * ksz, st>>>(d_off, d_occ, N, cap2, big1, ix->d_post + 0, big2, ix->d_post + 1);
+    } else {
+        rigk::segsort_smem_kernel<ull><<<(unsigned)N, 256, cap1 * ksz, st>>>(d_off, d_occ, N, cap1, nullptr, nullptr, big1, ix->d_post + 0);
+        rigk::segsort_smem_kernel<ull><<<(unsigned)nbig1, 1024, cap2 * ksz, st>>>(d_off, d_occ, N, cap2, big1, ix->d_post + 0, big2, ix->d_post + 1);
+    }
+    rigk::segsort_global_kernel<<<(unsigned)nbig2, 1024, 0, st>>>(d_off, d_occ, big2, ix->d_post + 1);
+    CU_TRY(cudaGetLastError());
+    return RIG_OK;
+}
+
+int check_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, const ull* d_lo, const ull* d_hi,
+              const ull* d_off, const ull* d_occ, uint64_t total, int sorted, rig_check_report* report, cudaStream_t st) {
+    if (!ix->has_text) return RIG_ERR_ARG;
+    if (N >= 0x7fffffffull) return RIG_ERR_ARG;
+    uint64_t tsize = 16;
+    while (tsize < 2 * N) tsize <<= 1;
+    int rc;
+    if ((rc = ix->ctable.ensure(tsize * 4)) || (rc = ix->crep.ensure((N + 1) * 4)) || (rc = ix->cfound.ensure((N + 1) * 8))) return rc;
+    rigk::CheckReport* rp = reinterpret_cast<rigk::CheckReport*>(ix->d_post + 2);
+    CU_TRY(cudaMemsetAsync(ix->ctable.p, 0, tsize * 4, st));
+    CU_TRY(cudaMemsetAsync(ix->cfound.p, 0, (N + 1) * 8, st));
+    ix->h_post[2] = N; ix->h_post[3] = 0; ix->h_post[4] = 0; ix->h_post[5] = 0; ix->h_post[6] = ~0ull; ix->h_post[7] = ~0ull;
+    CU_TRY(cudaMemcpyAsync(ix->d_post + 2, ix->h_post + 2, 6 * sizeof(ull), cudaMemcpyHostToDevice, st));
+    const uint8_t* text = (const uint8_t*)ix->text.p;
+    const uint64_t len = ix->text_len;
+    if (N) {
+        const unsigned nb = (unsigned)((N + 255) / 256);
+        if (m) {
+            rigk::check_build_kernel<<<nb, 256, 0, st>>>(d_patt, N, m, (uint32_t*)ix->ctable.p, tsize - 1, (uint32_t*)ix->crep.p);
+            if (len >= m) {
+                const uint64_t pos = len - m + 1;
+                if ((pos + 255) / 256 > 0x7fffffffull) return RIG_ERR_ARG;
+                rigk::check_scan_kernel<<<(unsigned)((pos + 255) / 256), 256, 0, st>>>(text, len, d_patt, m, (const uint32_t*)ix->ctable.p,
+                                                                                       tsize - 1, (ull*)ix->cfound.p);
+            }
+        }
+        rigk::check_counts_kernel<<<nb, 256, 0, st>>>(d_lo, d_hi, (const uint32_t*)ix->crep.p, (const ull*)ix->cfound.p, N, m, len, rp);
+        if (total) {
+            if ((total + 255) / 256 > 0x7fffffffull) return RIG_ERR_ARG;
+            rigk::check_positions_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(text, len, d_patt, N, m, d_off, d_occ, total, sorted, rp);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(ix->h_post + 2, ix->d_post + 2, 6 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (report) std::memcpy(report, ix->h_post + 2, sizeof(rig_check_report));
+    return RIG_OK;
+}
+
+}  // namespace
+
+int rig_text_attach(rig_index* ix, const uint8_t* text, uint64_t len) {
+    if (!ix || (len && !text)) return RIG_ERR_ARG;
+    if (len + 1 != ix->d.n) return RIG_ERR_ARG;  // must be the indexed text: n = |T| + 1 (r_index.hpp:88)
+    CU_TRY(cudaSetDevice(ix->device));
+    int rc;
+    if ((rc = ix->text.ensure(len + 16))) return rc;
+    if (len) CU_TRY(cudaMemcpy(ix->text.p, text, len, cudaMemcpyHostToDevice));
+    ix->text_len = len; ix->has_text = true;
+    return RIG_OK;
+}
+
+int rig_sort_occurrences_dev(rig_index* ix, uint64_t N, const uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t total,
+                             void* stream) {
+    if (!ix || (N && !d_occ_offsets) || (total && !d_occ)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    return sort_dev(ix, N, (const ull*)d_occ_offsets, (ull*)d_occ, total, stream ? (cudaStream_t)stream : ix->stream);
+}
+
+int rig_check_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, uint64_t m, const uint64_t* d_lo,
+                  const uint64_t* d_hi, const uint64_t* d_occ_offsets, const uint64_t* d_occ, uint64_t total, int sorted,
+                  rig_check_report* report, void* stream) {
+    if (!ix || !report || (N && (!d_lo || !d_hi || !d_occ_offsets || (m && !d_patterns))) || (total && !d_occ)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    return check_dev(ix, d_patterns, N, m, (const ull*)d_lo, (const ull*)d_hi, (const ull*)d_occ_offsets, (const ull*)d_occ,
+                     total, sorted, report, stream ? (cudaStream_t)stream : ix->stream);
+}
+
+int rig_locate_batch_ex(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                        uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
+                        rig_check_report* report) {
+    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
+    if ((flags & RIG_LOCATE_CHECK) && (!report || !ix->has_text)) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
+        (rc = ix->occoff.ensure((N + 2) * 8)))
+        return rc;
+    if (occ && occ_capacity && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
+    begin_call(ix);
+    if ((rc = rec(ix, 0, st))) return rc;
+    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
+                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
+    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
+    if (occ_total) *occ_total = total;
+    if (lrc == RIG_OK && (flags & (RIG_LOCATE_SORT | RIG_LOCATE_CHECK))) {  // the reference sorts for -o and for -c (:147,:159)
+        if ((rc = sort_dev(ix, N, (const ull*)ix->occoff.p, (ull*)ix->occ.p, total, st))) return rc;
+    }
+    if (lrc == RIG_OK && (flags & RIG_LOCATE_CHECK)) {
+        if ((rc = check_dev(ix, (const uint8_t*)ix->patt.p, N, m, (const ull*)ix->lo.p, (const ull*)ix->hi.p,
+                            (const ull*)ix->occoff.p, (const ull*)ix->occ.p, total, 1, report, st)))
+            return rc;
+    }
+    if (N) {
+        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ.p, total * 8, cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 5, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return lrc;
 }
 
 int rig_last_timing(const rig_index* cix, rig_timing* t) {

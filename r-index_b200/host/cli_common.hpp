@@ -72,6 +72,14 @@ public:
     }
     ~GpuFleet() { for (auto* p : idx) rig_index_destroy(p); }
     int size() const { return G; }
+    void attach_text(const uint8_t* text, uint64_t len) {  // -c: the indexed text goes to every GPU's HBM
+        std::vector<int> rcs(G, 0);
+        run([&](int g) { rcs[g] = rig_text_attach(idx[g], text, len); });
+        for (int g = 0; g < G; ++g) {
+            if (rcs[g] == RIG_ERR_ARG) { std::cout << "Error: the text given with -c is not the indexed text (length mismatch)" << std::endl; exit(0); }
+            if (rcs[g] != RIG_OK) die(rcs[g], "rig_text_attach");
+        }
+    }
     rig_index* handle(int g) { return idx[g]; }
 
     void count(const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi) {
@@ -84,22 +92,27 @@ public:
     }
     // Per-shard results: occ[g] holds the occurrences of shard g's patterns back to back;
     // off[g] (shard-local, size = shard patterns + 1) indexes into it.
+    // flags: RIG_LOCATE_SORT (-o) / RIG_LOCATE_CHECK (-c, needs attach_text) run on the device
+    // (ri-locate.cpp:146-190); reports[g] receives shard g's check report.
     uint64_t locate(const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
-                    std::vector<std::vector<uint64_t>>& off, std::vector<std::vector<uint64_t>>& occ) {
+                    std::vector<std::vector<uint64_t>>& off, std::vector<std::vector<uint64_t>>& occ,
+                    uint32_t flags = 0, std::vector<rig_check_report>* reports = nullptr) {
         off.assign(G, {}); occ.assign(G, {});
         std::vector<int> rcs(G, 0);
         std::vector<uint64_t> totals(G, 0);
+        std::vector<rig_check_report> reps(G);
         run([&](int g) {
             uint64_t a = N * g / G, b = N * (g + 1) / G;
             off[g].assign(b - a + 1, 0);
             int rc = rig_locate_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), nullptr, 0, &totals[g]);
-            if (rc == RIG_ERR_CAPACITY) {
+            if (rc == RIG_ERR_CAPACITY || (rc == RIG_OK && flags)) {
                 occ[g].resize(totals[g]);
-                rc = rig_locate_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), occ[g].data(),
-                                      occ[g].size(), &totals[g]);
+                rc = rig_locate_batch_ex(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), occ[g].data(),
+                                         occ[g].size(), &totals[g], flags, &reps[g]);
             }
             rcs[g] = rc;
         });
+        if (reports) *reports = reps;
         uint64_t total = 0;
         for (int g = 0; g < G; ++g) { if (rcs[g] != RIG_OK) die(rcs[g], "rig_locate_batch"); total += totals[g]; }
         return total;

@@ -62,7 +62,8 @@ int rih_gen_text(int kind, uint64_t n, uint64_t p0, uint64_t p1, uint64_t seed, 
         switch (kind) {
             case 0: t = rib::gen_dna_drift(n, p0, p1, seed); break;
             case 1: t = rib::gen_dna_indep(n, p0, (double)p1 * 1e-9, seed); break;
-            case 2: t = rib::gen_versioned_doc(n, p0, (unsigned)p1, 0.25, seed); break;
+            // p1 = sigma + 1000 * (edit probability per version in permille; 0 = SURVEY 8d's 0.25)
+            case 2: t = rib::gen_versioned_doc(n, p0, (unsigned)(p1 % 1000), p1 >= 1000 ? (double)(p1 / 1000) * 1e-3 : 0.25, seed); break;
             case 3: t = rib::gen_pangenome(n, p0, p1, seed); break;
             default: return RIH_ERR_ARG;
         }
