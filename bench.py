@@ -442,14 +442,21 @@ def run_ours(args):
     launches_count = args.steps
 
     # end to end through the host-buffer C-ABI call, pinned host memory
-    h_patt = torch.from_numpy(patt).pin_memory()
-    h_lo = torch.empty(N, dtype=torch.int64).pin_memory()
-    h_hi = torch.empty(N, dtype=torch.int64).pin_memory()
-    h_off = torch.empty(N + 1, dtype=torch.int64).pin_memory()
-    h_occ = torch.empty(max(need, 1), dtype=torch.int64).pin_memory()
+    # (a batch whose occurrences exceed 8 GB — full-size C3/C5 — is measured end to end on its leading patterns
+    # holding about 4 GB of occurrences: pinning tens of GB of host memory is not what this number is about)
+    NE, occ_e2e = N, occ_total
+    if occ_total * 8 > (8 << 30):
+        offs = d_off.cpu().numpy()
+        NE = max(1, int(np.searchsorted(offs, (4 << 30) // 8)) - 1)
+        occ_e2e = int(offs[NE])
+    h_patt = torch.from_numpy(patt[: NE * m].copy()).pin_memory()
+    h_lo = torch.empty(NE, dtype=torch.int64).pin_memory()
+    h_hi = torch.empty(NE, dtype=torch.int64).pin_memory()
+    h_off = torch.empty(NE + 1, dtype=torch.int64).pin_memory()
+    h_occ = torch.empty(max(occ_e2e, 1), dtype=torch.int64).pin_memory()
 
     def step_e2e():
-        return gpu.locate_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(),
+        return gpu.locate_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(),
                               h_occ.data_ptr(), h_occ.numel())
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -463,18 +470,37 @@ def run_ours(args):
         tot_e2e = step_e2e()
         e2e_t += time.perf_counter() - t1
     barrier()
-    assert tot_e2e == occ_total
+    assert tot_e2e == occ_e2e
     # cheap self-check of the e2e result (not a parity test: those live in tests/)
-    assert int(h_off[-1]) == occ_total
+    assert int(h_off[-1]) == occ_e2e
+
+    # ri-locate -o / -c post-processing on the device, timed once on the resident output of the last
+    # step: segmented sort of every pattern's occurrences, then the self-check (hash-join brute-force counts over
+    # the text + byte comparison of every occurrence). Not part of `value`.
+    post = None
+    if not args.no_post:
+        step_dev(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); gpu.sort_dev(N, d_off.data_ptr(), d_occ.data_ptr(), occ_total, stream); s1.record()
+        torch.cuda.synchronize()
+        gpu.text_attach(text)
+        t1 = time.perf_counter()
+        rep = gpu.check_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(),
+                            occ_total, True, stream)
+        check_ms = (time.perf_counter() - t1) * 1e3
+        assert rep.clean, rep.as_dict()
+        post = {"sort_ms": s0.elapsed_time(s1), "sort_keys_per_s": occ_total / (s0.elapsed_time(s1) * 1e-3),
+                "check_ms": check_ms, "check": rep.as_dict(),
+                "note": "rig_sort_occurrences_dev + rig_check_dev on the device-resident output (ri-locate -o / -c)"}
 
     # reduce over ranks: max time, sum work
     red = torch.tensor([total_ms, count_ms, e2e_t * 1e3 / e2e_steps * args.steps], dtype=torch.float64, device=dev)
-    work = torch.tensor([float(occ_total), float(N), float(launches)], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(occ_total), float(N), float(launches), float(occ_e2e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     total_ms_g, count_ms_g, e2e_ms_g = [float(x) for x in red.tolist()]
-    occ_g, N_g, launches_g = [float(x) for x in work.tolist()]
+    occ_g, N_g, launches_g, occ_e2e_g = [float(x) for x in work.tolist()]
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -517,9 +543,10 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
                        "timing": "CUDA events per step on the launch stream; max over ranks"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
-            "e2e": {"value": occ_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
-                    "h2d_bytes_per_step": int(N * m), "d2h_bytes_per_step": int(8 * (2 * N + N + 1 + occ_total)),
-                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
+            "e2e": {"value": occ_e2e_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
+                    "h2d_bytes_per_step": int(NE * m), "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1 + occ_e2e)),
+                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps,
+                    "patterns_per_step": NE, "occurrences_per_step": occ_e2e},
             "gpu_launches": int(launches_g) + launches_count * world,
             "count": {"metric": "count_patterns_per_s", "value": N_g * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
                       "ms_per_step": count_ms_g / args.steps},
@@ -536,6 +563,8 @@ def run_ours(args):
                                            "achieved": int(lf_steps) * 3 * B_RANK(ell) / (srch_ms * 1e-3) / 1e9 if srch_ms > 0 else None},
                          "scan_ms": statistics.mean(scan_ms)},
         }
+        if post is not None:
+            line["post"] = post
         if ref is not None:
             cores = os.cpu_count() or 1
             threads = cores if ref.kind == "reference" else 1
@@ -565,6 +594,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="patterns in the cpu_baseline sample (default: all)")
     ap.add_argument("--ref-sample", type=int, default=1 << 30, help="patterns per step of --impl reference (default: all)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-post", action="store_true", help="skip the -o / -c post-processing timing")
     ap.add_argument("--runs-per-block", type=int, default=0)
     ap.add_argument("--lf-log2", type=int, default=0)
     ap.add_argument("--phi-log2", type=int, default=0)
