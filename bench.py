@@ -604,6 +604,12 @@ def main():
     ap.add_argument("--mode", default="locate", choices=["locate", "count"], help="locate (default, C2) or count (ri-count configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner, ...)
+    # is sent to stderr, and the real stdout is restored for the final print() calls through sys.stdout.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours_count(args) if args.mode == "count" else run_ours(args)
