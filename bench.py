@@ -511,16 +511,15 @@ def run_ours(args):
         # the reference structure's TOUCHED bytes) is reported next to it as `survey_touched`: this layout
         # touches 32 B per 4 occurrences instead, and those bytes are served by L2.
         # Two-pass expansion: the dominant kernel is pass 2 (phi_window_kernel): it writes every occurrence,
-        # reads the Phi^1..D table once (the seed table is touched by pass 1 only), one seed + one count byte
-        # per window.
+        # reads the Phi^1..D table once (the seed table is touched by pass 1 only) and one 16-byte entry per item.
         two_pass = int(info.seed_jump) > 1 and statistics.mean(window_ms) > 0
         if two_pass:
             win_ms = statistics.mean(window_ms)
-            windows = (occ_total + int(info.seed_jump) - 1) // int(info.seed_jump)
+            items = occ_total // int(info.seed_jump) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
             phi_table_bytes = int(info.device_bytes) - int(info.seed_bytes)
-            alg_bytes = occ_total * 8 + phi_table_bytes + windows * 9
+            alg_bytes = occ_total * 8 + phi_table_bytes + items * 16
             dom_kernel, dom_ms = "phi_window_kernel", win_ms
-            alg_note = "8 B/occurrence output + one pass over the flattened index without the seed table + 9 B per window (seed, count)"
+            alg_note = "8 B/occurrence output + one pass over the flattened index without the seed table + 16 B per item (slot, count, seed)"
         else:
             phi_table_bytes = int(info.device_bytes)
             alg_bytes = occ_total * 8 + phi_table_bytes
