@@ -154,6 +154,22 @@ int rig_locate_batch_ex(rig_index* idx, const uint8_t* patterns, uint64_t N, uin
                         uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
                         rig_check_report* report);
 
+/* ---- single-position navigation as batches (no reference CLI calls these) ----
+ *   RIG_NAV_BWT   r_index<>::operator[](i)  bwt[i] (the terminator row holds 0x01)      internal/r_index.hpp:162-164
+ *   RIG_NAV_LF    r_index<>::LF(i)          F[c] + bwt.rank(i,c), c = bwt[i]            internal/r_index.hpp:224-229
+ *   RIG_NAV_FL    r_index<>::FL(i)          bwt.select(i - F[c], c), c = F_at(i)        internal/r_index.hpp:232-243
+ *   RIG_NAV_F_AT  r_index<>::F_at(i)        symbol of column F at row i                 internal/r_index.hpp:263-271
+ * out[k] = op(positions[k]) as uint64_t; positions >= n give ~0. */
+#define RIG_NAV_BWT 0
+#define RIG_NAV_LF 1
+#define RIG_NAV_FL 2
+#define RIG_NAV_F_AT 3
+int rig_navigate_batch(rig_index* idx, int op, const uint64_t* positions, uint64_t N, uint64_t* out);
+int rig_navigate_batch_dev(rig_index* idx, int op, const uint64_t* d_positions, uint64_t N, uint64_t* d_out, void* stream);
+/* r_index<>::get_bwt (internal/r_index.hpp:375-377, rle_string::toString) restricted to [from, from+len): the BWT
+ * as bytes, terminator row = 0x01 (HOST buffer). */
+int rig_get_bwt(rig_index* idx, uint64_t from, uint64_t len, uint8_t* out);
+
 int rig_last_timing(const rig_index* idx, rig_timing* t);
 
 #ifdef __cplusplus

@@ -76,6 +76,8 @@ def ref_lib():
         lib.ref_phi.restype = _u64
         lib.ref_phi.argtypes = [_vp, _u64]
         lib.ref_extract.argtypes = [_vp] * 7
+        lib.ref_navigate.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
+        lib.ref_get_bwt.argtypes = [_vp, _vp]
         _ref_lib = lib
     return _ref_lib
 
@@ -150,6 +152,18 @@ class RefIndex:
 
     def phi(self, i):
         return self.lib.ref_phi(self.h, i)
+
+    def navigate(self, op, positions):
+        """op 0: operator[](i), 1: LF(i), 2: FL(i), 3: F_at(i) — the reference's own methods."""
+        pos = np.ascontiguousarray(positions, dtype=np.uint64)
+        out = np.empty(pos.size, dtype=np.uint64)
+        self.lib.ref_navigate(self.h, op, _ptr(pos), pos.size, _ptr(out))
+        return out
+
+    def get_bwt(self):
+        out = np.empty(int(self.n), dtype=np.uint8)
+        self.lib.ref_get_bwt(self.h, _ptr(out))
+        return out
 
     def extract(self):
         r = int(self.r)

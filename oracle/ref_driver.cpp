@@ -128,6 +128,21 @@ double ref_locate_batch(void* h, const uint8_t* patt, uint64_t N, uint64_t m, co
 uint64_t ref_bwt_rank(void* h, uint64_t i, uint8_t c) { return ((ref_index_t*)h)->bwt.rank(i, c); }
 uint8_t ref_bwt_at(void* h, uint64_t i) { return ((ref_index_t*)h)->bwt[i]; }
 uint64_t ref_phi(void* h, uint64_t i) { return ((ref_index_t*)h)->Phi(i); }
+// single-position navigation through the reference's own methods (r_index.hpp:162-164, 224-271)
+//   op 0: operator[](i)   1: LF(i)   2: FL(i)   3: F_at(i)
+void ref_navigate(void* h, int op, const uint64_t* pos, uint64_t N, uint64_t* out) {
+    ref_index_t* idx = (ref_index_t*)h;
+    for (uint64_t k = 0; k < N; ++k) {
+        const uint64_t i = pos[k];
+        out[k] = op == 0 ? (uint64_t)(*idx)[i] : op == 1 ? idx->LF(i) : op == 2 ? idx->FL(i) : (uint64_t)idx->F_at(i);
+    }
+}
+// the BWT symbol by symbol through operator[] (what r_index::get_bwt / rle_string::toString return, r_index.hpp:375-377)
+void ref_get_bwt(void* h, uint8_t* out) {
+    ref_index_t* idx = (ref_index_t*)h;
+    const uint64_t n = idx->bwt_size();
+    for (uint64_t i = 0; i < n; ++i) out[i] = (*idx)[i];
+}
 
 // The logical content of a reference-built/loaded index, read through the reference's own
 // accessors. This is also the extraction INTEGRATION.md proposes for feeding rig_index_create.

@@ -18,6 +18,7 @@ DECLARED_SYMBOLS = [
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
+    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -60,6 +61,7 @@ class CheckReport(ctypes.Structure):
 
 
 LOCATE_SORT, LOCATE_CHECK = 1, 2
+NAV_BWT, NAV_LF, NAV_FL, NAV_F_AT = 0, 1, 2, 3
 
 
 class RigError(RuntimeError):
@@ -98,6 +100,9 @@ def gpu_lib():
         lib.rig_locate_batch_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _vp]
         lib.rig_digest_dev.argtypes = [_vp, _vp, _u64, ctypes.POINTER(_u64 * 2), _vp]
         lib.rig_last_timing.argtypes = [_vp, ctypes.POINTER(Timing)]
+        lib.rig_navigate_batch.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
+        lib.rig_navigate_batch_dev.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp, _vp]
+        lib.rig_get_bwt.argtypes = [_vp, _u64, _u64, _vp]
         lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
         lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
         lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
@@ -207,6 +212,23 @@ class GpuIndex:
         if occ is None:
             occ = np.empty(0, dtype=np.uint64)
         return lo, hi, off, occ[: int(tot.value)]
+
+    # ---- single-position navigation (r_index::operator[], LF, FL, F_at; get_bwt) ----
+    def navigate(self, op, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.uint64)
+        out = np.empty(pos.size, dtype=np.uint64)
+        rc = self.lib.rig_navigate_batch(self.h, op, _ptr(pos), pos.size, _ptr(out))
+        if rc != 0:
+            raise RigError(rc, "rig_navigate_batch")
+        return out
+
+    def get_bwt(self, start=0, length=None):
+        length = self.n - start if length is None else length
+        out = np.empty(length, dtype=np.uint8)
+        rc = self.lib.rig_get_bwt(self.h, start, length, _ptr(out))
+        if rc != 0:
+            raise RigError(rc, "rig_get_bwt")
+        return out
 
     # ---- ri-locate -o / -c post-processing on the device ----
     def text_attach(self, text):

@@ -175,4 +175,114 @@ check_positions_kernel(const uint8_t* __restrict__ text, u64 len, const uint8_t*
     if (sorted && i > __ldg(occ_off + p) && occ[i - 1] >= o) atomicAdd(&rp->unsorted_or_duplicate, 1ull);
 }
 
+// ------------------------------------------------------------------ navigation
+// Single-position operations of r_index<> as batches, one thread per position (they are off the count /
+// locate path; no CLI calls them):
+//   NAV_BWT   r_index::operator[](i)  = bwt[i]                      r_index.hpp:162-164, rle_string.hpp:126-131
+//   NAV_LF    r_index::LF(i)          = F[c] + bwt.rank(i, c), c = bwt[i]                 r_index.hpp:224-229
+//   NAV_FL    r_index::FL(i)          = bwt.select(i - F[c], c), c = F_at(i)              r_index.hpp:232-243
+//   NAV_F_AT  r_index::F_at(i)        = upper_bound(F, F + 256, i) - F - 1                r_index.hpp:263-271
+enum { NAV_BWT = 0, NAV_LF = 1, NAV_FL = 2, NAV_F_AT = 3 };
+
+// the block holding BWT position x: bdir bucket, then binary search over the blocks' first positions
+template <typename PT>
+__device__ __forceinline__ u32 nav_block_of(const FlatDev& ix, PT x) {
+    const u32 q = (u32)(x >> ix.lf_shift);
+    u32 b0 = __ldg(ix.bdir + q), b1 = __ldg(ix.bdir + q + 1);
+    while (b0 < b1) {
+        const u32 mid = b0 + ((b1 - b0 + 1) >> 1);
+        if (ld_pos<PT>(ix.bstart, mid) <= x) b0 = mid; else b1 = mid - 1;
+    }
+    return b0;
+}
+
+template <typename PT>
+__device__ __forceinline__ u32 nav_f_at(const FlatDev& ix, u64 i) {  // largest c in [0,255] with F[c] <= i
+    u32 lo = 0, hi = 255;
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (__ldg(ix.F + mid) <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256)
+navigate_kernel(const FlatDev ix, int op, const u64* __restrict__ pos, u64 N, u64* __restrict__ out) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const u64 i = pos[t];
+    if (i >= ix.n) { out[t] = ~0ull; return; }  // outside the BWT: the reference would read out of bounds
+    const u32 K = ix.K;
+    if (op == NAV_F_AT) { out[t] = nav_f_at<PT>(ix, i); return; }
+    if (op == NAV_BWT || op == NAV_LF) {
+        const u32 b = nav_block_of<PT>(ix, (PT)i);
+        const char* rp = ix.blk + (u64)b * ix.blk_stride;
+        const PT* st = reinterpret_cast<const PT*>(rp);
+        const uint8_t* hd = reinterpret_cast<const uint8_t*>(rp + ix.off_head);
+        u32 k = 0;  // run of the block holding i: the last one starting at or before i (padding starts are n > i)
+        for (u32 g = 1; g < K; ++g) if (__ldg(st + g) <= (PT)i) k = g;
+        const uint8_t c = __ldg(hd + k);
+        if (op == NAV_BWT) { out[t] = c; return; }
+        const u32 sidc = __ldg(ix.sid + c);
+        u64 rank = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);  // #c before the block
+        for (u32 g = 0; g < k; ++g)
+            if (__ldg(hd + g) == c) rank += (u64)(__ldg(st + g + 1) - __ldg(st + g));
+        rank += i - (u64)__ldg(st + k);  // #c in bwt[0, i): rle_string::rank(i, c), rle_string.hpp:170-218
+        out[t] = __ldg(ix.F + c) + rank;
+        return;
+    }
+    // NAV_FL
+    const u32 c = nav_f_at<PT>(ix, i);
+    const u64 j = i - __ldg(ix.F + c);  // this c is the j-th (from 0) in column F
+    const u32 sidc = __ldg(ix.sid + c);
+    // last block whose count of c before it is <= j (rle_string::select, rle_string.hpp:136-165)
+    u64 b0 = 0, b1 = ix.nblk - 1;
+    while (b0 < b1) {
+        const u64 mid = b0 + ((b1 - b0 + 1) >> 1);
+        const u64 before = __ldg(reinterpret_cast<const PT*>(ix.blk + mid * ix.blk_stride + ix.off_cum) + sidc);
+        if (before <= j) b0 = mid; else b1 = mid - 1;
+    }
+    const char* rp = ix.blk + b0 * ix.blk_stride;
+    const PT* st = reinterpret_cast<const PT*>(rp);
+    const uint8_t* hd = reinterpret_cast<const uint8_t*>(rp + ix.off_head);
+    u64 rem = j - (u64)__ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
+    u64 res = ~0ull;
+    for (u32 g = 0; g < K; ++g) {
+        if (__ldg(hd + g) != (uint8_t)c) continue;
+        const u64 s0 = __ldg(st + g);
+        const u64 s1 = (g + 1 < K) ? (u64)__ldg(st + g + 1) : (u64)ld_pos<PT>(ix.bstart, b0 + 1);
+        if (s0 >= ix.n) break;  // padding
+        const u64 len = s1 - s0;
+        if (rem < len) { res = s0 + rem; break; }
+        rem -= len;
+    }
+    out[t] = res;
+}
+
+// r_index::get_bwt (r_index.hpp:375-377) = rle_string::toString, restricted to a range: bwt[from, from+len) as bytes,
+// one thread per output byte group of 16 (binary search for the first run, then a linear walk over run starts).
+template <typename PT>
+__global__ void __launch_bounds__(256)
+bwt_range_kernel(const FlatDev ix, u64 from, u64 len, uint8_t* __restrict__ out) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 a = t * 16;
+    if (a >= len) return;
+    const u64 e = min(len, a + 16);
+    u64 x = from + a;
+    const u32 b = nav_block_of<PT>(ix, (PT)x);
+    u64 run = (u64)b * ix.K;
+    while (run + 1 < ix.r && (u64)ld_pos<PT>(ix.start, run + 1) <= x) ++run;
+    u64 next = (run + 1 < ix.r) ? (u64)ld_pos<PT>(ix.start, run + 1) : ix.n;
+    uint8_t c = __ldg(reinterpret_cast<const uint8_t*>(ix.blk + (run / ix.K) * ix.blk_stride + ix.off_head) + run % ix.K);
+    for (u64 o = a; o < e; ++o, ++x) {
+        if (x >= next) {
+            ++run;
+            next = (run + 1 < ix.r) ? (u64)ld_pos<PT>(ix.start, run + 1) : ix.n;
+            c = __ldg(reinterpret_cast<const uint8_t*>(ix.blk + (run / ix.K) * ix.blk_stride + ix.off_head) + run % ix.K);
+        }
+        out[o] = c;
+    }
+}
+
 }  // namespace rigk

@@ -717,6 +717,50 @@ int rig_locate_batch_ex(rig_index* ix, const uint8_t* patterns, uint64_t N, uint
     return lrc;
 }
 
+// ---- single-position navigation as batches --------------------------------------------
+int rig_navigate_batch_dev(rig_index* ix, int op, const uint64_t* d_positions, uint64_t N, uint64_t* d_out, void* stream) {
+    if (!ix || op < RIG_NAV_BWT || op > RIG_NAV_F_AT || (N && (!d_positions || !d_out))) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (!N) return RIG_OK;
+    const uint64_t nb = (N + 255) / 256;
+    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+    if (ix->d.w32) rigk::navigate_kernel<uint32_t><<<(unsigned)nb, 256, 0, st>>>(ix->d, op, (const ull*)d_positions, N, (ull*)d_out);
+    else rigk::navigate_kernel<ull><<<(unsigned)nb, 256, 0, st>>>(ix->d, op, (const ull*)d_positions, N, (ull*)d_out);
+    CU_TRY(cudaGetLastError());
+    return RIG_OK;
+}
+
+int rig_navigate_batch(rig_index* ix, int op, const uint64_t* positions, uint64_t N, uint64_t* out) {
+    if (!ix || op < RIG_NAV_BWT || op > RIG_NAV_F_AT || (N && (!positions || !out))) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    int rc;
+    if ((rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8))) return rc;
+    cudaStream_t st = ix->stream;
+    if (N) CU_TRY(cudaMemcpyAsync(ix->lo.p, positions, N * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = rig_navigate_batch_dev(ix, op, (const uint64_t*)ix->lo.p, N, (uint64_t*)ix->hi.p, st))) return rc;
+    if (N) CU_TRY(cudaMemcpyAsync(out, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
+int rig_get_bwt(rig_index* ix, uint64_t from, uint64_t len, uint8_t* out) {
+    if (!ix || (len && !out) || from > ix->d.n || len > ix->d.n - from) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    if (!len) return RIG_OK;
+    int rc;
+    if ((rc = ix->patt.ensure(len + 16))) return rc;
+    cudaStream_t st = ix->stream;
+    const uint64_t nb = ((len + 15) / 16 + 255) / 256;
+    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+    if (ix->d.w32) rigk::bwt_range_kernel<uint32_t><<<(unsigned)nb, 256, 0, st>>>(ix->d, from, len, (uint8_t*)ix->patt.p);
+    else rigk::bwt_range_kernel<ull><<<(unsigned)nb, 256, 0, st>>>(ix->d, from, len, (uint8_t*)ix->patt.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, ix->patt.p, len, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
 int rig_last_timing(const rig_index* cix, rig_timing* t) {
     if (!cix || !t) return RIG_ERR_ARG;
     rig_index* ix = const_cast<rig_index*>(cix);

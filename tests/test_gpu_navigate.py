@@ -1,0 +1,62 @@
+"""-m gpu: single-position navigation on the device — r_index<>::operator[], LF(i), FL(i),
+F_at(i), get_bwt (reference internal/r_index.hpp:162-164, 224-271, 375-377) — against (1) ground truth derived
+from an explicit suffix array and (2) the reference's own methods (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from conftest import rib, ob, repetitive_text, needs_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _truth(text, sa):
+    """bwt[i], LF(i), FL(i), F_at(i) for every row i from the suffix array of text + terminator."""
+    n = sa.size
+    t = np.concatenate([text, np.array([1], dtype=np.uint8)])  # the terminator sorts below every text byte; the index stores it as 0x01
+    isa = np.empty(n, dtype=np.int64)
+    isa[sa] = np.arange(n)
+    bwt = t[(sa - 1) % n]
+    lf = isa[(sa - 1) % n]
+    fl = isa[(sa + 1) % n]
+    f_at = t[sa]
+    return bwt, lf.astype(np.uint64), fl.astype(np.uint64), f_at
+
+
+@pytest.mark.parametrize("K", [4, 16])
+@pytest.mark.parametrize("variant", ["0", "8"])
+def test_navigation_equals_suffix_array_truth(K, variant, monkeypatch):
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    rng = np.random.default_rng(5 + K)
+    texts = [repetitive_text(int(rng.integers(1, 3000)), int(rng.integers(1, 200)), int(rng.integers(0, 4)), 40 + i,
+                             sigma=int(rng.choice([1, 2, 4, 15]))) for i in range(12)]
+    texts += [np.frombuffer(b"a", dtype=np.uint8), np.frombuffer(b"abracadabra\xff\xfe" * 9, dtype=np.uint8),
+              rib.gen_text("versioned_doc", 60_000, 2_000, 96, 3)]
+    for text in texts:
+        sa = rib.suffix_array(text)
+        bwt, lf, fl, f_at = _truth(text, sa)
+        gpu = rib.GpuIndex(rib.HostIndex.from_text(text), runs_per_block=K)
+        pos = np.arange(sa.size, dtype=np.uint64)
+        assert np.array_equal(gpu.navigate(rib.NAV_BWT, pos), bwt.astype(np.uint64))
+        assert np.array_equal(gpu.navigate(rib.NAV_LF, pos), lf)
+        assert np.array_equal(gpu.navigate(rib.NAV_FL, pos), fl)
+        assert np.array_equal(gpu.navigate(rib.NAV_F_AT, pos), f_at.astype(np.uint64))
+        assert np.array_equal(gpu.get_bwt(), bwt)
+        if sa.size > 40:
+            assert np.array_equal(gpu.get_bwt(17, 23), bwt[17:40])
+        assert gpu.navigate(rib.NAV_LF, np.array([sa.size, 2**63], dtype=np.uint64)).tolist() == [2**64 - 1] * 2
+        assert gpu.navigate(rib.NAV_LF, np.zeros(0, dtype=np.uint64)).size == 0
+        gpu.close()
+
+
+@needs_ref
+def test_navigation_equals_reference_methods():
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 17)
+    ref = ob.RefIndex.from_text(text)
+    gpu = rib.GpuIndex(rib.HostIndex.from_text(text))
+    rng = np.random.default_rng(1)
+    pos = np.unique(np.concatenate([rng.integers(0, gpu.n, size=20000), [0, 1, gpu.n - 1]])).astype(np.uint64)
+    for op in (rib.NAV_BWT, rib.NAV_LF, rib.NAV_FL, rib.NAV_F_AT):
+        assert np.array_equal(gpu.navigate(op, pos), ref.navigate(op, pos)), "op %d" % op
+    assert np.array_equal(gpu.get_bwt(), ref.get_bwt())
+    # LF and FL are inverse permutations of the rows (r_index.hpp:224-243)
+    assert np.array_equal(gpu.navigate(rib.NAV_FL, gpu.navigate(rib.NAV_LF, pos)), pos)

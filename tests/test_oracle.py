@@ -146,3 +146,20 @@ def test_known_answers_world_leaders():
     assert int(nocc.sum()) == 29_781_174
     assert nocc[:5].tolist() == [298060, 306619, 25029, 22721, 252]
     assert hashlib.sha256(nocc.astype("<u8").tobytes()).hexdigest()[:16] == "f5e5ac89a564dacc"
+
+
+@needs_ref
+def test_reference_navigation_equals_suffix_array_truth():
+    """Pins the oracle side of the navigation row: the reference's own operator[], LF(i), FL(i),
+    F_at(i) and get_bwt (r_index.hpp:162-164, 224-271, 375-377) equal what an explicit suffix array gives."""
+    from test_gpu_navigate import _truth
+    for text in (rib.gen_text("dna_drift", 30_000, 700, 3, 17), np.frombuffer(b"abracadabra\xff\xfe" * 9, dtype=np.uint8)):
+        sa = rib.suffix_array(text)
+        bwt, lf, fl, f_at = _truth(text, sa)
+        ref = ob.RefIndex.from_text(text)
+        pos = np.arange(sa.size, dtype=np.uint64)
+        assert np.array_equal(ref.navigate(0, pos), bwt.astype(np.uint64))
+        assert np.array_equal(ref.navigate(1, pos), lf)
+        assert np.array_equal(ref.navigate(2, pos), fl)
+        assert np.array_equal(ref.navigate(3, pos), f_at.astype(np.uint64))
+        assert np.array_equal(ref.get_bwt(), bwt)
