@@ -106,24 +106,66 @@ def prepare(workload, need_ref=False, rank=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe). NVML is polled from a
+    thread every ~2 ms (a timed region of 10 steps lasts ~20 ms: `nvidia-smi -lms` cannot be relied on to land a
+    sample inside it, and with 8 GPUs it did not); falls back to an nvidia-smi loop if pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.samples, self.mask, self.max_mhz = [], 0, None
+        self.stop_flag = False
+        self.thread = None
         self.p = None
+        self.f = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(get_reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(0.5)
         except Exception:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                hi = [x for x in self.samples if x >= 0.5 * max(self.samples)]
+                out.update(sm_mhz=statistics.median(hi), sm_max_mhz=self.max_mhz, samples=len(self.samples),
+                           reasons=sorted(name for bit, name in self.REASONS.items() if self.mask & bit))
+            return out
         if self.p is None:
             return out
         time.sleep(0.15)
@@ -247,7 +289,7 @@ def run_ours_count(args):
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
-                       phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1)
+                       phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1, seed_jump=1)  # count only: smallest locate tables
     load_s = time.time() - t0
     info = gpu.info
     tstream = torch.cuda.Stream(device=dev)
@@ -327,7 +369,7 @@ def run_ours_count(args):
                        "runs_per_block": int(info.runs_per_block), "parallelism": "patterns sharded x%d, index replicated" % world,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                        "timing": "CUDA events per step on the launch stream; max over ranks"},
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": N_g * args.steps / (e2e_ms_g * 1e-3), "unit": "patterns/s", "h2d_bytes_per_step": int(N * m),
                     "d2h_bytes_per_step": int(16 * N), "api": "rig_count_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
             "gpu_launches": args.steps * world,
@@ -541,7 +583,7 @@ def run_ours(args):
                        "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes), "parallelism": "patterns sharded x%d, index replicated" % world,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
                        "timing": "CUDA events per step on the launch stream; max over ranks"},
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": occ_e2e_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
                     "h2d_bytes_per_step": int(NE * m), "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1 + occ_e2e)),
                     "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps,

@@ -57,7 +57,7 @@ def build_gpu(force=False):
     if force or _newer(GPU_SO, srcs):
         nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
         _run([nvcc] + NVCC_FLAGS + ["-shared", "-ccbin", "/usr/bin/g++", "-I", INC, "-o", GPU_SO,
-                                     os.path.join(csrc, "rindex_gpu.cu"), "-lcudart"],
+                                     os.path.join(csrc, "rindex_gpu.cu"), "-lcudart", "-Xcompiler", "-pthread"],
              log=os.path.join(PKG, "csrc", "ptxas.log"))
     return GPU_SO
 

@@ -53,7 +53,7 @@ int main(int argc, char** argv) {
     cout << "searching patterns ... " << endl;
     PatternFile pf = read_patterns(patt_file);  // a malformed header exits(0) here, as upstream (utils.hpp:51-55)
     auto u1 = high_resolution_clock::now();
-    GpuFleet fleet(L, gpus);                    // flatten + upload: accounted as load time, not search time
+    GpuFleet fleet(L, gpus, true);                    // flatten + upload: accounted as load time, not search time
     auto u2 = high_resolution_clock::now();
     const uint64_t n = pf.n, m = pf.m;
     std::vector<uint64_t> lo(n), hi(n);

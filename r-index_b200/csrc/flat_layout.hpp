@@ -37,6 +37,10 @@
 #include <vector>
 #include <algorithm>
 #include <cstring>
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "../../include/rindex_gpu.h"
 
 namespace rigf {
@@ -171,37 +175,49 @@ struct JumpTable {
         while (((n - 1) >> shift) + 1 > target) ++shift;
         nbkt = ((n - 1) >> shift) + 1;
         const u64 P = pieces();
-        rec.assign(nbkt * SEED_RW, 0);
+        rec.resize(nbkt * SEED_RW);
         pent.resize(P * 2);
-        for (u64 k = 0; k < P; ++k) { pent[2 * k] = delta[k]; pent[2 * k + 1] = start[k]; }
-        u64 a = 0;
-        for (u64 q = 0; q < nbkt; ++q) {
-            const u64 lo = q << shift, hi = (q + 1) << shift;
-            while (a + 1 < P && start[a + 1] <= lo) ++a;
-            u64 e = a + 1;
-            while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
-            u64* R = &rec[q * SEED_RW];
-            const u64 cnt = e - (a + 1);
-            R[0] = delta[a];
-            for (u32 i = 0; i < SEED_INLINE; ++i) {
-                R[1 + 2 * i] = i < cnt ? start[a + 1 + i] : ~(u64)0;
-                R[2 + 2 * i] = i < cnt ? delta[a + 1 + i] : 0;
+        unsigned T = std::thread::hardware_concurrency();
+        if (T > 32) T = 32;
+        if (T < 1 || nbkt < (1u << 16)) T = 1;
+        auto fill = [&](u64 q0, u64 q1, u64 k0, u64 k1) {
+            for (u64 k = k0; k < k1; ++k) { pent[2 * k] = delta[k]; pent[2 * k + 1] = start[k]; }
+            if (q0 >= q1) return;
+            u64 a = piece_of(q0 << shift);  // the piece covering the first bucket's first position
+            for (u64 q = q0; q < q1; ++q) {
+                const u64 lo = q << shift, hi = (q + 1) << shift;
+                while (a + 1 < P && start[a + 1] <= lo) ++a;
+                u64 e = a + 1;
+                while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
+                u64* R = &rec[q * SEED_RW];
+                const u64 cnt = e - (a + 1);
+                R[0] = delta[a];
+                for (u32 i = 0; i < SEED_INLINE; ++i) {
+                    R[1 + 2 * i] = i < cnt ? start[a + 1 + i] : ~(u64)0;
+                    R[2 + 2 * i] = i < cnt ? delta[a + 1 + i] : 0;
+                }
+                R[13] = cnt >= 1 ? a + 1 : 0;
+                R[14] = cnt;
+                R[15] = 0;
             }
-            R[13] = cnt >= 1 ? a + 1 : 0;
-            R[14] = cnt;
-        }
+        };
+        if (T == 1) { fill(0, nbkt, 0, P); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t]() { fill(nbkt * t / T, nbkt * (t + 1) / T, P * t / T, P * (t + 1) / T); });
+        for (auto& x : th) x.join();
     }
 };
 
 // C = B o A (apply A, then B) for two piecewise translations of [0,n) given as (start, delta) lists:
 // every piece of A is cut where its image crosses a piece boundary of B; delta_C = delta_A + delta_B.
-static inline void compose_translations(const std::vector<u64>& As, const std::vector<u64>& Ad,
-                                        const std::vector<u64>& Bs, const std::vector<u64>& Bd, u64 n,
-                                        std::vector<u64>& Cs, std::vector<u64>& Cd) {
-    Cs.clear(); Cd.clear();
+// Pieces of A are independent: large inputs are cut into contiguous chunks, one host thread each.
+static inline void compose_range(const std::vector<u64>& As, const std::vector<u64>& Ad, const std::vector<u64>& Bs,
+                                 const std::vector<u64>& Bd, u64 n, u64 k0, u64 k1, std::vector<u64>& Cs,
+                                 std::vector<u64>& Cd) {
     const u64 PA = As.size(), PB = Bs.size();
-    Cs.reserve(PA * 2); Cd.reserve(PA * 2);
-    for (u64 k = 0; k < PA; ++k) {
+    Cs.reserve((k1 - k0) * 2 + 16); Cd.reserve((k1 - k0) * 2 + 16);
+    for (u64 k = k0; k < k1; ++k) {
         const u64 s = As[k], e = (k + 1 < PA) ? As[k + 1] : n, a = Ad[k], len = e - s;
         u64 u = s + a;  // image of s
         if (u >= n) u -= n;
@@ -222,6 +238,29 @@ static inline void compose_translations(const std::vector<u64>& As, const std::v
             }
             done += lin_end - pos;
         }
+    }
+}
+
+static inline void compose_translations(const std::vector<u64>& As, const std::vector<u64>& Ad,
+                                        const std::vector<u64>& Bs, const std::vector<u64>& Bd, u64 n,
+                                        std::vector<u64>& Cs, std::vector<u64>& Cd) {
+    Cs.clear(); Cd.clear();
+    const u64 PA = As.size();
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 32) T = 32;
+    if (T < 2 || PA < (1u << 16)) { compose_range(As, Ad, Bs, Bd, n, 0, PA, Cs, Cd); return; }
+    std::vector<std::vector<u64>> ps(T), pd(T);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() { compose_range(As, Ad, Bs, Bd, n, PA * t / T, PA * (t + 1) / T, ps[t], pd[t]); });
+    for (auto& x : th) x.join();
+    u64 total = 0;
+    for (unsigned t = 0; t < T; ++t) total += ps[t].size();
+    Cs.reserve(total); Cd.reserve(total);
+    for (unsigned t = 0; t < T; ++t) {
+        Cs.insert(Cs.end(), ps[t].begin(), ps[t].end());
+        Cd.insert(Cd.end(), pd[t].begin(), pd[t].end());
+        std::vector<u64>().swap(ps[t]); std::vector<u64>().swap(pd[t]);
     }
 }
 
@@ -266,6 +305,14 @@ static inline u32 pick_shift(u64 n, u64 target_buckets) {
 
 // Returns RIG_OK or RIG_ERR_INDEX / RIG_ERR_ARG. `max_bytes` (0 = unlimited) bounds the footprint.
 static inline int flatten(const rig_logical_view& v, const rig_options& opt, FlatHost& f, u64 max_bytes = 0) {
+    const bool timing = getenv("RIG_FLATTEN_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[flatten] %-28s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+        t_last = t;
+    };
     if (!v.F || !v.run_heads || !v.run_lens || !v.samples_last || !v.pred_pos || !v.pred_to_run) return RIG_ERR_ARG;
     if (v.n < 1 || v.r < 1 || v.r > v.n || v.r >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
     if (opt.runs_per_block != 0 && opt.runs_per_block != 4 && opt.runs_per_block != 8 && opt.runs_per_block != 16)
@@ -335,6 +382,7 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         if (f.F[c + 1] - f.F[c] != have) return RIG_ERR_INDEX;
     }
 
+    lap("runs + directory counts");
     // interleaved block records
     {
         const u32 W = f.w32 ? 4 : 8;
@@ -369,6 +417,7 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         f.bdir[f.lf_nbkt] = (u32)(nblk - 1);
     }
 
+    lap("block records + bdir");
     // samples
     f.samples_last.assign(v.samples_last, v.samples_last + r);
     for (u64 j = 0; j < r; ++j) if (f.samples_last[j] >= n) return RIG_ERR_INDEX;
@@ -394,29 +443,35 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     }
     // buckets per piece: 2 (measured on C2: 0.51 ms vs 0.57 ms with 4 — the smaller table stays in L2)
     const u32 fp = opt.phi_bucket_log2 ? opt.phi_bucket_log2 : 1;
-    // D = occurrences produced per record lookup: requested, or the largest of {4,2} whose bucket
-    // records stay L2-friendly (they compete with the streamed occurrence output for the 126 MB L2).
+    // D = occurrences produced per record lookup: requested, or the largest of {4,2,1} whose table fits the
+    // byte budget (8 GB, or a quarter of the caller's limit). More occurrences per lookup win whether or not the
+    // table stays in L2: measured on C5s (r = 3.4e5) D=4 at 93 MB 0.44 ms vs D=2 at 50 MB 0.94 ms; beyond L2 a
+    // lookup is one random DRAM access (~55 G sectors/s) whatever it yields.
     u32 D = opt.reserved[0];
     if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
     if (D == 0) {
-        const u64 budget = 192ull << 20;  // measured: C5s (r = 3.4e5) D=4 at 93 MB: 0.44 ms vs D=2 at 50 MB: 0.94 ms
+        u64 budget = 8ull << 30;
+        if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
         const u64 wb = f.w32 ? 4 : 8;
         auto cost = [&](u32 d) { return (u64)d * r * ((PhiTable::record_words(d) * wb) << fp); };
         D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);
     }
+    lap("Phi pieces");
     f.phi = P1;
     for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
+    lap("Phi^D composition");
     f.phi.build_directory(n, fp);
+    lap("Phi^D directory");
     if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
 
     // Seed table Phi^SEG for the two-pass expansion (phi_kernels.cuh): requested (reserved[2] = 16..256,
     // 1 = off), or the largest of {64, 32, 16} whose table (72 B per piece with 32-bit words: one
-    // 64-byte bucket record per piece + an 8-byte piece entry) stays within ~2 GB / a quarter of the
+    // 64-byte bucket record per piece + an 8-byte piece entry) stays within 16 GB / a quarter of the
     // caller's byte limit. pieces(Phi^J) = sum over runs of min(J, run length), known before building.
     u32 SEG = opt.reserved[2];
     if (SEG != 0 && SEG != 1 && SEG != 16 && SEG != 32 && SEG != 64 && SEG != 128 && SEG != 256) return RIG_ERR_ARG;
     if (SEG == 0) {
-        u64 budget = 2ull << 30;
+        u64 budget = 16ull << 30;
         if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
         const u64 per_piece = f.w32 ? 72 : 144;
         SEG = 1;
@@ -433,10 +488,12 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
             compose_translations(s0, d0, s0, d0, n, s1, d1);
             s0.swap(s1); d0.swap(d1);
         }
+        lap("seed composition (doubling)");
         f.seed.J = SEG;
         f.seed.start.swap(s0); f.seed.delta.swap(d0);
         if (f.seed.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
         f.seed.build_directory(n, 0);
+        lap("seed directory");
     }
     return RIG_OK;
 }

@@ -57,7 +57,8 @@ inline void die(int rc, const char* where) {
 // One rig_index per device; shard p covers patterns [N*p/G, N*(p+1)/G).
 class GpuFleet {
 public:
-    explicit GpuFleet(const rib::LogicalIndex& L, int gpus) {
+    // count_only: ri-count never expands occurrences, so the Phi tables are built at their smallest (D = 1, no seed table)
+    explicit GpuFleet(const rib::LogicalIndex& L, int gpus, bool count_only = false) {
         int have = rig_device_count();
         if (have < 1) { std::cout << "Error: no CUDA device available (this build has no CPU query path)" << std::endl; exit(1); }
         G = gpus <= 0 ? 1 : (gpus > have ? have : gpus);
@@ -67,7 +68,10 @@ public:
         v.run_heads = L.run_heads.data(); v.run_lens = L.run_lens.data(); v.samples_last = L.samples_last.data();
         v.pred_pos = L.pred_pos.data(); v.pred_to_run = L.pred_to_run.data();
         std::vector<int> rcs(G, 0);
-        run([&](int g) { rcs[g] = rig_index_create(&v, g, &idx[g]); });
+        rig_options opt;
+        std::memset(&opt, 0, sizeof(opt));
+        if (count_only) { opt.reserved[0] = 1; opt.reserved[2] = 1; }
+        run([&](int g) { rcs[g] = rig_index_create_ex(&v, g, &opt, &idx[g]); });
         for (int g = 0; g < G; ++g) if (rcs[g] != RIG_OK) die(rcs[g], "rig_index_create");
     }
     ~GpuFleet() { for (auto* p : idx) rig_index_destroy(p); }

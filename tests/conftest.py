@@ -36,7 +36,7 @@ def _build_flatcheck():
     src = os.path.join(SUPPORT, "flat_check.cpp")
     dep = os.path.join(ROOT, "r-index_b200", "csrc", "flat_layout.hpp")
     if (not os.path.exists(FLATCHECK_SO) or os.path.getmtime(FLATCHECK_SO) < max(os.path.getmtime(src), os.path.getmtime(dep))):
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-o", FLATCHECK_SO, src], check=True)
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-o", FLATCHECK_SO, src], check=True)
 
 
 @pytest.fixture(scope="session", autouse=True)
