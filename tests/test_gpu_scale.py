@@ -73,3 +73,35 @@ def test_scaled_config_against_reference(name):
         for p in rng.integers(0, N, size=50):
             o = occ[int(off[p]):int(off[p + 1])]
             assert np.unique(o).size == o.size
+
+
+@pytest.mark.parametrize("name", ["c3", "c5"])
+def test_full_size_config_self_check(name):
+    """BASELINE.json configs 3 and 5 at FULL size (1 GB sigma=96 text; 4 GB DNA with n > 2^32: the 64-bit paths).
+    No CPU oracle finishes at this size, so the device runs the reference's own -c self-check
+    (ri-locate.cpp:156-190) on the located output: brute-force occurrence counts from the text (hash join)
+    equal hi-lo+1 for every pattern, text[o, o+m) equals the pattern for every located o, and the positions of
+    a pattern are distinct. The index comes from .cache/ (built in the dev container: 5 / 29 minutes)."""
+    rib_path = os.path.join(CACHE, name + ".rib")
+    if not os.path.exists(rib_path):
+        pytest.skip("cached index for %s not present" % name)
+    kind, n, p0, p1, tseed, N, m, pseed, limit, desc = _workload(name)
+    N = 20_000
+    text = rib.gen_text(kind, n, p0, p1, tseed)
+    patt = rib.gen_patterns(text, N, m, pseed, limit)
+    host = rib.HostIndex.load(rib_path)
+    assert host.n == n + 1
+    gpu = rib.GpuIndex(host)
+    assert gpu.info.words32 == (1 if n + 1 < 2**32 - 1 else 0) and gpu.info.seed_jump == 64
+    gpu.text_attach(text)
+    del text
+    lo, hi, off, occ, rep = gpu.locate_ex(patt, N, m, rib.LOCATE_SORT | rib.LOCATE_CHECK)
+    assert rep.patterns_checked == N and rep.clean, rep.as_dict()
+    nocc = np.where(hi >= lo, hi - lo + np.uint64(1), np.uint64(0)).astype(np.uint64)
+    assert (nocc > 0).all() and np.array_equal(np.diff(off), nocc) and occ.size == int(nocc.sum())
+    lo2, hi2 = gpu.count(patt, N, m)
+    assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+    # the unsorted locate_all order holds the same multiset per pattern (spot check)
+    lo3, hi3, off3, occ3 = gpu.locate(patt[: 50 * m], 50, m)
+    for p in range(50):
+        assert np.array_equal(np.sort(occ3[int(off3[p]):int(off3[p + 1])]), occ[int(off[p]):int(off[p + 1])])
