@@ -27,6 +27,14 @@ typedef struct rih_index rih_index;
 #define RIH_ERR_ARG -4
 
 int rih_build_from_text(const uint8_t* text, uint64_t len, rih_index** out);
+/* Scalable construction by prefix-free parsing (r-index_b200/host/pfp_builder.hpp): same
+ * result as rih_build_from_text, memory proportional to the dictionary and the parse of the text instead of
+ * 5-9 bytes per symbol. w = window length (0 = 10), p = trigger modulus (0 = 100). stats_out (may be NULL):
+ * distinct phrases, dictionary bytes, parse length, suffix groups, BWT rows emitted as whole blocks, rows merged
+ * one by one. */
+int rih_build_from_text_pfp(const uint8_t* text, uint64_t len, uint32_t w, uint32_t p, uint64_t stats_out[6], rih_index** out);
+/* What ri-build uses: prefix-free parsing from 16 MB up (SA-IS fallback), SA-IS below; env RIB_BUILDER=sais|pfp forces one. */
+int rih_build_auto(const uint8_t* text, uint64_t len, int* used_pfp, rih_index** out);
 void rih_destroy(rih_index* idx);
 /* Borrowed pointers, valid until rih_destroy. */
 int rih_view(const rih_index* idx, rig_logical_view* view);

@@ -25,6 +25,8 @@ def host_lib():
             _build.build_host()
         lib = ctypes.CDLL(_build.HOST_SO)
         lib.rih_build_from_text.argtypes = [_vp, _u64, ctypes.POINTER(_vp)]
+        lib.rih_build_from_text_pfp.argtypes = [_vp, _u64, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.POINTER(_vp)]
+        lib.rih_build_auto.argtypes = [_vp, _u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_vp)]
         lib.rih_destroy.argtypes = [_vp]
         lib.rih_view.argtypes = [_vp, ctypes.POINTER(LogicalView)]
         lib.rih_save.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int]
@@ -81,6 +83,37 @@ class HostIndex:
         if rc != 0:
             raise RuntimeError("rih_build_from_text failed: %d" % rc)
         return cls(h)
+
+    @classmethod
+    def from_text_auto(cls, text):
+        """The builder ri-build uses: prefix-free parsing for large texts, SA-IS otherwise (.used_pfp tells which)."""
+        t = _as_u8(text)
+        h = _vp()
+        used = ctypes.c_int(0)
+        rc = host_lib().rih_build_auto(_ptr(t), t.size, ctypes.byref(used), ctypes.byref(h))
+        if rc == -1:
+            raise ValueError("input string contains one of the reserved characters 0x0, 0x1")
+        if rc != 0:
+            raise RuntimeError("rih_build_auto failed: %d" % rc)
+        obj = cls(h)
+        obj.used_pfp = bool(used.value)
+        return obj
+
+    @classmethod
+    def from_text_pfp(cls, text, w=0, p=0):
+        """Prefix-free-parsing builder (same arrays as from_text); .pfp_stats holds the parse statistics."""
+        t = _as_u8(text)
+        h = _vp()
+        stats = np.zeros(6, dtype=np.uint64)
+        rc = host_lib().rih_build_from_text_pfp(_ptr(t), t.size, w, p, _ptr(stats), ctypes.byref(h))
+        if rc == -1:
+            raise ValueError("input string contains one of the reserved characters 0x0, 0x1")
+        if rc != 0:
+            raise RuntimeError("rih_build_from_text_pfp failed: %d" % rc)
+        obj = cls(h)
+        obj.pfp_stats = dict(zip(("phrases", "dict_bytes", "parse_len", "groups", "uniform_rows", "merged_rows"),
+                                 (int(x) for x in stats)))
+        return obj
 
     @classmethod
     def load(cls, path, with_flag_byte=True):

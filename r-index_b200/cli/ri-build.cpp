@@ -1,6 +1,7 @@
 // ri-build — builds the r-index of a text file (reference ri-build.cpp: same usage text, options,
 // stdout lines and the leading 1-byte `fast` flag in the .ri file, :133). Construction is host-only:
-// this repo's own SA-IS + run/sample scan (host/logical_index.hpp); the container is this repo's own.
+// prefix-free parsing for texts from 16 MB up (host/pfp_builder.hpp), this repo's own SA-IS +
+// run/sample scan below that (host/logical_index.hpp); both give the same arrays. The container is this repo's own.
 #include <chrono>
 #include <fstream>
 #include <iostream>

@@ -1,0 +1,327 @@
+// pfp_builder.hpp — scalable index construction by PREFIX-FREE PARSING
+// (Boucher, Gagie, Kuhnle, Langmead, Manzini, Mun: "Prefix-free parsing for building big BWTs", 2019).
+//
+// Replaces, for large repetitive inputs, the suffix-array route of the reference's constructor
+// (internal/r_index.hpp:42-150 with sufsort :553-634: construct_sa over the whole text, then one scan of SA
+// that emits BWT runs and both sample sets). The in-memory SA-IS builder (logical_index.hpp) needs 5-9
+// bytes per text symbol; this one needs memory proportional to the DICTIONARY and the PARSE of the text:
+//
+//   S = T·0x00 is cut into overlapping phrases at every window of w bytes whose Karp-Rabin hash is 0 mod p
+//   (each phrase starts with the trigger window that ended the previous one). The distinct phrases form
+//   the dictionary D (sorted, ranks = new alphabet), the sequence of ranks the parse P.
+//   Every suffix of S starts inside exactly one phrase occurrence at an offset that leaves more than w
+//   bytes of the phrase; those phrase suffixes form a prefix-free set, so two text suffixes compare
+//   (1) by their phrase suffixes, and, when these are the same string, (2) by the parse suffixes that
+//   follow — i.e. by the suffix array of P.
+//   So: suffix array of P (|P| ~ n/p integers), suffix array of D (a few bytes per dictionary byte), one
+//   sweep over D's suffixes in order. A group of equal phrase suffixes that are all preceded by the same
+//   byte is ONE block of the BWT (count = number of occurrences of its phrases): O(1) work however many
+//   text positions it covers; only groups with different preceding bytes (the neighbourhood of BWT run
+//   boundaries) are merged occurrence by occurrence.
+//
+// The sweep feeds the same run/sample logic as the SA scan (terminator 0x01 in the row with SA = 0,
+// samples = SA-1 with wrap to n-1, run-first samples sorted by text position: r_index.hpp:587-623,
+// :108,:141-146), so both builders produce identical LogicalIndex arrays (tests/test_host.py).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cstdlib>
+#include <memory>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+#include "logical_index.hpp"
+
+namespace rib {
+namespace pfp {
+
+struct Params {
+    uint32_t w = 10;   // window (overlap) length
+    uint32_t p = 100;  // a window triggers when hash mod p == 0: phrases average ~p bytes
+};
+
+struct Stats {
+    uint64_t phrases = 0, dict_bytes = 0, parse_len = 0, groups = 0, uniform_rows = 0, merged_rows = 0;
+};
+
+// Consumer of BWT rows in suffix-array order: (symbol, number of consecutive rows, SA of the first and last row).
+class RunBuilder {
+public:
+    RunBuilder(LogicalIndex& L_, uint64_t n_) : L(L_), n(n_) {
+        L.run_heads.clear(); L.run_lens.clear(); L.samples_last.clear();
+        std::memset(hist, 0, sizeof(hist));
+    }
+    inline void emit(uint8_t c, uint64_t count, uint64_t sa_first, uint64_t sa_last) {
+        if (!open || c != cur) {
+            if (open) close();
+            open = true; cur = c; run_len = 0;
+            first.push_back({smp(sa_first), (uint64_t)L.run_heads.size()});
+            if (c == kTerminator) L.terminator_position = rows;
+        }
+        run_len += count; rows += count; last_sa = sa_last;
+    }
+    uint64_t rows_emitted() const { return rows; }
+    void finish() {
+        if (open) close();
+        L.n = n;
+        L.r = L.run_heads.size();
+        uint64_t acc = 0;
+        for (int c = 0; c < 256; ++c) { L.F[c] = acc; acc += hist[c]; }
+        L.F[256] = n;
+        std::sort(first.begin(), first.end());  // r_index.hpp:108
+        L.pred_pos.resize(L.r); L.pred_to_run.resize(L.r);
+        for (uint64_t k = 0; k < L.r; ++k) { L.pred_pos[k] = first[k].first; L.pred_to_run[k] = first[k].second; }
+    }
+
+private:
+    inline uint64_t smp(uint64_t sa) const { return sa > 0 ? sa - 1 : n - 1; }  // r_index.hpp:599,604,614,619
+    void close() {
+        L.run_heads.push_back(cur); L.run_lens.push_back(run_len); L.samples_last.push_back(smp(last_sa));
+        hist[cur] += run_len;
+    }
+    LogicalIndex& L;
+    uint64_t n;
+    std::vector<std::pair<uint64_t, uint64_t>> first;  // (text position, run id)
+    uint64_t hist[256];
+    bool open = false;
+    uint8_t cur = 0;
+    uint64_t run_len = 0, rows = 0, last_sa = 0;
+};
+
+// dictionary symbols: 0 = end of the concatenation (SA-IS sentinel), 1 = phrase separator, 2 = the 0x00 that ends S,
+// text byte b (>= 2) -> b + 1
+static inline uint16_t sym_of(uint8_t b) { return b == 0 ? (uint16_t)2 : (uint16_t)(b + 1); }
+static inline uint8_t byte_of(uint16_t s) { return s == 2 ? (uint8_t)0 : (uint8_t)(s - 1); }
+
+inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm = Params(), Stats* stats = nullptr) {
+    if (contains_reserved_chars(text, len)) throw std::invalid_argument("reserved");
+    const uint64_t n = len + 1;  // S = T·0x00
+    const uint32_t w = prm.w < 1 ? 1 : prm.w, p = prm.p < 1 ? 1 : prm.p;
+    auto S = [&](uint64_t i) -> uint8_t { return i < len ? text[i] : (uint8_t)0; };
+
+    // ---- 1. parse -------------------------------------------------------------------------------------------
+    struct Phrase { const uint8_t* ptr; uint32_t len; };
+    std::vector<Phrase> phrases;                       // by id (first-seen order)
+    std::vector<std::unique_ptr<uint8_t[]>> arena;     // phrase bytes, chunked so that pointers stay valid
+    size_t arena_used = 0, arena_cap = 0;
+    auto arena_put = [&](uint64_t b, uint64_t e) -> const uint8_t* {  // copy S[b..e]
+        const size_t L = (size_t)(e - b + 1);
+        if (arena_used + L > arena_cap) {
+            arena_cap = std::max<size_t>(L, (size_t)64 << 20);
+            arena.emplace_back(new uint8_t[arena_cap]);
+            arena_used = 0;
+        }
+        uint8_t* dst = arena.back().get() + arena_used;
+        for (size_t t = 0; t < L; ++t) dst[t] = S(b + t);
+        arena_used += L;
+        return dst;
+    };
+    std::unordered_multimap<uint64_t, uint32_t> seen;  // content hash -> phrase id (content verified)
+    std::vector<uint32_t> parse;                       // phrase ids
+    std::vector<uint64_t> tpos;                        // start of every phrase occurrence in S
+    {
+        const uint64_t prime = 1999999973ull;
+        uint64_t hw = 0, pw = 1;  // Karp-Rabin hash of the current window, 256^(w-1) mod prime
+        for (uint32_t t = 1; t < w; ++t) pw = (pw * 256) % prime;
+        uint64_t b = 0, h2 = 1469598103934665603ull;  // phrase start, FNV-1a of the phrase so far
+        // the phrase hash must cover the phrase from its first byte: restart it at every phrase start by
+        // re-hashing the w overlap bytes
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint8_t c = S(i);
+            if (i >= w) hw = (hw + prime - (pw * S(i - w)) % prime) % prime;
+            hw = (hw * 256 + c) % prime;
+            h2 = (h2 ^ c) * 1099511628211ull;
+            const bool trigger = (i + 1 >= w) && (hw % p == 0) && (i - b + 1 > w);
+            if (trigger || i == n - 1) {
+                const uint32_t L = (uint32_t)(i - b + 1);
+                if ((uint64_t)L != i - b + 1) throw std::length_error("phrase longer than 2^32");
+                uint32_t id = ~0u;
+                auto range = seen.equal_range(h2);
+                for (auto it = range.first; it != range.second; ++it) {
+                    const Phrase& q = phrases[it->second];
+                    if (q.len != L) continue;
+                    bool eq = true;
+                    for (uint32_t t = 0; t < L && eq; ++t) eq = q.ptr[t] == S(b + t);
+                    if (eq) { id = it->second; break; }
+                }
+                if (id == ~0u) {
+                    id = (uint32_t)phrases.size();
+                    if (phrases.size() >= 0x7fffff00ull) throw std::length_error("too many distinct phrases");
+                    phrases.push_back({arena_put(b, i), L});
+                    seen.emplace(h2, id);
+                }
+                parse.push_back(id);
+                tpos.push_back(b);
+                if (i < n - 1) {
+                    b = i + 1 - w;
+                    h2 = 1469598103934665603ull;
+                    for (uint64_t t = b; t <= i; ++t) h2 = (h2 ^ S(t)) * 1099511628211ull;
+                }
+            }
+        }
+    }
+    seen.clear();
+    const uint64_t ND = phrases.size(), NP = parse.size();
+    if (NP >= 0x7fffff00ull) throw std::length_error("parse longer than 2^31");
+
+    // ---- 2. sort the dictionary, rename the parse --------------------------------------------------------------
+    std::vector<uint32_t> order(ND);
+    for (uint32_t i = 0; i < ND; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const Phrase &x = phrases[a], &y = phrases[b];
+        const int c = std::memcmp(x.ptr, y.ptr, std::min(x.len, y.len));
+        return c != 0 ? c < 0 : x.len < y.len;
+    });
+    std::vector<uint32_t> rank_of(ND);
+    for (uint32_t i = 0; i < ND; ++i) rank_of[order[i]] = i;
+    for (auto& x : parse) x = rank_of[x];
+    const uint32_t last_d = parse[NP - 1];  // the phrase that ends with S's 0x00: unique, occurs once
+
+    // dictionary in rank order as 16-bit symbols with separators
+    std::vector<uint64_t> dstart(ND + 1);
+    std::vector<uint32_t> dlen(ND);
+    uint64_t M = 0;
+    for (uint32_t d = 0; d < ND; ++d) { dstart[d] = M; dlen[d] = phrases[order[d]].len; M += (uint64_t)dlen[d] + 1; }
+    dstart[ND] = M;
+    std::vector<uint16_t> C(M + 1);
+    for (uint32_t d = 0; d < ND; ++d) {
+        const Phrase& q = phrases[order[d]];
+        uint16_t* dst = &C[dstart[d]];
+        for (uint32_t t = 0; t < q.len; ++t) dst[t] = sym_of(q.ptr[t]);
+        dst[q.len] = 1;
+    }
+    C[M] = 0;
+    arena.clear(); phrases.clear(); phrases.shrink_to_fit(); order.clear(); order.shrink_to_fit();
+    rank_of.clear(); rank_of.shrink_to_fit();
+
+    // ---- 3. suffix array of the parse; occurrences of every phrase ordered by the parse suffix that follows --------
+    std::vector<uint32_t> occ_begin(ND + 1, 0), occ_rank(NP), occ_k(NP);
+    {
+        std::vector<uint32_t> P1(NP + 1);
+        for (uint64_t k = 0; k < NP; ++k) P1[k] = parse[k] + 1;
+        P1[NP] = 0;
+        std::vector<int32_t> SAP(NP + 1);
+        sais_detail::sais_rec<uint32_t, int32_t>(P1.data(), SAP.data(), (int32_t)(NP + 1), (int32_t)ND);
+        for (uint64_t k = 0; k < NP; ++k) occ_begin[parse[k] + 1]++;
+        for (uint32_t d = 0; d < ND; ++d) occ_begin[d + 1] += occ_begin[d];
+        std::vector<uint32_t> fill(occ_begin.begin(), occ_begin.end() - 1);
+        for (uint64_t i = 0; i <= NP; ++i) {  // i = rank of the parse suffix starting at SAP[i]
+            const int32_t j = SAP[i];
+            if (j < 1) continue;
+            const uint32_t k = (uint32_t)j - 1, d = parse[k];
+            occ_rank[fill[d]] = (uint32_t)i; occ_k[fill[d]] = k; ++fill[d];
+        }
+    }
+
+    // ---- 4. suffix array of the dictionary -----------------------------------------------------------------------
+    if (M + 1 >= 0x7fffff00ull) throw std::length_error("dictionary longer than 2^31");
+    std::vector<int32_t> SAD(M + 1);
+    sais_detail::sais_rec<uint16_t, int32_t>(C.data(), SAD.data(), (int32_t)(M + 1), (int32_t)257);
+
+    // ---- 5. sweep ------------------------------------------------------------------------------------------------
+    LogicalIndex L;
+    RunBuilder rb(L, n);
+    Stats st;
+    st.phrases = ND; st.dict_bytes = M; st.parse_len = NP;
+    struct Member { uint32_t d, o; };
+    std::vector<Member> grp;
+    auto pred_byte_of_occurrence = [&](uint32_t k) -> uint8_t {  // the byte of S before phrase occurrence k
+        if (k == 0) return kTerminator;                           // the row with SA = 0 (r_index.hpp:587-590)
+        const uint32_t pd = parse[k - 1];
+        return byte_of(C[dstart[pd] + dlen[pd] - w - 1]);
+    };
+    auto flush_group = [&]() {
+        if (grp.empty()) return;
+        ++st.groups;
+        bool uniform = true;
+        uint8_t c0 = 0;
+        bool have = false;
+        for (const Member& m : grp) {
+            if (m.o == 0) { uniform = false; break; }
+            const uint8_t c = byte_of(C[dstart[m.d] + m.o - 1]);
+            if (!have) { c0 = c; have = true; } else if (c != c0) { uniform = false; break; }
+        }
+        if (uniform) {
+            uint64_t total = 0, sa_first = 0, sa_last = 0;
+            uint32_t rmin = ~0u, rmax = 0;
+            bool any = false;
+            for (const Member& m : grp) {
+                const uint32_t a = occ_begin[m.d], b = occ_begin[m.d + 1];
+                if (a == b) continue;
+                total += b - a;
+                if (!any || occ_rank[a] < rmin) { rmin = occ_rank[a]; sa_first = tpos[occ_k[a]] + m.o; }
+                if (!any || occ_rank[b - 1] > rmax) { rmax = occ_rank[b - 1]; sa_last = tpos[occ_k[b - 1]] + m.o; }
+                any = true;
+            }
+            if (total) { rb.emit(c0, total, sa_first, sa_last); st.uniform_rows += total; }
+        } else if (grp.size() == 1) {
+            const Member m = grp[0];
+            for (uint32_t x = occ_begin[m.d]; x < occ_begin[m.d + 1]; ++x) {
+                const uint32_t k = occ_k[x];
+                const uint64_t sa = tpos[k] + m.o;
+                rb.emit(m.o > 0 ? byte_of(C[dstart[m.d] + m.o - 1]) : pred_byte_of_occurrence(k), 1, sa, sa);
+                ++st.merged_rows;
+            }
+        } else {  // merge the members' occurrence lists by the rank of the following parse suffix
+            typedef std::pair<uint32_t, uint32_t> QE;  // (rank, member index)
+            std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+            std::vector<uint32_t> cur(grp.size());
+            for (uint32_t g = 0; g < grp.size(); ++g) {
+                cur[g] = occ_begin[grp[g].d];
+                if (cur[g] < occ_begin[grp[g].d + 1]) pq.push({occ_rank[cur[g]], g});
+            }
+            while (!pq.empty()) {
+                const uint32_t g = pq.top().second;
+                pq.pop();
+                const Member m = grp[g];
+                const uint32_t k = occ_k[cur[g]];
+                const uint64_t sa = tpos[k] + m.o;
+                rb.emit(m.o > 0 ? byte_of(C[dstart[m.d] + m.o - 1]) : pred_byte_of_occurrence(k), 1, sa, sa);
+                ++st.merged_rows;
+                if (++cur[g] < occ_begin[m.d + 1]) pq.push({occ_rank[cur[g]], g});
+            }
+        }
+        grp.clear();
+    };
+    uint64_t rep_pos = 0, rep_rem = 0;  // representative suffix of the current group
+    for (uint64_t idx = 1; idx <= M; ++idx) {  // SAD[0] is the end-of-concatenation sentinel
+        const uint64_t pos = (uint64_t)SAD[idx];
+        if (C[pos] == 1) continue;  // a separator
+        const uint32_t d = (uint32_t)(std::upper_bound(dstart.begin(), dstart.begin() + ND, pos) - dstart.begin()) - 1;
+        const uint32_t o = (uint32_t)(pos - dstart[d]);
+        const uint64_t rem = dlen[d] - o;
+        if (!(rem > w || d == last_d)) continue;  // owned by the next phrase occurrence (the overlap)
+        const bool same = !grp.empty() && rem == rep_rem && std::memcmp(&C[pos], &C[rep_pos], rem * sizeof(uint16_t)) == 0;
+        if (!same) { flush_group(); rep_pos = pos; rep_rem = rem; }
+        grp.push_back({d, o});
+    }
+    flush_group();
+    if (rb.rows_emitted() != n) throw std::logic_error("prefix-free parsing: row count differs from the text length");
+    rb.finish();
+    if (stats) *stats = st;
+    return L;
+}
+
+}  // namespace pfp
+
+// Builder selection: prefix-free parsing from 16 MB up (identical result, memory ~ dictionary + parse; on a
+// text that is not repetitive the dictionary approaches the text and a 2^31 limit may be hit: the in-memory
+// SA-IS route is the fallback), SA-IS below. RIB_BUILDER=sais|pfp forces one.
+inline LogicalIndex build_logical_index_auto(const uint8_t* text, uint64_t len, bool* used_pfp = nullptr) {
+    const char* force = getenv("RIB_BUILDER");
+    bool try_pfp = len >= ((uint64_t)1 << 24);
+    if (force && std::strcmp(force, "sais") == 0) try_pfp = false;
+    if (force && std::strcmp(force, "pfp") == 0) try_pfp = true;
+    if (used_pfp) *used_pfp = false;
+    if (try_pfp) {
+        try {
+            LogicalIndex L = pfp::build(text, len);
+            if (used_pfp) *used_pfp = true;
+            return L;
+        } catch (const std::length_error&) {
+        }
+    }
+    return build_logical_index(text, len);
+}
+
+}  // namespace rib

@@ -19,6 +19,7 @@
 #include <vector>
 #include <utility>
 #include "logical_index.hpp"
+#include "pfp_builder.hpp"
 #include "../../include/rindex_gpu.h"
 
 namespace ri {
@@ -51,7 +52,8 @@ public:
         cout << "(1/3) Building BWT and computing SA samples";
         if (sais) cout << " (SE-SAIS) ... " << flush;
         else cout << "(DIVSUFSORT) ... " << flush;  // both flags use this repo's own in-memory SA-IS
-        L = rib::build_logical_index((const uint8_t*)input.data(), input.size());
+        // construction: prefix-free parsing for large texts, in-memory SA-IS otherwise (pfp_builder.hpp; same arrays)
+        L = rib::build_logical_index_auto((const uint8_t*)input.data(), input.size());
         cout << "done.\n(2/3) RLE encoding BWT ... " << flush;
         cout << "done. " << endl << endl;
         cout << "Number of BWT equal-letter runs: r = " << L.r << endl;

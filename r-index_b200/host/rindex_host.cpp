@@ -1,6 +1,7 @@
 // rindex_host.cpp — C ABI over the host-side builder / container / generators (include/rindex_host.h).
 #include "../../include/rindex_host.h"
 #include "logical_index.hpp"
+#include "pfp_builder.hpp"
 #include "textgen.hpp"
 #include <new>
 
@@ -20,6 +21,44 @@ int rih_build_from_text(const uint8_t* text, uint64_t len, rih_index** out) {
     } catch (const std::invalid_argument&) {
         return RIH_ERR_RESERVED_CHARS;
     } catch (const std::bad_alloc&) {
+        return RIH_ERR_ARG;
+    }
+}
+
+int rih_build_from_text_pfp(const uint8_t* text, uint64_t len, uint32_t w, uint32_t p, uint64_t stats_out[6], rih_index** out) {
+    if (!out || (!text && len)) return RIH_ERR_ARG;
+    try {
+        rih_index* h = new rih_index();
+        rib::pfp::Params prm;
+        if (w) prm.w = w;
+        if (p) prm.p = p;
+        rib::pfp::Stats st;
+        h->L = rib::pfp::build(text, len, prm, &st);
+        if (stats_out) {
+            stats_out[0] = st.phrases; stats_out[1] = st.dict_bytes; stats_out[2] = st.parse_len;
+            stats_out[3] = st.groups; stats_out[4] = st.uniform_rows; stats_out[5] = st.merged_rows;
+        }
+        *out = h;
+        return RIH_OK;
+    } catch (const std::invalid_argument&) {
+        return RIH_ERR_RESERVED_CHARS;
+    } catch (const std::exception&) {
+        return RIH_ERR_ARG;
+    }
+}
+
+int rih_build_auto(const uint8_t* text, uint64_t len, int* used_pfp, rih_index** out) {
+    if (!out || (!text && len)) return RIH_ERR_ARG;
+    try {
+        rih_index* h = new rih_index();
+        bool pf = false;
+        h->L = rib::build_logical_index_auto(text, len, &pf);
+        if (used_pfp) *used_pfp = pf ? 1 : 0;
+        *out = h;
+        return RIH_OK;
+    } catch (const std::invalid_argument&) {
+        return RIH_ERR_RESERVED_CHARS;
+    } catch (const std::exception&) {
         return RIH_ERR_ARG;
     }
 }

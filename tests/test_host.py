@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rib, ob, repetitive_text, needs_ref
+from conftest import rib, ob, repetitive_text, needs_ref, GOLDEN
 
 
 def test_builder_equals_oracle_content():
@@ -93,3 +93,45 @@ def test_pattern_file_format(tmp_path):
         rib.parse_pattern_file(b"# nomber=7 length=10 file=x forbidden=\n")
     with pytest.raises(ValueError):
         rib.parse_pattern_file(b"# number=7 length=10\n")  # no space after the last field
+
+
+def _same_index(a, b):
+    A, B = a.arrays(), b.arrays()
+    assert (A["n"], A["r"]) == (B["n"], B["r"])
+    for k in ("F", "run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run"):
+        assert np.array_equal(A[k], B[k]), k
+
+
+def test_pfp_builder_equals_sais_builder_small():
+    """Scalable construction: prefix-free parsing gives exactly the arrays of the suffix-array
+    route — tiny windows and moduli force every phrase shape (one-phrase texts, phrases of length w+1, triggers
+    inside the first window, the final phrase holding the terminator), texts from empty to a few hundred bytes."""
+    rng = np.random.default_rng(11)
+    for it in range(400):
+        n = int(rng.integers(0, 500))
+        sigma = int(rng.choice([1, 2, 4, 20, 250]))
+        base = rng.integers(2, 2 + sigma, size=max(1, int(rng.integers(1, 80))), dtype=np.uint8)
+        t = np.resize(base, n).copy()
+        for _ in range(int(rng.integers(0, 8))):
+            if n:
+                t[int(rng.integers(0, n))] = int(rng.integers(2, 2 + sigma))
+        a = rib.HostIndex.from_text(t)
+        b = rib.HostIndex.from_text_pfp(t, w=int(rng.integers(1, 7)), p=int(rng.integers(1, 14)))
+        _same_index(a, b)
+        assert b.pfp_stats["uniform_rows"] + b.pfp_stats["merged_rows"] == n + 1
+
+
+def test_pfp_builder_equals_sais_builder_generators_and_golden():
+    for kind, args in (("dna_drift", (2_000_000, 20_000, 3, 7)), ("versioned_doc", (1_500_000, 5_000, 96, 8)),
+                       ("pangenome", (1_500_000, 100_000, 2_000, 9)), ("dna_indep", (1_500_000, 50_000, 10_000, 10))):
+        t = rib.gen_text(kind, *args)
+        b = rib.HostIndex.from_text_pfp(t)
+        _same_index(rib.HostIndex.from_text(t), b)
+        assert b.pfp_stats["dict_bytes"] < t.size // 2          # the point of the method on repetitive input
+    for fname in sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")):
+        t = np.load(os.path.join(GOLDEN, fname))["text"]
+        _same_index(rib.HostIndex.from_text(t), rib.HostIndex.from_text_pfp(t, w=4, p=11))
+    with pytest.raises(ValueError):
+        rib.HostIndex.from_text_pfp(np.frombuffer(b"ab\x01cd", dtype=np.uint8))
+    small = rib.HostIndex.from_text_auto(np.frombuffer(b"abracadabra", dtype=np.uint8))
+    assert small.used_pfp is False                                # below 16 MB the SA-IS route is used
