@@ -120,7 +120,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
@@ -276,15 +276,24 @@ namespace {
 template <bool LOCATE>
 int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi,
                   cudaStream_t st) {
-    const int threads = 256;
     const uint32_t G = ix->d.K;
+    ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
+    ull* steps = ix->d_counters + 0;
+    const bool n32 = ix->d.w32 != 0;
+    if (G == 4 && !(ix->variant & 128)) {  // one lane per pattern over the K = 4 block records (bit7: cooperative kernel, A/B switch)
+        const int lt = 128;
+        const uint64_t lb = (N + lt - 1) / lt;
+        if (lb > 0x7fffffffull) return RIG_ERR_ARG;
+        if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);
+        else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);
+        CU_TRY(cudaGetLastError());
+        return RIG_OK;
+    }
+    const int threads = 256;
     const uint64_t ppw = 32 / (2 * G);
     const uint64_t warps = (N + ppw - 1) / ppw;
     const uint64_t blocks = (warps + (threads / 32) - 1) / (threads / 32);
     if (blocks > 0x7fffffffull) return RIG_ERR_ARG;
-    ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
-    ull* steps = ix->d_counters + 0;
-    const bool n32 = ix->d.w32 != 0;
 #define RIG_LAUNCH(GG)                                                                                          \
     do {                                                                                                        \
         if (n32) rigk::search_kernel<GG, LOCATE, uint32_t><<<(unsigned)blocks, threads, 0, st>>>(               \

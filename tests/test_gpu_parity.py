@@ -285,3 +285,21 @@ def test_two_pass_unaligned_output_falls_back_to_single_pass():
         assert tot == eocc.size and np.array_equal(d_occ.cpu().numpy().view(np.uint64), eocc)
         t = gpu.timing()
         assert (t["window_ms"] > 0) == (shift == 0)
+
+
+@pytest.mark.parametrize("variant", ["128", "136", "8"])
+def test_both_search_kernels_k4(variant, monkeypatch):
+    """K = 4 block records are searched by one lane per pattern (default) or by the cooperative group kernel
+    (RIG_VARIANT bit 7); both, in 32- and 64-bit words (bit 3), give the oracle's ranges, toeholds and occurrences,
+    including early exits, absent symbols and patterns running off the text."""
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    rng = np.random.default_rng(int(variant))
+    for it in range(12):
+        n = int(rng.integers(1, 6000))
+        text = repetitive_text(n, int(rng.integers(1, 300)), int(rng.integers(0, 4)), 300 + it, sigma=int(rng.choice([1, 2, 4, 15])))
+        gpu = rib.GpuIndex(rib.HostIndex.from_text(text), runs_per_block=4)
+        port = ob.PortIndex(text)
+        for m in (1, 3, int(rng.integers(4, 40))):
+            patt = mixed_patterns(text, 100, m, it)
+            _check_all(gpu, port, patt, 100, m, "variant=%s it=%d m=%d" % (variant, it, m))
+        gpu.close()
