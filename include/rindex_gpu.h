@@ -54,7 +54,9 @@ typedef struct rig_options {
     uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup;
                                   reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths);
                                   reserved[2] = SEG of the two-pass Phi expansion: 0 = auto, 1 = off (single pass),
-                                  16/32/64/128/256 = occurrences per seed-table hop (window size in output slots) */
+                                  16/32/64/128/256 = occurrences per seed-table hop (window size in output slots);
+                                  reserved[3] low byte = slices of a locate call: 0 = auto (two pipelined slices from 16384
+                                  patterns up), 1 = never slice */
 } rig_options;
 
 typedef struct rig_index_info {
@@ -77,7 +79,8 @@ typedef struct rig_timing {
     float expand_ms;  /* Phi expansion kernel (locate only) */
     float d2h_ms;     /* result download (host-buffer entry points only) */
     uint32_t launches;      /* kernels launched by the call */
-    uint32_t reserved;
+    uint32_t slices;        /* locate: 2 when the batch was cut into two slices pipelined on two streams (then search_ms,
+                               scan_ms, seed_ms, window_ms describe slice 0; expand_ms runs from slice 0's scan to the end) */
     uint64_t lf_steps;      /* executed LF steps (early exits excluded), r_index.hpp:297 */
     uint64_t occ_total;     /* occurrences written */
     uint64_t chains;        /* independent Phi chains the ranges were split into */
@@ -169,6 +172,10 @@ int rig_navigate_batch_dev(rig_index* idx, int op, const uint64_t* d_positions, 
 /* r_index<>::get_bwt (internal/r_index.hpp:375-377, rle_string::toString) restricted to [from, from+len): the BWT
  * as bytes, terminator row = 0x01 (HOST buffer). */
 int rig_get_bwt(rig_index* idx, uint64_t from, uint64_t len, uint8_t* out);
+
+/* Change the slicing of locate calls after creation (0 = auto, 1 = never slice): lets a caller time the kernels of a
+ * whole batch alone. */
+int rig_set_slices(rig_index* idx, uint32_t slices);
 
 int rig_last_timing(const rig_index* idx, rig_timing* t);
 

@@ -18,7 +18,7 @@ DECLARED_SYMBOLS = [
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
-    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt",
+    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_set_slices",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -39,7 +39,7 @@ class IndexInfo(ctypes.Structure):
 
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("search_ms", ctypes.c_float), ("scan_ms", ctypes.c_float),
-                ("expand_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float), ("launches", _u32), ("reserved", _u32),
+                ("expand_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float), ("launches", _u32), ("slices", _u32),
                 ("lf_steps", _u64), ("occ_total", _u64), ("chains", _u64), ("seed_ms", ctypes.c_float),
                 ("window_ms", ctypes.c_float)]
 
@@ -103,6 +103,7 @@ def gpu_lib():
         lib.rig_navigate_batch.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
         lib.rig_navigate_batch_dev.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp, _vp]
         lib.rig_get_bwt.argtypes = [_vp, _u64, _u64, _vp]
+        lib.rig_set_slices.argtypes = [_vp, _u32]
         lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
         lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
         lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
@@ -305,6 +306,12 @@ class GpuIndex:
         if rc != 0:
             raise RigError(rc, "rig_digest_dev")
         return int(out[0]), int(out[1])
+
+    def set_slices(self, slices):
+        """0 = auto (large locate batches run as two pipelined slices), 1 = never slice."""
+        rc = self.lib.rig_set_slices(self.h, slices)
+        if rc != 0:
+            raise RigError(rc, "rig_set_slices")
 
     def timing(self):
         t = Timing()

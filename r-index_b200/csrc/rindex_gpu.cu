@@ -56,16 +56,19 @@ struct rig_index {
     rig_options opt{};
     void* arena = nullptr;  // one allocation holding every flat array
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes
+    cudaStream_t stream2 = nullptr;   // second slice of a pipelined locate call
+    cudaEvent_t ev_fork = nullptr, ev_scan[2] = {nullptr, nullptr}, ev_join = nullptr;
+    uint32_t slices = 0;             // 0 = auto (2 for large batches), 1 = never slice
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes, [7] = end of slice 0's window pass
     // workspace (grow-only)
-    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items;
+    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items, items2;
     DevBuf text, big1, big2, ctable, crep, cfound;  // post-processing (-o / -c): attached text, sort tiers, hash join
     uint64_t text_len = 0;
     bool has_text = false;
     bool sort_attr_done = false;  // dynamic shared memory opt-in of the sort kernels (per device)
     ull* d_post = nullptr;      // [0] big1 count [1] big2 count [2..7] check report
     ull* h_post = nullptr;      // pinned mirror
-    ull* d_counters = nullptr;  // [0] lf_steps [1] chain queue [2..3] totals (occ, chains) [4..5] digest [6] expansion items
+    ull* d_counters = nullptr;  // [0] lf_steps [2..3] totals (occ, chains) of slice 0 [4..5] digest [6] items of slice 0 [8..9] totals, [10] items of slice 1
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
@@ -73,7 +76,7 @@ struct rig_index {
     size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
     float l2_hit_ratio = 1.f;
     bool timing_pending = false;
-    bool ev_valid[7] = {false, false, false, false, false, false, false};
+    bool ev_valid[8] = {false, false, false, false, false, false, false, false};
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -120,7 +123,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit8 never cut a locate batch into two pipelined slices, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
@@ -223,11 +226,16 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
         }
     }
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
+    for (auto& e2 : ix->ev_scan) CU_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    ix->slices = opt.reserved[3] & 0xffu;
     for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
-    CU_TRY(cudaMalloc((void**)&ix->d_counters, 8 * sizeof(ull)));
-    CU_TRY(cudaMemset(ix->d_counters, 0, 8 * sizeof(ull)));
-    CU_TRY(cudaMallocHost((void**)&ix->h_counters, 8 * sizeof(ull)));
-    std::memset(ix->h_counters, 0, 8 * sizeof(ull));
+    CU_TRY(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
+    CU_TRY(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
+    CU_TRY(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
+    std::memset(ix->h_counters, 0, 16 * sizeof(ull));
     CU_TRY(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
     CU_TRY(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
     CU_TRY(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
@@ -250,7 +258,7 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ, &ix->items, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
+                      &ix->occoff, &ix->occ, &ix->items, &ix->items2, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
@@ -258,6 +266,10 @@ void rig_index_destroy(rig_index* ix) {
     if (ix->d_post) cudaFree(ix->d_post);
     if (ix->h_post) cudaFreeHost(ix->h_post);
     for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
+    if (ix->stream2) { cudaStreamSynchronize(ix->stream2); cudaStreamDestroy(ix->stream2); }
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
+    for (auto& e2 : ix->ev_scan) if (e2) cudaEventDestroy(e2);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -275,9 +287,9 @@ namespace {
 
 template <bool LOCATE>
 int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi,
-                  cudaStream_t st) {
+                  cudaStream_t st, uint64_t poff = 0) {
     const uint32_t G = ix->d.K;
-    ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
+    ull* toe = (ull*)ix->toe.p + poff; ull* jl = (ull*)ix->jl.p + poff; ull* nch = (ull*)ix->nch.p + poff; ull* nocc = (ull*)ix->nocc.p + poff;
     ull* steps = ix->d_counters + 0;
     const bool n32 = ix->d.w32 != 0;
     if (G == 4 && !(ix->variant & 128)) {  // one lane per pattern over the K = 4 block records (bit7: cooperative kernel, A/B switch)
@@ -330,7 +342,7 @@ int finish_timing(rig_index* ix) {
     if ((rc = el(3, 4, ix->timing.expand_ms))) return rc;
     if ((rc = el(4, 5, ix->timing.d2h_ms))) return rc;
     if ((rc = el(3, 6, ix->timing.seed_ms))) return rc;
-    if ((rc = el(6, 4, ix->timing.window_ms))) return rc;
+    if ((rc = el(6, ix->ev_valid[7] ? 7 : 4, ix->timing.window_ms))) return rc;
     ix->timing.lf_steps = ix->h_counters[0];
     ix->timing_pending = false;
     return RIG_OK;
@@ -362,97 +374,75 @@ int count_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull*
     return RIG_OK;
 }
 
-// search + scans (sync) + expansion; events 1..4
-int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
-               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
+// One slice of a locate call: patterns [p0, p0 + np) with their own chain offsets, scan scratch, item list,
+// counters and stream.
+struct Slice {
+    uint64_t p0 = 0, np = 0, ntiles = 0;
+    ull* choff = nullptr;     // [np + 1] slice-local chain offsets
+    ull* sums = nullptr;      // [2 * ntiles + 2]
+    ull* totals = nullptr;    // device: occurrences, chains of the slice
+    ull* icount = nullptr;    // device: items appended by the seed pass
+    ull* h_totals = nullptr;  // pinned mirror of totals
+    DevBuf* items = nullptr;
+    cudaStream_t st = nullptr;
+    uint64_t total = 0, chains = 0;
+};
+
+// Phi expansion of one slice (seed pass + window pass, or the single-pass walk). `first` records event 6 between
+// the passes and warms the Phi tables into L2.
+int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_hi, const ull* d_occoff, ull* d_occ, bool first) {
     int rc;
-    const uint64_t ntiles = (N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE;
-    if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
-        (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 2) * 8)) ||
-        (rc = ix->sums.ensure((2 * ntiles + 2) * 8)))
-        return rc;
-    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
-    if ((rc = rec(ix, 1, st))) return rc;
-    if (N) {
-        if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, st))) return rc;
+    cudaStream_t st = sl.st;
+    const uint64_t total = sl.total, chains = sl.chains;
+    if (!chains) return RIG_OK;
+    const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 128;  // measured: 0.445 ms (128) vs 0.463 ms (256) on C2
+    const bool w32 = ix->d.w32 != 0;
+    const uint64_t nb = (chains + threads - 1) / threads;
+    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)nb); cfg.blockDim = dim3((unsigned)threads); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (ix->l2_window_bytes) {  // persisting-L2 experiment (RIG_VARIANT bit 0)
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(ix->d.phi.rec);
+        attr[0].val.accessPolicyWindow.num_bytes = ix->l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = ix->l2_hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    const ull* a_choff = sl.choff; const ull* a_occoff = d_occoff + sl.p0;
+    const ull* a_lo = d_lo + sl.p0; const ull* a_hi = d_hi + sl.p0;
+    const ull* a_toe = (const ull*)ix->toe.p + sl.p0; const ull* a_jl = (const ull*)ix->jl.p + sl.p0;
+    ull a_N = sl.np, a_chains = chains;
+    const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
+    if (first && !(ix->variant & 4) && ix->phi_bytes) {  // warm the Phi tables into L2 (bit2 disables: A/B switch)
+        const uint64_t lines = (ix->phi_bytes + 127) / 128;
+        rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
         ix->timing.launches += 1;
     }
-    if ((rc = rec(ix, 2, st))) return rc;
-    ull* totals = ix->d_counters + 2;
-    if (N) {
-        rigk::scan_tile_sums<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>((ull*)ix->nocc.p, (ull*)ix->nch.p, N,
-                                                                             (ull*)ix->sums.p, ntiles);
-        rigk::scan_sums_inplace<<<1, 1024, 0, st>>>((ull*)ix->sums.p, ntiles, totals);
-        rigk::scan_tiles<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>((ull*)ix->nocc.p, (ull*)ix->nch.p, N,
-                                                                         (ull*)ix->sums.p, ntiles, d_occoff,
-                                                                         (ull*)ix->choff.p, totals);
-        CU_TRY(cudaGetLastError());
-        ix->timing.launches += 3;
-    } else {
-        CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
-    }
-    CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    if ((rc = rec(ix, 3, st))) return rc;
-    CU_TRY(cudaStreamSynchronize(st));
-    const uint64_t total = ix->h_counters[2], chains = ix->h_counters[3];
-    ix->timing.occ_total = total;
-    ix->timing.chains = chains;
-    if (occ_total) *occ_total = total;
-    if (total > cap || (total && !d_occ)) {
-        if ((rc = rec(ix, 4, st))) return rc;
-        return RIG_ERR_CAPACITY;
-    }
-    if (chains) {
-        const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 128;  // measured: 0.445 ms (128) vs 0.463 ms (256) on C2
-        const bool w32 = ix->d.w32 != 0;
-        const uint64_t nb = (chains + threads - 1) / threads;
-        if (nb > 0x7fffffffull) return RIG_ERR_ARG;
-        // Keep the Phi bucket records resident in L2 while ~10-100x more occurrence bytes stream past
-        // them: persisting access-policy window on the record array for this launch.
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)nb); cfg.blockDim = dim3((unsigned)threads); cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        if (ix->l2_window_bytes) {
-            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(ix->d.phi.rec);
-            attr[0].val.accessPolicyWindow.num_bytes = ix->l2_window_bytes;
-            attr[0].val.accessPolicyWindow.hitRatio = ix->l2_hit_ratio;
-            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-        }
-        const ull* a_choff = (const ull*)ix->choff.p; const ull* a_occoff = d_occoff;
-        const ull* a_lo = d_lo; const ull* a_hi = d_hi;
-        const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
-        ull a_N = N, a_chains = chains;
-        const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
-        if (!(ix->variant & 4) && ix->phi_bytes) {  // warm the Phi tables into L2 (bit2 disables: A/B switch)
-            const uint64_t lines = (ix->phi_bytes + 127) / 128;
-            rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
-            ix->timing.launches += 1;
-        }
-        // Two passes when the index has a seed table and the output array is line-aligned (the window
-        // kernel writes whole 128-byte lines); otherwise the single-pass walk.
-        const uint32_t SEG = ix->d.seed.J;
-        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
-        uint32_t seg_shift = 0;
-        while ((1u << seg_shift) < SEG) ++seg_shift;
-        // a chain of L occurrences is cut into at most (L - 1) / SEG + 1 items
-        const uint64_t items_max = two_pass ? total / SEG + chains : 0;
-        if (two_pass && (rc = ix->items.ensure((items_max + 32) * 16))) return rc;
-        ull* a_items = (ull*)ix->items.p;
-        ull* a_icount = ix->d_counters + 6;  // zeroed with the other counters at the start of the call
-        const int wthreads = w32 ? 256 : 128;  // 32 KB of staging rows per block either way
-        const uint64_t wnb = (items_max + wthreads - 1) / wthreads;
-        if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
+    // Two passes when the index has a seed table and the output array is line-aligned (the window
+    // kernel writes whole 128-byte lines); otherwise the single-pass walk.
+    const uint32_t SEG = ix->d.seed.J;
+    const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
+    uint32_t seg_shift = 0;
+    while ((1u << seg_shift) < SEG) ++seg_shift;
+    // a chain of L occurrences is cut into at most (L - 1) / SEG + 1 items
+    const uint64_t items_max = two_pass ? total / SEG + chains : 0;
+    if (two_pass && (rc = sl.items->ensure((items_max + 32) * 16))) return rc;
+    ull* a_items = (ull*)sl.items->p;
+    ull* a_icount = sl.icount;  // zeroed with the other counters at the start of the call
+    const int wthreads = w32 ? 256 : 128;  // 32 KB of staging rows per block either way
+    const uint64_t wnb = (items_max + wthreads - 1) / wthreads;
+    if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
 #define RIG_EXPAND2(W, DD, KP)                                                                                  \
     do {                                                                                                        \
         if (two_pass) {                                                                                         \
             CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, true>, ix->d, a_N, a_choff,      \
                                       a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
                                       seg_shift));                                                              \
-            if ((rc = rec(ix, 6, st))) return rc;                                                               \
+            if (first && (rc = rec(ix, 6, st))) return rc;                                                      \
             cudaLaunchConfig_t cfg2 = cfg;                                                                      \
             cfg2.gridDim = dim3((unsigned)wnb); cfg2.blockDim = dim3((unsigned)wthreads);                       \
             const ull* c_items = a_items; const ull* c_icount = a_icount;                                       \
@@ -475,24 +465,102 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         if (keep) RIG_EXPAND2(W, DD, true);                                                                   \
         else RIG_EXPAND2(W, DD, false);                                                                       \
     } while (0)
-        switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
-            case 2: RIG_EXPAND(ull, 1); break;
-            case 3: RIG_EXPAND(uint32_t, 1); break;
-            case 4: RIG_EXPAND(ull, 2); break;
-            case 5: RIG_EXPAND(uint32_t, 2); break;
-            case 8: RIG_EXPAND(ull, 4); break;
-            case 9: RIG_EXPAND(uint32_t, 4); break;
-            case 16: RIG_EXPAND(ull, 8); break;
-            case 17: RIG_EXPAND(uint32_t, 8); break;
-            default: return RIG_ERR_ARG;
-        }
+    switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
+        case 2: RIG_EXPAND(ull, 1); break;
+        case 3: RIG_EXPAND(uint32_t, 1); break;
+        case 4: RIG_EXPAND(ull, 2); break;
+        case 5: RIG_EXPAND(uint32_t, 2); break;
+        case 8: RIG_EXPAND(ull, 4); break;
+        case 9: RIG_EXPAND(uint32_t, 4); break;
+        case 16: RIG_EXPAND(ull, 8); break;
+        case 17: RIG_EXPAND(uint32_t, 8); break;
+        default: return RIG_ERR_ARG;
+    }
 #undef RIG_EXPAND2
 #undef RIG_EXPAND
-        CU_TRY(cudaGetLastError());
-        ix->timing.launches += 1;
-    }
-    if ((rc = rec(ix, 4, st))) return rc;
+    CU_TRY(cudaGetLastError());
+    ix->timing.launches += 1;
+    if (first && two_pass && (rc = rec(ix, 7, st))) return rc;
     return RIG_OK;
+}
+
+// search + scans (sync) + expansion; events 1..4 on `st`.
+// A large batch is cut into TWO slices that run on two streams: the search and the seed pass are latency-bound
+// (0.5 waves, ~30% issue on C2) and the window pass is bound by L2 requests, so slice 1's search / scans / seed
+// pass hide under slice 0's window pass. The slices share every per-pattern array (disjoint ranges); slice 1's
+// occurrence offsets start at slice 0's total (added on the device by its scan). rig_timing then describes
+// slice 0's phases; `slices` tells.
+int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
+               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
+    int rc;
+    const uint32_t nsl = (ix->slices != 1 && N >= 16384 && !(ix->variant & 256)) ? 2u : 1u;
+    Slice sl[2];
+    sl[0].p0 = 0; sl[0].np = nsl == 2 ? (N / 2) & ~(uint64_t)127 : N;
+    sl[1].p0 = sl[0].np; sl[1].np = N - sl[0].np;
+    for (uint32_t k = 0; k < nsl; ++k) sl[k].ntiles = (sl[k].np + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE;
+    if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
+        (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 4) * 8)) ||
+        (rc = ix->sums.ensure((2 * (sl[0].ntiles + sl[1].ntiles) + 8) * 8)))
+        return rc;
+    sl[0].choff = (ull*)ix->choff.p;            sl[1].choff = (ull*)ix->choff.p + sl[0].np + 2;
+    sl[0].sums = (ull*)ix->sums.p;              sl[1].sums = (ull*)ix->sums.p + 2 * sl[0].ntiles + 4;
+    sl[0].totals = ix->d_counters + 2;          sl[1].totals = ix->d_counters + 8;
+    sl[0].icount = ix->d_counters + 6;          sl[1].icount = ix->d_counters + 10;
+    sl[0].h_totals = ix->h_counters + 2;        sl[1].h_totals = ix->h_counters + 8;
+    sl[0].items = &ix->items;                   sl[1].items = &ix->items2;
+    sl[0].st = st;                              sl[1].st = ix->stream2;
+    ix->timing.slices = nsl;
+    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(ull), st));
+    if ((rc = rec(ix, 1, st))) return rc;
+    if (nsl == 2) {
+        CU_TRY(cudaEventRecord(ix->ev_fork, st));
+        CU_TRY(cudaStreamWaitEvent(sl[1].st, ix->ev_fork, 0));
+    }
+    for (uint32_t k = 0; k < nsl; ++k) {
+        Slice& s = sl[k];
+        if (s.np) {
+            if ((rc = launch_search<true>(ix, d_patt + s.p0 * m, s.np, m, d_lo + s.p0, d_hi + s.p0, s.st, s.p0))) return rc;
+            ix->timing.launches += 1;
+        }
+        if (k == 0 && (rc = rec(ix, 2, st))) return rc;
+        if (s.np) {
+            ull* nocc = (ull*)ix->nocc.p + s.p0; ull* nch = (ull*)ix->nch.p + s.p0;
+            rigk::scan_tile_sums<<<(unsigned)s.ntiles, RIG_SCAN_THREADS, 0, s.st>>>(nocc, nch, s.np, s.sums, s.ntiles);
+            rigk::scan_sums_inplace<<<1, 1024, 0, s.st>>>(s.sums, s.ntiles, s.totals);
+            if (k == 1) CU_TRY(cudaStreamWaitEvent(s.st, ix->ev_scan[0], 0));  // slice 1's offsets start at slice 0's total
+            rigk::scan_tiles<<<(unsigned)s.ntiles, RIG_SCAN_THREADS, 0, s.st>>>(nocc, nch, s.np, s.sums, s.ntiles, d_occoff + s.p0,
+                                                                                  s.choff, s.totals, k == 1 ? sl[0].totals : nullptr);
+            CU_TRY(cudaGetLastError());
+            ix->timing.launches += 3;
+        } else {
+            CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, s.st));
+        }
+        // the last slice's copy also carries the LF-step counter: every search kernel has finished by then
+        if (k + 1 == nsl) CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 16 * sizeof(ull), cudaMemcpyDeviceToHost, s.st));
+        else CU_TRY(cudaMemcpyAsync(s.h_totals, s.totals, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s.st));
+        CU_TRY(cudaEventRecord(ix->ev_scan[k], s.st));
+        if (k == 0 && (rc = rec(ix, 3, st))) return rc;
+    }
+    // slice 0: learn its totals, start its expansion while slice 1 is still searching
+    CU_TRY(cudaEventSynchronize(ix->ev_scan[0]));
+    sl[0].total = sl[0].h_totals[0]; sl[0].chains = sl[0].h_totals[1];
+    bool fits = !(sl[0].total > cap || (sl[0].total && !d_occ));
+    if (fits && (rc = expand_slice(ix, sl[0], d_lo, d_hi, d_occoff, d_occ, true))) return rc;
+    uint64_t total = sl[0].total, chains = sl[0].chains;
+    if (nsl == 2) {
+        CU_TRY(cudaEventSynchronize(ix->ev_scan[1]));
+        sl[1].total = sl[1].h_totals[0]; sl[1].chains = sl[1].h_totals[1];
+        total += sl[1].total; chains += sl[1].chains;
+        fits = fits && !(total > cap || (total && !d_occ));
+        if (fits && (rc = expand_slice(ix, sl[1], d_lo, d_hi, d_occoff, d_occ, false))) return rc;
+        CU_TRY(cudaEventRecord(ix->ev_join, sl[1].st));
+        CU_TRY(cudaStreamWaitEvent(st, ix->ev_join, 0));
+    }
+    ix->timing.occ_total = total;
+    ix->timing.chains = chains;
+    if (occ_total) *occ_total = total;
+    if ((rc = rec(ix, 4, st))) return rc;
+    return fits ? RIG_OK : RIG_ERR_CAPACITY;
 }
 
 }  // namespace
@@ -767,6 +835,12 @@ int rig_get_bwt(rig_index* ix, uint64_t from, uint64_t len, uint8_t* out) {
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(out, ix->patt.p, len, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
+int rig_set_slices(rig_index* ix, uint32_t slices) {
+    if (!ix || slices > 2) return RIG_ERR_ARG;
+    ix->slices = slices;
     return RIG_OK;
 }
 

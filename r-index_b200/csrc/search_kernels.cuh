@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(1024) scan_sums_inplace(u64* __restrict__ sums
 // per tile: exclusive scan with the tile's offset; out arrays have N+1 entries
 __global__ void __launch_bounds__(RIG_SCAN_THREADS)
 scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u64* __restrict__ sums, u64 ntiles,
-           u64* __restrict__ out_a, u64* __restrict__ out_b, const u64* __restrict__ totals) {
+           u64* __restrict__ out_a, u64* __restrict__ out_b, const u64* __restrict__ totals,
+           const u64* __restrict__ base_a) {  // *base_a (if given) is added to every out_a entry
     __shared__ u64 wsum[2][RIG_SCAN_THREADS / 32];
     const u64 base = (u64)blockIdx.x * RIG_SCAN_TILE + (u64)threadIdx.x * RIG_SCAN_ITEMS;
     u64 va[RIG_SCAN_ITEMS], vb[RIG_SCAN_ITEMS];
@@ -466,7 +467,8 @@ scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u6
     __syncthreads();
     u64 wa = 0, wb = 0;
     for (int j = 0; j < w; ++j) { wa += wsum[0][j]; wb += wsum[1][j]; }
-    u64 ea = sums[blockIdx.x] + wa + ia - ta;
+    const u64 ba = base_a ? __ldcg(base_a) : 0;
+    u64 ea = ba + sums[blockIdx.x] + wa + ia - ta;
     u64 eb = sums[ntiles + blockIdx.x] + wb + ib - tb;
 #pragma unroll
     for (int i = 0; i < RIG_SCAN_ITEMS; ++i) {
@@ -474,7 +476,7 @@ scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u6
         if (idx < N) { out_a[idx] = ea; out_b[idx] = eb; }
         ea += va[i]; eb += vb[i];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { out_a[N] = totals[0]; out_b[N] = totals[1]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out_a[N] = ba + totals[0]; out_b[N] = totals[1]; }
 }
 
 // out[0] += sum v, out[1] += sum v*(i+1)   (mod 2^64)

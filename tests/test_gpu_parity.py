@@ -303,3 +303,51 @@ def test_both_search_kernels_k4(variant, monkeypatch):
             patt = mixed_patterns(text, 100, m, it)
             _check_all(gpu, port, patt, 100, m, "variant=%s it=%d m=%d" % (variant, it, m))
         gpu.close()
+
+
+def test_two_slice_pipelined_locate_equals_unsliced_and_oracle():
+    """Batches of >= 16384 patterns run as two slices pipelined on two streams (slice 1's search and seed pass
+    hide under slice 0's window pass). Same ranges, offsets and occurrences as the unsliced call and the oracle;
+    the capacity protocol and the device-buffer entry point behave the same."""
+    torch = pytest.importorskip("torch")
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 41)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host)
+    for (N, m, seed) in [(16384, 12, 1), (20001, 7, 2), (40000, 16, 3)]:
+        patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+        elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+        gpu.set_slices(0)
+        lo, hi, off, occ = gpu.locate(patt, N, m)
+        assert gpu.timing()["slices"] == 2
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(off, eoff) and np.array_equal(occ, eocc)
+        gpu.set_slices(1)
+        lo1, hi1, off1, occ1 = gpu.locate(patt, N, m)
+        assert gpu.timing()["slices"] == 1
+        assert np.array_equal(lo1, elo) and np.array_equal(off1, eoff) and np.array_equal(occ1, eocc)
+    # capacity protocol with two slices: too small for slice 0, and large enough for slice 0 only
+    gpu.set_slices(0)
+    import ctypes
+    N, m = 20001, 7
+    patt = mixed_patterns(text, N, m, 2, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
+    half = int(eoff[(N // 2) & ~127])
+    for cap in (3, half + 5):
+        lo = np.zeros(N, dtype=np.uint64); hi = np.zeros(N, dtype=np.uint64); off = np.zeros(N + 1, dtype=np.uint64)
+        small = np.zeros(cap, dtype=np.uint64)
+        tot = ctypes.c_uint64(0)
+        rc = gpu.lib.rig_locate_batch(gpu.h, patt.ctypes.data, N, m, lo.ctypes.data, hi.ctypes.data, off.ctypes.data,
+                                      small.ctypes.data, small.size, ctypes.byref(tot))
+        assert rc == -4 and tot.value == eocc.size and np.array_equal(off, eoff) and np.array_equal(lo, elo)
+    # device-buffer entry point on a caller's stream
+    dev = torch.device("cuda:0")
+    d_patt = torch.from_numpy(patt).to(dev)
+    d_lo = torch.zeros(N, dtype=torch.int64, device=dev); d_hi = torch.zeros(N, dtype=torch.int64, device=dev)
+    d_off = torch.zeros(N + 1, dtype=torch.int64, device=dev); d_occ = torch.zeros(eocc.size, dtype=torch.int64, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        tot = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(),
+                             d_occ.numel(), s.cuda_stream)
+    s.synchronize()
+    assert tot == eocc.size and np.array_equal(d_occ.cpu().numpy().view(np.uint64), eocc)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), eoff)
