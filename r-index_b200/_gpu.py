@@ -308,7 +308,7 @@ class GpuIndex:
         return int(out[0]), int(out[1])
 
     def set_slices(self, slices):
-        """0 = auto (large locate batches run as two pipelined slices), 1 = never slice."""
+        """2 = large locate batches run as two pipelined slices (opt-in), 0/1 = never slice."""
         rc = self.lib.rig_set_slices(self.h, slices)
         if rc != 0:
             raise RigError(rc, "rig_set_slices")

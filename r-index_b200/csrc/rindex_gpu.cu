@@ -58,7 +58,7 @@ struct rig_index {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // second slice of a pipelined locate call
     cudaEvent_t ev_fork = nullptr, ev_scan[2] = {nullptr, nullptr}, ev_join = nullptr;
-    uint32_t slices = 0;             // 0 = auto (2 for large batches), 1 = never slice
+    uint32_t slices = 0;             // 2 = cut large locate batches into two pipelined slices (opt-in), else never
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes, [7] = end of slice 0's window pass
     // workspace (grow-only)
     DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items, items2;
@@ -123,7 +123,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit8 never cut a locate batch into two pipelined slices, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     rigf::FlatHost f;
@@ -485,15 +485,17 @@ int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_h
 }
 
 // search + scans (sync) + expansion; events 1..4 on `st`.
-// A large batch is cut into TWO slices that run on two streams: the search and the seed pass are latency-bound
-// (0.5 waves, ~30% issue on C2) and the window pass is bound by L2 requests, so slice 1's search / scans / seed
-// pass hide under slice 0's window pass. The slices share every per-pattern array (disjoint ranges); slice 1's
-// occurrence offsets start at slice 0's total (added on the device by its scan). rig_timing then describes
-// slice 0's phases; `slices` tells.
+// OPT-IN (rig_set_slices(2) / rig_options.reserved[3] = 2): a batch of >= 16384 patterns is cut into TWO slices that
+// run on two streams, so that slice 1's search / scans / seed pass (latency-bound: 0.5 waves, ~30% issue on C2) hide
+// under slice 0's window pass (bound by L2 requests). The slices share every per-pattern array (disjoint ranges);
+// slice 1's occurrence offsets start at slice 0's total (added on the device by its scan). rig_timing then describes
+// slice 0's phases; `slices` tells. Measured gain: 1.5% (C2), 4.5% (C3s, C5s) — the latency-bound phases take as long
+// for half a batch as for a whole one, and two half-size window passes take 0.34 ms against 0.27 ms for one: off by
+// default.
 int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
                ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
     int rc;
-    const uint32_t nsl = (ix->slices != 1 && N >= 16384 && !(ix->variant & 256)) ? 2u : 1u;
+    const uint32_t nsl = (ix->slices == 2 && N >= 16384) ? 2u : 1u;
     Slice sl[2];
     sl[0].p0 = 0; sl[0].np = nsl == 2 ? (N / 2) & ~(uint64_t)127 : N;
     sl[1].p0 = sl[0].np; sl[1].np = N - sl[0].np;
