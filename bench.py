@@ -517,6 +517,21 @@ def run_ours(args):
     assert tot_e2e == occ_e2e
     # cheap self-check of the e2e result (not a parity test: those live in tests/)
     assert int(h_off[-1]) == occ_e2e
+    # the same call with 32-bit positions (rig_locate_batch32; texts below 4 GiB): half the D2H bytes
+    e2e32_ms = None
+    if int(info.n) <= 0xFFFFFFFF:
+        h_occ32 = torch.empty(max(occ_e2e, 1), dtype=torch.int32).pin_memory()
+        for _ in range(2):
+            gpu.locate32_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(), h_occ32.data_ptr(), h_occ32.numel())
+        t32 = 0.0
+        for k in range(e2e_steps):
+            flush.zero_(); torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            gpu.locate32_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(), h_occ32.data_ptr(), h_occ32.numel())
+            t32 += time.perf_counter() - t1
+        e2e32_ms = t32 * 1e3 / e2e_steps
+        assert torch.equal(h_occ32[:4096].to(torch.int64) & 0xFFFFFFFF, h_occ[:4096])
+        del h_occ32
 
     # ri-locate -o / -c post-processing on the device, timed once on the resident output of the last
     # step: segmented sort of every pattern's occurrences, then the self-check (hash-join brute-force counts over
@@ -606,6 +621,10 @@ def run_ours(args):
                                            "achieved": int(lf_steps) * 3 * B_RANK(ell) / (srch_ms * 1e-3) / 1e9 if srch_ms > 0 else None},
                          "scan_ms": statistics.mean(scan_ms)},
         }
+        if e2e32_ms is not None:  # rank 0's own figure (not reduced over ranks)
+            line["e2e_u32"] = {"value": occ_e2e / (e2e32_ms * 1e-3), "unit": "occ/s", "ms_per_step": e2e32_ms,
+                               "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1) + 4 * occ_e2e),
+                               "api": "rig_locate_batch32 (32-bit positions, n < 2^32; an addition to the reference's 64-bit surface)"}
         if post is not None:
             line["post"] = post
         if ref is not None:

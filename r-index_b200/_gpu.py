@@ -18,7 +18,7 @@ DECLARED_SYMBOLS = [
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
-    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_set_slices",
+    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_set_slices", "rig_locate_batch32",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -104,6 +104,7 @@ def gpu_lib():
         lib.rig_navigate_batch_dev.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp, _vp]
         lib.rig_get_bwt.argtypes = [_vp, _u64, _u64, _vp]
         lib.rig_set_slices.argtypes = [_vp, _u32]
+        lib.rig_locate_batch32.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _u32]
         lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
         lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
         lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
@@ -270,6 +271,30 @@ class GpuIndex:
         if rc != 0:
             raise RigError(rc, "rig_check_dev")
         return rep
+
+    def locate32(self, patterns, N, m, flags=0):
+        """rig_locate_batch32: (lo, hi, occ_offsets, occ as uint32)."""
+        p = _as_u8(patterns)
+        lo = np.empty(N, dtype=np.uint64)
+        hi = np.empty(N, dtype=np.uint64)
+        off = np.empty(N + 1, dtype=np.uint64)
+        tot = _u64(0)
+        rc = self.lib.rig_locate_batch32(self.h, _ptr(p), N, m, _ptr(lo), _ptr(hi), _ptr(off), None, 0, ctypes.byref(tot), 0)
+        if rc not in (0, RIG_ERR_CAPACITY):
+            raise RigError(rc, "rig_locate_batch32")
+        occ = np.empty(int(tot.value), dtype=np.uint32)
+        rc = self.lib.rig_locate_batch32(self.h, _ptr(p), N, m, _ptr(lo), _ptr(hi), _ptr(off), _ptr(occ), occ.size,
+                                         ctypes.byref(tot), flags)
+        if rc != 0:
+            raise RigError(rc, "rig_locate_batch32")
+        return lo, hi, off, occ
+
+    def locate32_raw(self, p_ptr, N, m, lo_ptr, hi_ptr, off_ptr, occ_ptr, cap):
+        tot = _u64(0)
+        rc = self.lib.rig_locate_batch32(self.h, p_ptr, N, m, lo_ptr, hi_ptr, off_ptr, occ_ptr, cap, ctypes.byref(tot), 0)
+        if rc != 0:
+            raise RigError(rc, "rig_locate_batch32")
+        return int(tot.value)
 
     def locate_raw(self, p_ptr, N, m, lo_ptr, hi_ptr, off_ptr, occ_ptr, cap):
         """Host-pointer call with caller-managed (e.g. pinned) buffers given as integer addresses."""

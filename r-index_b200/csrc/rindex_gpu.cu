@@ -62,6 +62,7 @@ struct rig_index {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes, [7] = end of slice 0's window pass
     // workspace (grow-only)
     DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items, items2;
+    DevBuf occ32;             // rig_locate_batch32: narrowed positions
     DevBuf text, big1, big2, ctable, crep, cfound;  // post-processing (-o / -c): attached text, sort tiers, hash join
     uint64_t text_len = 0;
     bool has_text = false;
@@ -258,7 +259,7 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ, &ix->items, &ix->items2, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
+                      &ix->occoff, &ix->occ, &ix->items, &ix->items2, &ix->occ32, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
@@ -791,6 +792,45 @@ int rig_locate_batch_ex(rig_index* ix, const uint8_t* patterns, uint64_t N, uint
     }
     CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ.p, total * 8, cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 5, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return lrc;
+}
+
+// ---- 32-bit positions for texts below 4 GiB: half the bytes over PCIe -------------------------------------
+int rig_locate_batch32(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                       uint64_t* occ_offsets, uint32_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags) {
+    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns) || (flags & RIG_LOCATE_CHECK)) return RIG_ERR_ARG;
+    if (ix->d.n > 0xFFFFFFFFull) return RIG_ERR_ARG;  // positions would not fit
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
+        (rc = ix->occoff.ensure((N + 2) * 8)))
+        return rc;
+    if (occ && occ_capacity && ((rc = ix->occ.ensure(occ_capacity * 8)) || (rc = ix->occ32.ensure(occ_capacity * 4 + 16)))) return rc;
+    begin_call(ix);
+    if ((rc = rec(ix, 0, st))) return rc;
+    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
+                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
+    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
+    if (occ_total) *occ_total = total;
+    if (lrc == RIG_OK && total) {
+        if ((flags & RIG_LOCATE_SORT) && (rc = sort_dev(ix, N, (const ull*)ix->occoff.p, (ull*)ix->occ.p, total, st))) return rc;
+        const uint64_t nb = ((total + 3) / 4 + 255) / 256;
+        if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+        rigk::narrow_kernel<<<(unsigned)nb, 256, 0, st>>>((const ull*)ix->occ.p, (uint32_t*)ix->occ32.p, total);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 1;
+    }
+    if (N) {
+        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ32.p, total * 4, cudaMemcpyDeviceToHost, st));
     if ((rc = rec(ix, 5, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     return lrc;

@@ -479,6 +479,17 @@ scan_tiles(const u64* __restrict__ a, const u64* __restrict__ b, u64 N, const u6
     if (blockIdx.x == 0 && threadIdx.x == 0) { out_a[N] = ba + totals[0]; out_b[N] = totals[1]; }
 }
 
+// 64-bit positions -> 32-bit positions (rig_locate_batch32: every position < n < 2^32), 4 per thread
+__global__ void __launch_bounds__(256) narrow_kernel(const u64* __restrict__ in, u32* __restrict__ out, u64 count) {
+    const u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= count) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(in + i), b = *reinterpret_cast<const ulonglong2*>(in + i + 2);
+        *reinterpret_cast<uint4*>(out + i) = make_uint4((u32)a.x, (u32)a.y, (u32)b.x, (u32)b.y);
+    } else {
+        for (u64 k = i; k < count; ++k) out[k] = (u32)in[k];
+    }
+}
+
 // out[0] += sum v, out[1] += sum v*(i+1)   (mod 2^64)
 __global__ void __launch_bounds__(256) digest_kernel(const u64* __restrict__ v, u64 count, u64* __restrict__ out) {
     __shared__ u64 sm[32];

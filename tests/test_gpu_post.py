@@ -122,3 +122,23 @@ def test_edge_cases_sort_and_check():
     assert rep.clean and np.diff(off.astype(np.int64)).tolist() == [ob.brute_count(text, np.frombuffer(q, dtype=np.uint8)) for q in pats]
     lo, hi, off, occ, rep = gpu.locate_ex(np.zeros(0, dtype=np.uint8), 2, 0, rib.LOCATE_SORT | rib.LOCATE_CHECK)  # m = 0
     assert rep.clean and occ[: text.size + 1].tolist() == list(range(text.size + 1))
+
+
+def test_locate32_equals_locate():
+    """rig_locate_batch32: the same positions as rig_locate_batch, as uint32, plain and sorted; refused when
+    positions would not fit (64-bit index)."""
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 19)
+    host = rib.HostIndex.from_text(text)
+    gpu = rib.GpuIndex(host)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for (N, m, seed) in [(700, 8, 1), (0, 5, 2), (33, 1, 3), (17001, 11, 4)]:
+        patt = mixed_patterns(text, N, m, seed, alphabet=acgt) if N else np.zeros(0, dtype=np.uint8)
+        lo, hi, off, occ = gpu.locate(patt, N, m)
+        lo2, hi2, off2, occ32 = gpu.locate32(patt, N, m)
+        assert occ32.dtype == np.uint32
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2) and np.array_equal(off, off2)
+        assert np.array_equal(occ32.astype(np.uint64), occ)
+        _, _, _, occ32s = gpu.locate32(patt, N, m, rib.LOCATE_SORT)
+        assert np.array_equal(occ32s.astype(np.uint64), _sorted_per_pattern(off, occ))
+    with pytest.raises(rib.RigError):
+        gpu.locate32(patt, N, m, rib.LOCATE_CHECK)
