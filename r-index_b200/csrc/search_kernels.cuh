@@ -228,15 +228,16 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
 // warp collective at all, so a warp carries 32 patterns instead of 4 and the kernel turns from issue-bound
 // into latency-bound (2 dependent loads per LF step: directory, record). Both rank queries of an LF step
 // are done by the same lane with their loads interleaved.
-struct LaneRec {           // one K = 4 block record as a lane reads it
-    u64 s0, s1, s2, s3;    // run starts (padding runs start at n)
+template <typename PT>
+struct LaneRec {           // one K = 4 block record as a lane reads it (position words: PT)
+    PT s0, s1, s2, s3;     // run starts (padding runs start at n)
     u32 heads;             // 4 run heads, one byte each
-    u64 before;            // #c in the BWT before the block
+    PT before;             // #c in the BWT before the block
 };
 
 template <typename PT>
 __device__ __forceinline__ u32 lane_block_of(const FlatDev& ix, PT x, u32 b0, u32 b1) {
-    while (b0 < b1) {      // the bucket straddles blocks (4 buckets per block: rarely more than one step)
+    while (b0 < b1) {      // the bucket straddles blocks (clustered short runs: a few steps at most)
         const u32 mid = b0 + ((b1 - b0 + 1) >> 1);
         if (ld_pos<PT>(ix.bstart, mid) <= x) b0 = mid; else b1 = mid - 1;
     }
@@ -244,7 +245,7 @@ __device__ __forceinline__ u32 lane_block_of(const FlatDev& ix, PT x, u32 b0, u3
 }
 
 template <typename PT>
-__device__ __forceinline__ void lane_load(const FlatDev& ix, u32 b, u32 sidc, LaneRec& r) {
+__device__ __forceinline__ void lane_load(const FlatDev& ix, u32 b, u32 sidc, LaneRec<PT>& r) {
     const char* rp = ix.blk + (u64)b * ix.blk_stride;
     if constexpr (sizeof(PT) == 4) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp));
@@ -254,21 +255,21 @@ __device__ __forceinline__ void lane_load(const FlatDev& ix, u32 b, u32 sidc, La
         r.s0 = a.x; r.s1 = a.y; r.s2 = c.x; r.s3 = c.y;
     }
     r.heads = __ldg(reinterpret_cast<const u32*>(rp + ix.off_head));
-    r.before = (u64)__ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
+    r.before = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
 }
 
-// rank / run / head of position x from its block record (same outputs as block_query)
+// rank / run / head of position x from its block record (same outputs as block_query); all arithmetic in PT
 template <bool WANT_RUN, typename PT>
-__device__ __forceinline__ void lane_eval(const FlatDev& ix, const LaneRec& r, u32 b, u64 x, uint8_t c, u32 sidc,
-                                          u64& cnt, u32& run, bool& head_is_c, u32& prev_c_run) {
+__device__ __forceinline__ void lane_eval(const FlatDev& ix, const LaneRec<PT>& r, u32 b, PT x, uint8_t c, u32 sidc,
+                                          PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run) {
     const u32 t = (u32)(r.s1 <= x) + (u32)(r.s2 <= x) + (u32)(r.s3 <= x);  // run of the block holding x
     const u32 cc = (u32)c * 0x01010101u, eq = r.heads ^ cc;                 // byte g is 0 iff head g == c
     const bool m0 = (eq & 0xffu) == 0, m1 = (eq & 0xff00u) == 0, m2 = (eq & 0xff0000u) == 0, m3 = (eq & 0xff000000u) == 0;
-    u64 add = 0;
+    PT add = 0;
     if (m0 && t > 0) add += r.s1 - r.s0;
     if (m1 && t > 1) add += r.s2 - r.s1;
     if (m2 && t > 2) add += r.s3 - r.s2;
-    const u64 st = t == 0 ? r.s0 : (t == 1 ? r.s1 : (t == 2 ? r.s2 : r.s3));
+    const PT st = t == 0 ? r.s0 : (t == 1 ? r.s1 : (t == 2 ? r.s2 : r.s3));
     const bool mt = t == 0 ? m0 : (t == 1 ? m1 : (t == 2 ? m2 : m3));
     if (mt) add += x - st + 1;
     cnt = r.before + add;
@@ -287,17 +288,17 @@ __global__ void __launch_bounds__(128)
 search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
                    u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
                    u64* __restrict__ nch_out, u64* __restrict__ nocc_out, u64* __restrict__ lf_steps) {
-    struct SymEnt { u64 f0, f1; u32 sid, pad; };
+    struct SymEnt { PT f0, f1; u32 sid, pad; };  // F[256] = n fits: n < 2^32-1 when PT = u32
     __shared__ SymEnt sSym[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        sSym[i].f0 = ix.F[i]; sSym[i].f1 = ix.F[i + 1]; sSym[i].sid = ix.sid[i]; sSym[i].pad = 0;
+        sSym[i].f0 = (PT)ix.F[i]; sSym[i].f1 = (PT)ix.F[i + 1]; sSym[i].sid = ix.sid[i]; sSym[i].pad = 0;
     }
     __syncthreads();
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = p < N;
     const uint8_t* P = patt + (alive ? p : 0) * m;
-    u64 lo = 0, hi = ix.n - 1;  // full_range, r_index.hpp:155-160
-    u64 k = ix.toe0;            // SA[n-1], r_index.hpp:489
+    PT lo = 0, hi = (PT)(ix.n - 1);  // full_range, r_index.hpp:155-160
+    PT k = (PT)ix.toe0;              // SA[n-1], r_index.hpp:489
     u32 steps = 0;
     for (u64 i = 0; i < m; ++i) {
         if (!__any_sync(RIG_FULL, alive)) break;  // r_index.hpp:297 (early exit on empty range)
@@ -308,14 +309,14 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
         ++steps;
         // rank(lo, c) = #c in bwt[0, lo) and rank(hi + 1, c): r_index.hpp:178,181 — both queries' loads interleaved
         const bool need_a = lo > 0;
-        const PT xa = (PT)(need_a ? lo - 1 : 0), xb = (PT)hi;
+        const PT xa = need_a ? (PT)(lo - 1) : (PT)0, xb = hi;
         const u32 qa = (u32)(xa >> ix.lf_shift), qb = (u32)(xb >> ix.lf_shift);
         const u32 a0 = __ldg(ix.bdir + qa), a1 = __ldg(ix.bdir + qa + 1), b0 = __ldg(ix.bdir + qb), b1 = __ldg(ix.bdir + qb + 1);
         const u32 ba = lane_block_of<PT>(ix, xa, a0, a1), bb = lane_block_of<PT>(ix, xb, b0, b1);
-        LaneRec ra, rb;
+        LaneRec<PT> ra, rb;
         lane_load<PT>(ix, ba, se.sid, ra);
         lane_load<PT>(ix, bb, se.sid, rb);
-        u64 A = 0, B;
+        PT A = 0, B;
         u32 run = 0, prevc = 0;
         bool hic = false;
         {
@@ -326,8 +327,8 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
         lane_eval<LOCATE, PT>(ix, rb, bb, xb, c, se.sid, B, run, hic, prevc);
         if (B == A) { lo = 1; hi = 0; alive = false; continue; }  // r_index.hpp:175,184
         if (LOCATE) {
-            if (hic) k -= 1;                                        // r_index.hpp:505-509
-            else k = (u64)ld_pos<PT>(ix.samples_last, prevc);       // r_index.hpp:516-533
+            if (hic) k -= 1;                                   // r_index.hpp:505-509
+            else k = ld_pos<PT>(ix.samples_last, prevc);       // r_index.hpp:516-533
         }
         lo = se.f0 + A;        // r_index.hpp:186
         hi = se.f0 + B - 1;    // r_index.hpp:188
@@ -337,22 +338,21 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
             const bool ne = hi >= lo;
             u32 jL = 0, jR = 0;
             if (ne) {
-                const PT xa = (PT)lo, xb = (PT)hi;
-                const u32 qa = (u32)(xa >> ix.lf_shift), qb = (u32)(xb >> ix.lf_shift);
-                const u32 ba = lane_block_of<PT>(ix, xa, __ldg(ix.bdir + qa), __ldg(ix.bdir + qa + 1));
-                const u32 bb = lane_block_of<PT>(ix, xb, __ldg(ix.bdir + qb), __ldg(ix.bdir + qb + 1));
-                LaneRec ra, rb;
+                const u32 qa = (u32)(lo >> ix.lf_shift), qb = (u32)(hi >> ix.lf_shift);
+                const u32 ba = lane_block_of<PT>(ix, lo, __ldg(ix.bdir + qa), __ldg(ix.bdir + qa + 1));
+                const u32 bb = lane_block_of<PT>(ix, hi, __ldg(ix.bdir + qb), __ldg(ix.bdir + qb + 1));
+                LaneRec<PT> ra, rb;
                 lane_load<PT>(ix, ba, 0, ra);
                 lane_load<PT>(ix, bb, 0, rb);
-                jL = ba * 4u + (u32)(ra.s1 <= (u64)xa) + (u32)(ra.s2 <= (u64)xa) + (u32)(ra.s3 <= (u64)xa);
-                jR = bb * 4u + (u32)(rb.s1 <= (u64)xb) + (u32)(rb.s2 <= (u64)xb) + (u32)(rb.s3 <= (u64)xb);
+                jL = ba * 4u + (u32)(ra.s1 <= lo) + (u32)(ra.s2 <= lo) + (u32)(ra.s3 <= lo);
+                jR = bb * 4u + (u32)(rb.s1 <= hi) + (u32)(rb.s2 <= hi) + (u32)(rb.s3 <= hi);
             }
-            toe_out[p] = k;
+            toe_out[p] = (u64)k;
             jl_out[p] = jL;
             nch_out[p] = ne ? (u64)(jR - jL + 1) : 0;
-            nocc_out[p] = ne ? (hi - lo) + 1 : 0;  // r_index.hpp:338
+            nocc_out[p] = ne ? (u64)(hi - lo) + 1 : 0;  // r_index.hpp:338
         }
-        lo_out[p] = lo; hi_out[p] = hi;
+        lo_out[p] = (u64)lo; hi_out[p] = (u64)hi;
     }
     // executed LF steps (for the algorithmic-bytes figure)
     u32 sum = steps;
