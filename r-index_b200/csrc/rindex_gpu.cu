@@ -418,11 +418,6 @@ int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_h
     const ull* a_toe = (const ull*)ix->toe.p + sl.p0; const ull* a_jl = (const ull*)ix->jl.p + sl.p0;
     ull a_N = sl.np, a_chains = chains;
     const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
-    if (first && !(ix->variant & 4) && ix->phi_bytes) {  // warm the Phi tables into L2 (bit2 disables: A/B switch)
-        const uint64_t lines = (ix->phi_bytes + 127) / 128;
-        rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
-        ix->timing.launches += 1;
-    }
     // Two passes when the index has a seed table and the output array is line-aligned (the window
     // kernel writes whole 128-byte lines); otherwise the single-pass walk.
     const uint32_t SEG = ix->d.seed.J;
@@ -543,6 +538,13 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         else CU_TRY(cudaMemcpyAsync(s.h_totals, s.totals, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s.st));
         CU_TRY(cudaEventRecord(ix->ev_scan[k], s.st));
         if (k == 0 && (rc = rec(ix, 3, st))) return rc;
+        // warm the Phi tables into L2 (RIG_VARIANT bit2 disables: A/B switch); queued BEFORE the host waits for the
+        // totals, so the device is not idle during the host's turnaround
+        if (k == 0 && N && d_occ && !(ix->variant & 4) && ix->phi_bytes) {
+            const uint64_t lines = (ix->phi_bytes + 127) / 128;
+            rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
+            ix->timing.launches += 1;
+        }
     }
     // slice 0: learn its totals, start its expansion while slice 1 is still searching
     CU_TRY(cudaEventSynchronize(ix->ev_scan[0]));

@@ -125,3 +125,20 @@ def test_cli_multi_gpu_flag_is_shard_invariant(tmp_path):
     assert a.returncode == 0 and b.returncode == 0
     assert mask(a.stdout) == mask(b.stdout)
     assert open(str(tmp_path / "a"), "rb").read() == open(str(tmp_path / "b"), "rb").read()
+
+
+def test_ri_build_large_text_takes_the_pfp_route_and_equals_sais(tmp_path):
+    """From 16 MB up ri-build constructs by prefix-free parsing; the .ri it writes holds exactly
+    the arrays the in-memory SA-IS route gives (forced with RIB_BUILDER=sais), and the stdout lines are the same."""
+    text = rib.gen_text("dna_drift", 17_000_000, 20_000, 3, 5)
+    tfile = str(tmp_path / "big.txt")
+    open(tfile, "wb").write(bytes(text))
+    a = run([os.path.join(BIN, "ri-build"), "-o", str(tmp_path / "pfp"), tfile])
+    b = run([os.path.join(BIN, "ri-build"), "-o", str(tmp_path / "sais"), tfile], env=dict(os.environ, RIB_BUILDER="sais"))
+    assert a.returncode == 0 and b.returncode == 0
+    assert mask(a.stdout).replace("pfp.ri", "X") == mask(b.stdout).replace("sais.ri", "X")
+    A, B = rib.HostIndex.load(str(tmp_path / "pfp.ri")).arrays(), rib.HostIndex.load(str(tmp_path / "sais.ri")).arrays()
+    assert (A["n"], A["r"]) == (B["n"], B["r"]) == (text.size + 1, B["r"])
+    for k in ("F", "run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run"):
+        assert np.array_equal(A[k], B[k]), k
+    assert rib.HostIndex.from_text_auto(text).used_pfp is True
