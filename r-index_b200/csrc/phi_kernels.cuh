@@ -246,17 +246,17 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
     } else {
         const u64 SEG = 1ull << seg_shift;
         const u64 a1 = (g0 + RIG_LINE - 1) & ~(u64)(RIG_LINE - 1);  // first line-aligned slot at or after g0
-        const u32 K = (active && a1 <= glast) ? (u32)((glast - a1) >> seg_shift) + 1u : 0u;  // items of this chain
+        const u64 K = (active && a1 <= glast) ? ((glast - a1) >> seg_shift) + 1 : 0;  // items of this chain
         // reserve K entries of items[]: inclusive warp scan, one atomic by the last lane
         const int lane = threadIdx.x & 31;
-        u32 incl = K;
+        u64 incl = K;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const u32 t = __shfl_up_sync(RIG_FULL, incl, d);
+            const u64 t = __shfl_up_sync(RIG_FULL, incl, d);
             if (lane >= d) incl += t;
         }
         u64 wbase = 0;
-        if (lane == 31 && incl) wbase = atomicAdd(item_count, (u64)incl);
+        if (lane == 31 && incl) wbase = atomicAdd(item_count, incl);
         wbase = __shfl_sync(RIG_FULL, wbase, 31);
         if (!active) return;
         const u64 pre_last = min(a1, glast);
