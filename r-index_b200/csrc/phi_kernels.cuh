@@ -3,12 +3,12 @@
 //
 // TWO PASSES when the index carries a seed table (Phi^SEG, flat_layout.hpp: JumpTable), one otherwise:
 //
-//   phi_expand_kernel<.., SEEDED=true>   one lane per chain: writes the toehold, walks the chain up to the
-//        next SEG-aligned slot of the OUTPUT array, then hops along the chain SEG occurrences at a time
-//        (one seed-table lookup per hop), writing only the occurrence that falls on each aligned slot
-//        (the window's SEED) and the number of further occurrences of that window (winfo[]).
-//   phi_window_kernel                    one lane per SEG-slot window of the output array: reads its seed,
-//        produces the window's occurrences with D per lookup, every store one aligned 32-byte sector.
+//   phi_expand_kernel<.., SEEDED=true>   "seed pass", one lane per chain: writes the toehold, walks the chain's
+//        head up to the next 128-byte line of the OUTPUT array (<= 16 occurrences), then hops along the chain
+//        SEG occurrences at a time (one seed-table lookup per hop) and appends one 16-byte ITEM per hop to a
+//        list: (first output slot, number of occurrences that follow, seed = the occurrence on that slot).
+//   phi_window_kernel                    "window pass", one lane per item: from the seed, every lookup yields D
+//        occurrences that leave as one aligned 32-byte sector.
 //
 // The single-pass form's time is (longest chain) x (load latency) with half-empty warps (chain lengths
 // differ by orders of magnitude inside a warp); the two-pass form turns the batch into uniform
