@@ -45,7 +45,7 @@ def build_host(force=False):
     srcs = [os.path.join(PKG, "host", f) for f in ("rindex_host.cpp", "logical_index.hpp", "sais.hpp", "textgen.hpp", "pfp_builder.hpp")]
     srcs += [os.path.join(INC, "rindex_host.h"), os.path.join(INC, "rindex_gpu.h")]
     if force or _newer(HOST_SO, srcs):
-        _run(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-w", "-I", INC,
+        _run(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", INC,
               "-o", HOST_SO, srcs[0]])
     return HOST_SO
 

@@ -26,8 +26,11 @@
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
+#include <chrono>
 #include <memory>
 #include <queue>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "logical_index.hpp"
@@ -98,78 +101,125 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
     const uint64_t n = len + 1;  // S = T·0x00
     const uint32_t w = prm.w < 1 ? 1 : prm.w, p = prm.p < 1 ? 1 : prm.p;
     auto S = [&](uint64_t i) -> uint8_t { return i < len ? text[i] : (uint8_t)0; };
+    const bool timing = getenv("RIB_PFP_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pfp] %-34s %.2f s\n", what, std::chrono::duration<double>(t - t_last).count());
+        t_last = t;
+    };
 
     // ---- 1. parse -------------------------------------------------------------------------------------------
-    struct Phrase { const uint8_t* ptr; uint32_t len; };
+    // (a) trigger positions: a window S[i-w+1..i] triggers when a mix of its rolling polynomial hash (mod 2^64)
+    //     falls below 2^32/p. A pure function of the window: text chunks are scanned by independent host threads.
+    // (b) phrase k = S[E[k-1]-w+1 .. E[k]] (the first starts at 0; the first cut needs i >= w so that the phrase is
+    //     longer than the window); (c) per-phrase content hashes, again in parallel; (d) dictionary, serial:
+    //     |P| ~ n/p hash lookups, each verified byte for byte. Phrases are kept as (offset, length) into the text;
+    //     only the last one, which ends with S's 0x00, is materialised.
+    struct Phrase { uint64_t off; uint32_t len; };    // bytes S[off .. off+len)
     std::vector<Phrase> phrases;                       // by id (first-seen order)
-    std::vector<std::unique_ptr<uint8_t[]>> arena;     // phrase bytes, chunked so that pointers stay valid
-    size_t arena_used = 0, arena_cap = 0;
-    auto arena_put = [&](uint64_t b, uint64_t e) -> const uint8_t* {  // copy S[b..e]
-        const size_t L = (size_t)(e - b + 1);
-        if (arena_used + L > arena_cap) {
-            arena_cap = std::max<size_t>(L, (size_t)64 << 20);
-            arena.emplace_back(new uint8_t[arena_cap]);
-            arena_used = 0;
-        }
-        uint8_t* dst = arena.back().get() + arena_used;
-        for (size_t t = 0; t < L; ++t) dst[t] = S(b + t);
-        arena_used += L;
-        return dst;
-    };
-    std::unordered_multimap<uint64_t, uint32_t> seen;  // content hash -> phrase id (content verified)
     std::vector<uint32_t> parse;                       // phrase ids
     std::vector<uint64_t> tpos;                        // start of every phrase occurrence in S
+    std::unordered_multimap<uint64_t, uint32_t> seen;  // content hash -> phrase id (content verified)
     {
-        const uint64_t prime = 1999999973ull;
-        uint64_t hw = 0, pw = 1;  // Karp-Rabin hash of the current window, 256^(w-1) mod prime
-        for (uint32_t t = 1; t < w; ++t) pw = (pw * 256) % prime;
-        uint64_t b = 0, h2 = 1469598103934665603ull;  // phrase start, FNV-1a of the phrase so far
-        // the phrase hash must cover the phrase from its first byte: restart it at every phrase start by
-        // re-hashing the w overlap bytes
-        for (uint64_t i = 0; i < n; ++i) {
-            const uint8_t c = S(i);
-            if (i >= w) hw = (hw + prime - (pw * S(i - w)) % prime) % prime;
-            hw = (hw * 256 + c) % prime;
-            h2 = (h2 ^ c) * 1099511628211ull;
-            const bool trigger = (i + 1 >= w) && (hw % p == 0) && (i - b + 1 > w);
-            if (trigger || i == n - 1) {
-                const uint32_t L = (uint32_t)(i - b + 1);
-                if ((uint64_t)L != i - b + 1) throw std::length_error("phrase longer than 2^32");
-                uint32_t id = ~0u;
-                auto range = seen.equal_range(h2);
+        unsigned T = std::thread::hardware_concurrency();
+        if (T > 32) T = 32;
+        if (T < 1 || n < ((uint64_t)1 << 22)) T = 1;
+        const uint64_t B = 0x100000001b3ull;
+        uint64_t Bw = 1;
+        for (uint32_t t = 0; t < w; ++t) Bw *= B;
+        const uint64_t thr = ((uint64_t)1 << 32) / p;
+        std::vector<std::vector<uint64_t>> trig(T);
+        auto scan = [&](unsigned t) {
+            const uint64_t c0 = n * t / T, c1 = n * (t + 1) / T, i0 = c0 >= w ? c0 - w : 0;
+            uint64_t hw = 0;
+            std::vector<uint64_t>& out = trig[t];
+            for (uint64_t i = i0; i < c1; ++i) {
+                hw = hw * B + (uint64_t)S(i) + 1;
+                if (i - i0 >= w) hw -= Bw * ((uint64_t)S(i - w) + 1);
+                if (i < c0 || i < w) continue;  // i >= w: the window is complete and the first phrase is longer than it
+                const uint64_t mix = (hw ^ (hw >> 29)) * 0xBF58476D1CE4E5B9ull;
+                if ((mix >> 32) < thr) out.push_back(i);
+            }
+        };
+        if (T == 1) scan(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; ++t) th.emplace_back(scan, t);
+            for (auto& x : th) x.join();
+        }
+        std::vector<uint64_t> E;  // inclusive end of every phrase
+        {
+            uint64_t total = 1;
+            for (auto& v : trig) total += v.size();
+            E.reserve(total);
+            for (auto& v : trig) { E.insert(E.end(), v.begin(), v.end()); std::vector<uint64_t>().swap(v); }
+            if (E.empty() || E.back() != n - 1) E.push_back(n - 1);
+        }
+        const uint64_t NPh = E.size();
+        if (NPh >= 0x7fffff00ull) throw std::length_error("parse longer than 2^31");
+        tpos.resize(NPh);
+        std::vector<uint64_t> phash(NPh);
+        auto hash_range = [&](unsigned t) {
+            for (uint64_t k = NPh * t / T; k < NPh * (t + 1) / T; ++k) {
+                const uint64_t b0 = k == 0 ? 0 : E[k - 1] + 1 - w, e0 = E[k];
+                if (e0 - b0 + 1 > 0xffffffffull) continue;  // reported by the serial pass
+                uint64_t h = 1469598103934665603ull;
+                for (uint64_t i = b0; i <= e0; ++i) h = (h ^ S(i)) * 1099511628211ull;
+                tpos[k] = b0; phash[k] = h;
+            }
+        };
+        if (T == 1) hash_range(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; ++t) th.emplace_back(hash_range, t);
+            for (auto& x : th) x.join();
+        }
+        parse.resize(NPh);
+        for (uint64_t k = 0; k < NPh; ++k) {
+            const uint64_t b0 = k == 0 ? 0 : E[k - 1] + 1 - w, L64 = E[k] - b0 + 1;
+            if (L64 > 0xffffffffull) throw std::length_error("phrase longer than 2^32");
+            const uint32_t L = (uint32_t)L64;
+            uint32_t id = ~0u;
+            if (k + 1 < NPh) {  // the last phrase holds the unique 0x00: always new
+                auto range = seen.equal_range(phash[k]);
                 for (auto it = range.first; it != range.second; ++it) {
                     const Phrase& q = phrases[it->second];
-                    if (q.len != L) continue;
-                    bool eq = true;
-                    for (uint32_t t = 0; t < L && eq; ++t) eq = q.ptr[t] == S(b + t);
-                    if (eq) { id = it->second; break; }
-                }
-                if (id == ~0u) {
-                    id = (uint32_t)phrases.size();
-                    if (phrases.size() >= 0x7fffff00ull) throw std::length_error("too many distinct phrases");
-                    phrases.push_back({arena_put(b, i), L});
-                    seen.emplace(h2, id);
-                }
-                parse.push_back(id);
-                tpos.push_back(b);
-                if (i < n - 1) {
-                    b = i + 1 - w;
-                    h2 = 1469598103934665603ull;
-                    for (uint64_t t = b; t <= i; ++t) h2 = (h2 ^ S(t)) * 1099511628211ull;
+                    if (q.len == L && std::memcmp(text + q.off, text + b0, L) == 0) { id = it->second; break; }
                 }
             }
+            if (id == ~0u) {
+                id = (uint32_t)phrases.size();
+                if (phrases.size() >= 0x7fffff00ull) throw std::length_error("too many distinct phrases");
+                phrases.push_back({b0, L});
+                if (k + 1 < NPh) seen.emplace(phash[k], id);
+            }
+            parse[k] = id;
         }
     }
     seen.clear();
+    lap("parse");
     const uint64_t ND = phrases.size(), NP = parse.size();
     if (NP >= 0x7fffff00ull) throw std::length_error("parse longer than 2^31");
 
     // ---- 2. sort the dictionary, rename the parse --------------------------------------------------------------
     std::vector<uint32_t> order(ND);
     for (uint32_t i = 0; i < ND; ++i) order[i] = i;
+    // phrase bytes: text[off .. off+len), with the virtual 0x00 of S as the last byte of the last phrase only
+    const uint32_t last_id = parse[NP - 1];
+    auto pbyte = [&](const Phrase& q, uint32_t t) -> uint8_t { return q.off + t < len ? text[q.off + t] : (uint8_t)0; };
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         const Phrase &x = phrases[a], &y = phrases[b];
-        const int c = std::memcmp(x.ptr, y.ptr, std::min(x.len, y.len));
+        uint32_t m = std::min(x.len, y.len);
+        if (a == last_id || b == last_id) {  // compare byte-wise through the virtual terminator
+            for (uint32_t t = 0; t < m; ++t) {
+                const uint8_t cx = pbyte(x, t), cy = pbyte(y, t);
+                if (cx != cy) return cx < cy;
+            }
+            return x.len < y.len;
+        }
+        const int c = std::memcmp(text + x.off, text + y.off, m);
         return c != 0 ? c < 0 : x.len < y.len;
     });
     std::vector<uint32_t> rank_of(ND);
@@ -187,13 +237,14 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
     for (uint32_t d = 0; d < ND; ++d) {
         const Phrase& q = phrases[order[d]];
         uint16_t* dst = &C[dstart[d]];
-        for (uint32_t t = 0; t < q.len; ++t) dst[t] = sym_of(q.ptr[t]);
+        for (uint32_t t = 0; t < q.len; ++t) dst[t] = sym_of(pbyte(q, t));
         dst[q.len] = 1;
     }
     C[M] = 0;
-    arena.clear(); phrases.clear(); phrases.shrink_to_fit(); order.clear(); order.shrink_to_fit();
+    phrases.clear(); phrases.shrink_to_fit(); order.clear(); order.shrink_to_fit();
     rank_of.clear(); rank_of.shrink_to_fit();
 
+    lap("dictionary sort + rename");
     // ---- 3. suffix array of the parse; occurrences of every phrase ordered by the parse suffix that follows --------
     std::vector<uint32_t> occ_begin(ND + 1, 0), occ_rank(NP), occ_k(NP);
     {
@@ -213,11 +264,13 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
         }
     }
 
+    lap("suffix array of the parse + lists");
     // ---- 4. suffix array of the dictionary -----------------------------------------------------------------------
     if (M + 1 >= 0x7fffff00ull) throw std::length_error("dictionary longer than 2^31");
     std::vector<int32_t> SAD(M + 1);
     sais_detail::sais_rec<uint16_t, int32_t>(C.data(), SAD.data(), (int32_t)(M + 1), (int32_t)257);
 
+    lap("suffix array of the dictionary");
     // ---- 5. sweep ------------------------------------------------------------------------------------------------
     LogicalIndex L;
     RunBuilder rb(L, n);
@@ -297,7 +350,9 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
     }
     flush_group();
     if (rb.rows_emitted() != n) throw std::logic_error("prefix-free parsing: row count differs from the text length");
+    lap("sweep");
     rb.finish();
+    lap("finish (sort run-first samples)");
     if (stats) *stats = st;
     return L;
 }
