@@ -323,15 +323,39 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
                 cur[g] = occ_begin[grp[g].d];
                 if (cur[g] < occ_begin[grp[g].d + 1]) pq.push({occ_rank[cur[g]], g});
             }
+            // Pop the list with the smallest next rank and drain it up to the next list's head: the occurrences of one
+            // phrase suffix often come in long stretches of consecutive ranks, and when the suffix does not start
+            // its phrase (o > 0) they all carry the same BWT symbol — a whole stretch is one emit().
             while (!pq.empty()) {
                 const uint32_t g = pq.top().second;
                 pq.pop();
+                const uint32_t limit = pq.empty() ? ~0u : pq.top().first;  // ranks are distinct across lists
                 const Member m = grp[g];
-                const uint32_t k = occ_k[cur[g]];
-                const uint64_t sa = tpos[k] + m.o;
-                rb.emit(m.o > 0 ? byte_of(C[dstart[m.d] + m.o - 1]) : pred_byte_of_occurrence(k), 1, sa, sa);
-                ++st.merged_rows;
-                if (++cur[g] < occ_begin[m.d + 1]) pq.push({occ_rank[cur[g]], g});
+                const uint32_t end = occ_begin[m.d + 1];
+                uint32_t x = cur[g];
+                if (m.o > 0) {
+                    // gallop to the first occurrence whose rank exceeds the limit: everything below lo2 is known to be
+                    // under it, hi2 is `end` or the first probe at or above it
+                    uint32_t lo2 = x + 1, hi2 = x + 1, step = 1;
+                    while (hi2 < end && occ_rank[hi2] < limit) {
+                        lo2 = hi2 + 1;
+                        hi2 = (end - hi2 > step) ? hi2 + step : end;
+                        step <<= 1;
+                    }
+                    const uint32_t stop = (uint32_t)(std::lower_bound(occ_rank.begin() + lo2, occ_rank.begin() + hi2, limit) - occ_rank.begin());
+                    rb.emit(byte_of(C[dstart[m.d] + m.o - 1]), stop - x, tpos[occ_k[x]] + m.o, tpos[occ_k[stop - 1]] + m.o);
+                    st.merged_rows += stop - x;
+                    x = stop;
+                } else {
+                    do {
+                        const uint32_t k = occ_k[x];
+                        rb.emit(pred_byte_of_occurrence(k), 1, tpos[k], tpos[k]);
+                        ++st.merged_rows;
+                        ++x;
+                    } while (x < end && occ_rank[x] < limit);
+                }
+                cur[g] = x;
+                if (x < end) pq.push({occ_rank[x], g});
             }
         }
         grp.clear();
