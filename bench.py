@@ -201,6 +201,33 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa(gpu_index):
+    """Bind this process (and the pinned host buffers it allocates afterwards: first touch) to the NUMA node the GPU
+    hangs off. With one process per GPU the host-buffer path (`e2e`) otherwise crosses sockets for half the ranks.
+    Returns the node or None; never fails the run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:   # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -288,6 +315,7 @@ def run_ours_count(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local) if world > 1 else None
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
@@ -409,6 +437,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local) if world > 1 else None
 
     text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
     t0 = time.time()
@@ -603,7 +632,7 @@ def run_ours(args):
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": occ_e2e_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
                     "h2d_bytes_per_step": int(NE * m), "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1 + occ_e2e)),
-                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps,
+                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps, "numa_node_rank0": numa,
                     "patterns_per_step": NE, "occurrences_per_step": occ_e2e},
             "gpu_launches": int(launches_g) + launches_count * world,
             "count": {"metric": "count_patterns_per_s", "value": N_g * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
