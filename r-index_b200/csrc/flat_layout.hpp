@@ -283,6 +283,7 @@ struct FlatHost {
     // instead of three separate arrays. W = 4 when w32 else 8.
     std::vector<uint8_t> blk;      // [nblk * blk_stride]
     u32 blk_stride = 0, off_head = 0, off_cum = 0;
+    u32 rec_w = 8;       // bytes per position word INSIDE the block records: 4 (w32), 8, or 5 = 40-bit packed (n < 2^40)
     std::vector<u64> last;         // [nblk*S] id of the last run of each symbol before the block (locate toehold misses)
     std::vector<u32> bdir;         // [lf_nbkt + 1]
     std::vector<u64> samples_last; // [r]
@@ -341,10 +342,10 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     const bool w32_pos = f.w32;
     u32 K = opt.runs_per_block;
     if (K == 0) {  // smallest K whose block records (K starts + K heads + S counts, 32-byte padded) stay within ~2 GB
-        const u64 W = w32_pos ? 4 : 8, budget = 2ull << 30;
+        const u64 W = w32_pos ? 4 : (n < (1ull << 40) ? 5 : 8), budget = 2ull << 30;
         K = 16;
         for (u32 k : {4u, 8u}) {
-            const u64 stride = ((k * W + k + W - 1) / W * W + S * W + 31) / 32 * 32;
+            const u64 stride = (k * W + k + S * W + 3 + 31) / 32 * 32;
             if (((r + k - 1) / k) * stride <= budget) { K = k; break; }
         }
     }
@@ -385,13 +386,18 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     lap("runs + directory counts");
     // interleaved block records
     {
-        const u32 W = f.w32 ? 4 : 8;
+        // Position words inside the records: 32-bit when w32; otherwise 40-bit packed while n < 2^40 (a K = 4 DNA
+        // record is then 64 bytes = one DRAM burst instead of 96: the count kernel on a 10 GB text runs at the rate
+        // DRAM delivers random sectors, 3 of its 4.4 sectors per rank query were the record), 64-bit beyond.
+        // reserved[1] bit1 keeps 64-bit words (A/B switch).
+        const u32 W = f.w32 ? 4 : ((n < (1ull << 40) && !(opt.reserved[1] & 2)) ? 5 : 8);
+        f.rec_w = W;
         f.off_head = K * W;
-        f.off_cum = (K * W + K + W - 1) / W * W;
-        f.blk_stride = (f.off_cum + S * W + 31) / 32 * 32;
+        f.off_cum = W == 5 ? K * W + K : (K * W + K + W - 1) / W * W;
+        f.blk_stride = (f.off_cum + S * W + (W == 5 ? 3 : 0) + 31) / 32 * 32;
         f.blk.assign(nblk * (u64)f.blk_stride, 0);
         f.last.assign(nblk * (u64)S, 0);
-        auto put = [&](uint8_t* dst, u64 v) { if (W == 4) { uint32_t x = (uint32_t)v; memcpy(dst, &x, 4); } else memcpy(dst, &v, 8); };
+        auto put = [&](uint8_t* dst, u64 v) { memcpy(dst, &v, W); };  // little endian: the low W bytes
         for (u64 b = 0; b < nblk; ++b) {
             uint8_t* R = &f.blk[b * f.blk_stride];
             for (u32 t = 0; t < K; ++t) { put(R + t * W, f.start[b * K + t]); R[f.off_head + t] = f.head[b * K + t]; }

@@ -218,17 +218,16 @@ navigate_kernel(const FlatDev ix, int op, const u64* __restrict__ pos, u64 N, u6
     if (op == NAV_BWT || op == NAV_LF) {
         const u32 b = nav_block_of<PT>(ix, (PT)i);
         const char* rp = ix.blk + (u64)b * ix.blk_stride;
-        const PT* st = reinterpret_cast<const PT*>(rp);
         const uint8_t* hd = reinterpret_cast<const uint8_t*>(rp + ix.off_head);
         u32 k = 0;  // run of the block holding i: the last one starting at or before i (padding starts are n > i)
-        for (u32 g = 1; g < K; ++g) if (__ldg(st + g) <= (PT)i) k = g;
+        for (u32 g = 1; g < K; ++g) if (rec_word<PT>(ix, rp, 0, g) <= (PT)i) k = g;
         const uint8_t c = __ldg(hd + k);
         if (op == NAV_BWT) { out[t] = c; return; }
         const u32 sidc = __ldg(ix.sid + c);
-        u64 rank = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);  // #c before the block
+        u64 rank = rec_word<PT>(ix, rp, ix.off_cum, sidc);  // #c before the block
         for (u32 g = 0; g < k; ++g)
-            if (__ldg(hd + g) == c) rank += (u64)(__ldg(st + g + 1) - __ldg(st + g));
-        rank += i - (u64)__ldg(st + k);  // #c in bwt[0, i): rle_string::rank(i, c), rle_string.hpp:170-218
+            if (__ldg(hd + g) == c) rank += (u64)(rec_word<PT>(ix, rp, 0, g + 1) - rec_word<PT>(ix, rp, 0, g));
+        rank += i - (u64)rec_word<PT>(ix, rp, 0, k);  // #c in bwt[0, i): rle_string::rank(i, c), rle_string.hpp:170-218
         out[t] = __ldg(ix.F + c) + rank;
         return;
     }
@@ -240,18 +239,17 @@ navigate_kernel(const FlatDev ix, int op, const u64* __restrict__ pos, u64 N, u6
     u64 b0 = 0, b1 = ix.nblk - 1;
     while (b0 < b1) {
         const u64 mid = b0 + ((b1 - b0 + 1) >> 1);
-        const u64 before = __ldg(reinterpret_cast<const PT*>(ix.blk + mid * ix.blk_stride + ix.off_cum) + sidc);
+        const u64 before = rec_word<PT>(ix, ix.blk + mid * ix.blk_stride, ix.off_cum, sidc);
         if (before <= j) b0 = mid; else b1 = mid - 1;
     }
     const char* rp = ix.blk + b0 * ix.blk_stride;
-    const PT* st = reinterpret_cast<const PT*>(rp);
     const uint8_t* hd = reinterpret_cast<const uint8_t*>(rp + ix.off_head);
-    u64 rem = j - (u64)__ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
+    u64 rem = j - (u64)rec_word<PT>(ix, rp, ix.off_cum, sidc);
     u64 res = ~0ull;
     for (u32 g = 0; g < K; ++g) {
         if (__ldg(hd + g) != (uint8_t)c) continue;
-        const u64 s0 = __ldg(st + g);
-        const u64 s1 = (g + 1 < K) ? (u64)__ldg(st + g + 1) : (u64)ld_pos<PT>(ix.bstart, b0 + 1);
+        const u64 s0 = rec_word<PT>(ix, rp, 0, g);
+        const u64 s1 = (g + 1 < K) ? (u64)rec_word<PT>(ix, rp, 0, g + 1) : (u64)ld_pos<PT>(ix.bstart, b0 + 1);
         if (s0 >= ix.n) break;  // padding
         const u64 len = s1 - s0;
         if (rem < len) { res = s0 + rem; break; }

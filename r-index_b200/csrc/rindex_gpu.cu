@@ -127,6 +127,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
+    if (variant & 512) opt.reserved[1] |= 2;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
     rigf::FlatHost f;
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
@@ -193,7 +194,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.sid = (const uint16_t*)(A + parts[1].off);
     d.start = (const void*)(A + parts[2].off);
     d.blk = (const char*)(A + parts[3].off);
-    d.blk_stride = f.blk_stride; d.off_head = f.off_head; d.off_cum = f.off_cum; d.pad1 = 0;
+    d.blk_stride = f.blk_stride; d.off_head = f.off_head; d.off_cum = f.off_cum; d.rec_w = f.rec_w;
     d.bstart = (const void*)(A + parts[4].off);
     d.last = (const void*)(A + parts[5].off);
     d.bdir = (const uint32_t*)(A + parts[6].off);

@@ -45,7 +45,7 @@ struct FlatDev {
     const void* start;        // [nblk*K+1]  PT (u32 when w32, else u64)
     const char* blk;          // [nblk] interleaved block records: K starts (PT), K heads (u8), S counts (PT)
     const void* last;         // [nblk*S]    PT: last run of each symbol before the block
-    u32 blk_stride, off_head, off_cum, pad1;
+    u32 blk_stride, off_head, off_cum, rec_w;  // rec_w: bytes per position word inside the records (4, 8, or 5 = 40-bit packed)
     const void* bstart;       // [nblk+1]    PT
     const u32* bdir;          // [lf_nbkt+1]
     const void* samples_last; // [r]         PT
@@ -73,6 +73,22 @@ __device__ __forceinline__ T greduce_add(T v) {
 // are then stored as 32-bit words: half the bytes per block, 32-bit compares/adds), u64 otherwise.
 template <typename PT>
 __device__ __forceinline__ PT ld_pos(const void* base, u64 idx) { return __ldg(reinterpret_cast<const PT*>(base) + idx); }
+
+// Position word g of the record field that starts at byte `off` of record rp: 32-bit words, 64-bit words, or 40-bit
+// packed little-endian words (FlatDev::rec_w = 5: two aligned 32-bit loads and a shift; the record is padded so
+// that the second load stays inside it).
+template <typename PT>
+__device__ __forceinline__ PT rec_word(const FlatDev& ix, const char* rp, u32 off, u32 g) {
+    if constexpr (sizeof(PT) == 4) {
+        return __ldg(reinterpret_cast<const u32*>(rp + off) + g);
+    } else {
+        if (ix.rec_w == 8) return __ldg(reinterpret_cast<const u64*>(rp + off) + g);
+        const u32 o = off + 5u * g;
+        const u32* w = reinterpret_cast<const u32*>(rp + (o & ~3u));
+        const u64 v = ((u64)__ldg(w + 1) << 32) | (u64)__ldg(w);
+        return (v >> ((o & 3u) * 8u)) & 0xFFFFFFFFFFull;
+    }
+}
 
 // One cooperative query by a group of G lanes (all 32 lanes of the warp execute this together,
 // each group with its own x / c): locate the run holding BWT position x (0 <= x < n) and return
@@ -109,9 +125,9 @@ __device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, 
     }
     const u32 base = b0 * G;
     const char* rp = ix.blk + (u64)b0 * ix.blk_stride;  // the block record: starts | heads | counts
-    const PT st = __ldg(reinterpret_cast<const PT*>(rp) + gl);
+    const PT st = rec_word<PT>(ix, rp, 0, (u32)gl);
     const uint8_t hd = __ldg(reinterpret_cast<const uint8_t*>(rp + ix.off_head) + gl);
-    const PT cm = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
+    const PT cm = rec_word<PT>(ix, rp, ix.off_cum, sidc);
     const PT nxt = __shfl_down_sync(RIG_FULL, st, 1, G);
     const u32 mle = gballot<G>(st <= x, gbase);
     const int t = __popc(mle) - 1;  // >= 0: the block's first run starts at or before x
@@ -250,12 +266,23 @@ __device__ __forceinline__ void lane_load(const FlatDev& ix, u32 b, u32 sidc, La
     if constexpr (sizeof(PT) == 4) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp));
         r.s0 = v.x; r.s1 = v.y; r.s2 = v.z; r.s3 = v.w;
-    } else {
+    } else if (ix.rec_w == 8) {
         const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(rp)), c = __ldg(reinterpret_cast<const ulonglong2*>(rp) + 1);
         r.s0 = a.x; r.s1 = a.y; r.s2 = c.x; r.s3 = c.y;
+    } else {  // 40-bit packed: starts = bytes 0..19, heads = bytes 20..23: one 128-bit and one 64-bit load
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp));
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(rp) + 2);
+        const u64 m40 = 0xFFFFFFFFFFull;
+        r.s0 = (((u64)v.y << 32) | v.x) & m40;
+        r.s1 = ((((u64)v.z << 32) | v.y) >> 8) & m40;
+        r.s2 = ((((u64)v.w << 32) | v.z) >> 16) & m40;
+        r.s3 = ((((u64)t.x << 32) | v.w) >> 24) & m40;
+        r.heads = t.y;
+        r.before = rec_word<PT>(ix, rp, ix.off_cum, sidc);
+        return;
     }
     r.heads = __ldg(reinterpret_cast<const u32*>(rp + ix.off_head));
-    r.before = __ldg(reinterpret_cast<const PT*>(rp + ix.off_cum) + sidc);
+    r.before = rec_word<PT>(ix, rp, ix.off_cum, sidc);
 }
 
 // rank / run / head of position x from its block record (same outputs as block_query); all arithmetic in PT

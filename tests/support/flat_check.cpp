@@ -16,9 +16,9 @@ namespace {
 struct Q { u64 cnt, run, prev_c_run; bool head_is_c; };
 
 // mirrors rigk::block_query, reading the interleaved block records exactly as the device does
-u64 rd(const uint8_t* p, bool w32) { if (w32) { uint32_t x; memcpy(&x, p, 4); return x; } u64 x; memcpy(&x, p, 8); return x; }
+u64 rd(const uint8_t* p, u32 W) { u64 x = 0; memcpy(&x, p, W); return x; }  // W = 4, 5 (40-bit packed) or 8 bytes, little endian
 Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
-    const u32 K = f.K, W = f.w32 ? 4 : 8;
+    const u32 K = f.K, W = f.rec_w;
     u64 q = x >> f.lf_shift;
     u64 b0 = f.bdir[q], b1 = f.bdir[q + 1];
     while (b1 > b0) {  // same G-ary narrowing as the kernel, G = K probes per round
@@ -34,7 +34,7 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
     const uint8_t* R = &f.blk[b0 * f.blk_stride];
     u64 base = b0 * K;
     u64 st[16];
-    for (u32 g = 0; g < K; ++g) st[g] = rd(R + g * W, f.w32);
+    for (u32 g = 0; g < K; ++g) st[g] = rd(R + g * W, W);
     int t = -1;
     for (u32 g = 0; g < K; ++g) if (st[g] <= x) ++t;
     Q r;
@@ -44,7 +44,7 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
         if (isc) mc |= 1u << g;
         if (isc) sum += ((int)g < t) ? (st[g + 1] - st[g]) : (((int)g == t) ? (x - st[g] + 1) : 0);
     }
-    r.cnt = rd(R + f.off_cum + sidc * W, f.w32) + sum;
+    r.cnt = rd(R + f.off_cum + sidc * W, W) + sum;
     r.head_is_c = (mc >> t) & 1u;
     u32 below = mc & ((1u << t) - 1u);
     r.prev_c_run = below ? base + (31 - __builtin_clz(below)) : f.last[b0 * f.S + sidc];
@@ -170,7 +170,7 @@ void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_
     rig_options opt;
     std::memset(&opt, 0, sizeof(opt));
     opt.runs_per_block = K; opt.lf_bucket_log2 = lf_log2; opt.phi_bucket_log2 = phi_log2; opt.reserved[0] = jump;
-    opt.reserved[1] = force_wide ? 1 : 0;
+    opt.reserved[1] = force_wide;  // bit0: 64-bit position words, bit1: 64-bit (not 40-bit packed) words inside the block records
     opt.reserved[2] = seed_jump;
     FlatHost* f = new FlatHost();
     int rc = rigf::flatten(*v, opt, *f);

@@ -27,7 +27,7 @@ def test_flat_walk_equals_oracle(K):
 
 
 @pytest.mark.parametrize("jump", [1, 2, 4, 8])
-@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("wide", [False, True, 3])   # 32-bit words; 64-bit with 40-bit packed block records; plain 64-bit
 def test_jump_tables_equal_repeated_phi(jump, wide):
     """Phi^j (j = 1..D, composition of piecewise translations) == j applications of Phi, for every SA
     value it can legally be applied to, through the scalar table AND the bucket-record lookup (32- and

@@ -23,7 +23,7 @@ def _truth(text, sa):
 
 
 @pytest.mark.parametrize("K", [4, 16])
-@pytest.mark.parametrize("variant", ["0", "8"])
+@pytest.mark.parametrize("variant", ["0", "8", "520"])
 def test_navigation_equals_suffix_array_truth(K, variant, monkeypatch):
     monkeypatch.setenv("RIG_VARIANT", variant)
     rng = np.random.default_rng(5 + K)

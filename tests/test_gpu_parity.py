@@ -23,6 +23,23 @@ def _check_all(gpu, oracle, patt, N, m, tag=""):
 
 
 @pytest.mark.parametrize("K", [4, 8, 16])
+def test_wide_words_all_group_sizes(K, monkeypatch):
+    """64-bit position words (as for n >= 2^32) with 40-bit packed block records, for every group size of the
+    cooperative search kernel and the one-lane kernel."""
+    monkeypatch.setenv("RIG_VARIANT", "8")
+    rng = np.random.default_rng(900 + K)
+    for it in range(15):
+        n = int(rng.integers(1, 3000))
+        text = repetitive_text(n, int(rng.integers(1, 200)), int(rng.integers(0, 4)), 7000 * K + it, sigma=int(rng.choice([1, 2, 4, 15, 200])))
+        m = int(rng.integers(1, 9))
+        patt = mixed_patterns(text, 64, m, it)
+        gpu = rib.GpuIndex(rib.HostIndex.from_text(text), runs_per_block=K)
+        assert gpu.info.words32 == 0
+        _check_all(gpu, ob.PortIndex(text), patt, 64, m, "wide K=%d it=%d" % (K, it))
+        gpu.close()
+
+
+@pytest.mark.parametrize("K", [4, 8, 16])
 def test_small_random_texts(K):
     rng = np.random.default_rng(100 + K)
     for it in range(40):
@@ -287,7 +304,7 @@ def test_two_pass_unaligned_output_falls_back_to_single_pass():
         assert (t["window_ms"] > 0) == (shift == 0)
 
 
-@pytest.mark.parametrize("variant", ["128", "136", "8"])
+@pytest.mark.parametrize("variant", ["128", "136", "8", "520", "648"])   # +512: 64-bit (not 40-bit packed) block records
 def test_both_search_kernels_k4(variant, monkeypatch):
     """K = 4 block records are searched by one lane per pattern (default) or by the cooperative group kernel
     (RIG_VARIANT bit 7); both, in 32- and 64-bit words (bit 3), give the oracle's ranges, toeholds and occurrences,
