@@ -289,11 +289,16 @@ struct FlatHost {
     std::vector<u64> samples_last; // [r]
     bool w32 = false;              // n < 2^32-1: Phi records and deltas are stored as 32-bit words
     PhiTable phi;                  // Phi^1..Phi^D refined
+    // 64-bit index, D = 4, n < 2^40-1: the device gets 32-byte PACKED entries (4 x 40-bit deltas | 40-bit s1 or start |
+    // 32-bit nxt | 24-bit cnt) instead of 8 x 8 bytes: one sector per lookup. With a table far beyond L2 (C5 at full
+    // size: 493 MB) the window pass is DRAM-bound and half of its DRAM reads were the second sector of each entry.
+    bool phi_packed = false;
+    std::vector<uint8_t> phi_rec_p, phi_pent_p;
     JumpTable seed;                // Phi^SEG (seed.J = SEG; 0 = single-pass expansion only)
     u64 bytes() const {
         const u64 W = w32 ? 4 : 8;
         return F.size() * 8 + sid.size() * 2 + start.size() * W + blk.size() + bstart.size() * W + last.size() * W +
-               bdir.size() * 4 + samples_last.size() * W + phi.bytes(w32) + seed.bytes(w32);
+               bdir.size() * 4 + samples_last.size() * W + (phi_packed ? phi_rec_p.size() + phi_pent_p.size() : phi.bytes(w32)) + seed.bytes(w32);
     }
 };
 
@@ -467,6 +472,29 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
     lap("Phi^D composition");
     f.phi.build_directory(n, fp);
+    f.phi_packed = false;
+    if (!f.w32 && D == 4 && n < (1ull << 40) - 1 && !(opt.reserved[1] & 4)) {  // reserved[1] bit2: keep 8-byte words (A/B switch)
+        bool fits = true;
+        for (u64 q = 0; q < f.phi.nbkt && fits; ++q) fits = f.phi.rec[q * 8 + 6] < (1ull << 24);
+        if (fits) {
+            auto pack = [](const std::vector<u64>& src, std::vector<uint8_t>& dst) {
+                const u64 cnt = src.size() / 8;
+                dst.assign(cnt * 32, 0);
+                for (u64 k = 0; k < cnt; ++k) {
+                    const u64* w = &src[k * 8];
+                    uint8_t* o = &dst[k * 32];
+                    for (int t = 0; t < 5; ++t) { const u64 v = w[t] & 0xFFFFFFFFFFull; memcpy(o + 5 * t, &v, 5); }  // ~0 -> all ones
+                    const uint32_t nxt = (uint32_t)w[5];
+                    memcpy(o + 25, &nxt, 4);
+                    const uint32_t c3 = (uint32_t)w[6];
+                    memcpy(o + 29, &c3, 3);
+                }
+            };
+            pack(f.phi.rec, f.phi_rec_p);
+            pack(f.phi.pent, f.phi_pent_p);
+            f.phi_packed = true;
+        }
+    }
     lap("Phi^D directory");
     if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
 

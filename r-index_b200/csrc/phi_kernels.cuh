@@ -45,9 +45,27 @@ __device__ __forceinline__ void stg256_stream(void* p, u64 a, u64 b, u64 c, u64 
                  :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-// Load the RW-word entry at `p` (RW*sizeof(WT) aligned).
+// Load the RW-word entry at `p` (entry-size aligned). packed (64-bit words, RW = 8 only): the entry is 32 bytes,
+// 4 x 40-bit deltas | 40-bit s1/start | 32-bit nxt | 24-bit cnt, unpacked into the same word positions.
 template <typename WT, int RW, bool KEEP>
-__device__ __forceinline__ void load_entry(const void* p, WT (&w)[RW]) {
+__device__ __forceinline__ void load_entry(const void* p, WT (&w)[RW], bool packed = false) {
+    if constexpr (sizeof(WT) == 8 && RW == 8) {
+        if (packed) {
+            u64 q0, q1, q2, q3;
+            ldg256<KEEP>(p, q0, q1, q2, q3);
+            const u64 m40 = 0xFFFFFFFFFFull;
+            w[0] = q0 & m40;
+            w[1] = ((q0 >> 40) | (q1 << 24)) & m40;
+            w[2] = (q1 >> 16) & m40;
+            w[3] = ((q1 >> 56) | (q2 << 8)) & m40;
+            w[4] = ((q2 >> 32) | (q3 << 32)) & m40;
+            if (w[4] == m40) w[4] = ~0ull;  // the "no piece begins inside this bucket" sentinel
+            w[5] = (q3 >> 8) & 0xFFFFFFFFull;
+            w[6] = q3 >> 40;
+            w[7] = 0;
+            return;
+        }
+    }
     if constexpr (sizeof(WT) == 4) {
         if constexpr (RW == 4) {
             const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
@@ -98,7 +116,8 @@ __global__ void __launch_bounds__(256) l2_warm_kernel(const char* base, u64 byte
 template <typename WT, int D, bool KEEP>
 __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT remaining) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
-    constexpr u32 ESZ = RW * (u32)sizeof(WT);  // entry size in bytes
+    const u32 ESZ = ix.phi.esz;  // entry size in bytes (RW words, or 32 when packed)
+    const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
@@ -115,7 +134,7 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
     // (measured: 55% of the stall samples sat on the first use of the loaded entry).
     u32 probe = 0;
     WT e[RW];
-    if (remaining > 0) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
+    if (remaining > 0) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
     while (remaining > 0) {
         bool emit;
         if (!searching) {
@@ -151,7 +170,7 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
         if (rem_next > 0)
-            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
+            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
         // ---- this iteration's occurrences (off the critical path) ----
         if (emit) {
             if (cnt == (u32)D) {
@@ -305,7 +324,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ item_count,
                   u64* __restrict__ out) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
-    constexpr u32 ESZ = RW * (u32)sizeof(WT);
+    const u32 ESZ = ix.phi.esz;
+    const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
     constexpr int GPL = RIG_LINE / D;  // groups per line
     // a lane emits at most one group per trip: with a flush every <= GPL trips it cannot complete a second row
@@ -335,7 +355,7 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
     u32 slo = 0, shi = 0, probe = 0, fill = 0, cur = 0, trip = 0;  // fill: groups staged in row cur
     u64* pend_line = out;
     WT e[RW];
-    if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e);
+    if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
     for (;;) {
         const bool more = __any_sync(RIG_FULL, left > 1);
         // ---- write out completed rows: every FLUSH_TRIPS trips and once at the end (warp-uniform) ----
@@ -396,7 +416,7 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
         if (left_next > 1)
-            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2);
+            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
         if (emit) {
             // stage the line iff all of its GPL groups will be emitted as full groups (with D = 1 the loop ends
             // at left == 1, one slot early, so one more slot is needed)

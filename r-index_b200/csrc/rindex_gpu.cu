@@ -127,7 +127,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
-    if (variant & 512) opt.reserved[1] |= 2;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
+    if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
     rigf::FlatHost f;
     int rc = rigf::flatten(*view, opt, f, (uint64_t)(free_b * 0.9));
     if (rc != RIG_OK) return rc;
@@ -174,8 +174,13 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
         parts.push_back({srec32.data(), srec32.size() * 4, 0});
         parts.push_back({spent32.data(), spent32.size() * 4, 0});
     } else {
-        parts.push_back({f.phi.rec.data(), f.phi.rec.size() * 8, 0});
-        parts.push_back({f.phi.pent.data(), f.phi.pent.size() * 8, 0});
+        if (f.phi_packed) {
+            parts.push_back({f.phi_rec_p.data(), f.phi_rec_p.size(), 0});
+            parts.push_back({f.phi_pent_p.data(), f.phi_pent_p.size(), 0});
+        } else {
+            parts.push_back({f.phi.rec.data(), f.phi.rec.size() * 8, 0});
+            parts.push_back({f.phi.pent.data(), f.phi.pent.size() * 8, 0});
+        }
         parts.push_back({f.seed.rec.data(), f.seed.rec.size() * 8, 0});
         parts.push_back({f.seed.pent.data(), f.seed.pent.size() * 8, 0});
     }
@@ -202,6 +207,8 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.phi.rec = (const void*)(A + parts[8].off);
     d.phi.pent = (const void*)(A + parts[9].off);
     d.phi.shift = f.phi.shift; d.phi.D = f.phi.D;
+    d.phi.packed = f.phi_packed ? 1u : 0u;
+    d.phi.esz = f.phi_packed ? 32u : f.phi.RW * (f.w32 ? 4u : 8u);
     d.seed.rec = (const void*)(A + parts[10].off);
     d.seed.pent = (const void*)(A + parts[11].off);
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;

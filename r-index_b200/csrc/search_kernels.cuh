@@ -27,6 +27,8 @@ struct PhiTabDev {
     const void* rec;    // [nbkt]   bucket records: D deltas, s1, nxt, cnt
     const void* pent;   // [pieces] piece entries:  D deltas, start
     u32 shift, D;
+    u32 esz, packed;    // entry size in bytes; packed = 1: 64-bit index, D = 4, entries packed into 32 bytes
+                        // (4 x 40-bit deltas | 40-bit s1 or start | 32-bit nxt | 24-bit cnt) instead of 8 x 8 bytes
 };
 
 // Phi^J as one piecewise translation (flat_layout.hpp: JumpTable), the seed table of the two-pass

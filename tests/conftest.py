@@ -80,6 +80,7 @@ class FlatCheck:
         self.rc = rc.value
         self.w32 = bool(self.lib.fc_w32(self.h)) if self.h else None
         self.jump = int(self.lib.fc_jump(self.h)) if self.h else 0
+        self.phi_packed = bool(self.lib.fc_phi_packed(self.h)) if self.h else False
         self.seed_jump = int(self.lib.fc_seed_jump(self.h)) if self.h else 0
 
     def count(self, patt, N, m):

@@ -52,6 +52,23 @@ Q block_query(const FlatHost& f, u64 x, uint8_t c, u32 sidc) {
     return r;
 }
 
+// mirrors the packed branch of rigk::load_entry (32-byte entries of a 64-bit index: 4 x 40-bit deltas | 40-bit
+// s1/start | 32-bit nxt | 24-bit cnt)
+void unpack32(const uint8_t* p, u64* w) {
+    u64 q0, q1, q2, q3;
+    memcpy(&q0, p, 8); memcpy(&q1, p + 8, 8); memcpy(&q2, p + 16, 8); memcpy(&q3, p + 24, 8);
+    const u64 m40 = 0xFFFFFFFFFFull;
+    w[0] = q0 & m40;
+    w[1] = ((q0 >> 40) | (q1 << 24)) & m40;
+    w[2] = (q1 >> 16) & m40;
+    w[3] = ((q1 >> 56) | (q2 << 8)) & m40;
+    w[4] = ((q2 >> 32) | (q3 << 32)) & m40;
+    if (w[4] == m40) w[4] = ~(u64)0;
+    w[5] = (q3 >> 8) & 0xFFFFFFFFull;
+    w[6] = q3 >> 40;
+    w[7] = 0;
+}
+
 // mirrors the per-lane state machine of rigk::phi_expand_kernel for ONE lookup: returns
 // e[t] = Phi^(t+1)(i), reading only rec[] / pent[] entries (with the 32-bit truncation when w32).
 // *loads counts the entry loads the lane needed.
@@ -64,6 +81,11 @@ void phi_lookup(const FlatHost& f, u64 i, u64* e, u64* loads = nullptr) {
     for (;;) {
         const u64 probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         const u64* w = searching ? &T.pent[probe * RW] : &T.rec[(i >> T.shift) * RW];
+        u64 unpacked[8];
+        if (f.phi_packed) {  // what the device reads
+            unpack32(searching ? &f.phi_pent_p[probe * 32] : &f.phi_rec_p[(i >> T.shift) * 32], unpacked);
+            w = unpacked;
+        }
         ++nload;
         bool emit;
         if (!searching) {
@@ -181,6 +203,7 @@ void* fc_create(const rig_logical_view* v, uint32_t K, uint32_t lf_log2, uint32_
 void fc_destroy(void* h) { delete (FlatHost*)h; }
 uint64_t fc_bytes(void* h) { return ((FlatHost*)h)->bytes(); }
 uint64_t fc_jump(void* h) { return ((FlatHost*)h)->phi.D; }
+int fc_phi_packed(void* h) { return ((FlatHost*)h)->phi_packed ? 1 : 0; }
 uint64_t fc_seed_jump(void* h) { return ((FlatHost*)h)->seed.J; }
 uint64_t fc_seed_pieces(void* h) { return ((FlatHost*)h)->seed.pieces(); }
 // Phi^SEG through the seed table (scalar and bucket-record lookup) == SEG applications of Phi

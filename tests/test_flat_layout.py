@@ -27,7 +27,7 @@ def test_flat_walk_equals_oracle(K):
 
 
 @pytest.mark.parametrize("jump", [1, 2, 4, 8])
-@pytest.mark.parametrize("wide", [False, True, 3])   # 32-bit words; 64-bit with 40-bit packed block records; plain 64-bit
+@pytest.mark.parametrize("wide", [False, True, 7])   # 32-bit words; 64-bit with 40-bit packed records and Phi entries; plain 64-bit
 def test_jump_tables_equal_repeated_phi(jump, wide):
     """Phi^j (j = 1..D, composition of piecewise translations) == j applications of Phi, for every SA
     value it can legally be applied to, through the scalar table AND the bucket-record lookup (32- and
@@ -39,6 +39,7 @@ def test_jump_tables_equal_repeated_phi(jump, wide):
         host = rib.HostIndex.from_text(t)
         fc = FlatCheck(host, K=4, phi_log2=int(rng.choice([0, 1, 4])), jump=jump, force_wide=wide)
         assert fc.rc == 0 and fc.jump == jump
+        assert fc.phi_packed == (wide is True and jump == 4)   # 64-bit index, D = 4: 32-byte packed Phi entries
         assert host.r <= fc.lib.fc_pieces(fc.h) <= jump * host.r
         sa = rib.suffix_array(t)
         for x in range(jump, n + 1):  # SA[x] with at least D predecessors in SA order
