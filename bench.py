@@ -53,7 +53,7 @@ WORKLOADS = {
     "c3": ("versioned_doc", 1_000_000_000, 25_000, 50_096, 0xB2000003, 125_000, 30, 0xB2001003, 0,
            "C3 ri-locate at FULL size: 1 GB einstein-like sigma=96 versioned document; 125k len-30 patterns per GPU (the 1M patterns of the config sharded 8x)"),
     "c5": ("dna_indep", 4_000_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
-           "C5 ri-locate at FULL size: 4 GB synthetic DNA sigma=4, 10k copies, ~10k occ/pattern, 100k len-15 patterns (n > 2^32: 64-bit words)"),
+           "C5 ri-locate at FULL size: 4 GB synthetic DNA sigma=4, 10k copies, ~10k occ/pattern, 100k len-15 patterns (n = 4.0e9, just under 2^32: 32-bit words)"),
     "c4": ("pangenome", 10_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_250_000, 100, 0xB2001004, 0,
            "C4 ri-count at FULL size: 10 GB synthetic pan-genome sigma=5 (1000 haplotypes); 1.25M len-100 reads per GPU (the 10M reads of the config sharded 8x)"),
     "c4s": ("pangenome", 1_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_000_000, 100, 0xB2001004, 0,

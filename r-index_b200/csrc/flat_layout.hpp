@@ -464,7 +464,8 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         u64 budget = 8ull << 30;
         if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
         const u64 wb = f.w32 ? 4 : 8;
-        auto cost = [&](u32 d) { return (u64)d * r * ((PhiTable::record_words(d) * wb) << fp); };
+        const bool can_pack = !f.w32 && n < (1ull << 40) - 1 && !(opt.reserved[1] & 4);  // D = 4 entries packed into 32 bytes
+        auto cost = [&](u32 d) { return (u64)d * r * (((d == 4 && can_pack) ? 32 : PhiTable::record_words(d) * wb) << fp); };
         D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);
     }
     lap("Phi pieces");

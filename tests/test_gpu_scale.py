@@ -77,7 +77,7 @@ def test_scaled_config_against_reference(name):
 
 @pytest.mark.parametrize("name", ["c3", "c5"])
 def test_full_size_config_self_check(name):
-    """BASELINE.json configs 3 and 5 at FULL size (1 GB sigma=96 text; 4 GB DNA with n > 2^32: the 64-bit paths).
+    """BASELINE.json configs 3 and 5 at FULL size (1 GB sigma=96 text; 4 GB DNA, n = 4.0e9: 7% under 2^32, still 32-bit words).
     No CPU oracle finishes at this size, so the device runs the reference's own -c self-check
     (ri-locate.cpp:156-190) on the located output: brute-force occurrence counts from the text (hash join)
     equal hi-lo+1 for every pattern, text[o, o+m) equals the pattern for every located o, and the positions of
