@@ -86,33 +86,44 @@ struct PhiTable {
         rec.assign(nbkt * RW, 0);
         const u64 P = pieces();
         pent.assign(P * RW, 0);
-        for (u64 k = 0; k < P; ++k) {
-            for (u32 j = 0; j < D; ++j) pent[k * RW + j] = delta[k * D + j];
-            pent[k * RW + D] = start[k];
-        }
-        u64 a = 0;
-        for (u64 q = 0; q < nbkt; ++q) {
-            const u64 lo = q << shift, hi = (q + 1) << shift;
-            while (a + 1 < P && start[a + 1] <= lo) ++a;
-            u64 e = a + 1;
-            while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
-            u64* R = &rec[q * RW];
-            for (u32 j = 0; j < D; ++j) R[j] = delta[a * D + j];
-            R[D] = (e > a + 1) ? start[a + 1] : ~(u64)0;
-            R[D + 1] = (e > a + 1) ? a + 1 : 0;
-            R[D + 2] = e - (a + 1);
-        }
+        unsigned T = std::thread::hardware_concurrency();
+        if (T > 32) T = 32;
+        if (T < 1 || nbkt < (1u << 16)) T = 1;
+        auto fill = [&](u64 q0, u64 q1, u64 k0, u64 k1) {
+            for (u64 k = k0; k < k1; ++k) {
+                for (u32 j = 0; j < D; ++j) pent[k * RW + j] = delta[k * D + j];
+                pent[k * RW + D] = start[k];
+            }
+            if (q0 >= q1) return;
+            u64 a = piece_of(q0 << shift);  // the piece covering the first bucket's first position
+            for (u64 q = q0; q < q1; ++q) {
+                const u64 lo = q << shift, hi = (q + 1) << shift;
+                while (a + 1 < P && start[a + 1] <= lo) ++a;
+                u64 e = a + 1;
+                while (e < P && start[e] < hi) ++e;  // pieces a+1 .. e-1 begin inside the bucket
+                u64* R = &rec[q * RW];
+                for (u32 j = 0; j < D; ++j) R[j] = delta[a * D + j];
+                R[D] = (e > a + 1) ? start[a + 1] : ~(u64)0;
+                R[D + 1] = (e > a + 1) ? a + 1 : 0;
+                R[D + 2] = e - (a + 1);
+            }
+        };
+        if (T == 1) { fill(0, nbkt, 0, P); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t]() { fill(nbkt * t / T, nbkt * (t + 1) / T, P * t / T, P * (t + 1) / T); });
+        for (auto& x : th) x.join();
     }
 };
 
 // Extend a table holding Phi^1..Phi^j to Phi^1..Phi^(j+1): every piece is cut where its image under
 // Phi^j crosses a piece boundary of Phi (the single-step table), and gets delta_{j+1} = delta_j + delta_Phi.
-static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64 n) {
-    PhiTable C;
+static inline void extend_range(const PhiTable& A, const PhiTable& Phi, u64 n, u64 k0, u64 k1, std::vector<u64>& Cs,
+                                std::vector<u64>& Cd) {
     const u32 j = A.D;
-    C.D = j + 1;
     const u64 PA = A.pieces(), PB = Phi.pieces();
-    for (u64 k = 0; k < PA; ++k) {
+    Cs.reserve((k1 - k0) * 2 + 16); Cd.reserve(((k1 - k0) * 2 + 16) * (j + 1));
+    for (u64 k = k0; k < k1; ++k) {
         const u64 s = A.start[k], e = (k + 1 < PA) ? A.start[k + 1] : n, a = A.delta[k * j + (j - 1)];
         const u64 len = e - s;
         u64 u = s + a;  // image of s under Phi^j
@@ -128,13 +139,36 @@ static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64
                 const u64 pend = std::min(lin_end, (b + 1 < PB) ? Phi.start[b + 1] : n);
                 u64 d = a + Phi.delta[b];
                 if (d >= n) d -= n;
-                C.start.push_back(s + done + (cur - pos));
-                for (u32 t = 0; t < j; ++t) C.delta.push_back(A.delta[k * j + t]);
-                C.delta.push_back(d);
+                Cs.push_back(s + done + (cur - pos));
+                for (u32 t = 0; t < j; ++t) Cd.push_back(A.delta[k * j + t]);
+                Cd.push_back(d);
                 cur = pend; ++b;
             }
             done += lin_end - pos;
         }
+    }
+}
+
+// (pieces of A are independent: large tables are cut into contiguous chunks, one host thread each)
+static inline PhiTable extend_by_phi(const PhiTable& A, const PhiTable& Phi, u64 n) {
+    PhiTable C;
+    C.D = A.D + 1;
+    const u64 PA = A.pieces();
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 32) T = 32;
+    if (T < 2 || PA < (1u << 16)) { extend_range(A, Phi, n, 0, PA, C.start, C.delta); return C; }
+    std::vector<std::vector<u64>> ps(T), pd(T);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() { extend_range(A, Phi, n, PA * t / T, PA * (t + 1) / T, ps[t], pd[t]); });
+    for (auto& x : th) x.join();
+    u64 total = 0;
+    for (unsigned t = 0; t < T; ++t) total += ps[t].size();
+    C.start.reserve(total); C.delta.reserve(total * C.D);
+    for (unsigned t = 0; t < T; ++t) {
+        C.start.insert(C.start.end(), ps[t].begin(), ps[t].end());
+        C.delta.insert(C.delta.end(), pd[t].begin(), pd[t].end());
+        std::vector<u64>().swap(ps[t]); std::vector<u64>().swap(pd[t]);
     }
     return C;
 }
