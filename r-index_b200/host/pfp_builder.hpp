@@ -126,6 +126,7 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
         unsigned T = std::thread::hardware_concurrency();
         if (T > 32) T = 32;
         if (T < 1 || n < ((uint64_t)1 << 22)) T = 1;
+        if (const char* e = getenv("RIB_PFP_THREADS")) T = std::max(1, std::min(64, atoi(e)));  // tests: force the threaded paths
         const uint64_t B = 0x100000001b3ull;
         uint64_t Bw = 1;
         for (uint32_t t = 0; t < w; ++t) Bw *= B;
@@ -272,107 +273,161 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
 
     lap("suffix array of the dictionary");
     // ---- 5. sweep ------------------------------------------------------------------------------------------------
+    // The dictionary's suffix array is cut at group boundaries into one range per host thread; every thread emits
+    // the BWT runs of its range into a private list, and the lists are fed in order to the run/sample builder.
     LogicalIndex L;
     RunBuilder rb(L, n);
     Stats st;
     st.phrases = ND; st.dict_bytes = M; st.parse_len = NP;
     struct Member { uint32_t d, o; };
-    std::vector<Member> grp;
+    struct RunList {  // maximal runs of one range: symbol, length, SA of the first and last row
+        std::vector<uint8_t> c; std::vector<uint64_t> cnt, sf, sl;
+        inline void emit(uint8_t ch, uint64_t count, uint64_t sa_first, uint64_t sa_last) {
+            if (!c.empty() && c.back() == ch) { cnt.back() += count; sl.back() = sa_last; }
+            else { c.push_back(ch); cnt.push_back(count); sf.push_back(sa_first); sl.push_back(sa_last); }
+        }
+    };
     auto pred_byte_of_occurrence = [&](uint32_t k) -> uint8_t {  // the byte of S before phrase occurrence k
         if (k == 0) return kTerminator;                           // the row with SA = 0 (r_index.hpp:587-590)
         const uint32_t pd = parse[k - 1];
         return byte_of(C[dstart[pd] + dlen[pd] - w - 1]);
     };
-    auto flush_group = [&]() {
-        if (grp.empty()) return;
-        ++st.groups;
-        bool uniform = true;
-        uint8_t c0 = 0;
-        bool have = false;
-        for (const Member& m : grp) {
-            if (m.o == 0) { uniform = false; break; }
-            const uint8_t c = byte_of(C[dstart[m.d] + m.o - 1]);
-            if (!have) { c0 = c; have = true; } else if (c != c0) { uniform = false; break; }
-        }
-        if (uniform) {
-            uint64_t total = 0, sa_first = 0, sa_last = 0;
-            uint32_t rmin = ~0u, rmax = 0;
-            bool any = false;
-            for (const Member& m : grp) {
-                const uint32_t a = occ_begin[m.d], b = occ_begin[m.d + 1];
-                if (a == b) continue;
-                total += b - a;
-                if (!any || occ_rank[a] < rmin) { rmin = occ_rank[a]; sa_first = tpos[occ_k[a]] + m.o; }
-                if (!any || occ_rank[b - 1] > rmax) { rmax = occ_rank[b - 1]; sa_last = tpos[occ_k[b - 1]] + m.o; }
-                any = true;
-            }
-            if (total) { rb.emit(c0, total, sa_first, sa_last); st.uniform_rows += total; }
-        } else if (grp.size() == 1) {
-            const Member m = grp[0];
-            for (uint32_t x = occ_begin[m.d]; x < occ_begin[m.d + 1]; ++x) {
-                const uint32_t k = occ_k[x];
-                const uint64_t sa = tpos[k] + m.o;
-                rb.emit(m.o > 0 ? byte_of(C[dstart[m.d] + m.o - 1]) : pred_byte_of_occurrence(k), 1, sa, sa);
-                ++st.merged_rows;
-            }
-        } else {  // merge the members' occurrence lists by the rank of the following parse suffix
-            typedef std::pair<uint32_t, uint32_t> QE;  // (rank, member index)
-            std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
-            std::vector<uint32_t> cur(grp.size());
-            for (uint32_t g = 0; g < grp.size(); ++g) {
-                cur[g] = occ_begin[grp[g].d];
-                if (cur[g] < occ_begin[grp[g].d + 1]) pq.push({occ_rank[cur[g]], g});
-            }
-            // Pop the list with the smallest next rank and drain it up to the next list's head: the occurrences of one
-            // phrase suffix often come in long stretches of consecutive ranks, and when the suffix does not start
-            // its phrase (o > 0) they all carry the same BWT symbol — a whole stretch is one emit().
-            while (!pq.empty()) {
-                const uint32_t g = pq.top().second;
-                pq.pop();
-                const uint32_t limit = pq.empty() ? ~0u : pq.top().first;  // ranks are distinct across lists
-                const Member m = grp[g];
-                const uint32_t end = occ_begin[m.d + 1];
-                uint32_t x = cur[g];
-                if (m.o > 0) {
-                    // gallop to the first occurrence whose rank exceeds the limit: everything below lo2 is known to be
-                    // under it, hi2 is `end` or the first probe at or above it
-                    uint32_t lo2 = x + 1, hi2 = x + 1, step = 1;
-                    while (hi2 < end && occ_rank[hi2] < limit) {
-                        lo2 = hi2 + 1;
-                        hi2 = (end - hi2 > step) ? hi2 + step : end;
-                        step <<= 1;
-                    }
-                    const uint32_t stop = (uint32_t)(std::lower_bound(occ_rank.begin() + lo2, occ_rank.begin() + hi2, limit) - occ_rank.begin());
-                    rb.emit(byte_of(C[dstart[m.d] + m.o - 1]), stop - x, tpos[occ_k[x]] + m.o, tpos[occ_k[stop - 1]] + m.o);
-                    st.merged_rows += stop - x;
-                    x = stop;
-                } else {
-                    do {
-                        const uint32_t k = occ_k[x];
-                        rb.emit(pred_byte_of_occurrence(k), 1, tpos[k], tpos[k]);
-                        ++st.merged_rows;
-                        ++x;
-                    } while (x < end && occ_rank[x] < limit);
-                }
-                cur[g] = x;
-                if (x < end) pq.push({occ_rank[x], g});
-            }
-        }
-        grp.clear();
+    // a dictionary suffix that stands for text suffixes: not a separator, and longer than the overlap (or in the last phrase)
+    auto decode = [&](uint64_t idx, uint64_t& pos, uint32_t& dd, uint32_t& oo, uint64_t& rem) -> bool {
+        pos = (uint64_t)SAD[idx];
+        if (C[pos] == 1) return false;
+        dd = (uint32_t)(std::upper_bound(dstart.begin(), dstart.begin() + ND, pos) - dstart.begin()) - 1;
+        oo = (uint32_t)(pos - dstart[dd]);
+        rem = dlen[dd] - oo;
+        return rem > w || dd == last_d;
     };
-    uint64_t rep_pos = 0, rep_rem = 0;  // representative suffix of the current group
-    for (uint64_t idx = 1; idx <= M; ++idx) {  // SAD[0] is the end-of-concatenation sentinel
-        const uint64_t pos = (uint64_t)SAD[idx];
-        if (C[pos] == 1) continue;  // a separator
-        const uint32_t d = (uint32_t)(std::upper_bound(dstart.begin(), dstart.begin() + ND, pos) - dstart.begin()) - 1;
-        const uint32_t o = (uint32_t)(pos - dstart[d]);
-        const uint64_t rem = dlen[d] - o;
-        if (!(rem > w || d == last_d)) continue;  // owned by the next phrase occurrence (the overlap)
-        const bool same = !grp.empty() && rem == rep_rem && std::memcmp(&C[pos], &C[rep_pos], rem * sizeof(uint16_t)) == 0;
-        if (!same) { flush_group(); rep_pos = pos; rep_rem = rem; }
-        grp.push_back({d, o});
+    auto same_string = [&](uint64_t pa, uint64_t ra, uint64_t pb, uint64_t rbm) {
+        return ra == rbm && std::memcmp(&C[pa], &C[pb], ra * sizeof(uint16_t)) == 0;
+    };
+    auto sweep_range = [&](uint64_t i0, uint64_t i1, RunList& sink, Stats& lst) {
+        std::vector<Member> grp;
+        auto flush_group = [&]() {
+            if (grp.empty()) return;
+            ++lst.groups;
+            bool uniform = true;
+            uint8_t c0 = 0;
+            bool have = false;
+            for (const Member& m : grp) {
+                if (m.o == 0) { uniform = false; break; }
+                const uint8_t c = byte_of(C[dstart[m.d] + m.o - 1]);
+                if (!have) { c0 = c; have = true; } else if (c != c0) { uniform = false; break; }
+            }
+            if (uniform) {
+                uint64_t total = 0, sa_first = 0, sa_last = 0;
+                uint32_t rmin = ~0u, rmax = 0;
+                bool any = false;
+                for (const Member& m : grp) {
+                    const uint32_t a = occ_begin[m.d], b = occ_begin[m.d + 1];
+                    if (a == b) continue;
+                    total += b - a;
+                    if (!any || occ_rank[a] < rmin) { rmin = occ_rank[a]; sa_first = tpos[occ_k[a]] + m.o; }
+                    if (!any || occ_rank[b - 1] > rmax) { rmax = occ_rank[b - 1]; sa_last = tpos[occ_k[b - 1]] + m.o; }
+                    any = true;
+                }
+                if (total) { sink.emit(c0, total, sa_first, sa_last); lst.uniform_rows += total; }
+            } else if (grp.size() == 1) {
+                const Member m = grp[0];
+                for (uint32_t x = occ_begin[m.d]; x < occ_begin[m.d + 1]; ++x) {
+                    const uint32_t k = occ_k[x];
+                    const uint64_t sa = tpos[k] + m.o;
+                    sink.emit(m.o > 0 ? byte_of(C[dstart[m.d] + m.o - 1]) : pred_byte_of_occurrence(k), 1, sa, sa);
+                    ++lst.merged_rows;
+                }
+            } else {  // merge the members' occurrence lists by the rank of the following parse suffix
+                typedef std::pair<uint32_t, uint32_t> QE;  // (rank, member index)
+                std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+                std::vector<uint32_t> cur(grp.size());
+                for (uint32_t g = 0; g < grp.size(); ++g) {
+                    cur[g] = occ_begin[grp[g].d];
+                    if (cur[g] < occ_begin[grp[g].d + 1]) pq.push({occ_rank[cur[g]], g});
+                }
+                // Pop the list with the smallest next rank and drain it up to the next list's head: the occurrences of one
+                // phrase suffix often come in long stretches of consecutive ranks, and when the suffix does not start
+                // its phrase (o > 0) they all carry the same BWT symbol — a whole stretch is one emit().
+                while (!pq.empty()) {
+                    const uint32_t g = pq.top().second;
+                    pq.pop();
+                    const uint32_t limit = pq.empty() ? ~0u : pq.top().first;  // ranks are distinct across lists
+                    const Member m = grp[g];
+                    const uint32_t end = occ_begin[m.d + 1];
+                    uint32_t x = cur[g];
+                    if (m.o > 0) {
+                        // gallop to the first occurrence whose rank exceeds the limit: everything below lo2 is known to be
+                        // under it, hi2 is `end` or the first probe at or above it
+                        uint32_t lo2 = x + 1, hi2 = x + 1, step = 1;
+                        while (hi2 < end && occ_rank[hi2] < limit) {
+                            lo2 = hi2 + 1;
+                            hi2 = (end - hi2 > step) ? hi2 + step : end;
+                            step <<= 1;
+                        }
+                        const uint32_t stop = (uint32_t)(std::lower_bound(occ_rank.begin() + lo2, occ_rank.begin() + hi2, limit) - occ_rank.begin());
+                        sink.emit(byte_of(C[dstart[m.d] + m.o - 1]), stop - x, tpos[occ_k[x]] + m.o, tpos[occ_k[stop - 1]] + m.o);
+                        lst.merged_rows += stop - x;
+                        x = stop;
+                    } else {
+                        do {
+                            const uint32_t k = occ_k[x];
+                            sink.emit(pred_byte_of_occurrence(k), 1, tpos[k], tpos[k]);
+                            ++lst.merged_rows;
+                            ++x;
+                        } while (x < end && occ_rank[x] < limit);
+                    }
+                    cur[g] = x;
+                    if (x < end) pq.push({occ_rank[x], g});
+                }
+            }
+            grp.clear();
+        };
+        uint64_t rep_pos = 0, rep_rem = 0;  // representative suffix of the current group
+        for (uint64_t idx = i0; idx < i1; ++idx) {
+            uint64_t pos, rem; uint32_t dd, oo;
+            if (!decode(idx, pos, dd, oo, rem)) continue;
+            if (!(!grp.empty() && same_string(pos, rem, rep_pos, rep_rem))) { flush_group(); rep_pos = pos; rep_rem = rem; }
+            grp.push_back({dd, oo});
+        }
+        flush_group();
+    };
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 32) T = 32;
+    if (T < 1 || M < ((uint64_t)1 << 20)) T = 1;
+    if (const char* e = getenv("RIB_PFP_THREADS")) T = std::max(1, std::min(64, atoi(e)));
+    // range t starts at the first group boundary at or after 1 + M*t/T (SAD[0] is the end-of-concatenation sentinel)
+    std::vector<uint64_t> cut(T + 1, M + 1);
+    cut[0] = 1;
+    for (unsigned t = 1; t < T; ++t) {
+        uint64_t idx = 1 + M * t / T;
+        uint64_t ppos = 0, prem = 0; bool have_prev = false;
+        for (uint64_t b = idx; b-- > 1;) {  // the valid suffix before idx, if any
+            uint64_t pos, rem; uint32_t dd, oo;
+            if (decode(b, pos, dd, oo, rem)) { ppos = pos; prem = rem; have_prev = true; break; }
+        }
+        for (; idx <= M; ++idx) {
+            uint64_t pos, rem; uint32_t dd, oo;
+            if (!decode(idx, pos, dd, oo, rem)) continue;
+            if (!have_prev || !same_string(pos, rem, ppos, prem)) break;  // a group starts here
+            ppos = pos; prem = rem;
+        }
+        cut[t] = idx;
     }
-    flush_group();
+    for (unsigned t = 1; t <= T; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<RunList> lists(T);
+    std::vector<Stats> lstats(T);
+    if (T == 1) sweep_range(cut[0], cut[1], lists[0], lstats[0]);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back([&, t]() { sweep_range(cut[t], cut[t + 1], lists[t], lstats[t]); });
+        for (auto& x : th) x.join();
+    }
+    for (unsigned t = 0; t < T; ++t) {
+        const RunList& rl = lists[t];
+        for (size_t k = 0; k < rl.c.size(); ++k) rb.emit(rl.c[k], rl.cnt[k], rl.sf[k], rl.sl[k]);
+        st.groups += lstats[t].groups; st.uniform_rows += lstats[t].uniform_rows; st.merged_rows += lstats[t].merged_rows;
+    }
     if (rb.rows_emitted() != n) throw std::logic_error("prefix-free parsing: row count differs from the text length");
     lap("sweep");
     rb.finish();

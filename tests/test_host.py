@@ -121,6 +121,25 @@ def test_pfp_builder_equals_sais_builder_small():
         assert b.pfp_stats["uniform_rows"] + b.pfp_stats["merged_rows"] == n + 1
 
 
+@pytest.mark.parametrize("threads", ["2", "5", "13"])
+def test_pfp_builder_threaded_paths(threads, monkeypatch):
+    """The parse (trigger scan, phrase hashes) and the sweep (ranges cut at group boundaries) run on several host
+    threads for large inputs; forced here on small ones, including more threads than phrases or groups."""
+    monkeypatch.setenv("RIB_PFP_THREADS", threads)
+    rng = np.random.default_rng(int(threads))
+    for it in range(150):
+        n = int(rng.integers(0, 700))
+        sigma = int(rng.choice([1, 2, 4, 20]))
+        base = rng.integers(2, 2 + sigma, size=max(1, int(rng.integers(1, 90))), dtype=np.uint8)
+        t = np.resize(base, n).copy()
+        for _ in range(int(rng.integers(0, 8))):
+            if n:
+                t[int(rng.integers(0, n))] = int(rng.integers(2, 2 + sigma))
+        _same_index(rib.HostIndex.from_text(t), rib.HostIndex.from_text_pfp(t, w=int(rng.integers(1, 7)), p=int(rng.integers(1, 14))))
+    t = rib.gen_text("pangenome", 1_500_000, 100_000, 2_000, 9)
+    _same_index(rib.HostIndex.from_text(t), rib.HostIndex.from_text_pfp(t))
+
+
 def test_pfp_builder_equals_sais_builder_generators_and_golden():
     for kind, args in (("dna_drift", (2_000_000, 20_000, 3, 7)), ("versioned_doc", (1_500_000, 5_000, 96, 8)),
                        ("pangenome", (1_500_000, 100_000, 2_000, 9)), ("dna_indep", (1_500_000, 50_000, 10_000, 10))):
