@@ -6,8 +6,9 @@
 //   range_t count(string&)         :292    ulint occ(string&)          :307
 //   vector<ulint> locate_all(string&) :328 ulint serialize(ostream&)   :382  void load(istream&) :407
 //   number_of_runs() :361  text_size() :450  bwt_size() :454  get_terminator_position() :368
+//   operator[](i) :162  LF(i) :224  FL(i) :232  F_at(i) :263  get_char_range(c) :276  get_bwt() :375
 // plus the batch surface this repo adds (one FFI call per batch instead of one call per pattern):
-//   count_batch(), locate_batch().
+//   count_batch(), locate_batch(), navigate_batch().
 // Every query — single-pattern calls included — runs on the GPU through include/rindex_gpu.h.
 // There is no CPU query path: if no device is available the query members print the error and exit(1).
 #pragma once
@@ -106,6 +107,28 @@ public:
         return total;
     }
 
+    // ---- single-position navigation (reference :162-164, :224-271, :375-377), each a batch of one on the device;
+    //      navigate_batch / get_bwt take whole arrays ----
+    uchar operator[](ulint i) { return (uchar)navigate1(RIG_NAV_BWT, i); }
+    ulint LF(ulint i) { return navigate1(RIG_NAV_LF, i); }
+    ulint FL(ulint i) { return navigate1(RIG_NAV_FL, i); }
+    uchar F_at(ulint i) { return (uchar)navigate1(RIG_NAV_F_AT, i); }
+    void navigate_batch(int op, const ulint* positions, ulint N, ulint* out) {
+        ensure_device();
+        check(rig_navigate_batch(dev, op, positions, N, out), "rig_navigate_batch");
+    }
+    std::string get_bwt() {  // the BWT as a string, terminator row = 0x01 (rle_string::toString)
+        ensure_device();
+        std::string s(L.n, '\0');
+        check(rig_get_bwt(dev, 0, L.n, (uint8_t*)&s[0]), "rig_get_bwt");
+        return s;
+    }
+    // BWT range of character c (reference :276-290): {1,0} if c does not occur
+    range_t get_char_range(uchar c) {
+        if (L.F[c] >= L.F[(unsigned)c + 1]) return {1, 0};
+        return {L.F[c], L.F[(unsigned)c + 1] - 1};
+    }
+
     ulint number_of_runs() { return L.r; }
     ulint get_terminator_position() { return L.terminator_position; }
     ulint text_size() { return L.n - 1; }
@@ -141,6 +164,11 @@ private:
         rig_index_info_get(dev, &info);
     }
     void release_device() { if (dev) { rig_index_destroy(dev); dev = nullptr; } }
+    ulint navigate1(int op, ulint i) {
+        ulint out = 0;
+        navigate_batch(op, &i, 1, &out);
+        return out;
+    }
     void check(int rc, const char* where) {
         if (rc == RIG_OK) return;
         std::cout << "Error: " << where << ": " << rig_strerror(rc);

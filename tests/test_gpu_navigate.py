@@ -60,3 +60,48 @@ def test_navigation_equals_reference_methods():
     assert np.array_equal(gpu.get_bwt(), ref.get_bwt())
     # LF and FL are inverse permutations of the rows (r_index.hpp:224-243)
     assert np.array_equal(gpu.navigate(rib.NAV_FL, gpu.navigate(rib.NAV_LF, pos)), pos)
+
+
+def test_host_class_navigation_members(tmp_path):
+    """The C++ mirror of ri::r_index<> (r-index_b200/host/r_index.hpp) offers operator[], LF, FL, F_at, get_bwt and
+    get_char_range with the reference's signatures; a small program built against it must print the suffix-array truth."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    src = tmp_path / "nav.cpp"
+    src.write_text(r'''
+#include "r_index.hpp"
+#include <streambuf>
+int main() {
+    std::string t;
+    for (int k = 0; k < 40; ++k) t += (k % 7 == 3) ? "abracadabrx" : "abracadabra";
+    std::streambuf* old = std::cout.rdbuf(nullptr);   // the build constructor prints progress lines
+    ri::r_index<> idx(t);
+    std::cout.rdbuf(old);
+    const ri::ulint n = idx.bwt_size();
+    for (ri::ulint i = 0; i < n; ++i)
+        std::cout << (int)idx[i] << " " << idx.LF(i) << " " << idx.FL(i) << " " << (int)idx.F_at(i) << "\n";
+    std::string b = idx.get_bwt();
+    std::cout << "BWT";
+    for (unsigned char c : b) std::cout << " " << (int)c;
+    std::cout << "\n";
+    auto ra = idx.get_char_range('a'); auto rz = idx.get_char_range('z');
+    std::cout << "RANGE " << ra.first << " " << ra.second << " " << rz.first << " " << rz.second << "\n";
+    return 0;
+}
+''')
+    exe = tmp_path / "nav"
+    pkg = os.path.join(ROOT, "r-index_b200")
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-w", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host"),
+                    "-o", str(exe), str(src), "-L", pkg, "-lrindex_gpu", "-Wl,-rpath," + pkg, "-L/usr/local/cuda/lib64"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    text = np.frombuffer(b"".join(b"abracadabrx" if k % 7 == 3 else b"abracadabra" for k in range(40)), dtype=np.uint8)
+    sa = rib.suffix_array(text)
+    bwt, lf, fl, f_at = _truth(text, sa)
+    rows = np.array([[int(x) for x in l.split()] for l in out[: sa.size]], dtype=np.uint64)
+    assert np.array_equal(rows[:, 0], bwt.astype(np.uint64)) and np.array_equal(rows[:, 1], lf)
+    assert np.array_equal(rows[:, 2], fl) and np.array_equal(rows[:, 3], f_at.astype(np.uint64))
+    assert [int(x) for x in out[sa.size].split()[1:]] == bwt.tolist()
+    first_a = int(np.searchsorted(np.sort(f_at), ord("a")))
+    n_a = int((text == ord("a")).sum())
+    assert out[sa.size + 1] == "RANGE %d %d 1 0" % (first_a, first_a + n_a - 1)
