@@ -150,6 +150,7 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
             for (unsigned t = 0; t < T; ++t) th.emplace_back(scan, t);
             for (auto& x : th) x.join();
         }
+        lap("parse: trigger scan");
         std::vector<uint64_t> E;  // inclusive end of every phrase
         {
             uint64_t total = 1;
@@ -177,6 +178,7 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
             for (unsigned t = 0; t < T; ++t) th.emplace_back(hash_range, t);
             for (auto& x : th) x.join();
         }
+        lap("parse: phrase hashes");
         parse.resize(NPh);
         for (uint64_t k = 0; k < NPh; ++k) {
             const uint64_t b0 = k == 0 ? 0 : E[k - 1] + 1 - w, L64 = E[k] - b0 + 1;
@@ -200,7 +202,7 @@ inline LogicalIndex build(const uint8_t* text, uint64_t len, const Params& prm =
         }
     }
     seen.clear();
-    lap("parse");
+    lap("parse: dictionary (serial)");
     const uint64_t ND = phrases.size(), NP = parse.size();
     if (NP >= 0x7fffff00ull) throw std::length_error("parse longer than 2^31");
 
