@@ -6,6 +6,10 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "r_index.hpp"
 #include "utils.hpp"
 
@@ -55,20 +59,33 @@ int main(int argc, char** argv) {
     idx_file.append(".ri");
     cout << "Building r-index of input file " << input_file << endl;
     cout << "Index will be saved to " << idx_file << endl;
-    string input;
-    {
+    // The reference copies the file into a string (ri-build.cpp:121-129). Here the file is mapped: the prefix-free
+    // parsing builder reads the text twice, front to back, and keeps only (offset, length) references into it, so the
+    // resident memory of a large build is the dictionary and the parse, not the text.
+    int fd = open(input_file.c_str(), O_RDONLY);
+    struct stat sb;
+    const uint8_t* text = nullptr;
+    size_t text_len = 0;
+    string fallback;
+    if (fd >= 0 && fstat(fd, &sb) == 0 && sb.st_size > 0) {
+        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) { text = (const uint8_t*)m; text_len = (size_t)sb.st_size; madvise(m, text_len, MADV_SEQUENTIAL); }
+    }
+    if (!text) {  // empty or unmappable input (a pipe, ...): read it as the reference does
         std::ifstream fs(input_file, std::ios::binary);
         std::stringstream buffer;
         buffer << fs.rdbuf();
-        input = buffer.str();
+        fallback = buffer.str();
+        text = (const uint8_t*)fallback.data(); text_len = fallback.size();
     }
     std::ofstream out(idx_file, std::ios::binary);
     bool fast = false;  // flag storing whether index is fast or small (reference ri-build.cpp:133)
     out.write((char*)&fast, sizeof(fast));
     {
-        r_index<> idx(input, sais);
+        r_index<> idx(text, text_len, sais);
         idx.serialize(out);
     }
+    if (fd >= 0) close(fd);
     auto t2 = high_resolution_clock::now();
     uint64_t total = std::chrono::duration_cast<std::chrono::duration<double, std::ratio<1>>>(t2 - t1).count();
     cout << "Build time : " << get_time(total) << endl;

@@ -43,8 +43,11 @@ public:
     r_index& operator=(const r_index&) = delete;
 
     // Build index (reference r_index.hpp:42-150: same progress lines on stdout, exit(1) on reserved bytes).
-    r_index(std::string& input, bool sais = true) {
+    r_index(std::string& input, bool sais = true) : r_index((const uint8_t*)input.data(), input.size(), sais) {}
+    // the same constructor over a byte range (ri-build maps large files instead of copying them into a string)
+    r_index(const uint8_t* text, size_t text_len, bool sais = true) {
         using std::cout; using std::endl; using std::flush;
+        struct View { const uint8_t* p; size_t n; const uint8_t* data() const { return p; } size_t size() const { return n; } } input{text, text_len};
         if (rib::contains_reserved_chars((const uint8_t*)input.data(), input.size())) {
             cout << "Error: input string contains one of the reserved characters 0x0, 0x1" << endl;
             exit(1);
