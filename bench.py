@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — the hot path's headline measurement (BASELINE.json metric), one JSON line.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2s|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5|...]
 
-A "step" = one pass of the locate hot path (backward search + toehold, scans, Phi expansion) over
-one batch of synthetic patterns. Default workload = BASELINE.json configs[1] (C2): ri-locate on
-100 MB synthetic repetitive DNA (sigma=4), 100k patterns of length 20, 1xB200.
+A "step" = one pass of the locate hot path (backward search + toehold, offsets, Phi expansion) over ONE JOB = one
+batch of synthetic patterns.
 
-  value      occurrences/s, device-resident inputs, CUDA-event timed (whole job, all ranks)
-  e2e        occurrences/s through the host-buffer C-ABI call (rig_locate_batch) with pinned host
-             buffers: H2D of the patterns and D2H of ranges, offsets and every occurrence inside
-  roofline   dominant kernel (Phi expansion): algorithmic bytes (264 B/occurrence) /
-             CUDA-event duration vs the measured HBM copy bandwidth
-  cpu_baseline  the reference's own code (oracle/_ref) on the box's host cores, bounded sample
+  N = 1   default workload = BASELINE.json configs[1] (C2): ri-locate, 100 MB synthetic repetitive DNA (sigma=4),
+          100k patterns of length 20.
+  N > 1   default workload = BASELINE.json configs[4] (C5): ri-locate, 4 GB synthetic DNA, 100k patterns of length 15,
+          ~10k occurrences each (~1e9 occurrences per job) — the config BASELINE names for 1 -> 8 GPU scaling. STRONG
+          scaling: the job is FIXED, the index replicated in every GPU's HBM, the patterns sharded. Per step every
+          rank (1) counts its equal-count shard, (2) the ranks all-gather the per-pattern counts (8 B per pattern:
+          NCCL for the device-resident number, gloo for the host-buffer one), (3) the batch is re-cut into contiguous
+          shards of equal OCCURRENCE mass, (4) every rank locates its shard. No collective on the
+          search path. In the same run rank 0 also runs the WHOLE job alone (`strong_scaling.n1`), so every line
+          carries the one-GPU figure of its own job.
 
-N > 1: one process per GPU (torchrun), index replicated per GPU, patterns sharded (each rank its
-own batch: weak scaling), no collective on the data path; times are max over ranks.
+  value      occurrences/s of the whole job, device-resident inputs and outputs, CUDA-event timed, max over ranks
+  e2e        occurrences/s through the host-buffer C-ABI calls (rig_count_batch / rig_locate_batch) with pinned host
+             buffers: H2D of the patterns and D2H of ranges, offsets and every occurrence inside the timed region
+  roofline   dominant kernel (phi_window_kernel): bytes that must cross HBM per launch (8 B per occurrence written +
+             one pass over the Phi tables + 16 B per item) / its CUDA-event duration, against the measured HBM copy
+             bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own code (oracle/_ref) on the box's host cores, bounded sample (N = 1 only)
 """
 import argparse
 import json
@@ -51,60 +59,100 @@ WORKLOADS = {
     # edit probability per version 0.05 instead of SURVEY 8d's 0.25: 0.25 gives r = 165k at 40k versions, outside
     # the config's r ~ 50k (measured: r = 21.7k + 14.3 per edit)
     "c3": ("versioned_doc", 1_000_000_000, 25_000, 50_096, 0xB2000003, 125_000, 30, 0xB2001003, 0,
-           "C3 ri-locate at FULL size: 1 GB einstein-like sigma=96 versioned document; 125k len-30 patterns per GPU (the 1M patterns of the config sharded 8x)"),
+           "C3 ri-locate at FULL size: 1 GB einstein-like sigma=96 versioned document; 125k len-30 patterns per GPU (the config's 1M patterns on 8 GPUs)"),
     "c5": ("dna_indep", 4_000_000_000, 400_000, 10_000, 0xB2000005, 100_000, 15, 0xB2001005, 400_000,
            "C5 ri-locate at FULL size: 4 GB synthetic DNA sigma=4, 10k copies, ~10k occ/pattern, 100k len-15 patterns (n = 4.0e9, just under 2^32: 32-bit words)"),
     "c4": ("pangenome", 10_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_250_000, 100, 0xB2001004, 0,
-           "C4 ri-count at FULL size: 10 GB synthetic pan-genome sigma=5 (1000 haplotypes); 1.25M len-100 reads per GPU (the 10M reads of the config sharded 8x)"),
+           "C4 ri-count at FULL size: 10 GB synthetic pan-genome sigma=5 (1000 haplotypes); 1.25M len-100 reads per GPU (the config's 10M reads on 8 GPUs)"),
     "c4s": ("pangenome", 1_000_000_000, 10_000_000, 100_000, 0xB2000004, 1_000_000, 100, 0xB2001004, 0,
             "C4 scaled to 1GB: synthetic pan-genome sigma=5 (100 haplotypes), 1M len-100 reads (count; index >> L2)"),
 }
-B_PHI = 264          # algorithmic bytes per occurrence: 4 x 64 B blocks + 8 B store
+# How a workload's JOB grows with the number of GPUs: "strong" = the job is WORKLOADS' N patterns whatever the GPU
+# count (C5: BASELINE's scaling config; C2); "weak" = N patterns per GPU, one job of N x gpus patterns (C3 and C4 are
+# defined on 8 GPUs: 125k x 8 = the config's 1M patterns, 1.25M x 8 = its 10M reads; one GPU cannot hold C3's output).
+STRONG = {"c2", "c2s", "c2x4", "c5", "c5s"}
+B_PHI = 264          # SURVEY §8d's touched-bytes figure per occurrence for the REFERENCE structure (4 x 64 B blocks + 8 B store); printed as survey_touched, not used for `roofline.frac`
 B_RANK = lambda ell: 64 * (3 + ell)  # noqa: E731  per rank query
 FALLBACK_HBM_GBS = 6650.0
+L2_BYTES = 126 << 20
+CONFIG_NOTE = ("GPU arm: 256 MiB memset between timed steps (L2 flush, outside the per-step event pair), CUDA events on the "
+               "launch stream, max over ranks; CPU arm: steady_clock around the query loop")
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def prepare(workload, need_ref=False, rank=0):
-    """Generate text + patterns (deterministic), build or load the cached indexes."""
+def job_size(workload, world):
+    N = WORKLOADS[workload][5]
+    return N if workload in STRONG else N * world
+
+
+def base_of(workload):
+    return {"c2x4": "c2"}.get(workload, workload)  # workloads that share a text share its index
+
+
+def shared_config(workload, world, n, r):
+    """`config` of the JSON line: identical keys and values in both arms (ours / --impl reference)."""
+    kind, _, _, _, _, _, m, _, _, desc = WORKLOADS[workload]
+    return {"workload": desc, "name": workload, "n": int(n), "r": int(r), "job_patterns": job_size(workload, world),
+            "pattern_length": m, "gpus": world,
+            "scaling": ("strong: one fixed job" if workload in STRONG else "weak: %d patterns per GPU, one job" % WORKLOADS[workload][5]),
+            "notes": CONFIG_NOTE}
+
+
+def job_inputs(workload, world, rank, need_text=False, barrier=None):
+    """The job's pattern array (the same on every rank) and this repo's logical index. Rank 0 builds what .cache/
+    lacks (text -> prefix-free-parsing builder; patterns drawn from the text) and the others load it after the
+    barrier: one build per box, not one per rank. Returns (text or None, patt, N, m, host)."""
     rib = ge.load_package()
-    kind, n, p0, p1, tseed, N, m, pseed, limit, desc = WORKLOADS[workload]
+    kind, n, p0, p1, tseed, _, m, pseed, limit, desc = WORKLOADS[workload]
+    N = job_size(workload, world)
     os.makedirs(CACHE, exist_ok=True)
+    rpath = os.path.join(CACHE, "%s.rib" % base_of(workload))
+    ppath = os.path.join(CACHE, "%s.N%d.m%d.patt.npy" % (workload, N, m))
+    text = None
     t0 = time.time()
+    if rank == 0:
+        if need_text or not (os.path.exists(rpath) and os.path.exists(ppath)):
+            text = rib.gen_text(kind, n, p0, p1, tseed)
+        if not os.path.exists(ppath):
+            patt = rib.gen_patterns(text, N, m, pseed, limit)
+            np.save(ppath + ".tmp.npy", patt)
+            os.replace(ppath + ".tmp.npy", ppath)
+        if not os.path.exists(rpath):
+            log("[bench] building index for %s (n=%d) ..." % (workload, n))
+            host = rib.HostIndex.from_text_auto(text)  # prefix-free parsing above 16 MB: C2 ~1 s, C3 (1 GB) ~6 s, C5 (4 GB) ~24 s
+            host.save(rpath + ".tmp")
+            os.replace(rpath + ".tmp", rpath)
+            del host
+    if barrier is not None:
+        barrier()
+    patt = np.load(ppath)
+    host = rib.HostIndex.load(rpath)
+    if rank == 0:
+        log("[bench] inputs of %s ready in %.1fs: n=%d r=%d n/r=%.1f, %d patterns" % (workload, time.time() - t0, host.n, host.r, host.n / host.r, N))
+    return text, patt, N, m, host
+
+
+def reference_index(workload, host=None):
+    """The reference's r_index<> for the workload (oracle/_ref), or the plain-C port when _ref did not travel."""
+    ob = ge.load_oracle()
+    rib = ge.load_package()
+    if ob.have_ref():
+        rpath = os.path.join(CACHE, "%s.ref.ri" % base_of(workload))
+        if os.path.exists(rpath):
+            return ob.RefIndex.load(rpath), "index built by the reference's own constructor (cached .ri, reference serialize/load)"
+        if host is None:
+            _, _, _, _, host = job_inputs(workload, 1, 0)
+        log("[bench] no cached reference index for %s: assembling the reference's structures over this repo's BWT + samples" % workload)
+        return ob.RefIndex.from_logical(host.arrays()), "reference structures built by their own constructors over this repo's BWT + samples (ref_from_logical: the suffix sort is bypassed)"
+    if not ob.have_port():
+        ob.build()
+    log("[bench] oracle/_ref missing: CPU baseline falls back to the plain-C port")
+    kind, n, p0, p1, tseed = WORKLOADS[workload][:5]
     text = rib.gen_text(kind, n, p0, p1, tseed)
-    patt = rib.gen_patterns(text, N, m, pseed + rank, limit)
-    base = {"c2x4": "c2"}.get(workload, workload)  # workloads that share a text share its index
-    path = os.path.join(CACHE, "%s.rib" % base)
-    if os.path.exists(path):
-        host = rib.HostIndex.load(path)
-    else:
-        log("[bench] building index for %s (n=%d) ..." % (workload, n))
-        host = rib.HostIndex.from_text_auto(text)  # prefix-free parsing above 16 MB: C2 in ~1 s, C3 (1 GB) in ~6 s
-        if rank == 0:
-            tmp = path + ".tmp%d" % os.getpid()
-            host.save(tmp)
-            os.replace(tmp, path)
-    ref = None
-    if need_ref:
-        ob = ge.load_oracle()
-        rpath = os.path.join(CACHE, "%s.ref.ri" % base)
-        if ob.have_ref():
-            if os.path.exists(rpath):
-                ref = ob.RefIndex.load(rpath)
-            else:
-                log("[bench] building REFERENCE index for %s ..." % workload)
-                ref = ob.RefIndex.from_text(text)
-                ref.save(rpath)
-        else:
-            if not ob.have_port():
-                ob.build()
-            log("[bench] oracle/_ref missing: CPU baseline falls back to the plain-C port")
-            ref = ob.PortIndex(text, sa=rib.suffix_array(text))
-    log("[bench] prepared %s in %.1fs: n=%d r=%d n/r=%.1f" % (workload, time.time() - t0, host.n, host.r, host.n / host.r))
-    return text, patt, N, m, host, ref, desc
+    return ob.PortIndex(text, sa=rib.suffix_array(text)), "plain-C port over a suffix array"
 
 
 class ClockSampler:
@@ -201,33 +249,6 @@ class ClockSampler:
         return out
 
 
-def pin_to_gpu_numa(gpu_index):
-    """Bind this process (and the pinned host buffers it allocates afterwards: first touch) to the NUMA node the GPU
-    hangs off. With one process per GPU the host-buffer path (`e2e`) otherwise crosses sockets for half the ranks.
-    Returns the node or None; never fails the run."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bdf = bus.lower()
-        if len(bdf.split(":")[0]) == 8:   # NVML prints an 8-digit domain, sysfs a 4-digit one
-            bdf = bdf[4:]
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        allowed = os.sched_getaffinity(0) & cpus
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-        return node
-    except Exception:
-        return None
-
-
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -238,85 +259,135 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch from the committed ncu summary (profiles/ncu_traffic.json), or None."""
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `workload` from the committed ncu
+    captures (profiles/ncu_traffic.json: {workload: {kernel: bytes}}), or None when no capture of that pair exists."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(kernel)
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(p)).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
-def cpu_baseline(ref, patt, N, m, sample_patterns, threads):
-    """Reference CPU path (locate_all per pattern, results dropped as ri-locate does) on a bounded sample."""
-    S = min(N, sample_patterns)
-    sub = patt[: S * m]
-    _, _, _, occ_total, secs = ref.locate(sub, S, m, threads=threads, want=False)
+def d2h_ceiling(world):
+    """Aggregate device->host GB/s this box sustains with `world` GPUs copying at once (profiles/r2_d2h_probe.json,
+    measured by tools/d2h_probe.py), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_d2h_probe.json")))["d2h_aggregate_GBps_by_ranks"]
+        return float(t[str(world)])
+    except Exception:
+        return None
+
+
+def regime(index_bytes, seed_bytes=0):
+    hot = int(index_bytes) - int(seed_bytes)
+    if hot <= L2_BYTES:
+        return "A (the tables the dominant kernel reads, %d MB, fit the 126 MB L2: DRAM traffic ~ the output stream)" % (hot >> 20)
+    return "B (the tables the dominant kernel reads, %d MB, exceed the 126 MB L2: lookups reach DRAM)" % (hot >> 20)
+
+
+def ref_locate_sample(ref, patt, N, m, S, threads):
+    """Reference CPU path (locate_all per pattern, results dropped as ri-locate does) on the first S patterns."""
+    S = max(1, min(N, S))
+    _, _, _, occ_total, secs = ref.locate(patt[: S * m], S, m, threads=threads, want=False)
     return occ_total, secs, S
 
 
+def bounded_sample(N, occ_per_pattern, target_occ):
+    """Patterns in a CPU sample of about target_occ occurrences."""
+    return int(max(1, min(N, target_occ / max(1.0, occ_per_pattern))))
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref) on the box's host threads,
+    on the same workload (`config` identical to our arm's); each step a bounded sample of the job."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=True)
-    S = min(N, args.ref_sample)
+    _, patt, N, m, _ = job_inputs(args.workload, world, 0)   # patterns only (the logical index is not used when a .ref.ri exists)
+    ref, how = reference_index(args.workload)
     threads = cores if ref.kind == "reference" else 1
-    if args.mode == "count":
-        for _ in range(args.warmup):
-            ref.count(patt[: max(1, S // 10) * m], max(1, S // 10), m, threads=threads, want=False)
-        tot_s = sum(ref.count(patt[: S * m], S, m, threads=threads, want=False)[2] for _ in range(args.steps))
-        val = S * args.steps / tot_s
-        print(json.dumps({
-            "impl": "reference", "metric": "count_patterns_per_s", "value": val, "unit": "patterns/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "n": host.n, "r": host.r, "patterns_per_step": S, "pattern_length": m},
-            "cpu_baseline": {"value": val, "unit": "patterns/s", "cores": threads, "kind": ref.kind,
-                             "sample": "first %d of %d patterns per step, count()" % (S, N)},
-            "e2e": {"value": val, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
-        return 0
+    count_mode = args.mode == "count"
+    metric, unit = ("count_patterns_per_s", "patterns/s") if count_mode else ("locate_occurrences_per_s", "occ/s")
+    if count_mode:
+        S = min(N, args.ref_sample or 200_000)
+        run = lambda k: (k, ref.count(patt[: k * m], k, m, threads=threads, want=False)[2])  # noqa: E731
+    else:
+        # size the sample from a probe: about 1.5e8 occurrences per step (~1 s on 16 threads)
+        occ_p, _, Sp = ref_locate_sample(ref, patt, N, m, min(N, 2000), threads)
+        S = args.ref_sample or bounded_sample(N, occ_p / Sp, 1.5e8)
+        run = lambda k: ref_locate_sample(ref, patt, N, m, k, threads)[:2]  # noqa: E731
     for _ in range(args.warmup):
-        cpu_baseline(ref, patt, N, m, max(1, S // 10), threads)
-    tot_occ, tot_s = 0, 0.0
-    for k in range(args.steps):
-        occ, secs, S = cpu_baseline(ref, patt, N, m, S, threads)
-        tot_occ += occ; tot_s += secs
-    val = tot_occ / tot_s
-    line = {
-        "impl": "reference", "metric": "locate_occurrences_per_s", "value": val, "unit": "occ/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": desc, "n": host.n, "r": host.r, "patterns_per_step": S, "pattern_length": m,
-                   "note": "reference CPU code (oracle/_ref: reference headers over SDSL-API shim), bounded sample of the same patterns"},
-        "cpu_baseline": {"value": val, "unit": "occ/s", "cores": threads, "kind": ref.kind,
-                         "sample": "first %d of %d patterns per step, locate_all, results dropped" % (S, N)},
-        "e2e": {"value": val, "unit": "occ/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+        run(max(1, S // 10))
+    work, secs = 0, 0.0
+    for _ in range(args.steps):
+        w, t = run(S)
+        work += w; secs += t
+    val = work / secs
+    sample = "first %d of the job's %d patterns per step, %s, all %d host threads" % (
+        S, N, "count()" if count_mode else "locate_all, results dropped as ri-locate does", threads)
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": shared_config(args.workload, world, ref.n, ref.r),
+        "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": ref.kind, "sample": sample, "index": how},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
     return 0
 
 
+class Dist:
+    """torch.distributed plumbing of one run: NCCL for device tensors, a gloo group for the host-buffer path."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.gloo = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.gloo = dist.new_group(backend="gloo")
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.gloo)
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
 def run_ours_count(args):
-    """--mode count: the ri-count configs (C4). A step = one backward-search pass (rig_count_batch_dev)
-    over the batch; value = patterns/s; roofline = the search kernel against HBM (regime B when the
-    flattened index is larger than L2)."""
+    """--mode count: the ri-count configs (C4). A step = one backward-search pass (rig_count_batch_dev) over the job,
+    every rank its contiguous equal-count shard (reads of one length cost the same: no re-balancing); value =
+    patterns/s; roofline = the search kernel against HBM (regime B when the flattened index is larger than L2)."""
     import torch
-    import torch.distributed as dist
     rib = ge.load_package()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = pin_to_gpu_numa(local) if world > 1 else None
-    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
+    D = Dist()
+    world, rank, local, dev = D.world, D.rank, D.local, D.dev
+    from rindex_b200 import _shard
+    text, patt, N, m, host = job_inputs(args.workload, world, rank, barrier=D.host_barrier)
+    a, b = _shard.shard_bounds(N, world, rank)
+    Ns = b - a
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
                        phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1, seed_jump=1)  # count only: smallest locate tables
@@ -325,121 +396,239 @@ def run_ours_count(args):
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    d_patt = torch.from_numpy(patt).to(dev)
-    d_lo = torch.empty(N, dtype=torch.int64, device=dev)
-    d_hi = torch.empty(N, dtype=torch.int64, device=dev)
+    shard = np.ascontiguousarray(patt[a * m: b * m])
+    d_patt = torch.from_numpy(shard).to(dev)
+    d_lo = torch.empty(max(Ns, 1), dtype=torch.int64, device=dev)
+    d_hi = torch.empty(max(Ns, 1), dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     def step():
-        gpu.count_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
+        gpu.count_dev(d_patt.data_ptr(), Ns, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
 
     for _ in range(args.warmup):
         step()
-    barrier()
+    D.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
-    barrier()
+    D.barrier()
     for k in range(args.steps):
         flush.zero_()
         ev[k][0].record(); step(); ev[k][1].record()
         torch.cuda.synchronize()
         t = gpu.timing()
         kern_ms.append(t["search_ms"])
-    barrier()
+    D.barrier()
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = sum(x.elapsed_time(y) for x, y in ev)
     lf_steps = t["lf_steps"]
     # end to end: host buffers (pinned) through rig_count_batch
-    h_patt = torch.from_numpy(patt).pin_memory()
-    h_lo = torch.empty(N, dtype=torch.int64).pin_memory()
-    h_hi = torch.empty(N, dtype=torch.int64).pin_memory()
+    h_patt = torch.from_numpy(shard).pin_memory()
+    h_lo = torch.empty(max(Ns, 1), dtype=torch.int64).pin_memory()
+    h_hi = torch.empty(max(Ns, 1), dtype=torch.int64).pin_memory()
     for _ in range(2):
-        gpu.count_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr())
-    barrier()
+        gpu.count_raw(h_patt.data_ptr(), Ns, m, h_lo.data_ptr(), h_hi.data_ptr())
+    D.barrier()
     e2e_steps = max(1, min(args.steps, 5))
-    e2e_t = 0.0
+    t1 = time.perf_counter()
     for k in range(e2e_steps):
-        flush.zero_(); torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        gpu.count_raw(h_patt.data_ptr(), N, m, h_lo.data_ptr(), h_hi.data_ptr())
-        e2e_t += time.perf_counter() - t1
-    barrier()
-    nocc = (h_hi - h_lo + 1).clamp(min=0)
-    occ_t = int(nocc[(h_hi >= h_lo)].sum())
-    red = torch.tensor([total_ms, e2e_t * 1e3 / e2e_steps * args.steps], dtype=torch.float64, device=dev)
-    work = torch.tensor([float(N), float(lf_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms_g, e2e_ms_g = [float(x) for x in red.tolist()]
-    N_g, lf_g = [float(x) for x in work.tolist()]
+        gpu.count_raw(h_patt.data_ptr(), Ns, m, h_lo.data_ptr(), h_hi.data_ptr())
+    e2e_t = time.perf_counter() - t1
+    D.barrier()
+    nocc = (h_hi[:Ns] - h_lo[:Ns] + 1).clamp(min=0)
+    occ_t = int(nocc[(h_hi[:Ns] >= h_lo[:Ns])].sum())
+    total_ms_g, e2e_ms_g = D.reduce([total_ms, e2e_t * 1e3 / e2e_steps * args.steps], "MAX")
+    N_g, lf_g, occ_g = D.reduce([float(Ns), float(lf_steps), float(occ_t)], "SUM")
     if rank == 0:
         peak, peak_src = hbm_peak()
         k_ms = statistics.mean(kern_ms)
         # per rank query this layout touches 4 sectors (bdir, start[], head[], cum[]) = 128 B; 2 queries per LF step
-        alg_bytes = int(lf_steps) * 2 * 128 + N * (m + 16)
+        alg_bytes = int(lf_steps) * 2 * 128 + Ns * (m + 16)
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
-        regime = "B (flattened index %d MB > L2: every touched sector is a DRAM fetch)" % (info.device_bytes >> 20) \
-            if info.device_bytes > (100 << 20) else "A (index resident in L2)"
         line = {
             "metric": "count_patterns_per_s", "value": N_g * args.steps / (total_ms_g * 1e-3), "unit": "patterns/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_g / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "n": int(info.n), "r": int(info.r), "sigma": int(info.sigma), "patterns_per_gpu": N,
-                       "pattern_length": m, "lf_steps_per_step": int(lf_steps), "total_occurrences": occ_t,
+            "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": shared_config(args.workload, world, info.n, info.r),
+            "detail": {"sigma": int(info.sigma), "patterns_rank0": Ns, "lf_steps_rank0": int(lf_steps), "total_occurrences": int(occ_g),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
-                       "runs_per_block": int(info.runs_per_block), "parallelism": "patterns sharded x%d, index replicated" % world,
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                       "timing": "CUDA events per step on the launch stream; max over ranks"},
+                       "runs_per_block": int(info.runs_per_block), "parallelism": "contiguous equal-count shards x%d, index replicated" % world},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": N_g * args.steps / (e2e_ms_g * 1e-3), "unit": "patterns/s", "h2d_bytes_per_step": int(N * m),
                     "d2h_bytes_per_step": int(16 * N), "api": "rig_count_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
             "gpu_launches": args.steps * world,
             "lf_steps_per_s": lf_g * args.steps / (total_ms_g * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("search_kernel_" + args.workload),
+            "roofline": {"bound": "hbm", "kernel": "search_lane_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(args.workload, "search_lane_kernel"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_ms,
                          "algorithmic_bytes": "per LF step 2 rank queries x 4 sectors x 32 B (bdir, run starts, run heads, symbol directory) + m + 16 B per pattern",
-                         "regime": regime,
+                         "regime": regime(info.device_bytes),
                          "survey_touched": {"bytes_per_lf_step": 2 * B_RANK(ell),
                                             "achieved": int(lf_steps) * 2 * B_RANK(ell) / (k_ms * 1e-3) / 1e9}},
         }
-        if ref is not None:
+        if world == 1 and not args.no_cpu:
+            ref, how = reference_index(args.workload, host)
             cores = os.cpu_count() or 1
             threads = cores if ref.kind == "reference" else 1
-            S = min(N, args.cpu_sample)
+            S = min(N, args.cpu_sample or 200_000)
             ref.count(patt[: max(1, S // 10) * m], max(1, S // 10), m, threads=threads, want=False)
             best = min(ref.count(patt[: S * m], S, m, threads=threads, want=False)[2] for _ in range(3))
-            line["cpu_baseline"] = {"value": S / best, "unit": "patterns/s", "cores": threads, "kind": ref.kind,
+            line["cpu_baseline"] = {"value": S / best, "unit": "patterns/s", "cores": threads, "kind": ref.kind, "index": how,
                                     "sample": "%d of %d patterns, reference count() loop, best of 3: %.2fs" % (S, N, best)}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
     return 0
+
+
+class LocateJob:
+    """One rank's part of a locate job: device-resident step and host-buffer (e2e) step, with the count -> all-gather
+    -> re-cut by occurrence mass -> locate sequence when there is more than one rank (`solo` = the whole job alone)."""
+
+    def __init__(self, D, gpu, patt, N, m, stream, solo=False):
+        torch = D.torch
+        self.D, self.gpu, self.N, self.m, self.stream = D, gpu, N, m, stream
+        self.world, self.rank = (1, 0) if solo else (D.world, D.rank)
+        from rindex_b200 import _shard
+        self.shard = _shard
+        self.patt = patt
+        self.d_patt = torch.from_numpy(patt).to(D.dev)          # the whole batch on every GPU (N x m bytes)
+        self.a, self.b = _shard.shard_bounds(N, self.world, self.rank)
+        self.per = max(_shard.shard_bounds(N, self.world, r)[1] - _shard.shard_bounds(N, self.world, r)[0] for r in range(self.world))
+        self.d_lo = torch.empty(N + 1, dtype=torch.int64, device=D.dev)
+        self.d_hi = torch.empty(N + 1, dtype=torch.int64, device=D.dev)
+        self.d_off = torch.empty(N + 2, dtype=torch.int64, device=D.dev)
+        self.d_cnt = torch.zeros(self.per, dtype=torch.int64, device=D.dev)
+        self.d_all = torch.zeros(self.world * self.per, dtype=torch.int64, device=D.dev)
+        self.d_occ = None
+        self.cuts = None
+        self.phase_ms = {}
+
+    # -- re-balancing (SURVEY 8e): equal-count count phase, all-gather of the counts, cuts of equal occurrence mass --
+    def _cuts_from(self, all_counts):
+        nocc = np.concatenate([all_counts[r * self.per: r * self.per + (self.shard.shard_bounds(self.N, self.world, r)[1] - self.shard.shard_bounds(self.N, self.world, r)[0])]
+                               for r in range(self.world)])
+        return self.shard.balanced_cuts(nocc, self.world), nocc
+
+    def plan_dev(self):
+        """count phase on the device + NCCL all-gather; returns this rank's [c0, c1) and the per-pattern counts."""
+        torch, dist = self.D.torch, self.D.dist
+        if self.world == 1:
+            return 0, self.N, None
+        n = self.b - self.a
+        self.gpu.count_dev(self.d_patt.data_ptr() + self.a * self.m, n, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.stream)
+        self.d_cnt.zero_()
+        self.d_cnt[:n] = (self.d_hi[:n] - self.d_lo[:n] + 1).clamp_(min=0)
+        dist.all_gather_into_tensor(self.d_all, self.d_cnt)
+        cuts, nocc = self._cuts_from(self.d_all.cpu().numpy())      # one small D2H: the cut points are host-side launch parameters
+        self.cuts = cuts
+        return cuts[self.rank], cuts[self.rank + 1], nocc
+
+    def step_dev(self):
+        c0, c1, _ = self.plan_dev()
+        return self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                                   self.d_off.data_ptr(), self.d_occ.data_ptr(), self.d_occ.numel(), self.stream)
+
+    def size_output(self):
+        """Two-call protocol on this rank's shard; allocates the device occurrence buffer. Returns its occurrences."""
+        torch = self.D.torch
+        c0, c1, _ = self.plan_dev()
+        try:
+            need = self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                                       self.d_off.data_ptr(), None, 0, self.stream)
+        except Exception as e:  # noqa: BLE001
+            if getattr(e, "code", 0) != -4:
+                raise
+            need = e.needed
+        self.d_occ = torch.empty(max(need, 1), dtype=torch.int64, device=self.D.dev)
+        self.c0, self.c1 = c0, c1
+        return need
+
+    # -- host-buffer path (the reference-facing calls): pinned buffers, gloo all-gather of the counts --
+    def setup_host(self, occ_cap):
+        torch = self.D.torch
+        self.h_patt = torch.from_numpy(self.patt).pin_memory()
+        self.h_lo = torch.empty(self.N + 1, dtype=torch.int64).pin_memory()
+        self.h_hi = torch.empty(self.N + 1, dtype=torch.int64).pin_memory()
+        self.h_off = torch.empty(self.N + 2, dtype=torch.int64).pin_memory()
+        self.h_occ = torch.empty(max(occ_cap, 1), dtype=torch.int64).pin_memory()
+        self.h_cnt = torch.zeros(self.per, dtype=torch.int64)
+        self.h_all = [torch.zeros(self.per, dtype=torch.int64) for _ in range(self.world)]
+
+    def step_host(self):
+        torch, dist = self.D.torch, self.D.dist
+        c0, c1 = 0, self.N
+        if self.world > 1:
+            n = self.b - self.a
+            self.gpu.count_raw(self.h_patt.data_ptr() + self.a * self.m, n, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr())
+            self.h_cnt.zero_()
+            self.h_cnt[:n] = (self.h_hi[:n] - self.h_lo[:n] + 1).clamp_(min=0)
+            dist.all_gather(self.h_all, self.h_cnt, group=self.D.gloo)
+            cuts, _ = self._cuts_from(torch.cat(self.h_all).numpy())
+            c0, c1 = cuts[self.rank], cuts[self.rank + 1]
+        tot = self.gpu.locate_raw(self.h_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr(),
+                                  self.h_off.data_ptr(), self.h_occ.data_ptr(), self.h_occ.numel())
+        return tot, c1 - c0
+
+
+def measure_locate(D, job, steps, warmup, e2e_steps, flush, solo=False):
+    """Timed region of one job: `steps` device-resident steps (CUDA events per step, L2 flushed in between) and
+    `e2e_steps` host-buffer steps (wall clock around the whole loop, barriers on both sides). Returns a dict of this
+    rank's figures; the caller reduces over ranks."""
+    torch = D.torch
+    gpu = job.gpu
+    barrier = (lambda: torch.cuda.synchronize()) if solo else D.barrier
+    occ_rank = job.size_output()
+    for _ in range(warmup):
+        job.step_dev()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ph = {k: [] for k in ("search_ms", "scan_ms", "seed_ms", "window_ms", "expand_ms")}
+    launches = 0
+    barrier()
+    for k in range(steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
+        ev[k][0].record()
+        tot = job.step_dev()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        t = gpu.timing()
+        for key in ph:
+            ph[key].append(t[key])
+        launches += t["launches"] + (1 if job.world > 1 else 0)
+    barrier()
+    assert tot == occ_rank
+    total_ms = sum(x.elapsed_time(y) for x, y in ev)
+    out = {"occ_rank": occ_rank, "patterns_rank": job.c1 - job.c0, "total_ms": total_ms, "launches": launches,
+           "lf_steps": t["lf_steps"], "chains": t["chains"], "phases": {k: statistics.mean(v) for k, v in ph.items()}}
+    # end to end through the host-buffer C-ABI calls, pinned host memory. A shard whose occurrences exceed 16 GB (C3 at
+    # full size) is not measured end to end: pinning that much host memory per rank is not what this number is about.
+    if e2e_steps and occ_rank * 8 <= (16 << 30):
+        job.setup_host(occ_rank)
+        for _ in range(2):
+            job.step_host()
+        barrier()
+        if not solo:
+            D.host_barrier()
+        t1 = time.perf_counter()
+        for k in range(e2e_steps):
+            tot_h, pat_h = job.step_host()
+        e2e_t = time.perf_counter() - t1
+        barrier()
+        assert tot_h == occ_rank and int(job.h_off[pat_h]) == occ_rank   # cheap self-check (parity tests live in tests/)
+        out.update(e2e_ms=e2e_t * 1e3 / e2e_steps, e2e_h2d=int((job.b - job.a if job.world > 1 else 0) * job.m + pat_h * job.m),
+                   e2e_d2h=int(8 * (2 * (job.b - job.a if job.world > 1 else 0) + 3 * pat_h + 1 + occ_rank)))
+    return out
 
 
 def run_ours(args):
     import torch
-    import torch.distributed as dist
     rib = ge.load_package()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = pin_to_gpu_numa(local) if world > 1 else None
-
-    text, patt, N, m, host, ref, desc = prepare(args.workload, need_ref=(rank == 0 and world == 1 and not args.no_cpu), rank=rank)
+    D = Dist()
+    world, rank, local, dev = D.world, D.rank, D.local, D.dev
+    need_text = world == 1 and not args.no_post
+    text, patt, N, m, host = job_inputs(args.workload, world, rank, need_text=need_text, barrier=D.host_barrier)
     t0 = time.time()
     gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
                        phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads, phi_jump=args.phi_jump,
@@ -451,227 +640,213 @@ def run_ours(args):
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-
-    d_patt = torch.from_numpy(patt).to(dev)
-    d_lo = torch.empty(N, dtype=torch.int64, device=dev)
-    d_hi = torch.empty(N, dtype=torch.int64, device=dev)
-    d_off = torch.empty(N + 1, dtype=torch.int64, device=dev)
-    # size the occurrence buffer with the two-call protocol
-    try:
-        need = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), None, 0, stream)
-    except rib.RigError as e:
-        if e.code != -4:
-            raise
-        need = e.needed
-    d_occ = torch.empty(max(need, 1), dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    e2e_steps = max(1, min(args.steps, 5))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    # ---- the same job on ONE GPU, measured in this run by rank 0 while the others wait (N > 1 only) ----
+    solo = None
+    if world > 1 and not args.no_solo:
+        if rank == 0:
+            sj = LocateJob(D, gpu, patt, N, m, stream, solo=True)
+            sm = measure_locate(D, sj, max(3, min(args.steps, 5)), 3, 2, flush, solo=True)
+            solo = {"value": sm["occ_rank"] * max(3, min(args.steps, 5)) / (sm["total_ms"] * 1e-3), "ms_per_step": sm["total_ms"] / max(3, min(args.steps, 5)),
+                    "e2e": (sm["occ_rank"] / (sm["e2e_ms"] * 1e-3)) if "e2e_ms" in sm else None,
+                    "e2e_ms_per_step": sm.get("e2e_ms"), "occurrences": sm["occ_rank"], "phases_ms": sm["phases"]}
+            del sj
+            torch.cuda.empty_cache()
+        D.barrier()
 
-    def step_dev():
-        return gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(),
-                              d_occ.data_ptr(), d_occ.numel(), stream)
-
-    def count_dev():
-        gpu.count_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), stream)
-
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
+    job = LocateJob(D, gpu, patt, N, m, stream)
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    expand_ms, search_ms, scan_ms, seed_ms, window_ms, launches = [], [], [], [], [], 0
-    occ_total = 0
-    barrier()
-    for k in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
-        ev[k][0].record()
-        occ_total = step_dev()
-        ev[k][1].record()
-        torch.cuda.synchronize()
-        t = gpu.timing()
-        expand_ms.append(t["expand_ms"]); search_ms.append(t["search_ms"]); scan_ms.append(t["scan_ms"])
-        seed_ms.append(t["seed_ms"]); window_ms.append(t["window_ms"])
-        launches += t["launches"]
-    barrier()
+    M = measure_locate(D, job, args.steps, args.warmup, e2e_steps, flush)
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    lf_steps, chains = t["lf_steps"], t["chains"]
+    occ_rank, lf_steps, chains = M["occ_rank"], M["lf_steps"], M["chains"]
 
-    # count-only pass (patterns/s), same patterns, device resident
+    # count-only pass (patterns/s) on the equal-count shard, device resident
+    a, b = job.a, job.b
     cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    count_dev(); barrier()
+
+    def count_dev():
+        gpu.count_dev(job.d_patt.data_ptr() + a * m, b - a, m, job.d_lo.data_ptr(), job.d_hi.data_ptr(), stream)
+
+    count_dev(); D.barrier()
     for k in range(args.steps):
         flush.zero_()
         cev[k][0].record(); count_dev(); cev[k][1].record()
-    barrier()
-    count_ms = sum(a.elapsed_time(b) for a, b in cev)
-    launches_count = args.steps
+    D.barrier()
+    count_ms = sum(x.elapsed_time(y) for x, y in cev)
 
-    # end to end through the host-buffer C-ABI call, pinned host memory
-    # (a batch whose occurrences exceed 8 GB — full-size C3/C5 — is measured end to end on its leading patterns
-    # holding about 4 GB of occurrences: pinning tens of GB of host memory is not what this number is about)
-    NE, occ_e2e = N, occ_total
-    if occ_total * 8 > (8 << 30):
-        offs = d_off.cpu().numpy()
-        NE = max(1, int(np.searchsorted(offs, (4 << 30) // 8)) - 1)
-        occ_e2e = int(offs[NE])
-    h_patt = torch.from_numpy(patt[: NE * m].copy()).pin_memory()
-    h_lo = torch.empty(NE, dtype=torch.int64).pin_memory()
-    h_hi = torch.empty(NE, dtype=torch.int64).pin_memory()
-    h_off = torch.empty(NE + 1, dtype=torch.int64).pin_memory()
-    h_occ = torch.empty(max(occ_e2e, 1), dtype=torch.int64).pin_memory()
-
-    def step_e2e():
-        return gpu.locate_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(),
-                              h_occ.data_ptr(), h_occ.numel())
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 5))
-    e2e_t = 0.0
-    for k in range(e2e_steps):
-        flush.zero_(); torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        tot_e2e = step_e2e()
-        e2e_t += time.perf_counter() - t1
-    barrier()
-    assert tot_e2e == occ_e2e
-    # cheap self-check of the e2e result (not a parity test: those live in tests/)
-    assert int(h_off[-1]) == occ_e2e
-    # the same call with 32-bit positions (rig_locate_batch32; texts below 4 GiB): half the D2H bytes
+    # the same host-buffer call with 32-bit positions (rig_locate_batch32; texts below 4 GiB): half the D2H bytes
     e2e32_ms = None
-    if int(info.n) <= 0xFFFFFFFF:
-        h_occ32 = torch.empty(max(occ_e2e, 1), dtype=torch.int32).pin_memory()
+    if world == 1 and int(info.n) <= 0xFFFFFFFF and "e2e_ms" in M:
+        h_occ32 = torch.empty(max(occ_rank, 1), dtype=torch.int32).pin_memory()
+        call32 = lambda: gpu.locate32_raw(job.h_patt.data_ptr(), N, m, job.h_lo.data_ptr(), job.h_hi.data_ptr(), job.h_off.data_ptr(),  # noqa: E731
+                                          h_occ32.data_ptr(), h_occ32.numel())
         for _ in range(2):
-            gpu.locate32_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(), h_occ32.data_ptr(), h_occ32.numel())
-        t32 = 0.0
+            call32()
+        t1 = time.perf_counter()
         for k in range(e2e_steps):
-            flush.zero_(); torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            gpu.locate32_raw(h_patt.data_ptr(), NE, m, h_lo.data_ptr(), h_hi.data_ptr(), h_off.data_ptr(), h_occ32.data_ptr(), h_occ32.numel())
-            t32 += time.perf_counter() - t1
-        e2e32_ms = t32 * 1e3 / e2e_steps
-        assert torch.equal(h_occ32[:4096].to(torch.int64) & 0xFFFFFFFF, h_occ[:4096])
+            call32()
+        e2e32_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+        assert torch.equal(h_occ32[:4096].to(torch.int64) & 0xFFFFFFFF, job.h_occ[:4096])
         del h_occ32
 
     # ri-locate -o / -c post-processing on the device, timed once on the resident output of the last
     # step: segmented sort of every pattern's occurrences, then the self-check (hash-join brute-force counts over
-    # the text + byte comparison of every occurrence). Not part of `value`.
+    # the text + byte comparison of every occurrence). Not part of `value`. One GPU only.
     post = None
-    if not args.no_post:
-        step_dev(); torch.cuda.synchronize()
+    if world == 1 and not args.no_post:
+        job.step_dev(); torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(); gpu.sort_dev(N, d_off.data_ptr(), d_occ.data_ptr(), occ_total, stream); s1.record()
+        s0.record(); gpu.sort_dev(N, job.d_off.data_ptr(), job.d_occ.data_ptr(), occ_rank, stream); s1.record()
         torch.cuda.synchronize()
         gpu.text_attach(text)
         t1 = time.perf_counter()
-        rep = gpu.check_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(),
-                            occ_total, True, stream)
+        rep = gpu.check_dev(job.d_patt.data_ptr(), N, m, job.d_lo.data_ptr(), job.d_hi.data_ptr(), job.d_off.data_ptr(), job.d_occ.data_ptr(),
+                            occ_rank, True, stream)
         check_ms = (time.perf_counter() - t1) * 1e3
         assert rep.clean, rep.as_dict()
-        post = {"sort_ms": s0.elapsed_time(s1), "sort_keys_per_s": occ_total / (s0.elapsed_time(s1) * 1e-3),
+        post = {"sort_ms": s0.elapsed_time(s1), "sort_keys_per_s": occ_rank / (s0.elapsed_time(s1) * 1e-3),
                 "check_ms": check_ms, "check": rep.as_dict(),
                 "note": "rig_sort_occurrences_dev + rig_check_dev on the device-resident output (ri-locate -o / -c)"}
 
+    # optional collation over NVLink (north_star: "an optional NCCL all-gather only to collate occurrence buffers"):
+    # every rank ends up with the whole job's occurrences in pattern order; exercised and timed once, not part of `value`
+    collate = None
+    if world > 1 and not args.no_collate:
+        job.step_dev(); torch.cuda.synchronize()
+        sizes = torch.tensor([occ_rank], dtype=torch.int64, device=dev)
+        all_sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        D.dist.all_gather_into_tensor(all_sizes, sizes)
+        all_sizes = [int(x) for x in all_sizes.cpu().tolist()]
+        mx = max(all_sizes)
+        if mx * 8 * (world + 1) < (120 << 30):
+            send = torch.zeros(mx, dtype=torch.int64, device=dev)
+            send[:occ_rank] = job.d_occ[:occ_rank]
+            recv = torch.empty(world * mx, dtype=torch.int64, device=dev)
+            mine = gpu.digest_dev(job.d_occ.data_ptr(), occ_rank, stream)
+            D.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); D.dist.all_gather_into_tensor(recv, send); c1.record()
+            torch.cuda.synchronize()
+            ok = True
+            dg = torch.tensor([mine[0] & 0x7FFFFFFFFFFFFFFF, mine[1] & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
+            all_dg = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+            D.dist.all_gather_into_tensor(all_dg, dg)
+            all_dg = all_dg.cpu().tolist()
+            for r in range(world):   # every rank checks every shard it received against the sender's own digest
+                got = gpu.digest_dev(recv.data_ptr() + r * mx * 8, all_sizes[r], stream)
+                ok = ok and (got[0] & 0x7FFFFFFFFFFFFFFF) == all_dg[2 * r] and (got[1] & 0x7FFFFFFFFFFFFFFF) == all_dg[2 * r + 1]
+            okg = D.reduce([1.0 if ok else 0.0], "MIN")[0]
+            ms = D.reduce([c0.elapsed_time(c1)], "MAX")[0]
+            collate = {"ms": ms, "bytes_received_per_rank": int(8 * sum(all_sizes)), "padded_bytes_per_rank": int(8 * mx * world),
+                       "algbw_GBps": 8 * sum(all_sizes) / (ms * 1e-3) / 1e9, "digests_match_on_all_ranks": bool(okg == 1.0),
+                       "api": "torch.distributed all_gather_into_tensor (NCCL over NVLink), shards padded to the largest"}
+            del send, recv
+
     # reduce over ranks: max time, sum work
-    red = torch.tensor([total_ms, count_ms, e2e_t * 1e3 / e2e_steps * args.steps], dtype=torch.float64, device=dev)
-    work = torch.tensor([float(occ_total), float(N), float(launches), float(occ_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms_g, count_ms_g, e2e_ms_g = [float(x) for x in red.tolist()]
-    occ_g, N_g, launches_g, occ_e2e_g = [float(x) for x in work.tolist()]
+    total_ms_g, count_ms_g, e2e_ms_g = D.reduce([M["total_ms"], count_ms, M.get("e2e_ms", 0.0)], "MAX")
+    occ_g, launches_g, h2d_g, d2h_g, has_e2e = D.reduce([float(occ_rank), float(M["launches"]), float(M.get("e2e_h2d", 0)),
+                                                           float(M.get("e2e_d2h", 0)), 1.0 if "e2e_ms" in M else 0.0], "SUM")
+    rank_ms = D.reduce([M["total_ms"] / args.steps], "SUM")[0] / world
+    occ_max = D.reduce([float(occ_rank)], "MAX")[0]
+    e2e_sum_ms = D.reduce([M.get("e2e_ms", 0.0)], "SUM")[0]
+    eq_occ = None
+    if world > 1:   # what equal-count shards would have given each rank (the imbalance the re-cut removes)
+        _, _, nocc_all = job.plan_dev()
+        eq = [float(nocc_all[job.shard.shard_bounds(N, world, r)[0]: job.shard.shard_bounds(N, world, r)[1]].sum()) for r in range(world)]
+        eq_occ = max(eq) / (sum(eq) / world) if sum(eq) else 1.0
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        exp_ms = statistics.mean(expand_ms)
-        # Roofline of the dominant kernel (Phi expansion), HBM-bound. ALGORITHMIC bytes = what must cross
-        # HBM for this launch: 8 B per occurrence written + one pass over the Phi tables (they are L2
-        # resident afterwards: regime A). SURVEY §8d's per-occurrence figure (264 B = 4 x 64 B blocks + 8 B,
-        # the reference structure's TOUCHED bytes) is reported next to it as `survey_touched`: this layout
-        # touches 32 B per 4 occurrences instead, and those bytes are served by L2.
-        # Two-pass expansion: the dominant kernel is pass 2 (phi_window_kernel): it writes every occurrence,
-        # reads the Phi^1..D table once (the seed table is touched by pass 1 only) and one 16-byte entry per item.
-        two_pass = int(info.seed_jump) > 1 and statistics.mean(window_ms) > 0
+        phs = M["phases"]
+        exp_ms = phs["expand_ms"]
+        # Roofline of the dominant kernel (second expansion pass, phi_window_kernel), HBM-bound. ALGORITHMIC bytes =
+        # what must cross HBM for this launch: 8 B per occurrence written + one pass over the tables it reads (the
+        # flattened index without the seed table, which only pass 1 touches) + 16 B per item read.
+        two_pass = int(info.seed_jump) > 1 and phs["window_ms"] > 0
         if two_pass:
-            win_ms = statistics.mean(window_ms)
-            items = occ_total // int(info.seed_jump) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
-            phi_table_bytes = int(info.device_bytes) - int(info.seed_bytes)
-            alg_bytes = occ_total * 8 + phi_table_bytes + items * 16
-            dom_kernel, dom_ms = "phi_window_kernel", win_ms
+            items = occ_rank // int(info.seed_jump) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
+            alg_bytes = occ_rank * 8 + int(info.device_bytes) - int(info.seed_bytes) + items * 16
+            dom_kernel, dom_ms = "phi_window_kernel", phs["window_ms"]
             alg_note = "8 B/occurrence output + one pass over the flattened index without the seed table + 16 B per item (slot, count, seed)"
         else:
-            phi_table_bytes = int(info.device_bytes)
-            alg_bytes = occ_total * 8 + phi_table_bytes
+            alg_bytes = occ_rank * 8 + int(info.device_bytes)
             dom_kernel, dom_ms = "phi_expand_kernel", exp_ms
             alg_note = "8 B/occurrence output + one pass over the flattened index"
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        touched = occ_total * B_PHI
+        step_ms = M["total_ms"] / args.steps
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
-        srch_ms = statistics.mean(search_ms)
+        e2e_val = occ_g / (e2e_ms_g * 1e-3) if has_e2e == world and e2e_ms_g > 0 else None
         line = {
             "metric": "locate_occurrences_per_s", "value": occ_g * args.steps / (total_ms_g * 1e-3), "unit": "occ/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_g / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "n": int(info.n), "r": int(info.r), "sigma": int(info.sigma),
-                       "patterns_per_gpu": N, "pattern_length": m, "occurrences_per_step_per_gpu": occ_total,
-                       "phi_chains_per_step": int(chains), "lf_steps_per_step": int(lf_steps),
+            "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": shared_config(args.workload, world, info.n, info.r),
+            "detail": {"sigma": int(info.sigma), "occurrences_per_step": int(occ_g), "occurrences_rank0": occ_rank,
+                       "patterns_rank0": M["patterns_rank"], "phi_chains_rank0": int(chains), "lf_steps_rank0": int(lf_steps),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
                        "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump),
-                       "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes), "parallelism": "patterns sharded x%d, index replicated" % world,
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pair); index < L2 (regime A)",
-                       "timing": "CUDA events per step on the launch stream; max over ranks"},
+                       "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes),
+                       "parallelism": ("index replicated x%d; per step: count on equal-count shards, NCCL all-gather of the counts (8 B/pattern), "
+                                       "contiguous shards re-cut at equal occurrence mass, locate" % world) if world > 1 else "one GPU",
+                       "phases_ms_rank0": phs},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
-            "e2e": {"value": occ_e2e_g * args.steps / (e2e_ms_g * 1e-3), "unit": "occ/s",
-                    "h2d_bytes_per_step": int(NE * m), "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1 + occ_e2e)),
-                    "api": "rig_locate_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps, "numa_node_rank0": numa,
-                    "patterns_per_step": NE, "occurrences_per_step": occ_e2e},
-            "gpu_launches": int(launches_g) + launches_count * world,
-            "count": {"metric": "count_patterns_per_s", "value": N_g * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
+            "e2e": {"value": e2e_val, "unit": "occ/s", "h2d_bytes_per_step": int(h2d_g), "d2h_bytes_per_step": int(d2h_g),
+                    "api": "rig_locate_batch (host buffers, pinned)" + ("; rig_count_batch + gloo all-gather of the counts before it" if world > 1 else ""),
+                    "ms_per_step": e2e_ms_g, "steps": e2e_steps},
+            "gpu_launches": int(launches_g) + args.steps * world,
+            "count": {"metric": "count_patterns_per_s", "value": N * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
                       "ms_per_step": count_ms_g / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
-                         "algorithmic_bytes": alg_note,
-                         "expansion": {"expand_ms": exp_ms, "seed_pass_ms": statistics.mean(seed_ms), "window_pass_ms": statistics.mean(window_ms),
-                                       "achieved_both_passes": (occ_total * 8 + int(info.device_bytes)) / (exp_ms * 1e-3) / 1e9},
-                         "regime": "A (index resident in L2: touched bytes are served by L2; DRAM traffic ~ output stream)",
-                         "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": touched / (exp_ms * 1e-3) / 1e9,
-                                            "note": "SURVEY 8d touched-bytes figure / launch time; L2-served, not an HBM fraction"},
-                         "search_kernel": {"launch_ms": srch_ms, "algorithmic_bytes": int(lf_steps) * 3 * B_RANK(ell),
-                                           "achieved": int(lf_steps) * 3 * B_RANK(ell) / (srch_ms * 1e-3) / 1e9 if srch_ms > 0 else None},
-                         "scan_ms": statistics.mean(scan_ms)},
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom_kernel), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "algorithmic_bytes": alg_note,
+                         "rank": 0, "regime": regime(info.device_bytes, info.seed_bytes),
+                         "whole_step": {"ms": step_ms, "achieved": (occ_rank * 8 + int(info.device_bytes)) / (step_ms * 1e-3) / 1e9,
+                                        "frac": (occ_rank * 8 + int(info.device_bytes)) / (step_ms * 1e-3) / 1e9 / peak},
+                         "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": occ_rank * B_PHI / (exp_ms * 1e-3) / 1e9,
+                                            "note": "SURVEY 8d's touched-bytes figure for the reference's structure / expansion time; L2-served, not an HBM fraction"},
+                         "search_kernel": {"launch_ms": phs["search_ms"], "algorithmic_bytes": int(lf_steps) * 3 * B_RANK(ell)}},
         }
-        if e2e32_ms is not None:  # rank 0's own figure (not reduced over ranks)
-            line["e2e_u32"] = {"value": occ_e2e / (e2e32_ms * 1e-3), "unit": "occ/s", "ms_per_step": e2e32_ms,
-                               "d2h_bytes_per_step": int(8 * (2 * NE + NE + 1) + 4 * occ_e2e),
+        if world > 1:
+            ceil = d2h_ceiling(world)
+            line["balance"] = {"occurrences_max_over_mean": occ_max / (occ_g / world), "equal_count_shards_would_give": eq_occ,
+                               "rank_step_ms_max_over_mean": (total_ms_g / args.steps) / rank_ms if rank_ms else None,
+                               "rank_e2e_ms_max_over_mean": (e2e_ms_g / (e2e_sum_ms / world)) if e2e_sum_ms else None}
+            line["strong_scaling"] = {"job": WORKLOADS[args.workload][9], "n1": solo,
+                                      "speedup_value": (line["value"] / solo["value"]) if solo else None,
+                                      "speedup_e2e": (e2e_val / solo["e2e"]) if solo and solo.get("e2e") and e2e_val else None}
+            if ceil and e2e_val:
+                line["e2e"]["box_d2h_ceiling"] = {"aggregate_GBps": ceil, "occ_per_s_at_ceiling": ceil * 1e9 / 8,
+                                                  "fraction_of_ceiling": e2e_val / (ceil * 1e9 / 8),
+                                                  "source": "profiles/r2_d2h_probe.json (tools/d2h_probe.py: %d GPUs copying to pinned host memory at once)" % world}
+        if collate is not None:
+            line["collate"] = collate
+        if e2e32_ms is not None:
+            line["e2e_u32"] = {"value": occ_rank / (e2e32_ms * 1e-3), "unit": "occ/s", "ms_per_step": e2e32_ms,
+                               "d2h_bytes_per_step": int(8 * (3 * N + 1) + 4 * occ_rank),
                                "api": "rig_locate_batch32 (32-bit positions, n < 2^32; an addition to the reference's 64-bit surface)"}
         if post is not None:
             line["post"] = post
-        if ref is not None:
+        if world == 1 and not args.no_cpu:
+            ref, how = reference_index(args.workload, host)
             cores = os.cpu_count() or 1
             threads = cores if ref.kind == "reference" else 1
-            cpu_baseline(ref, patt, N, m, max(1, min(N, args.cpu_sample) // 10), threads)  # warm-up
+            S = args.cpu_sample or bounded_sample(N, occ_rank / max(1, N), 2.0e8)
+            ref_locate_sample(ref, patt, N, m, max(1, S // 10), threads)  # warm-up
             best = None
             for _ in range(3):  # best of 3, all host threads
-                occ_c, secs_c, S = cpu_baseline(ref, patt, N, m, args.cpu_sample, threads)
+                occ_c, secs_c, S = ref_locate_sample(ref, patt, N, m, S, threads)
                 best = secs_c if best is None else min(best, secs_c)
-            line["cpu_baseline"] = {"value": occ_c / best, "unit": "occ/s", "cores": threads, "kind": ref.kind,
+            line["cpu_baseline"] = {"value": occ_c / best, "unit": "occ/s", "cores": threads, "kind": ref.kind, "index": how,
                                     "sample": "%d of %d patterns (%d occurrences), reference locate_all loop, results dropped as ri-locate does, best of 3: %.2fs" % (S, N, occ_c, best)}
             if ref.kind == "reference":  # the reference as shipped is single-threaded: 1-core figure on 1/8 of the sample
-                occ_1, secs_1, S1 = cpu_baseline(ref, patt, N, m, max(1, min(N, args.cpu_sample) // 8), 1)
+                occ_1, secs_1, S1 = ref_locate_sample(ref, patt, N, m, max(1, S // 8), 1)
                 line["cpu_baseline"]["single_core_value"] = occ_1 / secs_1
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 
@@ -681,19 +856,26 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="patterns in the cpu_baseline sample (default: all)")
-    ap.add_argument("--ref-sample", type=int, default=1 << 30, help="patterns per step of --impl reference (default: all)")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: c2 on one GPU, c5 (strong scaling) on several")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the cpu_baseline sample (default: ~2e8 occurrences)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="patterns per step of --impl reference (default: ~1.5e8 occurrences)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-post", action="store_true", help="skip the -o / -c post-processing timing")
+    ap.add_argument("--no-solo", action="store_true", help="N > 1: skip rank 0's one-GPU run of the same job")
+    ap.add_argument("--no-collate", action="store_true", help="N > 1: skip the NCCL collation of the occurrence buffers")
     ap.add_argument("--runs-per-block", type=int, default=0)
     ap.add_argument("--lf-log2", type=int, default=0)
     ap.add_argument("--phi-log2", type=int, default=0)
     ap.add_argument("--expand-threads", type=int, default=0)
     ap.add_argument("--phi-jump", type=int, default=0)
     ap.add_argument("--seed-jump", type=int, default=0, help="two-pass expansion window SEG: 0 auto, 1 off (single pass), 16..256")
-    ap.add_argument("--mode", default="locate", choices=["locate", "count"], help="locate (default, C2) or count (ri-count configs)")
+    ap.add_argument("--mode", default="locate", choices=["locate", "count"], help="locate (default) or count (ri-count configs: c4, c4s)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c5"
+    if args.workload in ("c4", "c4s"):
+        args.mode = "count"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner, ...)
     # is sent to stderr, and the real stdout is restored for the final print() calls through sys.stdout.

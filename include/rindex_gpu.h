@@ -55,8 +55,7 @@ typedef struct rig_options {
                                   reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths);
                                   reserved[2] = SEG of the two-pass Phi expansion: 0 = auto, 1 = off (single pass),
                                   16/32/64/128/256 = occurrences per seed-table hop (window size in output slots);
-                                  reserved[3] low byte = 2: locate batches of >= 16384 patterns run as two slices pipelined on
-                                  two streams (measured +1.5..4.5%; off by default) */
+                                  reserved[3]: unused, must be 0 */
 } rig_options;
 
 typedef struct rig_index_info {
@@ -79,8 +78,7 @@ typedef struct rig_timing {
     float expand_ms;  /* Phi expansion kernel (locate only) */
     float d2h_ms;     /* result download (host-buffer entry points only) */
     uint32_t launches;      /* kernels launched by the call */
-    uint32_t slices;        /* locate: 2 when the batch was cut into two slices pipelined on two streams (then search_ms,
-                               scan_ms, seed_ms, window_ms describe slice 0; expand_ms runs from slice 0's scan to the end) */
+    uint32_t slices;        /* always 1 (kept for layout compatibility) */
     uint64_t lf_steps;      /* executed LF steps (early exits excluded), r_index.hpp:297 */
     uint64_t occ_total;     /* occurrences written */
     uint64_t chains;        /* independent Phi chains the ranges were split into */
@@ -114,8 +112,10 @@ int rig_locate_batch(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64
                      uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total);
 
 /* Same operations on DEVICE buffers (pointers valid on the index's device); `stream` is a
- * cudaStream_t (NULL = the index's own stream). Count is fully asynchronous; locate
- * synchronises once after the scan to learn occ_total (returned on the host). */
+ * cudaStream_t (NULL = the index's own stream). Count is fully asynchronous. Locate queues the
+ * search AND the expansion, then waits only for the batch totals (occ_total is returned on the
+ * host): when it returns, the expansion may still be running on `stream`. The expansion kernels
+ * take the totals from device memory and skip themselves when occ_total > occ_capacity. */
 int rig_count_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
                         uint64_t* d_hi, void* stream);
 int rig_locate_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo,
@@ -180,8 +180,17 @@ int rig_navigate_batch_dev(rig_index* idx, int op, const uint64_t* d_positions, 
  * as bytes, terminator row = 0x01 (HOST buffer). */
 int rig_get_bwt(rig_index* idx, uint64_t from, uint64_t len, uint8_t* out);
 
-/* Change the slicing of locate calls after creation (2 = two pipelined slices for large batches, 0/1 = never slice). */
-int rig_set_slices(rig_index* idx, uint32_t slices);
+/* rle_string::break_range (internal/rle_string.hpp:261-302) for N queries (lo[k], hi[k], c[k]): the maximal sub-ranges
+ * of [lo, hi] that hold only c, in ascending order; requires bwt[lo] == bwt[hi] == c as the reference does (it asserts;
+ * here such a query yields no range). Query k's ranges are [out_first[j], out_last[j]] for j in
+ * [out_offsets[k], out_offsets[k+1]). HOST buffers; two-call protocol: with capacity (in ranges) too small,
+ * out_offsets and *total are still filled and RIG_ERR_CAPACITY is returned. */
+int rig_break_range_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N,
+                          uint64_t* out_offsets, uint64_t* out_first, uint64_t* out_last, uint64_t capacity, uint64_t* total);
+/* rle_string::closest_run_break (internal/rle_string.hpp:455-493) for N queries: bwt[lo] == c -> the last position of
+ * lo's run, otherwise the first position after lo that holds c (~0 if none: the reference asserts). hi is the
+ * range's end as in the reference's signature (its value does not enter the result). */
+int rig_closest_run_break_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N, uint64_t* out);
 
 int rig_last_timing(const rig_index* idx, rig_timing* t);
 

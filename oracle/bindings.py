@@ -76,8 +76,14 @@ def ref_lib():
         lib.ref_phi.restype = _u64
         lib.ref_phi.argtypes = [_vp, _u64]
         lib.ref_extract.argtypes = [_vp] * 7
+        lib.ref_from_logical.restype = _vp
+        lib.ref_from_logical.argtypes = [_u64, _u64, _vp, _vp, _vp, _vp, _vp]
         lib.ref_navigate.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
         lib.ref_get_bwt.argtypes = [_vp, _vp]
+        lib.ref_break_range.restype = _u64
+        lib.ref_break_range.argtypes = [_vp, _u64, _u64, ctypes.c_uint8, _vp, _vp]
+        lib.ref_closest_run_break.restype = _u64
+        lib.ref_closest_run_break.argtypes = [_vp, _u64, _u64, ctypes.c_uint8]
         _ref_lib = lib
     return _ref_lib
 
@@ -103,6 +109,15 @@ class RefIndex:
     @classmethod
     def load(cls, path):
         return cls(ref_lib().ref_load(path.encode()))
+
+    @classmethod
+    def from_logical(cls, arrays):
+        """The reference's structures (rle_string, sparse_sd_vector, int_vector: their own constructors) over a given
+        BWT + samples, i.e. the r_index constructor without its suffix sort. arrays: dict as extract() returns."""
+        a = {k: np.ascontiguousarray(arrays[k], dtype=(np.uint8 if k == "run_heads" else np.uint64))
+             for k in ("run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run")}
+        return cls(ref_lib().ref_from_logical(int(arrays["n"]), int(arrays["r"]), _ptr(a["run_heads"]), _ptr(a["run_lens"]),
+                                              _ptr(a["samples_last"]), _ptr(a["pred_pos"]), _ptr(a["pred_to_run"])))
 
     def save(self, path):
         if self.lib.ref_save(self.h, path.encode()) != 0:
@@ -159,6 +174,16 @@ class RefIndex:
         out = np.empty(pos.size, dtype=np.uint64)
         self.lib.ref_navigate(self.h, op, _ptr(pos), pos.size, _ptr(out))
         return out
+
+    def break_range(self, l, r, c):
+        """rle_string::break_range through the reference's own method: list of (first, last)."""
+        k = int(self.lib.ref_break_range(self.h, l, r, c, None, None))
+        a = np.zeros(k, dtype=np.uint64); b = np.zeros(k, dtype=np.uint64)
+        self.lib.ref_break_range(self.h, l, r, c, _ptr(a), _ptr(b))
+        return a, b
+
+    def closest_run_break(self, l, r, c):
+        return int(self.lib.ref_closest_run_break(self.h, l, r, c))
 
     def get_bwt(self):
         out = np.empty(int(self.n), dtype=np.uint8)

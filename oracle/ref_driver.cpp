@@ -137,11 +137,57 @@ void ref_navigate(void* h, int op, const uint64_t* pos, uint64_t N, uint64_t* ou
         out[k] = op == 0 ? (uint64_t)(*idx)[i] : op == 1 ? idx->LF(i) : op == 2 ? idx->FL(i) : (uint64_t)idx->F_at(i);
     }
 }
+// rle_string::break_range (rle_string.hpp:261-302) through the reference's own method. Two-call use: with first == NULL
+// only the number of sub-ranges is returned.
+uint64_t ref_break_range(void* h, uint64_t l, uint64_t r, uint8_t c, uint64_t* first, uint64_t* last) {
+    auto v = ((ref_index_t*)h)->bwt.break_range({l, r}, c);
+    if (first) for (size_t k = 0; k < v.size(); ++k) { first[k] = v[k].first; last[k] = v[k].second; }
+    return v.size();
+}
+// rle_string::closest_run_break (rle_string.hpp:455-493)
+uint64_t ref_closest_run_break(void* h, uint64_t l, uint64_t r, uint8_t c) { return ((ref_index_t*)h)->bwt.closest_run_break({l, r}, c); }
 // the BWT symbol by symbol through operator[] (what r_index::get_bwt / rle_string::toString return, r_index.hpp:375-377)
 void ref_get_bwt(void* h, uint8_t* out) {
     ref_index_t* idx = (ref_index_t*)h;
     const uint64_t n = idx->bwt_size();
     for (uint64_t i = 0; i < n; ++i) out[i] = (*idx)[i];
+}
+
+// A reference r_index<> assembled from the LOGICAL content of an index (the arrays ref_extract returns), by the
+// reference's own structure constructors: rle_string(string&) on the BWT spelled out from its runs (rle_string.hpp:
+// 52-124) and the statements of the r_index constructor that follow the suffix sort (r_index.hpp:67-146: F, the
+// terminator position, pred, samples_last, pred_to_run with the reference's bit widths). Only sufsort() (:553-634)
+// is bypassed: at 4 GB its suffix array needs half an hour, the structures below a minute. Used by bench.py's
+// reference arm when no reference-built .ri of the workload travelled to the box; the logical arrays come from this
+// repo's builder, whose output equals sufsort()'s on every text where both have been run (tests/test_host.py).
+void* ref_from_logical(uint64_t n, uint64_t r, const uint8_t* heads, const uint64_t* lens, const uint64_t* samples_last,
+                       const uint64_t* pred_pos, const uint64_t* pred_to_run) {
+    std::string bwt_s;
+    bwt_s.reserve(n);
+    for (uint64_t j = 0; j < r; ++j) bwt_s.append(lens[j], (char)heads[j]);
+    if (bwt_s.size() != n) return nullptr;
+    ref_index_t* idx = new ref_index_t();
+    idx->bwt = rle_string_sd(bwt_s);                                        // r_index.hpp:67
+    idx->F = std::vector<ulint>(256, 0);                                    // :70-82
+    for (uchar c : bwt_s) idx->F[c]++;
+    for (ulint i = 255; i > 0; --i) idx->F[i] = idx->F[i - 1];
+    idx->F[0] = 0;
+    for (ulint i = 1; i < 256; ++i) idx->F[i] += idx->F[i - 1];
+    for (ulint i = 0; i < bwt_s.size(); ++i)                                // :84-86
+        if (bwt_s[i] == ref_index_t::TERMINATOR) idx->terminator_position = i;
+    idx->r = idx->bwt.number_of_runs();                                     // :92
+    if (idx->r != r) { delete idx; return nullptr; }
+    const int log_r = bitsize(uint64_t(r)), log_n = bitsize(uint64_t(idx->bwt.size()));  // :97-98
+    {
+        auto pred_bv = std::vector<bool>(n, false);                         // :112-123
+        for (uint64_t k = 0; k < r; ++k) pred_bv[pred_pos[k]] = true;
+        idx->pred = sparse_sd_vector(pred_bv);
+    }
+    std::string().swap(bwt_s);
+    idx->samples_last = int_vector<>(r, 0, log_n);                          // :131-146
+    idx->pred_to_run = int_vector<>(r, 0, log_r);
+    for (uint64_t i = 0; i < r; ++i) { idx->samples_last[i] = samples_last[i]; idx->pred_to_run[i] = pred_to_run[i]; }
+    return idx;
 }
 
 // The logical content of a reference-built/loaded index, read through the reference's own

@@ -18,7 +18,8 @@ DECLARED_SYMBOLS = [
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
-    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_set_slices", "rig_locate_batch32",
+    "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_locate_batch32",
+    "rig_break_range_batch", "rig_closest_run_break_batch",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -103,8 +104,9 @@ def gpu_lib():
         lib.rig_navigate_batch.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
         lib.rig_navigate_batch_dev.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp, _vp]
         lib.rig_get_bwt.argtypes = [_vp, _u64, _u64, _vp]
-        lib.rig_set_slices.argtypes = [_vp, _u32]
         lib.rig_locate_batch32.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _u32]
+        lib.rig_break_range_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]
+        lib.rig_closest_run_break_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
         lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
         lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
         lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
@@ -224,6 +226,33 @@ class GpuIndex:
             raise RigError(rc, "rig_navigate_batch")
         return out
 
+    def break_range(self, lo, hi, c):
+        """rle_string::break_range for a batch: returns (offsets[N+1], first[], last[])."""
+        lo = np.ascontiguousarray(lo, dtype=np.uint64); hi = np.ascontiguousarray(hi, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        N = lo.size
+        off = np.zeros(N + 1, dtype=np.uint64)
+        tot = _u64(0)
+        rc = self.lib.rig_break_range_batch(self.h, _ptr(lo), _ptr(hi), _ptr(c), N, _ptr(off), None, None, 0, ctypes.byref(tot))
+        if rc not in (0, RIG_ERR_CAPACITY):
+            raise RigError(rc, "rig_break_range_batch")
+        first = np.zeros(int(tot.value), dtype=np.uint64); last = np.zeros(int(tot.value), dtype=np.uint64)
+        if tot.value:
+            rc = self.lib.rig_break_range_batch(self.h, _ptr(lo), _ptr(hi), _ptr(c), N, _ptr(off), _ptr(first), _ptr(last),
+                                                first.size, ctypes.byref(tot))
+            if rc != 0:
+                raise RigError(rc, "rig_break_range_batch")
+        return off, first, last
+
+    def closest_run_break(self, lo, hi, c):
+        lo = np.ascontiguousarray(lo, dtype=np.uint64); hi = np.ascontiguousarray(hi, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out = np.zeros(lo.size, dtype=np.uint64)
+        rc = self.lib.rig_closest_run_break_batch(self.h, _ptr(lo), _ptr(hi), _ptr(c), lo.size, _ptr(out))
+        if rc != 0:
+            raise RigError(rc, "rig_closest_run_break_batch")
+        return out
+
     def get_bwt(self, start=0, length=None):
         length = self.n - start if length is None else length
         out = np.empty(length, dtype=np.uint8)
@@ -331,12 +360,6 @@ class GpuIndex:
         if rc != 0:
             raise RigError(rc, "rig_digest_dev")
         return int(out[0]), int(out[1])
-
-    def set_slices(self, slices):
-        """2 = large locate batches run as two pipelined slices (opt-in), 0/1 = never slice."""
-        rc = self.lib.rig_set_slices(self.h, slices)
-        if rc != 0:
-            raise RigError(rc, "rig_set_slices")
 
     def timing(self):
         t = Timing()

@@ -12,6 +12,28 @@ def shard_bounds(N, world, rank):
     return N * rank // world, N * (rank + 1) // world
 
 
+def balanced_cuts(nocc, world, per_pattern_cost=64):
+    """SURVEY.md §8e re-balancing: cut the patterns [0, N) into `world` CONTIGUOUS shards of near-equal work,
+    work(p) = n_occ(p) + per_pattern_cost (the backward search of a pattern costs about as much as a few dozen
+    occurrences of expansion). nocc: per-pattern occurrence counts of the WHOLE batch (after the count phase and
+    the all-gather of the counts: 8 bytes per pattern). Returns world + 1 ascending cut points, cuts[0] = 0,
+    cuts[world] = N; rank k takes [cuts[k], cuts[k+1]). Contiguity keeps the output order = concatenation of the
+    shard outputs."""
+    w = np.asarray(nocc, dtype=np.uint64).astype(np.float64) + float(per_pattern_cost)
+    N = w.size
+    cum = np.cumsum(w)
+    total = float(cum[-1]) if N else 0.0
+    cuts = [0]
+    for k in range(1, world):
+        c = int(np.searchsorted(cum, total * k / world, side="left")) + 1 if N else 0
+        # the pattern that crosses the target goes to the side that leaves the smaller excess
+        if N and c > 0 and c <= N and (cum[c - 1] - total * k / world) > (total * k / world - (cum[c - 2] if c >= 2 else 0.0)):
+            c -= 1
+        cuts.append(min(max(c, cuts[-1]), N))
+    cuts.append(N)
+    return cuts
+
+
 def _torch():
     import torch
     import torch.distributed as dist

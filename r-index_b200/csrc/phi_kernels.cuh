@@ -7,8 +7,10 @@
 //        head up to the next 128-byte line of the OUTPUT array (<= 16 occurrences), then hops along the chain
 //        SEG occurrences at a time (one seed-table lookup per hop) and appends one 16-byte ITEM per hop to a
 //        list: (first output slot, number of occurrences that follow, seed = the occurrence on that slot).
-//   phi_window_kernel                    "window pass", one lane per item: from the seed, every lookup yields D
-//        occurrences that leave as one aligned 32-byte sector.
+//   phi_window_kernel                    "window pass", one lane per item at a time (persistent lanes): from the
+//        seed, every lookup yields D occurrences that leave as one aligned 32-byte sector.
+// Both kernels are PERSISTENT (grid sized to the machine) and read the batch totals from device memory, so a
+// locate call is queued without a host round trip between the search and the expansion.
 //
 // The single-pass form's time is (longest chain) x (load latency) with half-empty warps (chain lengths
 // differ by orders of magnitude inside a warp); the two-pass form turns the batch into uniform
@@ -174,7 +176,7 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
         // ---- this iteration's occurrences (off the critical path) ----
         if (emit) {
             if (cnt == (u32)D) {
-                if (!(ix.pad & 1)) store_group<WT, D>(o, x);  // pad bit0: diagnostic "no stores" run (RIG_VARIANT bit4)
+                store_group<WT, D>(o, x);
             } else {
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)
@@ -220,8 +222,29 @@ __device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
 
 #define RIG_LINE 16  // output slots per 128-byte line
 
+// Device-side view of a locate call's counters (rig_index::d_counters): the expansion kernels read the totals the
+// search produced instead of taking them as launch parameters, so the host can queue the whole call without
+// waiting for the scan (no idle gap between the search and the expansion).
+#define RIG_CTR_TOTAL 2    // occurrences of the batch
+#define RIG_CTR_CHAINS 3   // Phi chains of the batch
+#define RIG_CTR_ITEMS 6    // items appended by the seed pass
+
+// Both kernels return at once when the host will not want the output (total > capacity) or when the item list
+// could overflow (the host re-launches with a larger list: it evaluates the same two conditions from the same
+// totals). An upper bound of the items: a chain of L occurrences gives at most (L - 1) / SEG + 1.
+__device__ __forceinline__ bool expansion_enabled(const u64* ctr, u64 cap, u64 items_cap, u32 seg_shift, bool seeded,
+                                                  u64& total, u64& chains) {
+    total = __ldcg(ctr + RIG_CTR_TOTAL);
+    chains = __ldcg(ctr + RIG_CTR_CHAINS);
+    if (total > cap) return false;
+    if (seeded && (total >> seg_shift) + chains > items_cap) return false;
+    return true;
+}
+
 // Work item w -> (pattern p, run j): BWT positions [max(lo,start[j]), min(hi,start[j+1]-1)], walked
 // from the top down. Output slot of SA[x] is occ_off[p] + (hi - x): locate_all order (r_index.hpp:340-351).
+// PERSISTENT: the grid is sized to the machine (rig_index: SMs x resident CTAs), every warp strides over the
+// chains, and their number comes from device memory.
 //
 // SEEDED = false: the lane produces its whole chain.
 // SEEDED = true : the lane produces the chain's head up to the next 128-byte line of the output array
@@ -237,157 +260,125 @@ template <typename WT, int D, bool KEEP, bool SEEDED>
 __global__ void __launch_bounds__(256)
 phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
                   const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64 total_chains,
-                  u64* __restrict__ items, u64* __restrict__ item_count, u32 seg_shift) {
-    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = w < total_chains;
-    if (!SEEDED && !active) return;
-    u64 g0 = 0, glast = 0, v0 = 0;
-    if (active) {
-        u64 a = 0, b = N;  // largest p with ch_off[p] <= w
-        while (b - a > 1) {
-            const u64 mid = (a + b) >> 1;
-            if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
+                  u64* __restrict__ items, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, SEEDED, total, total_chains)) return;
+    const int lane = threadIdx.x & 31;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 wb = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < total_chains; wb += stride) {  // warp-uniform
+        const u64 w = wb + lane;
+        const bool active = w < total_chains;
+        u64 g0 = 0, glast = 0, v0 = 0;
+        if (active) {
+            u64 a = 0, b = N;  // largest p with ch_off[p] <= w
+            while (b - a > 1) {
+                const u64 mid = (a + b) >> 1;
+                if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+            }
+            const u64 p = a;
+            const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
+            const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
+            const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
+            const u64 top = min(H, ej), bot = max(L, sj);
+            if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
+            else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
+            g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
+            glast = g0 + (top - bot);             // slot of its last (a chain never exceeds n)
+            __stcs(out + g0, v0);
         }
-        const u64 p = a;
-        const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-        const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
-        const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
-        const u64 top = min(H, ej), bot = max(L, sj);
-        if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
-        else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
-        g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
-        glast = g0 + (top - bot);             // slot of its last (a chain never exceeds n)
-        __stcs(out + g0, v0);
-    }
-    if (!SEEDED) {
-        walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(glast - g0));
-    } else {
-        const u64 SEG = 1ull << seg_shift;
-        const u64 a1 = (g0 + RIG_LINE - 1) & ~(u64)(RIG_LINE - 1);  // first line-aligned slot at or after g0
-        const u64 K = (active && a1 <= glast) ? ((glast - a1) >> seg_shift) + 1 : 0;  // items of this chain
-        // reserve K entries of items[]: inclusive warp scan, one atomic by the last lane
-        const int lane = threadIdx.x & 31;
-        u64 incl = K;
+        if (!SEEDED) {
+            if (active) walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(glast - g0));
+        } else {
+            const u64 SEG = 1ull << seg_shift;
+            const u64 a1 = (g0 + RIG_LINE - 1) & ~(u64)(RIG_LINE - 1);  // first line-aligned slot at or after g0
+            const u64 K = (active && a1 <= glast) ? ((glast - a1) >> seg_shift) + 1 : 0;  // items of this chain
+            // reserve K entries of items[]: inclusive warp scan, one atomic by the last lane
+            u64 incl = K;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u64 t = __shfl_up_sync(RIG_FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        u64 wbase = 0;
-        if (lane == 31 && incl) wbase = atomicAdd(item_count, incl);
-        wbase = __shfl_sync(RIG_FULL, wbase, 31);
-        if (!active) return;
-        const u64 pre_last = min(a1, glast);
-        WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
-        if (K) {
-            ulonglong2* it = reinterpret_cast<ulonglong2*>(items) + wbase + (incl - K);
-            u64 s = a1;
-            for (;;) {
-                __stcs(it++, make_ulonglong2((s << 8) | min(SEG - 1, glast - s), (u64)v));
-                s += SEG;
-                if (s > glast) break;
-                v = seed_hop<WT>(ix, v);
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t = __shfl_up_sync(RIG_FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            u64 wbase = 0;
+            if (lane == 31 && incl) wbase = atomicAdd(ctr + RIG_CTR_ITEMS, incl);
+            wbase = __shfl_sync(RIG_FULL, wbase, 31);
+            if (!active) continue;
+            const u64 pre_last = min(a1, glast);
+            WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
+            if (K) {
+                ulonglong2* it = reinterpret_cast<ulonglong2*>(items) + wbase + (incl - K);
+                u64 s = a1;
+                for (;;) {
+                    __stcs(it++, make_ulonglong2((s << 8) | min(SEG - 1, glast - s), (u64)v));
+                    s += SEG;
+                    if (s > glast) break;
+                    v = seed_hop<WT>(ix, v);
+                }
             }
         }
     }
 }
 
-// pair access to a staging row (8-byte pairs of u32, 16-byte pairs of u64)
-__device__ __forceinline__ void st_pair(u32* row, u32 pair, u32 a, u32 b) { reinterpret_cast<uint2*>(row)[pair] = make_uint2(a, b); }
-__device__ __forceinline__ void st_pair(u64* row, u32 pair, u64 a, u64 b) { reinterpret_cast<ulonglong2*>(row)[pair] = make_ulonglong2(a, b); }
-__device__ __forceinline__ void ld_pair(const u32* row, u32 pair, u64& a, u64& b) { const uint2 x = reinterpret_cast<const uint2*>(row)[pair]; a = x.x; b = x.y; }
-__device__ __forceinline__ void ld_pair(const u64* row, u32 pair, u64& a, u64& b) { const ulonglong2 x = reinterpret_cast<const ulonglong2*>(row)[pair]; a = x.x; b = x.y; }
-
-__device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
-    // (the .L2::evict_first qualifier is only accepted on 256-bit stores; .cs is the 128-bit streaming form)
-    asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
-}
-
-// One lane per item: items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first
-// slot, cnt the number of further occurrences of the same chain that the item covers (< SEG). Each lookup
-// yields Phi^1..Phi^D(v); the lane emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] and continues from
-// Phi^D(v). Same per-lane state machine and software pipelining as walk_chain.
-//
-// STORES. A lane's groups are 32-byte sectors of its own 128-byte lines; stored directly (STAGE = false, the
-// default) they cost one L2 request per sector, and the kernel runs at the L2 tag-lookup rate
-// (lts__t_tag_requests 80%) and the SM's request port (l1tex2xbar 72%: one load request or one 32-byte store
-// payload per cycle), not at a byte rate. STAGE = true is the measured alternative (RIG_VARIANT bit 6): every
-// line that will be complete is staged in shared memory (two rows per lane, pair-swizzled; a lane emits at
-// most one group per trip, so between two flushes it completes at most one row and starts the other) and
-// every FLUSH_TRIPS trips the warp writes out the completed rows, 8 lanes x 16 bytes per line, 4 whole
-// lines per store instruction. That halves the tag requests (80% -> 37%) but the store payload through the
-// request port is unchanged and the extra instructions (+70%) make it issue-bound: 0.33 ms vs 0.27 ms on C2,
-// 1.93 vs 1.79 ms on C3s. Kept for the record, off by default.
-template <typename WT, int D, bool KEEP, bool STAGE, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ item_count,
-                  u64* __restrict__ out) {
+// "Window pass". PERSISTENT, one lane per ITEM AT A TIME: a lane walks the items i = t, t + T, t + 2T, .. (t its
+// global thread index, T the number of threads of the grid) one after the other, switching to its next item inside
+// the trip that ends the current one, so every lane of a warp has a lookup in flight until its own sequence ends —
+// items of different lengths (chain tails, crowded buckets) do not leave lanes idle until the warp's slowest one
+// is done, and the grid drains over one item's time instead of one CTA's. The next item's 16-byte entry is
+// prefetched one item ahead.
+// items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first slot, cnt the number of
+// further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v); the lane
+// emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] as one 32-byte sector store and continues from Phi^D(v).
+// Same per-lane state machine and software pipelining as walk_chain (one table load per lane per trip).
+template <typename WT, int D, bool KEEP>
+__global__ void __launch_bounds__(256)
+phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
+                  u64 cap, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;
     const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
-    constexpr int GPL = RIG_LINE / D;  // groups per line
-    // a lane emits at most one group per trip: with a flush every <= GPL trips it cannot complete a second row
-    // while one is pending (4 trips = one row per lane in lockstep for D = 4)
-    constexpr u32 FLUSH_TRIPS = GPL < 4 ? GPL : 4;
-    static_assert(FLUSH_TRIPS <= GPL && (FLUSH_TRIPS & (FLUSH_TRIPS - 1)) == 0, "flush period");
-    __shared__ __align__(16) WT stage[STAGE ? WARPS : 1][STAGE ? 2 : 1][STAGE ? 32 : 1][RIG_LINE];
-    __shared__ uint8_t sidx[STAGE ? WARPS : 1][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const u32 sw = lane & 7;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 n_items = __ldcg(item_count);
-    u32 left = 0;  // slots of this item still to be written, the seed's included
-    u64* o = out;
-    WT v = 0;
-    if (i < n_items) {
-        const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
-        left = (u32)(it.x & 255u) + 1;
-        o = out + (it.x >> 8);
-        v = (WT)it.y;
-    }
+    const u64 n_items = __ldcg(ctr + RIG_CTR_ITEMS);
+    const u64 T = (u64)gridDim.x * blockDim.x;
+    const ulonglong2* itp = reinterpret_cast<const ulonglong2*>(items);
+    u64 inext = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have_next = inext < n_items;
+    ulonglong2 nit = make_ulonglong2(0, 0);
+    if (have_next) nit = __ldcs(itp + inext);
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
-    bool searching = false, staging = false, pending = false;  // pending: row cur^1 is complete, not yet written out
-    u32 slo = 0, shi = 0, probe = 0, fill = 0, cur = 0, trip = 0;  // fill: groups staged in row cur
-    u64* pend_line = out;
+    u32 left = 0;  // slots of the current item still to be written, the seed's included
+    u64* o = out;
+    WT v = 0;
+    bool searching = false;
+    u32 slo = 0, shi = 0, probe = 0;
     WT e[RW];
-    if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
+#pragma unroll
+    for (int t = 0; t < RW; ++t) e[t] = 0;
+#define RIG_TAKE_ITEM(LEFT, O, V)                                          \
+    do {                                                                   \
+        LEFT = (u32)(nit.x & 255u) + 1;                                    \
+        O = out + (nit.x >> 8);                                            \
+        V = (WT)nit.y;                                                     \
+        inext += T;                                                        \
+        have_next = inext < n_items;                                       \
+        if (have_next) nit = __ldcs(itp + inext);                          \
+    } while (0)
     for (;;) {
-        const bool more = __any_sync(RIG_FULL, left > 1);
-        // ---- write out completed rows: every FLUSH_TRIPS trips and once at the end (warp-uniform) ----
-        if (STAGE && (!more || (trip & (FLUSH_TRIPS - 1)) == FLUSH_TRIPS - 1)) {
-            const u32 ready = __ballot_sync(RIG_FULL, pending);
-            if (ready) {
-                if (pending) sidx[wid][__popc(ready & ((1u << lane) - 1u))] = (uint8_t)(lane | ((cur ^ 1u) << 5));
-                __syncwarp();
-                const u32 nready = __popc(ready);
-                for (u32 t = 0; t < nready; t += 4) {
-                    const u32 k = t + (lane >> 3);
-                    const bool act = k < nready;
-                    const u32 sx = act ? sidx[wid][k] : 0u;
-                    const u32 src = sx & 31u;
-                    const u64 dst = __shfl_sync(RIG_FULL, (unsigned long long)pend_line, src);
-                    if (act && !(ix.pad & 1)) {
-                        u64 x0, x1;
-                        ld_pair(&stage[wid][sx >> 5][src][0], sw ^ (src & 7), x0, x1);  // slots 2*sw, 2*sw+1 of the line
-                        stg128_stream(reinterpret_cast<u64*>(dst) + 2 * sw, x0, x1);
-                    }
-                }
-                __syncwarp();
-                pending = false;
-            }
-        }
-        if (!more) break;
-        ++trip;
+        // lanes without a lookup in flight: one-slot items, the first item, the end of the sequence
+        bool fresh = false;
+        if (left == 1) { __stcs(o, (u64)v); left = 0; }
+        if (left == 0 && have_next) { RIG_TAKE_ITEM(left, o, v); fresh = true; searching = false; slo = shi = 0; }
+        if (!__any_sync(RIG_FULL, left > 0)) break;
         bool emit = false;
         WT g[D];          // the group to store: [v, Phi(v), ..]
         u32 cnt = 0;
         WT vn = v;
-        if (left > 1) {
+        if (left > 1 && !fresh) {
             if (!searching) {
                 emit = v < e[D];
                 slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
@@ -412,45 +403,42 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
                 cnt = min(left, (u32)D);
             }
         }
-        const u32 left_next = left - cnt;
+        u64* const so = o;           // where this trip's group goes
+        u32 left_next = left - cnt;
+        u64* o_next = o + cnt;
+        bool tail = false;           // the value carried out of the item's last full group goes on one more slot
+        WT tv = 0;
+        u64* to = o_next;
+        if (emit && left_next <= 1) {  // the item ends with this group: switch to the lane's next item in this trip
+            tail = left_next == 1; tv = vn;
+            left_next = 0;
+            if (have_next) RIG_TAKE_ITEM(left_next, o_next, vn);
+        }
+        // ---- next load (critical path) ----
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
+#pragma unroll
+        for (int t = 0; t < RW; ++t) e2[t] = e[t];
         if (left_next > 1)
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
+        // ---- this trip's occurrences (off the critical path) ----
         if (emit) {
-            // stage the line iff all of its GPL groups will be emitted as full groups (with D = 1 the loop ends
-            // at left == 1, one slot early, so one more slot is needed)
-            if (STAGE && fill == 0) staging = left >= (u32)(RIG_LINE + (D == 1 ? 1 : 0));
             if (cnt == (u32)D) {
-                if (STAGE && staging) {
-                    WT* row = &stage[wid][cur][lane][0];
-                    if constexpr (D == 1) {
-                        row[(((fill >> 1) ^ sw) << 1) | (fill & 1)] = g[0];
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < D; t += 2)
-                            st_pair(row, ((fill * D + t) >> 1) ^ sw, g[t], g[t + 1]);
-                    }
-                    if (++fill == (u32)GPL) {  // row complete: hand it to the next flush, continue in the other row
-                        fill = 0; cur ^= 1u; pending = true;
-                        pend_line = o + D - RIG_LINE;
-                    }
-                } else if (!(ix.pad & 1)) {
-                    store_group<WT, D>(o, g);
-                }
+                store_group<WT, D>(so, g);
             } else {
 #pragma unroll
                 for (int t = 0; t < D - 1; ++t)
-                    if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                    if ((u32)t < cnt) __stcs(so + t, (u64)g[t]);
             }
-            o += cnt;
+            if (tail) __stcs(to, (u64)tv);
         }
         v = vn;
         left = left_next;
+        o = o_next;
 #pragma unroll
         for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
-    if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+#undef RIG_TAKE_ITEM
 }
 
 }  // namespace rigk

@@ -283,4 +283,76 @@ bwt_range_kernel(const FlatDev ix, u64 from, u64 len, uint8_t* __restrict__ out)
     }
 }
 
+// ---- range utilities of the RLBWT as batches ------------------------------------------------
+//   RANGE_BREAK_COUNT / RANGE_BREAK_FILL   rle_string::break_range(rn, c)         rle_string.hpp:261-302
+//        the maximal sub-ranges of rn = [l, r] that hold only c, given bwt[l] == bwt[r] == c: [l, end of l's run],
+//        every c-run strictly between the runs of l and r, [start of r's run, r]; the range itself when l and r
+//        lie in one run. A query that breaks the precondition (l > r, r >= n, bwt[l] != c or bwt[r] != c: the
+//        reference asserts) yields no range.
+//   RANGE_CLOSEST                          rle_string::closest_run_break(rn, c)   rle_string.hpp:455-493
+//        bwt[l] == c: the last position of l's run; otherwise the first position >= l holding c (select(rank(l, c), c));
+//        ~0 when no c follows l.
+// One thread per query walking the run heads between the two runs: O(runs in the range) like the reference's
+// O(|result|) ranks and selects on a text with few distinct heads; not tuned (no CLI calls these).
+enum { RANGE_BREAK_COUNT = 0, RANGE_BREAK_FILL = 1, RANGE_CLOSEST = 2 };
+
+template <typename PT>
+__device__ __forceinline__ u64 nav_run_of(const FlatDev& ix, u64 x) {  // run holding BWT position x < n
+    const u32 b = nav_block_of<PT>(ix, (PT)x);
+    u64 run = (u64)b * ix.K;
+    while (run + 1 < ix.r && (u64)ld_pos<PT>(ix.start, run + 1) <= x) ++run;
+    return run;
+}
+__device__ __forceinline__ uint8_t nav_head(const FlatDev& ix, u64 run) {
+    return __ldg(reinterpret_cast<const uint8_t*>(ix.blk + (run / ix.K) * ix.blk_stride + ix.off_head) + run % ix.K);
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256)
+range_nav_kernel(const FlatDev ix, int op, const u64* __restrict__ lo, const u64* __restrict__ hi,
+                 const uint8_t* __restrict__ sym, u64 N, const u64* __restrict__ off, u64* __restrict__ out_a,
+                 u64* __restrict__ out_b) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const u64 l = lo[t], r = hi[t];
+    const uint8_t c = sym[t];
+    if (op == RANGE_CLOSEST) {
+        u64 res = ~0ull;
+        if (l < ix.n) {
+            u64 run = nav_run_of<PT>(ix, l);
+            if (nav_head(ix, run) == c) {
+                res = (u64)ld_pos<PT>(ix.start, run + 1) - 1;           // case 1: the range begins inside a c-run
+            } else {
+                for (++run; run < ix.r; ++run)                          // case 2: the first c-run after l
+                    if (nav_head(ix, run) == c) { res = ld_pos<PT>(ix.start, run); break; }
+            }
+        }
+        out_a[t] = res;
+        return;
+    }
+    u64 cnt = 0;
+    u64* oa = op == RANGE_BREAK_FILL ? out_a + off[t] : nullptr;
+    u64* ob = op == RANGE_BREAK_FILL ? out_b + off[t] : nullptr;
+    if (l <= r && r < ix.n) {
+        const u64 rl = nav_run_of<PT>(ix, l), rr = nav_run_of<PT>(ix, r);
+        if (nav_head(ix, rl) == c && nav_head(ix, rr) == c) {
+            if (rl == rr) {
+                if (oa) { oa[0] = l; ob[0] = r; }
+                cnt = 1;
+            } else {
+                if (oa) { oa[0] = l; ob[0] = (u64)ld_pos<PT>(ix.start, rl + 1) - 1; }
+                cnt = 1;
+                for (u64 j = rl + 1; j < rr; ++j)
+                    if (nav_head(ix, j) == c) {
+                        if (oa) { oa[cnt] = ld_pos<PT>(ix.start, j); ob[cnt] = (u64)ld_pos<PT>(ix.start, j + 1) - 1; }
+                        ++cnt;
+                    }
+                if (oa) { oa[cnt] = ld_pos<PT>(ix.start, rr); ob[cnt] = r; }
+                ++cnt;
+            }
+        }
+    }
+    if (op == RANGE_BREAK_COUNT) out_a[t] = cnt;
+}
+
 }  // namespace rigk

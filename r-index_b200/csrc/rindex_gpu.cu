@@ -28,6 +28,17 @@ static thread_local std::string g_cuda_err;
         }                                                                                         \
     } while (0)
 
+// inside rig_index_create_ex, once the handle exists: a failing CUDA call releases everything built so far
+#define CU_TRY_IX(expr)                                                                           \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+            rig_index_destroy(ix);                                                                \
+            return RIG_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
 namespace {
 
 struct DevBuf {
@@ -56,12 +67,10 @@ struct rig_index {
     rig_options opt{};
     void* arena = nullptr;  // one allocation holding every flat array
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;   // second slice of a pipelined locate call
-    cudaEvent_t ev_fork = nullptr, ev_scan[2] = {nullptr, nullptr}, ev_join = nullptr;
-    uint32_t slices = 0;             // 2 = cut large locate batches into two pipelined slices (opt-in), else never
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes, [7] = end of slice 0's window pass
+    cudaEvent_t ev_scan = nullptr;    // the totals of a locate call have reached the host
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [6] = between the two expansion passes, [7] = end of the window pass
     // workspace (grow-only)
-    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items, items2;
+    DevBuf toe, jl, nch, nocc, choff, sums, patt, lo, hi, occoff, occ, items;
     DevBuf occ32;             // rig_locate_batch32: narrowed positions
     DevBuf text, big1, big2, ctable, crep, cfound;  // post-processing (-o / -c): attached text, sort tiers, hash join
     uint64_t text_len = 0;
@@ -69,7 +78,7 @@ struct rig_index {
     bool sort_attr_done = false;  // dynamic shared memory opt-in of the sort kernels (per device)
     ull* d_post = nullptr;      // [0] big1 count [1] big2 count [2..7] check report
     ull* h_post = nullptr;      // pinned mirror
-    ull* d_counters = nullptr;  // [0] lf_steps [2..3] totals (occ, chains) of slice 0 [4..5] digest [6] items of slice 0 [8..9] totals, [10] items of slice 1
+    ull* d_counters = nullptr;  // [0] lf_steps [2..3] totals (occurrences, chains: RIG_CTR_TOTAL / _CHAINS) [4..5] digest [6] items of the seed pass (RIG_CTR_ITEMS)
     ull* h_counters = nullptr;  // pinned mirror
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
@@ -139,7 +148,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     ix->opt = opt;
     ix->variant = variant;
     cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    CU_TRY_IX(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
 
     // one arena, every array 256-byte aligned
@@ -187,10 +196,10 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t total = 0;
     for (auto& p : parts) { p.off = total; total += align_up(p.bytes + 128, 256); }
     cudaError_t e = cudaMalloc(&ix->arena, total);
-    if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc(arena): ") + cudaGetErrorString(e); delete ix; return RIG_ERR_NOMEM; }
-    CU_TRY(cudaMemset(ix->arena, 0, total));
+    if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc(arena): ") + cudaGetErrorString(e); ix->arena = nullptr; rig_index_destroy(ix); return RIG_ERR_NOMEM; }
+    CU_TRY_IX(cudaMemset(ix->arena, 0, total));
     for (auto& p : parts)
-        if (p.bytes) CU_TRY(cudaMemcpy((char*)ix->arena + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
+        if (p.bytes) CU_TRY_IX(cudaMemcpy((char*)ix->arena + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
     char* A = (char*)ix->arena;
     FlatDev& d = ix->d;
     d.n = f.n; d.r = f.r; d.nblk = f.nblk; d.toe0 = f.toe0;
@@ -213,7 +222,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.seed.pent = (const void*)(A + parts[11].off);
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
-    d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 16) ? 1u : 0u;  // diagnostic: expansion without its vector stores
+    d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
 
     // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
     // limit; harmless for other users of the context) and size the window / hit ratio to it.
@@ -234,20 +243,16 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
             }
         }
     }
-    CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
-    for (auto& e2 : ix->ev_scan) CU_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-    ix->slices = opt.reserved[3] & 0xffu;
-    for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
-    CU_TRY(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
-    CU_TRY(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
-    CU_TRY(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
+    CU_TRY_IX(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU_TRY_IX(cudaEventCreateWithFlags(&ix->ev_scan, cudaEventDisableTiming));
+    for (auto& ev : ix->ev) CU_TRY_IX(cudaEventCreate(&ev));
+    CU_TRY_IX(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
+    CU_TRY_IX(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
+    CU_TRY_IX(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
     std::memset(ix->h_counters, 0, 16 * sizeof(ull));
-    CU_TRY(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
-    CU_TRY(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
-    CU_TRY(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
+    CU_TRY_IX(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
+    CU_TRY_IX(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
+    CU_TRY_IX(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
 
     rig_index_info& I = ix->info;
     std::memset(&I, 0, sizeof(I));
@@ -267,7 +272,7 @@ void rig_index_destroy(rig_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->toe, &ix->jl, &ix->nch, &ix->nocc, &ix->choff, &ix->sums, &ix->patt, &ix->lo, &ix->hi,
-                      &ix->occoff, &ix->occ, &ix->items, &ix->items2, &ix->occ32, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
+                      &ix->occoff, &ix->occ, &ix->items, &ix->occ32, &ix->text, &ix->big1, &ix->big2, &ix->ctable, &ix->crep, &ix->cfound})
         b->release();
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
@@ -275,10 +280,7 @@ void rig_index_destroy(rig_index* ix) {
     if (ix->d_post) cudaFree(ix->d_post);
     if (ix->h_post) cudaFreeHost(ix->h_post);
     for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
-    if (ix->stream2) { cudaStreamSynchronize(ix->stream2); cudaStreamDestroy(ix->stream2); }
-    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
-    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
-    for (auto& e2 : ix->ev_scan) if (e2) cudaEventDestroy(e2);
+    if (ix->ev_scan) cudaEventDestroy(ix->ev_scan);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -294,20 +296,26 @@ int rig_index_info_get(const rig_index* ix, rig_index_info* info) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// workspace of the search kernel's fused offset scan: ticket + RIG_TILE_WORDS words per tile of 128 patterns
+size_t tile_ws_words(uint64_t N) { return 2 + RIG_TILE_WORDS * ((N + 127) / 128) + 2; }
+
 template <bool LOCATE>
-int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi,
-                  cudaStream_t st, uint64_t poff = 0) {
+int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
+                  cudaStream_t st) {
     const uint32_t G = ix->d.K;
-    ull* toe = (ull*)ix->toe.p + poff; ull* jl = (ull*)ix->jl.p + poff; ull* nch = (ull*)ix->nch.p + poff; ull* nocc = (ull*)ix->nocc.p + poff;
+    ull* toe = (ull*)ix->toe.p; ull* jl = (ull*)ix->jl.p; ull* nch = (ull*)ix->nch.p; ull* nocc = (ull*)ix->nocc.p;
     ull* steps = ix->d_counters + 0;
     const bool n32 = ix->d.w32 != 0;
     if (G == 4 && !(ix->variant & 128)) {  // one lane per pattern over the K = 4 block records (bit7: cooperative kernel, A/B switch)
         const int lt = 128;
         const uint64_t lb = (N + lt - 1) / lt;
         if (lb > 0x7fffffffull) return RIG_ERR_ARG;
-        if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);
-        else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, nch, nocc, steps);
+        ull* ws = (ull*)ix->sums.p; ull* choff = (ull*)ix->choff.p; ull* totals = ix->d_counters + RIG_CTR_TOTAL;
+        if (LOCATE) CU_TRY(cudaMemsetAsync(ws, 0, tile_ws_words(N) * sizeof(ull), st));
+        if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+        else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
         CU_TRY(cudaGetLastError());
+        ix->timing.launches += 1;
         return RIG_OK;
     }
     const int threads = 256;
@@ -330,6 +338,17 @@ int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, 
     }
 #undef RIG_LAUNCH
     CU_TRY(cudaGetLastError());
+    ix->timing.launches += 1;
+    if (LOCATE) {  // the cooperative kernel leaves n_occ / chain counts per pattern: three-kernel scan
+        const uint64_t ntiles = (N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE;
+        ull* sums = (ull*)ix->sums.p;
+        rigk::scan_tile_sums<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>(nocc, nch, N, sums, ntiles);
+        rigk::scan_sums_inplace<<<1, 1024, 0, st>>>(sums, ntiles, ix->d_counters + RIG_CTR_TOTAL);
+        rigk::scan_tiles<<<(unsigned)ntiles, RIG_SCAN_THREADS, 0, st>>>(nocc, nch, N, sums, ntiles, d_occoff, (ull*)ix->choff.p,
+                                                                          ix->d_counters + RIG_CTR_TOTAL, nullptr);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 3;
+    }
     return RIG_OK;
 }
 
@@ -337,7 +356,7 @@ int finish_timing(rig_index* ix) {
     if (!ix->timing_pending) return RIG_OK;
     CU_TRY(cudaSetDevice(ix->device));
     // the last recorded event closes the call
-    for (int i = 5; i >= 0; --i)  // ev[6] sits between ev[3] and ev[4] in stream order
+    for (int i = 5; i >= 0; --i)  // ev[6], ev[7] sit between ev[3] and ev[4] in stream order
         if (ix->ev_valid[i]) { CU_TRY(cudaEventSynchronize(ix->ev[i])); break; }
     auto el = [&](int a, int b, float& dst) -> int {
         dst = 0.f;
@@ -361,6 +380,7 @@ void begin_call(rig_index* ix) {
     std::memset(&ix->timing, 0, sizeof(ix->timing));
     for (bool& b : ix->ev_valid) b = false;
     ix->timing_pending = true;
+    ix->timing.slices = 1;
 }
 
 int rec(rig_index* ix, int i, cudaStream_t st) {
@@ -374,43 +394,32 @@ int count_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull*
     int rc;
     CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
     if ((rc = rec(ix, 1, st))) return rc;
-    if (N) {
-        if ((rc = launch_search<false>(ix, d_patt, N, m, d_lo, d_hi, st))) return rc;
-        ix->timing.launches += 1;
-    }
+    if (N && (rc = launch_search<false>(ix, d_patt, N, m, d_lo, d_hi, nullptr, st))) return rc;
     if ((rc = rec(ix, 2, st))) return rc;
     CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
     return RIG_OK;
 }
 
-// One slice of a locate call: patterns [p0, p0 + np) with their own chain offsets, scan scratch, item list,
-// counters and stream.
-struct Slice {
-    uint64_t p0 = 0, np = 0, ntiles = 0;
-    ull* choff = nullptr;     // [np + 1] slice-local chain offsets
-    ull* sums = nullptr;      // [2 * ntiles + 2]
-    ull* totals = nullptr;    // device: occurrences, chains of the slice
-    ull* icount = nullptr;    // device: items appended by the seed pass
-    ull* h_totals = nullptr;  // pinned mirror of totals
-    DevBuf* items = nullptr;
-    cudaStream_t st = nullptr;
-    uint64_t total = 0, chains = 0;
-};
+// resident CTAs of a kernel on this device (persistent grids are sized SMs x this)
+template <typename K>
+int resident_ctas(K kernel, int threads) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    return nb;
+}
 
-// Phi expansion of one slice (seed pass + window pass, or the single-pass walk). `first` records event 6 between
-// the passes and warms the Phi tables into L2.
-int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_hi, const ull* d_occoff, ull* d_occ, bool first) {
+// Phi expansion of the batch whose offsets and totals the search left on the device: seed pass + window pass, or the
+// single-pass walk. Both kernels are persistent and decide on the device whether to run (expansion_enabled): the
+// host queues them WITHOUT knowing the totals. `items_cap`: entries the item list can hold.
+int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi, const ull* d_occoff, ull* d_occ,
+                     uint64_t cap, bool two_pass, uint64_t items_cap, cudaStream_t st) {
     int rc;
-    cudaStream_t st = sl.st;
-    const uint64_t total = sl.total, chains = sl.chains;
-    if (!chains) return RIG_OK;
     const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 128;  // measured: 0.445 ms (128) vs 0.463 ms (256) on C2
+    if (threads < 32 || threads > 256 || (threads & 31)) return RIG_ERR_ARG;
     const bool w32 = ix->d.w32 != 0;
-    const uint64_t nb = (chains + threads - 1) / threads;
-    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)nb); cfg.blockDim = dim3((unsigned)threads); cfg.stream = st;
+    cfg.blockDim = dim3((unsigned)threads); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     if (ix->l2_window_bytes) {  // persisting-L2 experiment (RIG_VARIANT bit 0)
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -421,47 +430,47 @@ int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_h
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-    const ull* a_choff = sl.choff; const ull* a_occoff = d_occoff + sl.p0;
-    const ull* a_lo = d_lo + sl.p0; const ull* a_hi = d_hi + sl.p0;
-    const ull* a_toe = (const ull*)ix->toe.p + sl.p0; const ull* a_jl = (const ull*)ix->jl.p + sl.p0;
-    ull a_N = sl.np, a_chains = chains;
+    const ull* a_choff = (const ull*)ix->choff.p;
+    const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
+    ull* a_ctr = ix->d_counters;
+    ull a_N = N, a_cap = cap, a_icap = items_cap;
+    ull* a_items = (ull*)ix->items.p;
     const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
-    // Two passes when the index has a seed table and the output array is line-aligned (the window
-    // kernel writes whole 128-byte lines); otherwise the single-pass walk.
     const uint32_t SEG = ix->d.seed.J;
-    const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
     uint32_t seg_shift = 0;
     while ((1u << seg_shift) < SEG) ++seg_shift;
-    // a chain of L occurrences is cut into at most (L - 1) / SEG + 1 items
-    const uint64_t items_max = two_pass ? total / SEG + chains : 0;
-    if (two_pass && (rc = sl.items->ensure((items_max + 32) * 16))) return rc;
-    ull* a_items = (ull*)sl.items->p;
-    ull* a_icount = sl.icount;  // zeroed with the other counters at the start of the call
-    const int wthreads = w32 ? 256 : 128;  // 32 KB of staging rows per block either way
-    const uint64_t wnb = (items_max + wthreads - 1) / wthreads;
-    if (wnb > 0x7fffffffull) return RIG_ERR_ARG;
+    // the chains / items of the batch are not known here: persistent grids, bounded by what the batch can hold
+    // (a chain per occurrence at most; total <= cap when the kernels run at all)
+    const uint64_t max_chains = cap ? cap : 1;
+    const uint64_t max_items = items_cap ? items_cap : 1;
+    const int wthreads = 256;
 #define RIG_EXPAND2(W, DD, KP)                                                                                  \
     do {                                                                                                        \
         if (two_pass) {                                                                                         \
-            CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, true>, ix->d, a_N, a_choff,      \
-                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
-                                      seg_shift));                                                              \
-            if (first && (rc = rec(ix, 6, st))) return rc;                                                      \
+            auto k1 = rigk::phi_expand_kernel<W, DD, KP, true>;                                                 \
+            auto k2 = rigk::phi_window_kernel<W, DD, KP>;                                                       \
+            uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
+            uint64_t g2 = (uint64_t)ix->sm_count * resident_ctas(k2, wthreads);                                 \
+            g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
+            g2 = std::min<uint64_t>(g2, (max_items + wthreads - 1) / wthreads);                                 \
+            cfg.gridDim = dim3((unsigned)g1);                                                                   \
+            CU_TRY(cudaLaunchKernelEx(&cfg, k1, ix->d, a_N, a_choff, d_occoff, d_lo, d_hi, a_toe, a_jl, d_occ,  \
+                                      a_ctr, a_cap, a_items, a_icap, seg_shift));                               \
+            if ((rc = rec(ix, 6, st))) return rc;                                                               \
             cudaLaunchConfig_t cfg2 = cfg;                                                                      \
-            cfg2.gridDim = dim3((unsigned)wnb); cfg2.blockDim = dim3((unsigned)wthreads);                       \
-            const ull* c_items = a_items; const ull* c_icount = a_icount;                                       \
-            constexpr int WW = sizeof(W) == 4 ? 8 : 4;                                                          \
-            if (!(ix->variant & 64))                                                                            \
-                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, false, WW>, ix->d, c_items, \
-                                          c_icount, d_occ));                                                    \
-            else                                                                                                \
-                CU_TRY(cudaLaunchKernelEx(&cfg2, rigk::phi_window_kernel<W, DD, KP, true, WW>, ix->d, c_items,  \
-                                          c_icount, d_occ));                                                    \
-            ix->timing.launches += 1;                                                                           \
+            cfg2.gridDim = dim3((unsigned)g2); cfg2.blockDim = dim3((unsigned)wthreads);                        \
+            const ull* c_items = a_items; const ull* c_ctr = a_ctr;                                             \
+            CU_TRY(cudaLaunchKernelEx(&cfg2, k2, ix->d, c_items, c_ctr, d_occ, a_cap, a_icap, seg_shift));      \
+            ix->timing.launches += 2;                                                                           \
+            if ((rc = rec(ix, 7, st))) return rc;                                                               \
         } else {                                                                                                \
-            CU_TRY(cudaLaunchKernelEx(&cfg, rigk::phi_expand_kernel<W, DD, KP, false>, ix->d, a_N, a_choff,     \
-                                      a_occoff, a_lo, a_hi, a_toe, a_jl, d_occ, a_chains, a_items, a_icount,    \
-                                      seg_shift));                                                              \
+            auto k1 = rigk::phi_expand_kernel<W, DD, KP, false>;                                                \
+            uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
+            g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
+            cfg.gridDim = dim3((unsigned)g1);                                                                   \
+            CU_TRY(cudaLaunchKernelEx(&cfg, k1, ix->d, a_N, a_choff, d_occoff, d_lo, d_hi, a_toe, a_jl, d_occ,  \
+                                      a_ctr, a_cap, a_items, a_icap, seg_shift));                               \
+            ix->timing.launches += 1;                                                                           \
         }                                                                                                       \
     } while (0)
 #define RIG_EXPAND(W, DD)                                                                                     \
@@ -483,91 +492,62 @@ int expand_slice(rig_index* ix, const Slice& sl, const ull* d_lo, const ull* d_h
 #undef RIG_EXPAND2
 #undef RIG_EXPAND
     CU_TRY(cudaGetLastError());
-    ix->timing.launches += 1;
-    if (first && two_pass && (rc = rec(ix, 7, st))) return rc;
     return RIG_OK;
 }
 
-// search + scans (sync) + expansion; events 1..4 on `st`.
-// OPT-IN (rig_set_slices(2) / rig_options.reserved[3] = 2): a batch of >= 16384 patterns is cut into TWO slices that
-// run on two streams, so that slice 1's search / scans / seed pass (latency-bound: 0.5 waves, ~30% issue on C2) hide
-// under slice 0's window pass (bound by L2 requests). The slices share every per-pattern array (disjoint ranges);
-// slice 1's occurrence offsets start at slice 0's total (added on the device by its scan). rig_timing then describes
-// slice 0's phases; `slices` tells. Measured gain: 1.5% (C2), 4.5% (C3s, C5s) — the latency-bound phases take as long
-// for half a batch as for a whole one, and two half-size window passes take 0.34 ms against 0.27 ms for one: off by
-// default.
+// search (+ offsets) and expansion, queued back to back; the host then waits for the totals only (they are copied
+// out right after the search), while the expansion is already running: events 1..4 on `st`.
 int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
                ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
     int rc;
-    const uint32_t nsl = (ix->slices == 2 && N >= 16384) ? 2u : 1u;
-    Slice sl[2];
-    sl[0].p0 = 0; sl[0].np = nsl == 2 ? (N / 2) & ~(uint64_t)127 : N;
-    sl[1].p0 = sl[0].np; sl[1].np = N - sl[0].np;
-    for (uint32_t k = 0; k < nsl; ++k) sl[k].ntiles = (sl[k].np + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE;
     if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
         (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 4) * 8)) ||
-        (rc = ix->sums.ensure((2 * (sl[0].ntiles + sl[1].ntiles) + 8) * 8)))
+        (rc = ix->sums.ensure((std::max<uint64_t>(tile_ws_words(N), 2 * ((N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE) + 8)) * 8)))
         return rc;
-    sl[0].choff = (ull*)ix->choff.p;            sl[1].choff = (ull*)ix->choff.p + sl[0].np + 2;
-    sl[0].sums = (ull*)ix->sums.p;              sl[1].sums = (ull*)ix->sums.p + 2 * sl[0].ntiles + 4;
-    sl[0].totals = ix->d_counters + 2;          sl[1].totals = ix->d_counters + 8;
-    sl[0].icount = ix->d_counters + 6;          sl[1].icount = ix->d_counters + 10;
-    sl[0].h_totals = ix->h_counters + 2;        sl[1].h_totals = ix->h_counters + 8;
-    sl[0].items = &ix->items;                   sl[1].items = &ix->items2;
-    sl[0].st = st;                              sl[1].st = ix->stream2;
-    ix->timing.slices = nsl;
+    // Two passes when the index has a seed table and the output array is line-aligned (the window kernel writes
+    // whole 128-byte lines); otherwise the single-pass walk.
+    const uint32_t SEG = ix->d.seed.J;
+    const bool want = d_occ != nullptr && cap > 0 && N > 0;
+    const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
+    // Item list: sized BEFORE the totals are known, from the capacity the caller offers (total <= cap or nothing
+    // runs), the list kept from earlier calls, and a guess of two chains per pattern; the kernels check the exact
+    // bound on the device and the host re-launches them below if the guess was short.
+    auto items_bound = [&](uint64_t total, uint64_t chains) { return total / SEG + chains; };
+    uint64_t items_cap = 0;
+    if (want && two_pass) {
+        const uint64_t guess = items_bound(std::min<uint64_t>(cap, 1ull << 33), 2 * N + 1024) + 32;
+        if (ix->items.cap < guess * 16 && (rc = ix->items.ensure(std::min<uint64_t>(guess * 16, 1ull << 30)))) return rc;
+        items_cap = ix->items.cap / 16 - 32;
+    }
     CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(ull), st));
     if ((rc = rec(ix, 1, st))) return rc;
-    if (nsl == 2) {
-        CU_TRY(cudaEventRecord(ix->ev_fork, st));
-        CU_TRY(cudaStreamWaitEvent(sl[1].st, ix->ev_fork, 0));
+    if (N) {
+        if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, d_occoff, st))) return rc;
+    } else {
+        CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
     }
-    for (uint32_t k = 0; k < nsl; ++k) {
-        Slice& s = sl[k];
-        if (s.np) {
-            if ((rc = launch_search<true>(ix, d_patt + s.p0 * m, s.np, m, d_lo + s.p0, d_hi + s.p0, s.st, s.p0))) return rc;
-            ix->timing.launches += 1;
-        }
-        if (k == 0 && (rc = rec(ix, 2, st))) return rc;
-        if (s.np) {
-            ull* nocc = (ull*)ix->nocc.p + s.p0; ull* nch = (ull*)ix->nch.p + s.p0;
-            rigk::scan_tile_sums<<<(unsigned)s.ntiles, RIG_SCAN_THREADS, 0, s.st>>>(nocc, nch, s.np, s.sums, s.ntiles);
-            rigk::scan_sums_inplace<<<1, 1024, 0, s.st>>>(s.sums, s.ntiles, s.totals);
-            if (k == 1) CU_TRY(cudaStreamWaitEvent(s.st, ix->ev_scan[0], 0));  // slice 1's offsets start at slice 0's total
-            rigk::scan_tiles<<<(unsigned)s.ntiles, RIG_SCAN_THREADS, 0, s.st>>>(nocc, nch, s.np, s.sums, s.ntiles, d_occoff + s.p0,
-                                                                                  s.choff, s.totals, k == 1 ? sl[0].totals : nullptr);
-            CU_TRY(cudaGetLastError());
-            ix->timing.launches += 3;
-        } else {
-            CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, s.st));
-        }
-        // the last slice's copy also carries the LF-step counter: every search kernel has finished by then
-        if (k + 1 == nsl) CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 16 * sizeof(ull), cudaMemcpyDeviceToHost, s.st));
-        else CU_TRY(cudaMemcpyAsync(s.h_totals, s.totals, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s.st));
-        CU_TRY(cudaEventRecord(ix->ev_scan[k], s.st));
-        if (k == 0 && (rc = rec(ix, 3, st))) return rc;
-        // warm the Phi tables into L2 (RIG_VARIANT bit2 disables: A/B switch); queued BEFORE the host waits for the
-        // totals, so the device is not idle during the host's turnaround
-        if (k == 0 && N && d_occ && !(ix->variant & 4) && ix->phi_bytes) {
+    if ((rc = rec(ix, 2, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(ix->ev_scan, st));
+    if ((rc = rec(ix, 3, st))) return rc;
+    if (want) {
+        // warm the Phi tables into L2 (RIG_VARIANT bit2 disables: A/B switch)
+        if (!(ix->variant & 4) && ix->phi_bytes) {
             const uint64_t lines = (ix->phi_bytes + 127) / 128;
             rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
             ix->timing.launches += 1;
         }
+        if ((rc = launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st))) return rc;
     }
-    // slice 0: learn its totals, start its expansion while slice 1 is still searching
-    CU_TRY(cudaEventSynchronize(ix->ev_scan[0]));
-    sl[0].total = sl[0].h_totals[0]; sl[0].chains = sl[0].h_totals[1];
-    bool fits = !(sl[0].total > cap || (sl[0].total && !d_occ));
-    if (fits && (rc = expand_slice(ix, sl[0], d_lo, d_hi, d_occoff, d_occ, true))) return rc;
-    uint64_t total = sl[0].total, chains = sl[0].chains;
-    if (nsl == 2) {
-        CU_TRY(cudaEventSynchronize(ix->ev_scan[1]));
-        sl[1].total = sl[1].h_totals[0]; sl[1].chains = sl[1].h_totals[1];
-        total += sl[1].total; chains += sl[1].chains;
-        fits = fits && !(total > cap || (total && !d_occ));
-        if (fits && (rc = expand_slice(ix, sl[1], d_lo, d_hi, d_occoff, d_occ, false))) return rc;
-        CU_TRY(cudaEventRecord(ix->ev_join, sl[1].st));
-        CU_TRY(cudaStreamWaitEvent(st, ix->ev_join, 0));
+    CU_TRY(cudaEventSynchronize(ix->ev_scan));  // the expansion is queued (or running) behind it
+    const uint64_t total = ix->h_counters[RIG_CTR_TOTAL], chains = ix->h_counters[RIG_CTR_CHAINS];
+    const bool fits = !(total > cap || (total && !d_occ));
+    if (want && fits && two_pass && items_bound(total, chains) > items_cap) {
+        // the kernels above returned at once (same test on the device): grow the list and queue them again
+        if ((rc = ix->items.ensure((items_bound(total, chains) + 64) * 16))) return rc;
+        items_cap = ix->items.cap / 16 - 32;
+        CU_TRY(cudaMemsetAsync(ix->d_counters + RIG_CTR_ITEMS, 0, sizeof(ull), st));
+        if ((rc = launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st))) return rc;
     }
     ix->timing.occ_total = total;
     ix->timing.chains = chains;
@@ -890,9 +870,67 @@ int rig_get_bwt(rig_index* ix, uint64_t from, uint64_t len, uint8_t* out) {
     return RIG_OK;
 }
 
-int rig_set_slices(rig_index* ix, uint32_t slices) {
-    if (!ix || slices > 2) return RIG_ERR_ARG;
-    ix->slices = slices;
+// ---- range utilities of the RLBWT as batches: break_range, closest_run_break --------------------
+namespace {
+int range_nav_upload(rig_index* ix, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N, cudaStream_t st) {
+    int rc;
+    if ((rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) || (rc = ix->patt.ensure(N + 16)) ||
+        (rc = ix->occoff.ensure((N + 2) * 8)) || (rc = ix->nocc.ensure((N + 1) * 8)))
+        return rc;
+    CU_TRY(cudaMemcpyAsync(ix->lo.p, lo, N * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ix->hi.p, hi, N * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ix->patt.p, c, N, cudaMemcpyHostToDevice, st));
+    return RIG_OK;
+}
+int range_nav_launch(rig_index* ix, int op, uint64_t N, const ull* off, ull* out_a, ull* out_b, cudaStream_t st) {
+    const uint64_t nb = (N + 255) / 256;
+    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+    if (ix->d.w32) rigk::range_nav_kernel<uint32_t><<<(unsigned)nb, 256, 0, st>>>(ix->d, op, (const ull*)ix->lo.p, (const ull*)ix->hi.p,
+                                                                                  (const uint8_t*)ix->patt.p, N, off, out_a, out_b);
+    else rigk::range_nav_kernel<ull><<<(unsigned)nb, 256, 0, st>>>(ix->d, op, (const ull*)ix->lo.p, (const ull*)ix->hi.p,
+                                                                   (const uint8_t*)ix->patt.p, N, off, out_a, out_b);
+    CU_TRY(cudaGetLastError());
+    return RIG_OK;
+}
+}  // namespace
+
+int rig_closest_run_break_batch(rig_index* ix, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N, uint64_t* out) {
+    if (!ix || (N && (!lo || !hi || !c || !out))) return RIG_ERR_ARG;
+    if (!N) return RIG_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = range_nav_upload(ix, lo, hi, c, N, st))) return rc;
+    if ((rc = range_nav_launch(ix, rigk::RANGE_CLOSEST, N, nullptr, (ull*)ix->nocc.p, nullptr, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(out, ix->nocc.p, N * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return RIG_OK;
+}
+
+int rig_break_range_batch(rig_index* ix, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N,
+                          uint64_t* out_offsets, uint64_t* out_first, uint64_t* out_last, uint64_t capacity, uint64_t* total) {
+    if (!ix || !out_offsets || (N && (!lo || !hi || !c))) return RIG_ERR_ARG;
+    out_offsets[0] = 0;
+    if (total) *total = 0;
+    if (!N) return RIG_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = range_nav_upload(ix, lo, hi, c, N, st))) return rc;
+    if ((rc = range_nav_launch(ix, rigk::RANGE_BREAK_COUNT, N, nullptr, (ull*)ix->nocc.p, nullptr, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_offsets + 1, ix->nocc.p, N * 8, cudaMemcpyDeviceToHost, st));  // counts, turned into offsets below
+    CU_TRY(cudaStreamSynchronize(st));
+    for (uint64_t k = 1; k <= N; ++k) out_offsets[k] += out_offsets[k - 1];
+    const uint64_t tot = out_offsets[N];
+    if (total) *total = tot;
+    if (tot > capacity || (tot && (!out_first || !out_last))) return RIG_ERR_CAPACITY;
+    if (!tot) return RIG_OK;
+    if ((rc = ix->big1.ensure(tot * 8)) || (rc = ix->big2.ensure(tot * 8))) return rc;
+    CU_TRY(cudaMemcpyAsync(ix->occoff.p, out_offsets, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = range_nav_launch(ix, rigk::RANGE_BREAK_FILL, N, (const ull*)ix->occoff.p, (ull*)ix->big1.p, (ull*)ix->big2.p, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_first, ix->big1.p, tot * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out_last, ix->big2.p, tot * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
     return RIG_OK;
 }
 

@@ -237,6 +237,96 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
     if (lane == 0 && s) atomicAdd(lf_steps, (u64)s);
 }
 
+
+// ------------------------------------------------------------------ single-pass offsets (fused into the search)
+// The one-lane-per-pattern kernel also produces the exclusive prefix sums of n_occ and of the chain counts
+// (= where every pattern's occurrences and chains start) with a decoupled look-back over its own CTAs, so a
+// locate call needs no scan launches: tile t publishes its aggregate, then the inclusive prefix once the
+// tiles before it are known. Tiles are handed out by an atomic ticket, so every tile a CTA waits for has
+// already started (it is resident or finished): no deadlock whatever the grid size.
+//   ws[0]                       ticket counter
+//   ws[2 + 5t]                  status of tile t: 0 not ready, 1 aggregate available, 2 inclusive prefix available
+//   ws[3 + 5t], ws[4 + 5t]      aggregate of tile t (occurrences, chains)
+//   ws[5 + 5t], ws[6 + 5t]      inclusive prefix of tiles 0..t
+// The values are written first, then a device-scope fence, then the status word; a reader polls the status word
+// with relaxed device-scope loads, fences, and reads the values (the status / value protocol of the single-pass
+// scan with separate status and value arrays).
+#define RIG_TILE_WORDS 5
+
+__device__ __forceinline__ u64 ld_relaxed_gpu(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Called by every thread of a 128-thread CTA with its pattern's (n_occ, chains); ex_*: the exclusive prefix over
+// all patterns before it; incl_*: the inclusive prefix at the end of this tile (the grand totals in the last tile).
+__device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u64 b, u64& ex_a, u64& ex_b,
+                                                    u64& incl_a, u64& incl_b) {
+    __shared__ u64 s_wa[4], s_wb[4], s_base[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u64 ia = a, ib = b;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 xa = __shfl_up_sync(RIG_FULL, ia, off), xb = __shfl_up_sync(RIG_FULL, ib, off);
+        if (lane >= off) { ia += xa; ib += xb; }
+    }
+    if (lane == 31) { s_wa[w] = ia; s_wb[w] = ib; }
+    __syncthreads();
+    u64 pa = 0, pb = 0, ta = 0, tb = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < w) { pa += s_wa[j]; pb += s_wb[j]; }
+        ta += s_wa[j]; tb += s_wb[j];
+    }
+    if (w == 0) {
+        u64* st = ws + 2;
+        u64 sum_a = 0, sum_b = 0;
+        if (tile > 0) {
+            if (lane == 0) {
+                u64* me = st + (u64)tile * RIG_TILE_WORDS;
+                st_relaxed_gpu(me + 1, ta); st_relaxed_gpu(me + 2, tb);
+                __threadfence();
+                st_relaxed_gpu(me, 1);
+            }
+            long long j = (long long)tile - 1;
+            for (;;) {
+                const long long idx = j - lane;
+                u64 flag = 2, va = 0, vb = 0;  // before tile 0: prefix 0
+                if (idx >= 0) {
+                    const u64* t = st + (u64)idx * RIG_TILE_WORDS;
+                    do { flag = ld_relaxed_gpu(t); } while (flag == 0);
+                    __threadfence();
+                    va = ld_relaxed_gpu(t + (flag == 2 ? 3 : 1));
+                    vb = ld_relaxed_gpu(t + (flag == 2 ? 4 : 2));
+                }
+                const u32 pm = __ballot_sync(RIG_FULL, flag == 2);
+                if (pm && lane > __ffs(pm) - 1) { va = 0; vb = 0; }  // tiles beyond the nearest known prefix
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { va += __shfl_xor_sync(RIG_FULL, va, off); vb += __shfl_xor_sync(RIG_FULL, vb, off); }
+                sum_a += va; sum_b += vb;
+                if (pm) break;
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            u64* me = st + (u64)tile * RIG_TILE_WORDS;
+            st_relaxed_gpu(me + 3, sum_a + ta); st_relaxed_gpu(me + 4, sum_b + tb);
+            __threadfence();
+            st_relaxed_gpu(me, 2);
+            s_base[0] = sum_a; s_base[1] = sum_b;
+        }
+    }
+    __syncthreads();
+    ex_a = s_base[0] + pa + ia - a;
+    ex_b = s_base[1] + pb + ib - b;
+    incl_a = s_base[0] + ta;
+    incl_b = s_base[1] + tb;
+}
+
 // ------------------------------------------------------------------ one lane per pattern
 // The cooperative kernel above was measured issue-bound at every group size tried (16 -> 8 -> 4 lanes per
 // rank query: 0.50 -> 0.30 -> 0.19 ms on C2), each halving of the group paying off in full: the ballots,
@@ -316,14 +406,20 @@ template <bool LOCATE, typename PT>
 __global__ void __launch_bounds__(128)
 search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
                    u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
-                   u64* __restrict__ nch_out, u64* __restrict__ nocc_out, u64* __restrict__ lf_steps) {
+                   u64* __restrict__ choff_out, u64* __restrict__ occoff_out, u64* __restrict__ lf_steps,
+                   u64* __restrict__ tile_ws, u64* __restrict__ totals) {
     struct SymEnt { PT f0, f1; u32 sid, pad; };  // F[256] = n fits: n < 2^32-1 when PT = u32
     __shared__ SymEnt sSym[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sSym[i].f0 = (PT)ix.F[i]; sSym[i].f1 = (PT)ix.F[i + 1]; sSym[i].sid = ix.sid[i]; sSym[i].pad = 0;
     }
+    // locate: tiles (= 128 patterns) are taken by ticket, so that the look-back of the fused offset scan only
+    // waits for CTAs that have started (tile_exclusive_scan)
+    __shared__ u32 s_tile;
+    if (LOCATE && threadIdx.x == 0) s_tile = (u32)atomicAdd(tile_ws, 1ull);
     __syncthreads();
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 tile = LOCATE ? s_tile : blockIdx.x;
+    const u64 p = (u64)tile * blockDim.x + threadIdx.x;
     bool alive = p < N;
     const uint8_t* P = patt + (alive ? p : 0) * m;
     PT lo = 0, hi = (PT)(ix.n - 1);  // full_range, r_index.hpp:155-160
@@ -362,27 +458,35 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
         lo = se.f0 + A;        // r_index.hpp:186
         hi = se.f0 + B - 1;    // r_index.hpp:188
     }
-    if (p < N) {
-        if (LOCATE) {  // runs holding lo and hi: the range is cut into one Phi chain per overlapped run
-            const bool ne = hi >= lo;
-            u32 jL = 0, jR = 0;
-            if (ne) {
-                const u32 qa = (u32)(lo >> ix.lf_shift), qb = (u32)(hi >> ix.lf_shift);
-                const u32 ba = lane_block_of<PT>(ix, lo, __ldg(ix.bdir + qa), __ldg(ix.bdir + qa + 1));
-                const u32 bb = lane_block_of<PT>(ix, hi, __ldg(ix.bdir + qb), __ldg(ix.bdir + qb + 1));
-                LaneRec<PT> ra, rb;
-                lane_load<PT>(ix, ba, 0, ra);
-                lane_load<PT>(ix, bb, 0, rb);
-                jL = ba * 4u + (u32)(ra.s1 <= lo) + (u32)(ra.s2 <= lo) + (u32)(ra.s3 <= lo);
-                jR = bb * 4u + (u32)(rb.s1 <= hi) + (u32)(rb.s2 <= hi) + (u32)(rb.s3 <= hi);
-            }
+    if (LOCATE) {  // runs holding lo and hi: the range is cut into one Phi chain per overlapped run
+        const bool ne = (p < N) && hi >= lo;
+        u32 jL = 0, jR = 0;
+        if (ne) {
+            const u32 qa = (u32)(lo >> ix.lf_shift), qb = (u32)(hi >> ix.lf_shift);
+            const u32 ba = lane_block_of<PT>(ix, lo, __ldg(ix.bdir + qa), __ldg(ix.bdir + qa + 1));
+            const u32 bb = lane_block_of<PT>(ix, hi, __ldg(ix.bdir + qb), __ldg(ix.bdir + qb + 1));
+            LaneRec<PT> ra, rb;
+            lane_load<PT>(ix, ba, 0, ra);
+            lane_load<PT>(ix, bb, 0, rb);
+            jL = ba * 4u + (u32)(ra.s1 <= lo) + (u32)(ra.s2 <= lo) + (u32)(ra.s3 <= lo);
+            jR = bb * 4u + (u32)(rb.s1 <= hi) + (u32)(rb.s2 <= hi) + (u32)(rb.s3 <= hi);
+        }
+        const u64 nocc = ne ? (u64)(hi - lo) + 1 : 0;   // r_index.hpp:338
+        const u64 nch = ne ? (u64)(jR - jL + 1) : 0;
+        u64 ex_occ, ex_ch, in_occ, in_ch;
+        tile_exclusive_scan(tile_ws, tile, nocc, nch, ex_occ, ex_ch, in_occ, in_ch);
+        if (p < N) {
             toe_out[p] = (u64)k;
             jl_out[p] = jL;
-            nch_out[p] = ne ? (u64)(jR - jL + 1) : 0;
-            nocc_out[p] = ne ? (u64)(hi - lo) + 1 : 0;  // r_index.hpp:338
+            occoff_out[p] = ex_occ;
+            choff_out[p] = ex_ch;
         }
-        lo_out[p] = (u64)lo; hi_out[p] = (u64)hi;
+        if ((u64)(tile + 1) * blockDim.x >= N && threadIdx.x == 0) {  // the last tile closes both arrays
+            occoff_out[N] = in_occ; choff_out[N] = in_ch;
+            totals[0] = in_occ; totals[1] = in_ch;
+        }
     }
+    if (p < N) { lo_out[p] = (u64)lo; hi_out[p] = (u64)hi; }
     // executed LF steps (for the algorithmic-bytes figure)
     u32 sum = steps;
 #pragma unroll

@@ -7,6 +7,7 @@
 //   vector<ulint> locate_all(string&) :328 ulint serialize(ostream&)   :382  void load(istream&) :407
 //   number_of_runs() :361  text_size() :450  bwt_size() :454  get_terminator_position() :368
 //   operator[](i) :162  LF(i) :224  FL(i) :232  F_at(i) :263  get_char_range(c) :276  get_bwt() :375
+//   print_space() :462   and, of the BWT member (rle_string.hpp): break_range(rn, c) :261, closest_run_break(rn, c) :455
 // plus the batch surface this repo adds (one FFI call per batch instead of one call per pattern):
 //   count_batch(), locate_batch(), navigate_batch().
 // Every query — single-pattern calls included — runs on the GPU through include/rindex_gpu.h.
@@ -130,6 +131,42 @@ public:
     range_t get_char_range(uchar c) {
         if (L.F[c] >= L.F[(unsigned)c + 1]) return {1, 0};
         return {L.F[c], L.F[(unsigned)c + 1] - 1};
+    }
+
+    // rle_string::break_range (reference rle_string.hpp:261-302): maximal sub-ranges of rn holding only c; requires
+    // bwt[rn.first] == bwt[rn.second] == c (the reference asserts; here a violating call returns no range)
+    std::vector<range_t> break_range(range_t rn, uchar c) {
+        ensure_device();
+        uint64_t off[2] = {0, 0}, total = 0;
+        int rc = rig_break_range_batch(dev, &rn.first, &rn.second, &c, 1, off, nullptr, nullptr, 0, &total);
+        std::vector<ulint> a(total), b(total);
+        if (rc == RIG_ERR_CAPACITY) rc = rig_break_range_batch(dev, &rn.first, &rn.second, &c, 1, off, a.data(), b.data(), total, &total);
+        check(rc, "rig_break_range_batch");
+        std::vector<range_t> out(total);
+        for (uint64_t k = 0; k < total; ++k) out[k] = {a[k], b[k]};
+        return out;
+    }
+    // rle_string::closest_run_break (reference rle_string.hpp:455-493)
+    ulint closest_run_break(range_t rn, uchar c) {
+        ensure_device();
+        ulint out = 0;
+        check(rig_closest_run_break_batch(dev, &rn.first, &rn.second, &c, 1, &out), "rig_closest_run_break_batch");
+        return out;
+    }
+    // r_index::print_space (reference :462-472 over rle_string::print_space, rle_string.hpp:402-442): the same report
+    // lines. The byte counts are those of THIS index's containers — the run-length BWT as plain arrays on the host and
+    // its flattened form in HBM — not of SDSL's serialized structures, which this repo does not have.
+    ulint print_space() {
+        using std::cout; using std::endl;
+        cout << "Number of runs = " << L.r << endl << endl;
+        const ulint runs_bytes = L.run_lens.size() * sizeof(uint64_t), heads_bytes = L.run_heads.size();
+        cout << "main runs bitvector: " << runs_bytes << " Bytes" << endl;          // run lengths (the role of `runs`)
+        cout << "runs-per-letter bitvectors: " << 0 << " Bytes" << endl;             // folded into the block records on the device
+        cout << "run heads: " << heads_bytes << " Bytes" << endl;
+        const ulint tot_bytes = runs_bytes + heads_bytes;
+        cout << "\nTOT BWT space: " << tot_bytes << " Bytes" << endl << endl;
+        if (dev) cout << "flattened index in HBM (all tables): " << info.device_bytes << " Bytes" << endl << endl;
+        return tot_bytes;
     }
 
     ulint number_of_runs() { return L.r; }

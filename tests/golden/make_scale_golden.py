@@ -12,7 +12,7 @@ For every workload of bench.py named on the command line (default: all six):
   * a parity sample of patterns (the first K and K random ones; K = 1500 for the scaled configs, 150 for the
     full-size ones whose patterns have ~10^4 occurrences each) is run through the reference's own count() /
     locate_all() (oracle/ref_driver.cpp);
-  * tests/golden/scale_<name>.npz keeps: the sample's pattern indices, lo, hi, per-pattern (sum, index-weighted
+  * tests/golden/scale/<name>.npz keeps: the sample's pattern indices, lo, hi, per-pattern (sum, index-weighted
     sum) digests of the occurrences IN locate_all ORDER (r_index.hpp:340-351) and the sha256 of the whole sample's
     occurrence array; n, r and the sha256 of each logical array of the reference-built index (F, run heads, run
     lengths, samples_last, pred positions, pred_to_run — ref_extract), so the GPU box can check that the index it
@@ -92,7 +92,8 @@ def make(name):
     ex = ref.extract()
     for k in ARRAYS:
         out["sha256_" + k] = hashlib.sha256(np.ascontiguousarray(ex[k]).tobytes()).hexdigest()
-    np.savez_compressed(os.path.join(HERE, "scale_%s.npz" % name), **out)
+    os.makedirs(os.path.join(HERE, "scale"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "scale", "%s.npz" % name), **out)
     print("[%s] n=%d r=%d sample=%d patterns%s  (%.0f s)" % (
         name, ref.n, ref.r, S, "" if name in COUNT_ONLY else ", %d occurrences" % int(out["occ_total"]), time.time() - t0),
         flush=True)

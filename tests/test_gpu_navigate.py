@@ -105,3 +105,76 @@ int main() {
     first_a = int(np.searchsorted(np.sort(f_at), ord("a")))
     n_a = int((text == ord("a")).sum())
     assert out[sa.size + 1] == "RANGE %d %d 1 0" % (first_a, first_a + n_a - 1)
+
+
+def _range_truth(bwt, l, r, c):
+    """break_range by its definition: maximal sub-ranges of [l, r] holding only c (bwt[l] == bwt[r] == c)."""
+    seg = bwt[l:r + 1] == c
+    d = np.diff(np.concatenate([[0], seg.astype(np.int8), [0]]))
+    return (np.nonzero(d == 1)[0] + l).astype(np.uint64), (np.nonzero(d == -1)[0] + l - 1).astype(np.uint64)
+
+
+def _range_queries(bwt, count, rng):
+    """(l, r, c) with bwt[l] == bwt[r] == c, and ranges holding c and another symbol for closest_run_break."""
+    n = bwt.size
+    qs = []
+    while len(qs) < count:
+        l = int(rng.integers(0, n)); c = int(bwt[l])
+        same = np.nonzero(bwt[l:min(n, l + int(rng.choice([3, 50, 5000])))] == c)[0]
+        qs.append((l, l + int(rng.choice(same)), c))
+    return qs
+
+
+@needs_ref
+@pytest.mark.parametrize("K", [4, 16])
+@pytest.mark.parametrize("variant", ["0", "8"])
+def test_break_range_and_closest_run_break(K, variant, monkeypatch):
+    """rle_string::break_range / closest_run_break (rle_string.hpp:261-302, 455-493) as batches on the device, against
+    their definition on the explicit BWT and against the reference's own methods."""
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    rng = np.random.default_rng(9 + K)
+    for text in [rib.gen_text("dna_drift", 60_000, 1_500, 3, 21), rib.gen_text("versioned_doc", 40_000, 2_000, 96, 4),
+                 np.frombuffer(b"abracadabra" * 40, dtype=np.uint8), np.frombuffer(b"aaaaaaaaaaaaaaaaaaa", dtype=np.uint8)]:
+        ref = ob.RefIndex.from_text(text)
+        gpu = rib.GpuIndex(rib.HostIndex.from_text(text), runs_per_block=K)
+        bwt = ref.get_bwt()
+        n = bwt.size
+        qs = _range_queries(bwt, 400, rng)
+        lo = np.array([q[0] for q in qs], dtype=np.uint64); hi = np.array([q[1] for q in qs], dtype=np.uint64)
+        c = np.array([q[2] for q in qs], dtype=np.uint8)
+        off, first, last = gpu.break_range(lo, hi, c)
+        for k, (l, r, cc) in enumerate(qs):
+            ef, el = _range_truth(bwt, l, r, cc)
+            assert np.array_equal(first[int(off[k]):int(off[k + 1])], ef) and np.array_equal(last[int(off[k]):int(off[k + 1])], el), (l, r, cc)
+            if k < 60:
+                rf, rl = ref.break_range(l, r, cc)
+                assert np.array_equal(rf, ef) and np.array_equal(rl, el)
+        # queries that break the precondition give no range (the reference asserts)
+        bad_lo = np.array([5 if n > 6 else 0, n + 3], dtype=np.uint64); bad_hi = np.array([2, n + 9], dtype=np.uint64)
+        off2, f2, l2 = gpu.break_range(bad_lo, bad_hi, np.array([bwt[0], bwt[0]], dtype=np.uint8))
+        assert off2.tolist() == [0, 0, 0] and f2.size == 0
+        # closest_run_break: ranges holding c and at least one other symbol
+        cq = []
+        while len(cq) < 300 and np.unique(bwt).size > 1:
+            l = int(rng.integers(0, n - 1)); r = min(n - 1, l + int(rng.integers(1, 2000)))
+            syms = np.unique(bwt[l:r + 1])
+            if syms.size < 2:
+                continue
+            cq.append((l, r, int(rng.choice(syms))))
+        if cq:
+            lo = np.array([q[0] for q in cq], dtype=np.uint64); hi = np.array([q[1] for q in cq], dtype=np.uint64)
+            c = np.array([q[2] for q in cq], dtype=np.uint8)
+            got = gpu.closest_run_break(lo, hi, c)
+            for k, (l, r, cc) in enumerate(cq):
+                if bwt[l] == cc:
+                    e = l
+                    while e + 1 < n and bwt[e + 1] == cc:
+                        e += 1
+                    if e >= r:      # the reference's precondition (j < rn.second) does not hold: not comparable
+                        continue
+                else:
+                    e = l + int(np.nonzero(bwt[l:] == cc)[0][0])
+                assert int(got[k]) == e, (l, r, cc)
+                if k < 60:
+                    assert ref.closest_run_break(l, r, cc) == e
+        gpu.close()

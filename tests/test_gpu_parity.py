@@ -322,45 +322,39 @@ def test_both_search_kernels_k4(variant, monkeypatch):
         gpu.close()
 
 
-def test_two_slice_pipelined_locate_equals_unsliced_and_oracle():
-    """Opt-in: batches of >= 16384 patterns run as two slices pipelined on two streams (slice 1's search and seed
-    pass hide under slice 0's window pass). Same ranges, offsets and occurrences as the unsliced call and the oracle;
-    the capacity protocol and the device-buffer entry point behave the same."""
+def test_large_batch_capacity_protocol_and_caller_stream():
+    """Batches of tens of thousands of patterns (hundreds of tiles in the search kernel's fused offset scan, several
+    rounds of the persistent expansion kernels): same ranges, offsets and occurrences as the oracle; the capacity
+    protocol (the expansion skips itself on the device when the buffer is too small) and the device-buffer entry point
+    on a caller's stream behave the same; a second call on the same index reuses the grown item list."""
     torch = pytest.importorskip("torch")
     text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 41)
     host = rib.HostIndex.from_text(text)
     port = ob.PortIndex(text, sa=rib.suffix_array(text))
     gpu = rib.GpuIndex(host)
-    for (N, m, seed) in [(16384, 12, 1), (20001, 7, 2), (40000, 16, 3)]:
+    for (N, m, seed) in [(16384, 12, 1), (20001, 7, 2), (40000, 16, 3), (129, 3, 4), (128, 2, 5)]:
         patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
         elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
-        gpu.set_slices(2)
-        lo, hi, off, occ = gpu.locate(patt, N, m)
-        assert gpu.timing()["slices"] == 2
-        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(off, eoff) and np.array_equal(occ, eocc)
-        gpu.set_slices(1)
-        lo1, hi1, off1, occ1 = gpu.locate(patt, N, m)
-        assert gpu.timing()["slices"] == 1
-        assert np.array_equal(lo1, elo) and np.array_equal(off1, eoff) and np.array_equal(occ1, eocc)
-    # capacity protocol with two slices: too small for slice 0, and large enough for slice 0 only
-    gpu.set_slices(2)
+        for rep in range(2):
+            lo, hi, off, occ = gpu.locate(patt, N, m)
+            assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(off, eoff) and np.array_equal(occ, eocc)
     import ctypes
     N, m = 20001, 7
     patt = mixed_patterns(text, N, m, 2, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
     elo, ehi, eoff, eocc, _ = port.locate(patt, N, m)
-    half = int(eoff[(N // 2) & ~127])
-    for cap in (3, half + 5):
+    for cap in (3, eocc.size - 1):
         lo = np.zeros(N, dtype=np.uint64); hi = np.zeros(N, dtype=np.uint64); off = np.zeros(N + 1, dtype=np.uint64)
         small = np.zeros(cap, dtype=np.uint64)
         tot = ctypes.c_uint64(0)
         rc = gpu.lib.rig_locate_batch(gpu.h, patt.ctypes.data, N, m, lo.ctypes.data, hi.ctypes.data, off.ctypes.data,
                                       small.ctypes.data, small.size, ctypes.byref(tot))
         assert rc == -4 and tot.value == eocc.size and np.array_equal(off, eoff) and np.array_equal(lo, elo)
-    # device-buffer entry point on a caller's stream
+        assert not small.any()       # nothing was written into a buffer that is too small
+    # device-buffer entry point on a caller's stream; the output buffer is poisoned first
     dev = torch.device("cuda:0")
     d_patt = torch.from_numpy(patt).to(dev)
     d_lo = torch.zeros(N, dtype=torch.int64, device=dev); d_hi = torch.zeros(N, dtype=torch.int64, device=dev)
-    d_off = torch.zeros(N + 1, dtype=torch.int64, device=dev); d_occ = torch.zeros(eocc.size, dtype=torch.int64, device=dev)
+    d_off = torch.zeros(N + 1, dtype=torch.int64, device=dev); d_occ = torch.full((eocc.size,), -1, dtype=torch.int64, device=dev)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         tot = gpu.locate_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(),
@@ -368,3 +362,19 @@ def test_two_slice_pipelined_locate_equals_unsliced_and_oracle():
     s.synchronize()
     assert tot == eocc.size and np.array_equal(d_occ.cpu().numpy().view(np.uint64), eocc)
     assert np.array_equal(d_off.cpu().numpy().view(np.uint64), eoff)
+
+
+def test_item_list_regrows_when_chains_exceed_the_guess():
+    """The item list of the two-pass expansion is sized before the totals are known (two chains per pattern + the
+    capacity / SEG); short patterns on a text of many short runs cut every range into far more chains than that: the
+    kernels skip themselves on the device and the host queues them again with a list that fits."""
+    rng = np.random.default_rng(5)
+    text = rng.integers(97, 101, size=120_000, dtype=np.uint8)   # iid: r ~ n, every range spans ~ its length in runs
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    gpu = rib.GpuIndex(host, seed_jump=16)
+    assert gpu.info.seed_jump == 16
+    for (N, m) in [(8, 1), (40, 2), (300, 3)]:
+        patt = mixed_patterns(text, N, m, N, alphabet=np.frombuffer(b"abcd", dtype=np.uint8))
+        _check_all(gpu, port, patt, N, m, "many chains N=%d m=%d" % (N, m))
+        assert gpu.timing()["chains"] > 2 * N + 1024 or m == 3

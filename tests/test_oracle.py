@@ -163,3 +163,21 @@ def test_reference_navigation_equals_suffix_array_truth():
         assert np.array_equal(ref.navigate(2, pos), fl)
         assert np.array_equal(ref.navigate(3, pos), f_at.astype(np.uint64))
         assert np.array_equal(ref.get_bwt(), bwt)
+
+
+@needs_ref
+def test_reference_index_assembled_from_logical_arrays_equals_reference_built():
+    """ref_from_logical (the reference's structure constructors over a given BWT + samples: bench.py's reference arm uses
+    it when no reference-built .ri travelled) gives the index the reference's constructor builds: same logical content,
+    same count / locate_all answers."""
+    for text in [rib.gen_text("dna_drift", 150_000, 2_000, 3, 8), rib.gen_text("versioned_doc", 60_000, 2_000, 96, 2),
+                 np.frombuffer(b"abracadabra", dtype=np.uint8), np.frombuffer(b"a", dtype=np.uint8)]:
+        built = ob.RefIndex.from_text(text)
+        host = rib.HostIndex.from_text(text)
+        made = ob.RefIndex.from_logical(host.arrays())
+        e1, e2 = built.extract(), made.extract()
+        assert all(np.array_equal(e1[k], e2[k]) for k in ("F", "run_heads", "run_lens", "samples_last", "pred_pos", "pred_to_run"))
+        N, m = 200, min(6, text.size)
+        patt = mixed_patterns(text, N, m, 3)
+        a, b = built.locate(patt, N, m), made.locate(patt, N, m)
+        assert all(np.array_equal(x, y) for x, y in zip(a[:4], b[:4]))
