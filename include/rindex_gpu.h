@@ -142,6 +142,11 @@ typedef struct rig_check_report {
 
 #define RIG_LOCATE_SORT 1u   /* -o: per-pattern ascending order instead of locate_all order */
 #define RIG_LOCATE_CHECK 2u  /* -c: needs rig_text_attach; implies the sort, as in the reference */
+#define RIG_LOCATE_DEVICE_ONLY 4u /* rig_locate_batch_ex: the occurrences stay in the library's own device buffer (occ and
+                                     occ_capacity are ignored; the buffer grows to the batch as needed, without repeating the
+                                     search); ranges, offsets and *occ_total come back as usual. What ri-locate does with its
+                                     occurrences when neither -o nor -c is given: it drops them (ri-locate.cpp:144). Fetch any
+                                     part afterwards with rig_fetch_occurrences. */
 
 /* Copy the indexed text (len = n - 1 bytes, no terminator) into HBM for rig_check_dev / RIG_LOCATE_CHECK. */
 int rig_text_attach(rig_index* idx, const uint8_t* text, uint64_t len);
@@ -156,6 +161,14 @@ int rig_check_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_
 int rig_locate_batch_ex(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
                         uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
                         rig_check_report* report);
+
+/* Occurrences [first, first + count) of this index's most recent RIG_LOCATE_DEVICE_ONLY call, copied to a HOST buffer
+ * (after RIG_LOCATE_SORT / _CHECK: in per-pattern ascending order). */
+int rig_fetch_occurrences(rig_index* idx, uint64_t first, uint64_t count, uint64_t* out);
+/* Page-locked host memory for pattern / result buffers (cudaMallocHost / cudaFreeHost): downloads into pageable memory
+ * run at a fraction of the PCIe rate. NULL on failure. */
+void* rig_host_alloc(uint64_t bytes);
+void rig_host_free(void* p);
 
 /* rig_locate_batch with 32-bit positions, for indexes with n <= 2^32 (RIG_ERR_ARG otherwise): the same values as
  * rig_locate_batch narrowed on the device, half the bytes over PCIe (the host-buffer call is PCIe-bound: 8.4 ms

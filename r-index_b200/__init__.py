@@ -11,7 +11,7 @@ The directory name has a hyphen (it mirrors the reference repo's name), so impor
 """
 from ._build import build_all, build_gpu, build_host, build_cli, GPU_SO, HOST_SO, CLI_DIR  # noqa: F401
 from ._host import HostIndex, gen_text, gen_patterns, suffix_array, parse_pattern_file, write_pattern_file  # noqa: F401
-from ._gpu import (GpuIndex, RigError, CheckReport, LOCATE_SORT, LOCATE_CHECK, NAV_BWT, NAV_LF, NAV_FL, NAV_F_AT,  # noqa: F401
+from ._gpu import (GpuIndex, RigError, CheckReport, LOCATE_SORT, LOCATE_CHECK, LOCATE_DEVICE_ONLY, NAV_BWT, NAV_LF, NAV_FL, NAV_F_AT,  # noqa: F401
                    device_count, gpu_lib, DECLARED_SYMBOLS)
 
 __all__ = ["HostIndex", "GpuIndex", "RigError", "gen_text", "gen_patterns", "suffix_array", "device_count",

@@ -19,7 +19,7 @@ DECLARED_SYMBOLS = [
     "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
     "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_locate_batch32",
-    "rig_break_range_batch", "rig_closest_run_break_batch",
+    "rig_break_range_batch", "rig_closest_run_break_batch", "rig_fetch_occurrences", "rig_host_alloc", "rig_host_free",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -61,7 +61,7 @@ class CheckReport(ctypes.Structure):
         return self.wrong_count_patterns == 0 and self.wrong_occurrences == 0 and self.unsorted_or_duplicate == 0
 
 
-LOCATE_SORT, LOCATE_CHECK = 1, 2
+LOCATE_SORT, LOCATE_CHECK, LOCATE_DEVICE_ONLY = 1, 2, 4
 NAV_BWT, NAV_LF, NAV_FL, NAV_F_AT = 0, 1, 2, 3
 
 
@@ -107,6 +107,10 @@ def gpu_lib():
         lib.rig_locate_batch32.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _u32]
         lib.rig_break_range_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]
         lib.rig_closest_run_break_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
+        lib.rig_fetch_occurrences.argtypes = [_vp, _u64, _u64, _vp]
+        lib.rig_host_alloc.restype = _vp
+        lib.rig_host_alloc.argtypes = [_u64]
+        lib.rig_host_free.argtypes = [_vp]
         lib.rig_text_attach.argtypes = [_vp, _vp, _u64]
         lib.rig_sort_occurrences_dev.argtypes = [_vp, _u64, _vp, _vp, _u64, _vp]
         lib.rig_check_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.c_int,
@@ -287,6 +291,26 @@ class GpuIndex:
         if rc != 0:
             raise RigError(rc, "rig_locate_batch_ex")
         return lo, hi, off, occ, (rep if flags & LOCATE_CHECK else None)
+
+    def locate_keep(self, patterns, N, m, flags=0):
+        """rig_locate_batch_ex with RIG_LOCATE_DEVICE_ONLY: one call, occurrences stay on the device.
+        Returns (lo, hi, occ_offsets, total, report-or-None); fetch positions with fetch()."""
+        p = _as_u8(patterns)
+        lo = np.empty(N, dtype=np.uint64); hi = np.empty(N, dtype=np.uint64); off = np.empty(N + 1, dtype=np.uint64)
+        tot = _u64(0)
+        rep = CheckReport()
+        rc = self.lib.rig_locate_batch_ex(self.h, _ptr(p), N, m, _ptr(lo), _ptr(hi), _ptr(off), None, 0, ctypes.byref(tot),
+                                          flags | LOCATE_DEVICE_ONLY, ctypes.byref(rep))
+        if rc != 0:
+            raise RigError(rc, "rig_locate_batch_ex")
+        return lo, hi, off, int(tot.value), (rep if flags & LOCATE_CHECK else None)
+
+    def fetch(self, first, count):
+        out = np.empty(count, dtype=np.uint64)
+        rc = self.lib.rig_fetch_occurrences(self.h, first, count, _ptr(out))
+        if rc != 0:
+            raise RigError(rc, "rig_fetch_occurrences")
+        return out
 
     def sort_dev(self, N, d_off, d_occ, total, stream=None):
         rc = self.lib.rig_sort_occurrences_dev(self.h, N, d_off, d_occ, total, stream)

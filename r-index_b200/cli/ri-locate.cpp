@@ -90,22 +90,33 @@ int main(int argc, char** argv) {
     auto u2 = high_resolution_clock::now();
     const uint64_t n = pf.n, m = pf.m;
     std::vector<uint64_t> lo(n), hi(n);
-    std::vector<std::vector<uint64_t>> off, occ;
+    std::vector<std::vector<uint64_t>> off;
+    std::vector<uint64_t> cuts, totals;
     uint32_t flags = 0;
     if (ofile.compare(string()) != 0) flags |= RIG_LOCATE_SORT;
     if (c) { flags |= RIG_LOCATE_CHECK; fleet.attach_text((const uint8_t*)text.data(), text.size()); }
     std::vector<rig_check_report> reports;
-    uint64_t occ_tot = fleet.locate(pf.body.data(), n, m, lo.data(), hi.data(), off, occ, flags, &reports);
+    // the occurrences stay on the devices: the reference drops each pattern's vector unless -o / -c is given
+    // (ri-locate.cpp:144); the -c check itself runs on the device; only -o needs the positions on the host
+    uint64_t occ_tot = fleet.locate(pf.body.data(), n, m, lo.data(), hi.data(), off, cuts, totals, flags, &reports);
 
     const int G = fleet.size();
     if (ofile.compare(string()) != 0) {
-        for (int g = 0; g < G; ++g)  // already sorted per pattern on the device (reference :147)
-            for (uint64_t x : occ[g]) out << (int)x << endl;
+        const uint64_t CH = 1ull << 24;  // 128 MB of positions per download, page-locked
+        uint64_t* buf = (uint64_t*)rig_host_alloc(CH * 8);
+        if (!buf) die(RIG_ERR_NOMEM, "rig_host_alloc");
+        for (int g = 0; g < G; ++g)      // already sorted per pattern on the device (reference :147)
+            for (uint64_t f = 0; f < totals[g]; f += CH) {
+                const uint64_t k = std::min<uint64_t>(CH, totals[g] - f);
+                fleet.fetch(g, f, k, buf);
+                for (uint64_t t = 0; t < k; ++t) out << (int)buf[t] << endl;
+            }
+        rig_host_free(buf);
     }
     if (c) {  // check occurrences (reference :156-190): the first offending pattern, in shard order
         for (int g = 0; g < G; ++g) {
             const rig_check_report& r = reports[g];
-            const uint64_t a = n * g / G;
+            const uint64_t a = cuts[g];
             if (r.wrong_count_patterns || r.unsorted_or_duplicate) {
                 const uint64_t i = a + (r.first_bad_pattern != ~0ull ? r.first_bad_pattern : 0);
                 const uint64_t want = hi[i] >= lo[i] ? (hi[i] - lo[i]) + 1 : 0;

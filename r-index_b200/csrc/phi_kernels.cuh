@@ -31,6 +31,7 @@
 // All value arithmetic is done in the table's word type (u32 when n < 2^32-1): the kernel was
 // measured issue-bound at 113 instructions per iteration with 64-bit arithmetic.
 #pragma once
+#include <type_traits>
 #include "search_kernels.cuh"
 
 namespace rigk {
@@ -220,6 +221,11 @@ __device__ __forceinline__ WT seed_hop(const FlatDev& ix, WT v) {
     return x;
 }
 
+__device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
+    // (the .L2::evict_first qualifier is only accepted on 256-bit stores; .cs is the 128-bit streaming form)
+    asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
+
 #define RIG_LINE 16  // output slots per 128-byte line
 
 // Device-side view of a locate call's counters (rig_index::d_counters): the expansion kernels read the totals the
@@ -340,10 +346,10 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
     const u32 ESZ = ix.phi.esz;
     const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
-    const u64 n_items = __ldcg(ctr + RIG_CTR_ITEMS);
-    const u64 T = (u64)gridDim.x * blockDim.x;
+    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);   // the host keeps the item list below 2^31 entries
+    const u32 T = gridDim.x * blockDim.x;
     const ulonglong2* itp = reinterpret_cast<const ulonglong2*>(items);
-    u64 inext = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 inext = blockIdx.x * blockDim.x + threadIdx.x;
     bool have_next = inext < n_items;
     ulonglong2 nit = make_ulonglong2(0, 0);
     if (have_next) nit = __ldcs(itp + inext);
@@ -406,11 +412,8 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
         u64* const so = o;           // where this trip's group goes
         u32 left_next = left - cnt;
         u64* o_next = o + cnt;
-        bool tail = false;           // the value carried out of the item's last full group goes on one more slot
-        WT tv = 0;
-        u64* to = o_next;
         if (emit && left_next <= 1) {  // the item ends with this group: switch to the lane's next item in this trip
-            tail = left_next == 1; tv = vn;
+            if (left_next == 1) __stcs(o_next, (u64)vn);  // the value carried out of the item's last full group
             left_next = 0;
             if (have_next) RIG_TAKE_ITEM(left_next, o_next, vn);
         }
@@ -430,7 +433,6 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
                 for (int t = 0; t < D - 1; ++t)
                     if ((u32)t < cnt) __stcs(so + t, (u64)g[t]);
             }
-            if (tail) __stcs(to, (u64)tv);
         }
         v = vn;
         left = left_next;
@@ -439,6 +441,297 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
         for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
 #undef RIG_TAKE_ITEM
+}
+
+// The same pass with WARP-LEVEL batches (A/B alternative, RIG_VARIANT bit 6): a warp takes 32 consecutive items,
+// walks them in lockstep until its slowest lane is done, then strides to its next 32. Fewer live registers per
+// lane (no prefetched next item, no in-trip switch) = more resident warps; lanes idle while the warp's longest
+// item finishes.
+template <typename WT, int D, bool KEEP>
+__global__ void __launch_bounds__(256)
+phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
+                        u64 cap, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
+    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
+    const u32 ESZ = ix.phi.esz;
+    const bool PK = ix.phi.packed != 0;
+    constexpr bool W32 = sizeof(WT) == 4;
+    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);
+    const u32 T = gridDim.x * blockDim.x;
+    const WT n = (WT)ix.n;
+    const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
+    const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
+    const u32 shift = ix.phi.shift;
+    for (u32 ib = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); ib < n_items; ib += T) {  // warp-uniform
+        const u32 i = ib + (threadIdx.x & 31u);
+        u32 left = 0;  // slots of this item still to be written, the seed's included
+        u64* o = out;
+        WT v = 0;
+        if (i < n_items) {
+            const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
+            left = (u32)(it.x & 255u) + 1;
+            o = out + (it.x >> 8);
+            v = (WT)it.y;
+        }
+        bool searching = false;
+        u32 slo = 0, shi = 0, probe = 0;
+        WT e[RW];
+        if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
+        while (__any_sync(RIG_FULL, left > 1)) {
+            bool emit = false;
+            WT g[D];
+            u32 cnt = 0;
+            WT vn = v;
+            if (left > 1) {
+                if (!searching) {
+                    emit = v < e[D];
+                    slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+                    searching = !emit;
+                } else if (slo == shi) {
+                    emit = true;
+                } else if (e[D] <= v) {
+                    slo = probe; emit = (slo == shi);
+                } else {
+                    shi = probe - 1; emit = false;
+                }
+                if (emit) {
+                    searching = false;
+                    slo = shi = 0;
+                    g[0] = v;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        WT x = v + e[t];
+                        if ((W32 && x < v) || x >= n) x -= n;
+                        if (t < D - 1) g[t + 1] = x; else vn = x;
+                    }
+                    cnt = min(left, (u32)D);
+                }
+            }
+            const u32 left_next = left - cnt;
+            probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+            WT e2[RW];
+            if (left_next > 1)
+                load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
+            if (emit) {
+                if (cnt == (u32)D) {
+                    store_group<WT, D>(o, g);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < D - 1; ++t)
+                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                }
+                o += cnt;
+            }
+            v = vn;
+            left = left_next;
+#pragma unroll
+            for (int t = 0; t < RW; ++t) e[t] = e2[t];
+        }
+        if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+    }
+}
+
+// ---- lookup of one value: the D deltas of the piece holding v ------------------------------------------------
+// e holds the bucket record of v on entry (already loaded: the caller issued the load when it learned v); on return
+// e[0..D) are the deltas of v's piece. The search inside a crowded bucket runs HERE, inside the trip (its loads are
+// dependent ones and the other lanes of the warp wait), so that every lane of a warp finishes the trip with its
+// group emitted: the warp stays in lockstep and completes whole 128-byte lines together (phi_window_line_kernel).
+template <typename WT, int D, int RW, bool KEEP>
+__device__ __forceinline__ void resolve_piece(const char* pent, u32 ESZ, bool PK, WT v, WT (&e)[RW]) {
+    if (v < e[D]) return;                       // no piece begins inside the bucket at or below v: the record's deltas
+    u32 slo = (u32)e[D + 1], shi = slo + (u32)e[D + 2] - 1;  // invariant: start[slo] <= v
+    bool have = false;                          // e already holds pent[slo]
+    while (slo < shi) {
+        const u32 probe = (slo + shi + 1) >> 1;
+        load_entry<WT, RW, KEEP>(pent + (u64)probe * ESZ, e, PK);
+        if (e[D] <= v) { slo = probe; have = true; } else { shi = probe - 1; have = false; }
+    }
+    if (!have) load_entry<WT, RW, KEEP>(pent + (u64)slo * ESZ, e, PK);
+}
+
+// "Window pass" with WHOLE-LINE stores (the default). PERSISTENT; a warp takes 32 consecutive items and walks them in
+// LOCKSTEP: every trip, every active lane emits one group of D occurrences into its own row of a shared-memory
+// staging tile (as table words: 32-bit when n < 2^32); after 16 / D trips every active lane holds one complete
+// 128-byte output line, and the warp writes the rows out together — 8 lanes x 16 bytes per line, 4 whole lines per
+// store instruction, the 64-bit widening done on the way out. One L2 request per 128-byte line instead of one per
+// 32-byte sector: the direct-store form of this pass ran at the L2 tag-lookup rate (26 M lookups + 26 M sector
+// stores per launch on config C2, lts__t_tag_requests 75-80%), and its stores were half of those requests.
+// What is left of an item below a whole line (< 16 slots) is written by the direct path of the batch kernel.
+template <typename WT, int D, bool KEEP, int MINB, bool TMA>
+__global__ void __launch_bounds__(256, MINB)
+phi_window_line_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
+                       u64 cap, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
+    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
+    constexpr int GPL = RIG_LINE / D;                       // trips per line
+    // staged row: one line of table words (of 64-bit output words when the rows leave through the bulk-copy engine,
+    // which moves bytes as they are) + 16 bytes (bank spread)
+    typedef typename std::conditional<TMA, u64, WT>::type ST;
+    constexpr int ROWB = RIG_LINE * (int)sizeof(ST) + 16;
+    __shared__ __align__(128) unsigned char stage[8][32][ROWB];
+    const u32 ESZ = ix.phi.esz;
+    const bool PK = ix.phi.packed != 0;
+    constexpr bool W32 = sizeof(WT) == 4;
+    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);
+    const u32 T = gridDim.x * blockDim.x;
+    const WT n = (WT)ix.n;
+    const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
+    const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
+    const u32 shift = ix.phi.shift;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned char* const myrow = &stage[wid][lane][0];
+    for (u32 ib = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); ib < n_items; ib += T) {  // warp-uniform
+        const u32 i = ib + lane;
+        u32 left = 0;  // slots of this item still to be written, the seed's included
+        u64* o = out;
+        WT v = 0;
+        if (i < n_items) {
+            const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
+            left = (u32)(it.x & 255u) + 1;
+            o = out + (it.x >> 8);
+            v = (WT)it.y;
+        }
+        WT e[RW];
+#pragma unroll
+        for (int t = 0; t < RW; ++t) e[t] = 0;
+        if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
+        // ---- whole lines, in lockstep ----
+        while (__any_sync(RIG_FULL, left >= (u32)RIG_LINE)) {
+            const bool act = left >= (u32)RIG_LINE;
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) {
+                if (act) {
+                    WT x[D];
+                    x[0] = v;
+                    WT vn = v;
+                    // the group needs a lookup unless its only slot is the item's last one (D = 1, left = 16, g = 15):
+                    // no entry was loaded for it then
+                    if (D > 1 || left - (u32)(g * D) > 1) {
+                        resolve_piece<WT, D, RW, KEEP>(pent, ESZ, PK, v, e);
+#pragma unroll
+                        for (int t = 0; t < D; ++t) {
+                            WT y = v + e[t];
+                            if ((W32 && y < v) || y >= n) y -= n;
+                            if (t < D - 1) x[t + 1] = y; else vn = y;
+                        }
+                    }
+                    if (left - (u32)((g + 1) * D) > 1)   // a further lookup follows (one slot left needs none: it holds vn)
+                        load_entry<WT, RW, KEEP>(rec + (u64)(vn >> shift) * ESZ, e, PK);
+                    ST* dst = reinterpret_cast<ST*>(myrow) + g * D;
+                    if (TMA && g == 0) {   // the row's previous bulk copy must have read it (issued a whole trip ago)
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    if constexpr (std::is_same<ST, WT>::value && D * sizeof(WT) == 16) {
+                        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(x);
+                    } else if constexpr (std::is_same<ST, WT>::value && D * sizeof(WT) == 32) {
+                        reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(x)[0];
+                        reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(x)[1];
+                    } else if constexpr (D % 2 == 0) {
+#pragma unroll
+                        for (int t = 0; t < D; t += 2)
+                            reinterpret_cast<ulonglong2*>(dst)[t / 2] = make_ulonglong2((u64)x[t], (u64)x[t + 1]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < D; ++t) dst[t] = (ST)x[t];
+                    }
+                    v = vn;
+                }
+            }
+            if constexpr (TMA) {
+                // every lane hands its own row to the bulk-copy engine: 128 bytes shared -> global, one L2 request per
+                // line and no store payload through the LSU / L1-to-crossbar port (the engine reads shared memory itself)
+                if (act) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const u32 saddr = (u32)__cvta_generic_to_shared(myrow);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" :: "l"(o), "r"(saddr) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+            __syncwarp();
+            // write out the completed rows: lane L carries 16 bytes (2 slots) of line 4r + L/8
+            const u32 mask = __ballot_sync(RIG_FULL, act);
+            const u32 c = lane & 7u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const u32 j = 4u * r + (lane >> 3);
+                const unsigned long long lp = __shfl_sync(RIG_FULL, (unsigned long long)o, j);
+                if ((mask >> j) & 1u) {
+                    const unsigned char* src = &stage[wid][j][0];
+                    u64 a0, a1;
+                    if constexpr (W32) {
+                        const uint2 w2 = reinterpret_cast<const uint2*>(src)[c];
+                        a0 = w2.x; a1 = w2.y;
+                    } else {
+                        const ulonglong2 w2 = reinterpret_cast<const ulonglong2*>(src)[c];
+                        a0 = w2.x; a1 = w2.y;
+                    }
+                    stg128_stream(reinterpret_cast<u64*>(lp) + 2 * c, a0, a1);
+                }
+            }
+            __syncwarp();
+            }
+            if (act) { o += RIG_LINE; left -= RIG_LINE; }
+        }
+        if constexpr (TMA) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // ---- what is left of the item (< one line): direct stores, per-lane state machine ----
+        bool searching = false;
+        u32 slo = 0, shi = 0, probe = 0;
+        while (__any_sync(RIG_FULL, left > 1)) {
+            bool emit = false;
+            WT g[D];
+            u32 cnt = 0;
+            WT vn = v;
+            if (left > 1) {
+                if (!searching) {
+                    emit = v < e[D];
+                    slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+                    searching = !emit;
+                } else if (slo == shi) {
+                    emit = true;
+                } else if (e[D] <= v) {
+                    slo = probe; emit = (slo == shi);
+                } else {
+                    shi = probe - 1; emit = false;
+                }
+                if (emit) {
+                    searching = false;
+                    slo = shi = 0;
+                    g[0] = v;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        WT x = v + e[t];
+                        if ((W32 && x < v) || x >= n) x -= n;
+                        if (t < D - 1) g[t + 1] = x; else vn = x;
+                    }
+                    cnt = min(left, (u32)D);
+                }
+            }
+            const u32 left_next = left - cnt;
+            probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+            WT e2[RW];
+#pragma unroll
+            for (int t = 0; t < RW; ++t) e2[t] = e[t];
+            if (left_next > 1)
+                load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
+            if (emit) {
+                if (cnt == (u32)D) {
+                    store_group<WT, D>(o, g);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < D - 1; ++t)
+                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                }
+                o += cnt;
+            }
+            v = vn;
+            left = left_next;
+#pragma unroll
+            for (int t = 0; t < RW; ++t) e[t] = e2[t];
+        }
+        if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+    }
 }
 
 }  // namespace rigk

@@ -83,9 +83,13 @@ struct rig_index {
     rig_timing timing{};
     int variant = 0;  // see rig_index_create_ex
     size_t phi_bytes = 0;        // rec + pent span in the arena (warmed into L2 before each expansion)
+    size_t lf_bytes = 0;         // span of the backward-search arrays at the head of the arena (warmed into L2 before each search)
     size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
     float l2_hit_ratio = 1.f;
     bool timing_pending = false;
+    uint64_t last_items_cap = 0;   // item-list capacity the most recent expansion was queued with
+    bool last_two_pass = false;
+    uint64_t kept_total = 0;       // occurrences of the most recent RIG_LOCATE_DEVICE_ONLY call, still in `occ`
     bool ev_valid[8] = {false, false, false, false, false, false, false, false};
 };
 
@@ -133,7 +137,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit4 expansion without its stores (diagnostic), bit5 single-pass expansion, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern, bit6 window kernel stages whole output lines in shared memory (measured slower than direct group stores: DESIGN.md §5)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit6 window pass with direct sector stores and warp-level item batches, bit8 the same with per-lane refill (A/B alternatives of the default whole-line window pass), bit11 whole-line window pass whose rows leave through the bulk-copy engine (cp.async.bulk shared -> global) instead of the cooperative vector stores, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -222,6 +226,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.seed.pent = (const void*)(A + parts[11].off);
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
+    ix->lf_bytes = parts[8].off;  // F, sid, start, block records, bstart, last, bdir, samples_last
     d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
 
     // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
@@ -298,6 +303,17 @@ namespace {
 
 // workspace of the search kernel's fused offset scan: ticket + RIG_TILE_WORDS words per tile of 128 patterns
 size_t tile_ws_words(uint64_t N) { return 2 + RIG_TILE_WORDS * ((N + 127) / 128) + 2; }
+
+// Pull the backward-search structures (block records, directories, run starts, samples) into L2 with one streaming
+// pass before the search when they are small enough to stay there (<= 48 MB): the search is a chain of dependent
+// loads, and with 32 lanes in lockstep one cold line per warp-step costs the whole warp a DRAM round trip.
+// RIG_VARIANT bit 12 disables (A/B switch).
+void warm_lf(rig_index* ix, cudaStream_t st) {
+    if ((ix->variant & 4096) || !ix->lf_bytes || ix->lf_bytes > (48u << 20)) return;
+    const uint64_t lines = (ix->lf_bytes + 127) / 128;
+    rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->arena, ix->lf_bytes);
+    ix->timing.launches += 1;
+}
 
 template <bool LOCATE>
 int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
@@ -394,11 +410,16 @@ int count_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull*
     int rc;
     CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
     if ((rc = rec(ix, 1, st))) return rc;
+    if (N) warm_lf(ix, st);
     if (N && (rc = launch_search<false>(ix, d_patt, N, m, d_lo, d_hi, nullptr, st))) return rc;
     if ((rc = rec(ix, 2, st))) return rc;
     CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
     return RIG_OK;
 }
+
+int sort_dev(rig_index* ix, uint64_t N, const ull* d_off, ull* d_occ, uint64_t total, cudaStream_t st);
+int check_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, const ull* d_lo, const ull* d_hi,
+              const ull* d_off, const ull* d_occ, uint64_t total, int sorted, rig_check_report* report, cudaStream_t st);
 
 // resident CTAs of a kernel on this device (persistent grids are sized SMs x this)
 template <typename K>
@@ -448,7 +469,10 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
     do {                                                                                                        \
         if (two_pass) {                                                                                         \
             auto k1 = rigk::phi_expand_kernel<W, DD, KP, true>;                                                 \
-            auto k2 = rigk::phi_window_kernel<W, DD, KP>;                                                       \
+            auto k2 = (ix->variant & 64) ? rigk::phi_window_batch_kernel<W, DD, KP>                             \
+                      : ((ix->variant & 256) ? rigk::phi_window_kernel<W, DD, KP>                               \
+                      : ((ix->variant & 2048) ? rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), true>  \
+                                              : rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), false>)); \
             uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
             uint64_t g2 = (uint64_t)ix->sm_count * resident_ctas(k2, wthreads);                                 \
             g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
@@ -497,31 +521,42 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
 
 // search (+ offsets) and expansion, queued back to back; the host then waits for the totals only (they are copied
 // out right after the search), while the expansion is already running: events 1..4 on `st`.
+// own_occ (host-buffer entry points with RIG_LOCATE_DEVICE_ONLY): the occurrences go to the library's own buffer,
+// which is grown to the batch total when it is too small — only the expansion is queued again, not the search.
 int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
-               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st) {
+               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st, DevBuf* own_occ = nullptr) {
     int rc;
     if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
         (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 4) * 8)) ||
         (rc = ix->sums.ensure((std::max<uint64_t>(tile_ws_words(N), 2 * ((N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE) + 8)) * 8)))
         return rc;
-    // Two passes when the index has a seed table and the output array is line-aligned (the window kernel writes
-    // whole 128-byte lines); otherwise the single-pass walk.
+    if (own_occ) { d_occ = (ull*)own_occ->p; cap = own_occ->cap / 8; }
     const uint32_t SEG = ix->d.seed.J;
-    const bool want = d_occ != nullptr && cap > 0 && N > 0;
-    const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
-    // Item list: sized BEFORE the totals are known, from the capacity the caller offers (total <= cap or nothing
-    // runs), the list kept from earlier calls, and a guess of two chains per pattern; the kernels check the exact
-    // bound on the device and the host re-launches them below if the guess was short.
-    auto items_bound = [&](uint64_t total, uint64_t chains) { return total / SEG + chains; };
-    uint64_t items_cap = 0;
-    if (want && two_pass) {
-        const uint64_t guess = items_bound(std::min<uint64_t>(cap, 1ull << 33), 2 * N + 1024) + 32;
-        if (ix->items.cap < guess * 16 && (rc = ix->items.ensure(std::min<uint64_t>(guess * 16, 1ull << 30)))) return rc;
-        items_cap = ix->items.cap / 16 - 32;
-    }
+    auto items_bound = [&](uint64_t total, uint64_t chains) { return total / (SEG ? SEG : 1) + chains; };
+    // Two passes when the index has a seed table and the output array is line-aligned (the window kernel writes
+    // whole 128-byte lines); otherwise the single-pass walk. The item list is sized BEFORE the totals are known,
+    // from the capacity the caller offers (total <= cap or nothing runs), the list kept from earlier calls, and a
+    // guess of two chains per pattern; the kernels check the exact bound on the device, and the host queues them
+    // again below if the guess was short. `exact` = the totals are known (re-launch).
+    auto queue_expansion = [&](uint64_t exact_items) -> int {
+        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
+        uint64_t items_cap = 0;
+        if (two_pass) {
+            const uint64_t want_items = exact_items ? exact_items + 64 : items_bound(std::min<uint64_t>(cap, 1ull << 33), 2 * N + 1024) + 32;
+            if (exact_items && want_items >= (1ull << 31)) return RIG_ERR_ARG;  // 32-bit item indices in the window pass: > 1.3e11 occurrences in one call
+            if (ix->items.cap < want_items * 16) {
+                int r2 = ix->items.ensure(exact_items ? want_items * 16 : std::min<uint64_t>(want_items * 16, 1ull << 30));
+                if (r2) return r2;
+            }
+            items_cap = ix->items.cap / 16 - 32;
+        }
+        ix->last_items_cap = items_cap; ix->last_two_pass = two_pass;
+        return launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st);
+    };
     CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(ull), st));
     if ((rc = rec(ix, 1, st))) return rc;
     if (N) {
+        warm_lf(ix, st);
         if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, d_occoff, st))) return rc;
     } else {
         CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
@@ -530,30 +565,92 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
     CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaEventRecord(ix->ev_scan, st));
     if ((rc = rec(ix, 3, st))) return rc;
-    if (want) {
+    bool queued = false;
+    if (d_occ != nullptr && cap > 0 && N > 0) {
         // warm the Phi tables into L2 (RIG_VARIANT bit2 disables: A/B switch)
         if (!(ix->variant & 4) && ix->phi_bytes) {
             const uint64_t lines = (ix->phi_bytes + 127) / 128;
             rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
             ix->timing.launches += 1;
         }
-        if ((rc = launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st))) return rc;
+        if ((rc = queue_expansion(0))) return rc;
+        queued = true;
     }
     CU_TRY(cudaEventSynchronize(ix->ev_scan));  // the expansion is queued (or running) behind it
     const uint64_t total = ix->h_counters[RIG_CTR_TOTAL], chains = ix->h_counters[RIG_CTR_CHAINS];
-    const bool fits = !(total > cap || (total && !d_occ));
-    if (want && fits && two_pass && items_bound(total, chains) > items_cap) {
-        // the kernels above returned at once (same test on the device): grow the list and queue them again
-        if ((rc = ix->items.ensure((items_bound(total, chains) + 64) * 16))) return rc;
-        items_cap = ix->items.cap / 16 - 32;
+    bool fits = !(total > cap || (total && !d_occ));
+    if (!fits && own_occ && total) {   // grow the library's buffer to this batch; the search results stay valid on the device
+        if ((rc = own_occ->ensure(total * 8 + 128))) return rc;
+        d_occ = (ull*)own_occ->p; cap = own_occ->cap / 8;
+        fits = true; queued = false;
+    }
+    const bool need_items = fits && total && ix->d.seed.J > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
+    if (fits && total && (!queued || (need_items && items_bound(total, chains) > ix->last_items_cap))) {
+        // not queued yet (buffer just grown), or the kernels returned at once because the item list was too short
+        // (same test on the device): queue the expansion (again) with exact sizes
         CU_TRY(cudaMemsetAsync(ix->d_counters + RIG_CTR_ITEMS, 0, sizeof(ull), st));
-        if ((rc = launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st))) return rc;
+        if ((rc = queue_expansion(need_items ? items_bound(total, chains) : 0))) return rc;
     }
     ix->timing.occ_total = total;
     ix->timing.chains = chains;
     if (occ_total) *occ_total = total;
     if ((rc = rec(ix, 4, st))) return rc;
     return fits ? RIG_OK : RIG_ERR_CAPACITY;
+}
+
+// The host-buffer locate calls: upload the patterns, locate, optional -o / -c post-processing on the device, download.
+// occ32: narrow the positions to 32 bits on the device before the download (rig_locate_batch32).
+int locate_host(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
+                uint64_t* occ_offsets, void* occ, bool occ32, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
+                rig_check_report* report) {
+    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
+    if ((flags & RIG_LOCATE_CHECK) && (!report || !ix->has_text || occ32)) return RIG_ERR_ARG;
+    if (occ32 && ix->d.n > 0xFFFFFFFFull) return RIG_ERR_ARG;  // positions would not fit
+    const bool devonly = (flags & RIG_LOCATE_DEVICE_ONLY) != 0;
+    if (devonly && occ32) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc;
+    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
+        (rc = ix->occoff.ensure((N + 2) * 8)))
+        return rc;
+    const bool want = devonly || (occ && occ_capacity);
+    if (!devonly && want && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
+    if (occ32 && want && (rc = ix->occ32.ensure(occ_capacity * 4 + 16))) return rc;
+    begin_call(ix);
+    if ((rc = rec(ix, 0, st))) return rc;
+    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
+                         want ? (ull*)ix->occ.p : nullptr, want ? occ_capacity : 0, &total, st, devonly ? &ix->occ : nullptr);
+    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
+    if (occ_total) *occ_total = total;
+    ix->kept_total = (lrc == RIG_OK && devonly) ? total : 0;
+    if (lrc == RIG_OK && total && (flags & (RIG_LOCATE_SORT | RIG_LOCATE_CHECK))) {  // the reference sorts for -o and for -c (:147,:159)
+        if ((rc = sort_dev(ix, N, (const ull*)ix->occoff.p, (ull*)ix->occ.p, total, st))) return rc;
+    }
+    if (lrc == RIG_OK && (flags & RIG_LOCATE_CHECK)) {
+        if ((rc = check_dev(ix, (const uint8_t*)ix->patt.p, N, m, (const ull*)ix->lo.p, (const ull*)ix->hi.p,
+                            (const ull*)ix->occoff.p, (const ull*)ix->occ.p, total, 1, report, st)))
+            return rc;
+    }
+    if (lrc == RIG_OK && total && occ32) {
+        const uint64_t nb = ((total + 3) / 4 + 255) / 256;
+        if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+        rigk::narrow_kernel<<<(unsigned)nb, 256, 0, st>>>((const ull*)ix->occ.p, (uint32_t*)ix->occ32.p, total);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 1;
+    }
+    if (N) {
+        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (lrc == RIG_OK && total && !devonly)
+        CU_TRY(cudaMemcpyAsync(occ, occ32 ? ix->occ32.p : ix->occ.p, total * (occ32 ? 4 : 8), cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 5, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return lrc;
 }
 
 }  // namespace
@@ -602,31 +699,7 @@ int rig_count_batch(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t
 
 int rig_locate_batch(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
                      uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total) {
-    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
-    CU_TRY(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
-    int rc;
-    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
-        (rc = ix->occoff.ensure((N + 2) * 8)))
-        return rc;
-    if (occ && occ_capacity && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
-    begin_call(ix);
-    if ((rc = rec(ix, 0, st))) return rc;
-    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
-    uint64_t total = 0;
-    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
-                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
-    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
-    if (occ_total) *occ_total = total;
-    if (N) {
-        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
-    }
-    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ.p, total * 8, cudaMemcpyDeviceToHost, st));
-    if ((rc = rec(ix, 5, st))) return rc;
-    CU_TRY(cudaStreamSynchronize(st));
-    return lrc;
+    return locate_host(ix, patterns, N, m, lo, hi, occ_offsets, occ, false, occ ? occ_capacity : 0, occ_total, 0, nullptr);
 }
 
 int rig_digest_dev(rig_index* ix, const uint64_t* d_values, uint64_t count, uint64_t out[2], void* stream) {
@@ -649,6 +722,7 @@ int rig_digest_dev(rig_index* ix, const uint64_t* d_values, uint64_t count, uint
 }
 
 // ---- ri-locate -o / -c on the device -------------------------------------------------
+}  // extern "C"
 namespace {
 
 int sort_dev(rig_index* ix, uint64_t N, const ull* d_off, ull* d_occ, uint64_t total, cudaStream_t st) {
@@ -720,6 +794,7 @@ int check_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, cons
 }
 
 }  // namespace
+extern "C" {
 
 int rig_text_attach(rig_index* ix, const uint8_t* text, uint64_t len) {
     if (!ix || (len && !text)) return RIG_ERR_ARG;
@@ -751,80 +826,33 @@ int rig_check_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, uint64_t
 int rig_locate_batch_ex(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
                         uint64_t* occ_offsets, uint64_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags,
                         rig_check_report* report) {
-    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns)) return RIG_ERR_ARG;
-    if ((flags & RIG_LOCATE_CHECK) && (!report || !ix->has_text)) return RIG_ERR_ARG;
-    CU_TRY(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
-    int rc;
-    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
-        (rc = ix->occoff.ensure((N + 2) * 8)))
-        return rc;
-    if (occ && occ_capacity && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
-    begin_call(ix);
-    if ((rc = rec(ix, 0, st))) return rc;
-    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
-    uint64_t total = 0;
-    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
-                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
-    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
-    if (occ_total) *occ_total = total;
-    if (lrc == RIG_OK && (flags & (RIG_LOCATE_SORT | RIG_LOCATE_CHECK))) {  // the reference sorts for -o and for -c (:147,:159)
-        if ((rc = sort_dev(ix, N, (const ull*)ix->occoff.p, (ull*)ix->occ.p, total, st))) return rc;
-    }
-    if (lrc == RIG_OK && (flags & RIG_LOCATE_CHECK)) {
-        if ((rc = check_dev(ix, (const uint8_t*)ix->patt.p, N, m, (const ull*)ix->lo.p, (const ull*)ix->hi.p,
-                            (const ull*)ix->occoff.p, (const ull*)ix->occ.p, total, 1, report, st)))
-            return rc;
-    }
-    if (N) {
-        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
-    }
-    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ.p, total * 8, cudaMemcpyDeviceToHost, st));
-    if ((rc = rec(ix, 5, st))) return rc;
-    CU_TRY(cudaStreamSynchronize(st));
-    return lrc;
+    return locate_host(ix, patterns, N, m, lo, hi, occ_offsets, occ, false, occ ? occ_capacity : 0, occ_total, flags, report);
 }
 
 // ---- 32-bit positions for texts below 4 GiB: half the bytes over PCIe -------------------------------------
 int rig_locate_batch32(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
                        uint64_t* occ_offsets, uint32_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags) {
-    if (!ix || !occ_offsets || (N && (!lo || !hi)) || (N && m && !patterns) || (flags & RIG_LOCATE_CHECK)) return RIG_ERR_ARG;
-    if (ix->d.n > 0xFFFFFFFFull) return RIG_ERR_ARG;  // positions would not fit
-    CU_TRY(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->stream;
-    int rc;
-    if ((rc = ix->patt.ensure(N * m + 16)) || (rc = ix->lo.ensure((N + 1) * 8)) || (rc = ix->hi.ensure((N + 1) * 8)) ||
-        (rc = ix->occoff.ensure((N + 2) * 8)))
-        return rc;
-    if (occ && occ_capacity && ((rc = ix->occ.ensure(occ_capacity * 8)) || (rc = ix->occ32.ensure(occ_capacity * 4 + 16)))) return rc;
-    begin_call(ix);
-    if ((rc = rec(ix, 0, st))) return rc;
-    if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
-    uint64_t total = 0;
-    int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
-                         occ ? (ull*)ix->occ.p : nullptr, occ ? occ_capacity : 0, &total, st);
-    if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
-    if (occ_total) *occ_total = total;
-    if (lrc == RIG_OK && total) {
-        if ((flags & RIG_LOCATE_SORT) && (rc = sort_dev(ix, N, (const ull*)ix->occoff.p, (ull*)ix->occ.p, total, st))) return rc;
-        const uint64_t nb = ((total + 3) / 4 + 255) / 256;
-        if (nb > 0x7fffffffull) return RIG_ERR_ARG;
-        rigk::narrow_kernel<<<(unsigned)nb, 256, 0, st>>>((const ull*)ix->occ.p, (uint32_t*)ix->occ32.p, total);
-        CU_TRY(cudaGetLastError());
-        ix->timing.launches += 1;
-    }
-    if (N) {
-        CU_TRY(cudaMemcpyAsync(lo, ix->lo.p, N * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(hi, ix->hi.p, N * 8, cudaMemcpyDeviceToHost, st));
-    }
-    CU_TRY(cudaMemcpyAsync(occ_offsets, ix->occoff.p, (N + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (lrc == RIG_OK && total) CU_TRY(cudaMemcpyAsync(occ, ix->occ32.p, total * 4, cudaMemcpyDeviceToHost, st));
-    if ((rc = rec(ix, 5, st))) return rc;
-    CU_TRY(cudaStreamSynchronize(st));
-    return lrc;
+    if (flags & (RIG_LOCATE_CHECK | RIG_LOCATE_DEVICE_ONLY)) return RIG_ERR_ARG;
+    return locate_host(ix, patterns, N, m, lo, hi, occ_offsets, occ, true, occ ? occ_capacity : 0, occ_total, flags, nullptr);
 }
+
+// occurrences [first, first + count) of the most recent RIG_LOCATE_DEVICE_ONLY call -> host
+int rig_fetch_occurrences(rig_index* ix, uint64_t first, uint64_t count, uint64_t* out) {
+    if (!ix || (count && !out) || first > ix->kept_total || count > ix->kept_total - first) return RIG_ERR_ARG;
+    if (!count) return RIG_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    CU_TRY(cudaMemcpyAsync(out, (const ull*)ix->occ.p + first, count * 8, cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(cudaStreamSynchronize(ix->stream));
+    return RIG_OK;
+}
+
+// page-locked host memory for result buffers (a download into pageable memory runs at a fraction of the link rate)
+void* rig_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rig_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- single-position navigation as batches --------------------------------------------
 int rig_navigate_batch_dev(rig_index* ix, int op, const uint64_t* d_positions, uint64_t N, uint64_t* d_out, void* stream) {

@@ -241,9 +241,9 @@ search_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, 
 // ------------------------------------------------------------------ single-pass offsets (fused into the search)
 // The one-lane-per-pattern kernel also produces the exclusive prefix sums of n_occ and of the chain counts
 // (= where every pattern's occurrences and chains start) with a decoupled look-back over its own CTAs, so a
-// locate call needs no scan launches: tile t publishes its aggregate, then the inclusive prefix once the
-// tiles before it are known. Tiles are handed out by an atomic ticket, so every tile a CTA waits for has
-// already started (it is resident or finished): no deadlock whatever the grid size.
+// locate call needs no scan launches: tile t publishes its aggregate and adds up the aggregates of the tiles
+// before it. Tiles are handed out by an atomic ticket, so every tile a CTA waits for has already started (it is
+// resident or finished): no deadlock whatever the grid size.
 //   ws[0]                       ticket counter
 //   ws[2 + 5t]                  status of tile t: 0 not ready, 1 aggregate available, 2 inclusive prefix available
 //   ws[3 + 5t], ws[4 + 5t]      aggregate of tile t (occurrences, chains)
@@ -264,9 +264,18 @@ __device__ __forceinline__ void st_relaxed_gpu(u64* p, u64 v) {
 
 // Called by every thread of a 128-thread CTA with its pattern's (n_occ, chains); ex_*: the exclusive prefix over
 // all patterns before it; incl_*: the inclusive prefix at the end of this tile (the grand totals in the last tile).
+//
+// In a locate batch every CTA finishes its search at about the same time, so a look-back that waits for a
+// predecessor's PREFIX turns into a chain of rounds (tile t learns its prefix ~t / window rounds after tile 0:
+// measured +12..16 us on the 782 tiles of config C2 with 32- and 128-wide windows). Instead every tile publishes
+// its AGGREGATE as soon as it has it, and sums the aggregates of the tiles before it in its GROUP of
+// RIG_TILE_GROUP tiles directly — 128 threads, independent loads, no chain; only the last tile of a group publishes
+// an inclusive prefix, which the tiles of the next group add: the chain has one link per 1024 tiles (131072
+// patterns), and batches that large run in waves anyway.
+#define RIG_TILE_GROUP 1024u
 __device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u64 b, u64& ex_a, u64& ex_b,
                                                     u64& incl_a, u64& incl_b) {
-    __shared__ u64 s_wa[4], s_wb[4], s_base[2];
+    __shared__ u64 s_wa[4], s_wb[4], s_ra[4], s_rb[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u64 ia = a, ib = b;
 #pragma unroll
@@ -282,49 +291,42 @@ __device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u6
         if (j < w) { pa += s_wa[j]; pb += s_wb[j]; }
         ta += s_wa[j]; tb += s_wb[j];
     }
-    if (w == 0) {
-        u64* st = ws + 2;
-        u64 sum_a = 0, sum_b = 0;
-        if (tile > 0) {
-            if (lane == 0) {
-                u64* me = st + (u64)tile * RIG_TILE_WORDS;
-                st_relaxed_gpu(me + 1, ta); st_relaxed_gpu(me + 2, tb);
-                __threadfence();
-                st_relaxed_gpu(me, 1);
-            }
-            long long j = (long long)tile - 1;
-            for (;;) {
-                const long long idx = j - lane;
-                u64 flag = 2, va = 0, vb = 0;  // before tile 0: prefix 0
-                if (idx >= 0) {
-                    const u64* t = st + (u64)idx * RIG_TILE_WORDS;
-                    do { flag = ld_relaxed_gpu(t); } while (flag == 0);
-                    __threadfence();
-                    va = ld_relaxed_gpu(t + (flag == 2 ? 3 : 1));
-                    vb = ld_relaxed_gpu(t + (flag == 2 ? 4 : 2));
-                }
-                const u32 pm = __ballot_sync(RIG_FULL, flag == 2);
-                if (pm && lane > __ffs(pm) - 1) { va = 0; vb = 0; }  // tiles beyond the nearest known prefix
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) { va += __shfl_xor_sync(RIG_FULL, va, off); vb += __shfl_xor_sync(RIG_FULL, vb, off); }
-                sum_a += va; sum_b += vb;
-                if (pm) break;
-                j -= 32;
-            }
-        }
-        if (lane == 0) {
-            u64* me = st + (u64)tile * RIG_TILE_WORDS;
-            st_relaxed_gpu(me + 3, sum_a + ta); st_relaxed_gpu(me + 4, sum_b + tb);
-            __threadfence();
-            st_relaxed_gpu(me, 2);
-            s_base[0] = sum_a; s_base[1] = sum_b;
-        }
+    u64* st = ws + 2;
+    if (threadIdx.x == 0) {   // aggregate first: nobody waits for more than this tile's own search
+        u64* me = st + (u64)tile * RIG_TILE_WORDS;
+        st_relaxed_gpu(me + 1, ta); st_relaxed_gpu(me + 2, tb);
+        __threadfence();
+        st_relaxed_gpu(me, 1);
     }
+    const u32 base = tile & ~(RIG_TILE_GROUP - 1u);   // first tile of this tile's group
+    u64 va = 0, vb = 0;
+    for (u32 t = base + threadIdx.x; t < tile; t += blockDim.x) {   // aggregates of the group's earlier tiles
+        const u64* p = st + (u64)t * RIG_TILE_WORDS;
+        while (ld_relaxed_gpu(p) == 0) {}
+        __threadfence();
+        va += ld_relaxed_gpu(p + 1); vb += ld_relaxed_gpu(p + 2);
+    }
+    if (base > 0 && threadIdx.x == blockDim.x - 1) {               // inclusive prefix of the groups before
+        const u64* p = st + (u64)(base - 1) * RIG_TILE_WORDS;
+        while (ld_relaxed_gpu(p) != 2) {}
+        __threadfence();
+        va += ld_relaxed_gpu(p + 3); vb += ld_relaxed_gpu(p + 4);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { va += __shfl_xor_sync(RIG_FULL, va, off); vb += __shfl_xor_sync(RIG_FULL, vb, off); }
+    if (lane == 0) { s_ra[w] = va; s_rb[w] = vb; }
     __syncthreads();
-    ex_a = s_base[0] + pa + ia - a;
-    ex_b = s_base[1] + pb + ib - b;
-    incl_a = s_base[0] + ta;
-    incl_b = s_base[1] + tb;
+    const u64 sum_a = s_ra[0] + s_ra[1] + s_ra[2] + s_ra[3], sum_b = s_rb[0] + s_rb[1] + s_rb[2] + s_rb[3];
+    if (threadIdx.x == 0 && ((tile + 1u) & (RIG_TILE_GROUP - 1u)) == 0) {   // last tile of a group: prefix for the next group
+        u64* me = st + (u64)tile * RIG_TILE_WORDS;
+        st_relaxed_gpu(me + 3, sum_a + ta); st_relaxed_gpu(me + 4, sum_b + tb);
+        __threadfence();
+        st_relaxed_gpu(me, 2);
+    }
+    ex_a = sum_a + pa + ia - a;
+    ex_b = sum_b + pb + ib - b;
+    incl_a = sum_a + ta;
+    incl_b = sum_b + tb;
 }
 
 // ------------------------------------------------------------------ one lane per pattern

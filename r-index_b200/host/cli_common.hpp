@@ -2,6 +2,7 @@
 // lines, and the multi-GPU fan-out (index replicated on every GPU, patterns cut into contiguous
 // shards, one host thread per device, no collective on the search path — SURVEY.md §8e).
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <fstream>
@@ -94,32 +95,63 @@ public:
         });
         for (int g = 0; g < G; ++g) if (rcs[g] != RIG_OK) die(rcs[g], "rig_count_batch");
     }
-    // Per-shard results: occ[g] holds the occurrences of shard g's patterns back to back;
-    // off[g] (shard-local, size = shard patterns + 1) indexes into it.
+    // SURVEY §8e re-balancing: contiguous shards of near-equal WORK, work(p) = n_occ(p) + 64 (the backward search of a
+    // pattern costs about as much as a few dozen occurrences of expansion). Same rule as r-index_b200/_shard.py.
+    static std::vector<uint64_t> balanced_cuts(const uint64_t* lo, const uint64_t* hi, uint64_t N, int G) {
+        std::vector<double> cum(N);
+        double acc = 0;
+        for (uint64_t p = 0; p < N; ++p) { acc += (hi[p] >= lo[p] ? double(hi[p] - lo[p] + 1) : 0.0) + 64.0; cum[p] = acc; }
+        std::vector<uint64_t> cuts(1, 0);
+        for (int k = 1; k < G; ++k) {
+            const double target = acc * k / G;
+            uint64_t c = N ? uint64_t(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()) + 1 : 0;
+            if (N && c > 0 && c <= N && (cum[c - 1] - target) > (target - (c >= 2 ? cum[c - 2] : 0.0))) --c;
+            cuts.push_back(std::min<uint64_t>(std::max<uint64_t>(c, cuts.back()), N));
+        }
+        cuts.push_back(N);
+        return cuts;
+    }
+
+    // Locate the batch; the occurrences STAY ON THE DEVICES (one rig_locate_batch_ex call per shard with
+    // RIG_LOCATE_DEVICE_ONLY: no second search, no download). With more than one GPU the shards are first counted
+    // (equal-count shards), then re-cut at equal occurrence mass: cuts[g] .. cuts[g+1] are shard g's patterns.
+    // off[g] (shard-local, size = shard patterns + 1) indexes shard g's occurrences; fetch(g, ...) copies them out.
     // flags: RIG_LOCATE_SORT (-o) / RIG_LOCATE_CHECK (-c, needs attach_text) run on the device
     // (ri-locate.cpp:146-190); reports[g] receives shard g's check report.
     uint64_t locate(const uint8_t* patt, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
-                    std::vector<std::vector<uint64_t>>& off, std::vector<std::vector<uint64_t>>& occ,
+                    std::vector<std::vector<uint64_t>>& off, std::vector<uint64_t>& cuts, std::vector<uint64_t>& totals,
                     uint32_t flags = 0, std::vector<rig_check_report>* reports = nullptr) {
-        off.assign(G, {}); occ.assign(G, {});
+        off.assign(G, {});
+        totals.assign(G, 0);
+        if (G > 1) { count(patt, N, m, lo, hi); cuts = balanced_cuts(lo, hi, N, G); }
+        else cuts = {0, N};
         std::vector<int> rcs(G, 0);
-        std::vector<uint64_t> totals(G, 0);
+        std::vector<std::string> errs(G);
         std::vector<rig_check_report> reps(G);
         run([&](int g) {
-            uint64_t a = N * g / G, b = N * (g + 1) / G;
+            const uint64_t a = cuts[g], b = cuts[g + 1];
             off[g].assign(b - a + 1, 0);
-            int rc = rig_locate_batch(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), nullptr, 0, &totals[g]);
-            if (rc == RIG_ERR_CAPACITY || (rc == RIG_OK && flags)) {
-                occ[g].resize(totals[g]);
-                rc = rig_locate_batch_ex(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), occ[g].data(),
-                                         occ[g].size(), &totals[g], flags, &reps[g]);
-            }
-            rcs[g] = rc;
+            rcs[g] = rig_locate_batch_ex(idx[g], patt + a * m, b - a, m, lo + a, hi + a, off[g].data(), nullptr, 0, &totals[g],
+                                         flags | RIG_LOCATE_DEVICE_ONLY, &reps[g]);
+            if (rcs[g] != RIG_OK) errs[g] = rig_last_cuda_error();  // the CUDA error text is per host thread
         });
         if (reports) *reports = reps;
         uint64_t total = 0;
-        for (int g = 0; g < G; ++g) { if (rcs[g] != RIG_OK) die(rcs[g], "rig_locate_batch"); total += totals[g]; }
+        for (int g = 0; g < G; ++g) {
+            if (rcs[g] != RIG_OK) {
+                std::cout << "Error: rig_locate_batch_ex: " << rig_strerror(rcs[g]);
+                if (!errs[g].empty()) std::cout << " [" << errs[g] << "]";
+                std::cout << std::endl;
+                exit(1);
+            }
+            total += totals[g];
+        }
         return total;
+    }
+    // shard g's occurrences [first, first + count) -> host (page-locked buffers from rig_host_alloc download fastest)
+    void fetch(int g, uint64_t first, uint64_t count, uint64_t* out) {
+        int rc = rig_fetch_occurrences(idx[g], first, count, out);
+        if (rc != RIG_OK) die(rc, "rig_fetch_occurrences");
     }
 
 private:

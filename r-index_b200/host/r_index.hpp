@@ -95,19 +95,17 @@ public:
         ensure_device();
         check(rig_count_batch(dev, patt, N, m, lo, hi), "rig_count_batch");
     }
-    // occ_offsets gets N+1 entries; returns the total number of occurrences.
+    // occ_offsets gets N+1 entries; returns the total number of occurrences. One search: the occurrences are located
+    // into the library's device buffer (RIG_LOCATE_DEVICE_ONLY), then downloaded once their number is known.
     ulint locate_batch(const uint8_t* patt, ulint N, ulint m, ulint* lo, ulint* hi, std::vector<ulint>& occ_offsets,
                        std::vector<ulint>& occ) {
         ensure_device();
         occ_offsets.assign(N + 1, 0);
         uint64_t total = 0;
-        int rc = rig_locate_batch(dev, patt, N, m, lo, hi, occ_offsets.data(), occ.data(), occ.size(), &total);
-        if (rc == RIG_ERR_CAPACITY) {  // two-call protocol: first call sized the result
-            occ.resize(total);
-            rc = rig_locate_batch(dev, patt, N, m, lo, hi, occ_offsets.data(), occ.data(), occ.size(), &total);
-        }
-        check(rc, "rig_locate_batch");
+        check(rig_locate_batch_ex(dev, patt, N, m, lo, hi, occ_offsets.data(), nullptr, 0, &total, RIG_LOCATE_DEVICE_ONLY, nullptr),
+              "rig_locate_batch_ex");
         occ.resize(total);
+        check(rig_fetch_occurrences(dev, 0, total, occ.data()), "rig_fetch_occurrences");
         return total;
     }
 

@@ -277,6 +277,23 @@ def test_two_pass_expansion(seg, variant, monkeypatch):
         gpu.close()
 
 
+@pytest.mark.parametrize("variant", ["64", "72", "256", "264", "2048", "2056"])
+def test_window_pass_alternatives(variant, monkeypatch):
+    """The alternative forms of the window pass kept as A/B switches (RIG_VARIANT bit 6: direct sector stores with
+    warp-level item batches, bit 8: the same with per-lane refill, bit 11: whole lines through the bulk-copy engine), in
+    32- and 64-bit words (bit 3), give the oracle's output like the default whole-line form."""
+    monkeypatch.setenv("RIG_VARIANT", variant)
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 321)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    for jump, seg in ((4, 64), (1, 16), (8, 32), (2, 128)):
+        gpu = rib.GpuIndex(host, phi_jump=jump, seed_jump=seg)
+        for (N, m, seed) in [(1200, 9, 1), (200, 2, 2), (40, 1, 3)]:
+            patt = mixed_patterns(text, N, m, seed, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+            _check_all(gpu, port, patt, N, m, "window variant=%s jump=%d seg=%d" % (variant, jump, seg))
+        gpu.close()
+
+
 def test_two_pass_unaligned_output_falls_back_to_single_pass():
     """The window kernel's vector stores need a sector-aligned occurrence array; a caller-supplied device
     pointer that is only 8-byte aligned takes the single-pass walk and still gives the oracle's output."""
