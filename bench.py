@@ -600,7 +600,7 @@ def measure_locate(D, job, steps, warmup, e2e_steps, flush, solo=False):
     barrier()
     assert tot == occ_rank
     total_ms = sum(x.elapsed_time(y) for x, y in ev)
-    out = {"occ_rank": occ_rank, "patterns_rank": job.c1 - job.c0, "total_ms": total_ms, "launches": launches,
+    out = {"occ_rank": occ_rank, "patterns_rank": job.c1 - job.c0, "total_ms": total_ms, "launches": launches, "expansion_kernels": t["slices"],
            "lf_steps": t["lf_steps"], "chains": t["chains"], "phases": {k: statistics.mean(v) for k, v in ph.items()}}
     # end to end through the host-buffer C-ABI calls, pinned host memory. A shard whose occurrences exceed 16 GB (C3 at
     # full size) is not measured end to end: pinning that much host memory per rank is not what this number is about.
@@ -630,9 +630,23 @@ def run_ours(args):
     need_text = world == 1 and not args.no_post
     text, patt, N, m, host = job_inputs(args.workload, world, rank, need_text=need_text, barrier=D.host_barrier)
     t0 = time.time()
-    gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
-                       phi_bucket_log2=args.phi_log2, expand_threads=args.expand_threads, phi_jump=args.phi_jump,
-                       seed_jump=args.seed_jump)
+    kw = dict(device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2, phi_bucket_log2=args.phi_log2,
+              expand_threads=args.expand_threads, phi_jump=args.phi_jump, seed_jump=args.seed_jump)
+    if world > 1:
+        # one flatten per box, not one per rank: rank 0 flattens and writes the flattened index (rig_index_save_flat),
+        # the other ranks load that file (rig_index_load_flat: a read + an upload)
+        flat = os.path.join(CACHE, "%s.K%d.D%d.S%d.flat" % (base_of(args.workload), args.runs_per_block, args.phi_jump, args.seed_jump))
+        gpu = None
+        if rank == 0:
+            gpu = rib.GpuIndex(host, flat=flat, **kw)
+            if not gpu.from_flat:
+                gpu.save_flat(flat + ".tmp")
+                os.replace(flat + ".tmp", flat)
+        D.host_barrier()
+        if rank != 0:
+            gpu = rib.GpuIndex(host, flat=flat, **kw)
+    else:
+        gpu = rib.GpuIndex(host, **kw)
     load_s = time.time() - t0
     info = gpu.info
     # the library launches on the stream it is given (NULL would mean its own stream): use a real
@@ -766,10 +780,16 @@ def run_ours(args):
         # what must cross HBM for this launch: 8 B per occurrence written + one pass over the tables it reads (the
         # flattened index without the seed table, which only pass 1 touches) + 16 B per item read.
         two_pass = int(info.seed_jump) > 1 and phs["window_ms"] > 0
-        if two_pass:
-            items = occ_rank // int(info.seed_jump) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
+        items = occ_rank // max(1, int(info.seed_jump)) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
+        if two_pass and M["expansion_kernels"] == 1:
+            # fused producer/consumer kernel: it also writes the items and hops through the seed table (one 64-byte record per item)
+            alg_bytes = occ_rank * 8 + int(info.device_bytes) - int(info.seed_bytes) + items * (16 + 16 + 64)
+            dom_kernel, dom_ms = "phi_fused_kernel", phs["window_ms"]
+            alg_note = ("8 B/occurrence output + one pass over the flattened index without the seed table + per item: 16 B written, "
+                        "16 B read, one 64 B seed-table record")
+        elif two_pass:
             alg_bytes = occ_rank * 8 + int(info.device_bytes) - int(info.seed_bytes) + items * 16
-            dom_kernel, dom_ms = "phi_window_kernel", phs["window_ms"]
+            dom_kernel, dom_ms = "phi_window_batch_kernel", phs["window_ms"]
             alg_note = "8 B/occurrence output + one pass over the flattened index without the seed table + 16 B per item (slot, count, seed)"
         else:
             alg_bytes = occ_rank * 8 + int(info.device_bytes)
@@ -788,6 +808,7 @@ def run_ours(args):
             "detail": {"sigma": int(info.sigma), "occurrences_per_step": int(occ_g), "occurrences_rank0": occ_rank,
                        "patterns_rank0": M["patterns_rank"], "phi_chains_rank0": int(chains), "lf_steps_rank0": int(lf_steps),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
+                       "index_from_flat_file": bool(getattr(gpu, "from_flat", False)),
                        "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump),
                        "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes),
                        "parallelism": ("index replicated x%d; per step: count on equal-count shards, NCCL all-gather of the counts (8 B/pattern), "

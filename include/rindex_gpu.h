@@ -78,12 +78,13 @@ typedef struct rig_timing {
     float expand_ms;  /* Phi expansion kernel (locate only) */
     float d2h_ms;     /* result download (host-buffer entry points only) */
     uint32_t launches;      /* kernels launched by the call */
-    uint32_t slices;        /* always 1 (kept for layout compatibility) */
+    uint32_t slices;        /* locate: kernels of the Phi expansion: 1 = the fused producer/consumer kernel (or the single-pass
+                               walk), 2 = seed pass + window pass (seed_ms / window_ms then time them separately), 0 = none ran */
     uint64_t lf_steps;      /* executed LF steps (early exits excluded), r_index.hpp:297 */
     uint64_t occ_total;     /* occurrences written */
     uint64_t chains;        /* independent Phi chains the ranges were split into */
-    float seed_ms;          /* two-pass expansion: pass 1 (toeholds, chain heads, one seed per output window) */
-    float window_ms;        /* two-pass expansion: pass 2 (one lane per output window); both inside expand_ms */
+    float seed_ms;          /* two kernels: pass 1 (toeholds, chain heads, one seed per output window); fused: ~0 */
+    float window_ms;        /* two kernels: pass 2 (one lane per output window); fused: the whole kernel; inside expand_ms */
 } rig_timing;
 
 typedef struct rig_index rig_index;
@@ -98,6 +99,13 @@ const char* rig_version(void);
 int rig_index_create(const rig_logical_view* view, int device, rig_index** out);
 int rig_index_create_ex(const rig_logical_view* view, int device, const rig_options* opt, rig_index** out);
 void rig_index_destroy(rig_index* idx);
+/* The FLATTENED index as a file: what rig_index_create[_ex] builds in HBM, byte for byte, so that the next load is a
+ * file read + upload instead of a flatten (config C4, r = 2.4e7: a minute on the host -> seconds). The reference's
+ * "Load time" (ri-count.cpp:126-127) is the cost this shortens. rig_index_load_flat: `check` (may be NULL) = the
+ * logical index the file must belong to (n, r and a 64-bit digest of its arrays are compared); RIG_ERR_INDEX if the
+ * file is not a flat index of this library version or belongs to another index. */
+int rig_index_save_flat(const rig_index* idx, const char* path);
+int rig_index_load_flat(const char* path, const rig_logical_view* check, int device, rig_index** out);
 int rig_index_info_get(const rig_index* idx, rig_index_info* info);
 
 /* Replaces N calls of r_index<>::count (internal/r_index.hpp:292-302; LF :171-190;

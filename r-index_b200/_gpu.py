@@ -20,6 +20,7 @@ DECLARED_SYMBOLS = [
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
     "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_locate_batch32",
     "rig_break_range_batch", "rig_closest_run_break_batch", "rig_fetch_occurrences", "rig_host_alloc", "rig_host_free",
+    "rig_index_save_flat", "rig_index_load_flat",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -107,6 +108,8 @@ def gpu_lib():
         lib.rig_locate_batch32.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _u32]
         lib.rig_break_range_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]
         lib.rig_closest_run_break_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
+        lib.rig_index_save_flat.argtypes = [_vp, ctypes.c_char_p]
+        lib.rig_index_load_flat.argtypes = [ctypes.c_char_p, ctypes.POINTER(LogicalView), ctypes.c_int, ctypes.POINTER(_vp)]
         lib.rig_fetch_occurrences.argtypes = [_vp, _u64, _u64, _vp]
         lib.rig_host_alloc.restype = _vp
         lib.rig_host_alloc.argtypes = [_u64]
@@ -155,8 +158,24 @@ class GpuIndex:
     """A flattened r-index resident in one GPU's HBM (struct rig_index)."""
 
     def __init__(self, source, device=0, runs_per_block=0, lf_bucket_log2=0, phi_bucket_log2=0, expand_threads=0,
-                 phi_jump=0, seed_jump=0):
+                 phi_jump=0, seed_jump=0, flat=None):
+        """flat: path of a file written by save_flat(); when it exists and belongs to `source` the flatten step is
+        skipped (rig_index_load_flat), otherwise the index is flattened as usual."""
         lib = gpu_lib()
+        if flat is not None and os.path.exists(flat):
+            view = source.view if isinstance(source, HostIndex) else (view_from_arrays(source)[0] if source is not None else None)
+            h = _vp()
+            rc = lib.rig_index_load_flat(flat.encode(), ctypes.byref(view) if view is not None else None, device, ctypes.byref(h))
+            if rc == 0:
+                self.h, self.lib, self.device, self._keep = h, lib, device, None
+                self.info = IndexInfo()
+                lib.rig_index_info_get(self.h, ctypes.byref(self.info))
+                self.n, self.r = int(self.info.n), int(self.info.r)
+                self.from_flat = True
+                return
+            if rc != -5 or source is None:   # anything but "not this index's flat file" is an error
+                raise RigError(rc, "rig_index_load_flat")
+        self.from_flat = False
         if isinstance(source, HostIndex):
             view, self._keep = source.view, source
         elif isinstance(source, dict):
@@ -177,6 +196,11 @@ class GpuIndex:
         self.info = IndexInfo()
         lib.rig_index_info_get(self.h, ctypes.byref(self.info))
         self.n, self.r = int(self.info.n), int(self.info.r)
+
+    def save_flat(self, path):
+        rc = self.lib.rig_index_save_flat(self.h, path.encode())
+        if rc != 0:
+            raise RigError(rc, "rig_index_save_flat")
 
     def close(self):
         if getattr(self, "h", None):

@@ -10,6 +10,7 @@ using namespace ri;
 using namespace std;
 
 static int gpus = 1;
+static string flat_file;
 
 static void help() {
     cout << "ri-count: number of occurrences of the input patterns." << endl << endl;
@@ -24,6 +25,9 @@ static void parse_args(char** argv, int argc, int& ptr) {
     ptr++;
     if (s.compare("--gpus") == 0 && ptr < argc - 2) {  // addition: shard the patterns over N GPUs
         gpus = atoi(argv[ptr]);
+        ptr++;
+    } else if (s.compare("--flat") == 0 && ptr < argc - 2) {  // addition: file of the flattened index (loaded if present, else written)
+        flat_file = string(argv[ptr]);
         ptr++;
     } else {
         cout << "Error: unknown option " << s << endl;
@@ -53,7 +57,7 @@ int main(int argc, char** argv) {
     cout << "searching patterns ... " << endl;
     PatternFile pf = read_patterns(patt_file);  // a malformed header exits(0) here, as upstream (utils.hpp:51-55)
     auto u1 = high_resolution_clock::now();
-    GpuFleet fleet(L, gpus, true);                    // flatten + upload: accounted as load time, not search time
+    GpuFleet fleet(L, gpus, true, flat_file);                    // flatten + upload: accounted as load time, not search time
     auto u2 = high_resolution_clock::now();
     const uint64_t n = pf.n, m = pf.m;
     std::vector<uint64_t> lo(n), hi(n);

@@ -15,6 +15,7 @@ using namespace std;
 
 static string check_text_file, ofile;
 static int gpus = 1;
+static string flat_file;
 
 static void help() {
     cout << "ri-locate: locate all occurrences of the input patterns." << endl << endl;
@@ -45,6 +46,9 @@ static void parse_args(char** argv, int argc, int& ptr) {
         ptr++;
     } else if (s.compare("--gpus") == 0 && ptr < argc - 2) {  // addition
         gpus = atoi(argv[ptr]);
+        ptr++;
+    } else if (s.compare("--flat") == 0 && ptr < argc - 2) {  // addition: file of the flattened index (loaded if present, else written)
+        flat_file = string(argv[ptr]);
         ptr++;
     } else {
         cout << "Error: unknown option " << s << endl;
@@ -86,7 +90,7 @@ int main(int argc, char** argv) {
     cout << "searching patterns ... " << endl;
     PatternFile pf = read_patterns(patt_file);  // a malformed header exits(0) here, as upstream (utils.hpp:51-55)
     auto u1 = high_resolution_clock::now();
-    GpuFleet fleet(L, gpus);                    // flatten + upload: accounted as load time, not search time
+    GpuFleet fleet(L, gpus, false, flat_file);                    // flatten + upload: accounted as load time, not search time
     auto u2 = high_resolution_clock::now();
     const uint64_t n = pf.n, m = pf.m;
     std::vector<uint64_t> lo(n), hi(n);

@@ -534,7 +534,8 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     if (f.phi.pieces() >= 0xFFFFFFF0ull) return RIG_ERR_INDEX;
 
     // Seed table Phi^SEG for the two-pass expansion (phi_kernels.cuh): requested (reserved[2] = 16..256,
-    // 1 = off), or the largest of {64, 32, 16} whose table (72 B per piece with 32-bit words: one
+    // 1 = off), or the largest of {128, 64, 32, 16} (measured on B200, round 2: 128 beats 64 by 4-8% per step on
+    // C2 / C5s / C3s — half the dependent seed-table hops — and 256 loses: items of 256 slots balance badly) whose table (72 B per piece with 32-bit words: one
     // 64-byte bucket record per piece + an 8-byte piece entry) stays within 16 GB / a quarter of the
     // caller's byte limit. pieces(Phi^J) = sum over runs of min(J, run length), known before building.
     u32 SEG = opt.reserved[2];
@@ -544,7 +545,7 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
         if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
         const u64 per_piece = f.w32 ? 72 : 144;
         SEG = 1;
-        for (u32 cand : {64u, 32u, 16u}) {
+        for (u32 cand : {128u, 64u, 32u, 16u}) {
             u64 pieces = 0;
             for (u64 j = 0; j < r; ++j) pieces += std::min<u64>(cand, v.run_lens[j]);
             if (pieces * per_piece <= budget) { SEG = cand; break; }

@@ -108,6 +108,17 @@ __global__ void __launch_bounds__(256) l2_warm_kernel(const char* base, u64 byte
     if (line < bytes) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(base + line));
 }
 
+// Start of a batch call, ONE launch instead of two memset nodes and a warm-up kernel: zero the call's counters and
+// the workspace of the search kernel's offset scan, and pull the backward-search structures into L2 (warm_bytes = 0:
+// they are too large to stay there). The search is a chain of dependent loads: with 32 lanes in lockstep one cold
+// line per warp-step costs the whole warp a DRAM round trip.
+__global__ void __launch_bounds__(256) prep_kernel(u64* z0, u64 n0, u64* z1, u64 n1, const char* base, u64 warm_bytes) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x, T = (u64)gridDim.x * blockDim.x;
+    for (u64 i = t; i < n0; i += T) z0[i] = 0;
+    for (u64 i = t; i < n1; i += T) z1[i] = 0;
+    for (u64 line = t * 128; line < warm_bytes; line += T * 128) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(base + line));
+}
+
 // ---- walking a chain with the Phi^1..Phi^D table ---------------------------------------------------
 // From v = SA[x] (already written at o[-1]) produce `remaining` further occurrences SA[x-1], SA[x-2], ...
 // at o[0], o[1], ...; returns the last value produced (v itself when remaining == 0).
@@ -262,17 +273,22 @@ __device__ __forceinline__ bool expansion_enabled(const u64* ctr, u64 cap, u64 i
 //                 was measured bound by exactly that random-access rate. The chain's K entries are
 //                 reserved up front with ONE atomic per warp (shuffle scan of K), so the reservation's
 //                 latency hides behind the head walk. phi_window_kernel fills in the items.
+#define RIG_ITEM_MASK 0x0000FFFFFFFFFFFFull   // an item word without its epoch tag (fused expansion)
+
+// The chains wb .. of one warp-stride loop: toehold, head walk, items. TAG != 0: the fused kernel's consumers poll
+// the item list while it is being written; each 16-byte entry then carries the call's epoch in the top 16 bits of
+// BOTH words (slots and positions stay below 2^48) and is written with a device-scope relaxed store, so a reader
+// accepts an entry only when both tags are the current epoch.
 template <typename WT, int D, bool KEEP, bool SEEDED>
-__global__ void __launch_bounds__(256)
-phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
-                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
-                  u64* __restrict__ items, u64 items_cap, u32 seg_shift) {
-    u64 total, total_chains;
-    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, SEEDED, total, total_chains)) return;
+__device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u64* __restrict__ ch_off,
+                                               const u64* __restrict__ occ_off, const u64* __restrict__ lo_in,
+                                               const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
+                                               const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr,
+                                               u64* __restrict__ items, u32 seg_shift, u64 total_chains, u64 tag,
+                                               u32 block, u32 nblocks) {   // this CTA's rank among the nblocks producing CTAs
     const int lane = threadIdx.x & 31;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 wb = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < total_chains; wb += stride) {  // warp-uniform
+    const u64 stride = (u64)nblocks * blockDim.x;
+    for (u64 wb = (u64)block * blockDim.x + (threadIdx.x & ~31u); wb < total_chains; wb += stride) {  // warp-uniform
         const u64 w = wb + lane;
         const bool active = w < total_chains;
         u64 g0 = 0, glast = 0, v0 = 0;
@@ -316,7 +332,10 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
                 ulonglong2* it = reinterpret_cast<ulonglong2*>(items) + wbase + (incl - K);
                 u64 s = a1;
                 for (;;) {
-                    __stcs(it++, make_ulonglong2((s << 8) | min(SEG - 1, glast - s), (u64)v));
+                    const u64 w0 = (s << 8) | min(SEG - 1, glast - s), w1 = (u64)v;
+                    if (tag) asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" :: "l"(it), "l"(w0 | tag), "l"(w1 | tag) : "memory");
+                    else __stcs(it, make_ulonglong2(w0, w1));
+                    ++it;
                     s += SEG;
                     if (s > glast) break;
                     v = seed_hop<WT>(ix, v);
@@ -324,6 +343,18 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
             }
         }
     }
+}
+
+template <typename WT, int D, bool KEEP, bool SEEDED>
+__global__ void __launch_bounds__(256)
+phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
+                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
+                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
+                  u64* __restrict__ items, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, SEEDED, total, total_chains)) return;
+    produce_chains<WT, D, KEEP, SEEDED>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, 0,
+                                        blockIdx.x, gridDim.x);
 }
 
 // "Window pass". PERSISTENT, one lane per ITEM AT A TIME: a lane walks the items i = t, t + T, t + 2T, .. (t its
@@ -443,29 +474,91 @@ phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __
 #undef RIG_TAKE_ITEM
 }
 
-// The same pass with WARP-LEVEL batches (A/B alternative, RIG_VARIANT bit 6): a warp takes 32 consecutive items,
-// walks them in lockstep until its slowest lane is done, then strides to its next 32. Fewer live registers per
-// lane (no prefetched next item, no in-trip switch) = more resident warps; lanes idle while the warp's longest
-// item finishes.
+// One item per lane, the warp in lockstep until its slowest lane is done: left = slots of the item still to be written
+// (the seed's included, 0 = no item), o = its first slot, v = the seed. Direct 32-byte sector stores.
 template <typename WT, int D, bool KEEP>
-__global__ void __launch_bounds__(256)
-phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
-                        u64 cap, u64 items_cap, u32 seg_shift) {
-    u64 total, total_chains;
-    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
+__device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left, u64* o, WT v) {
     constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;
     const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
-    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);
-    const u32 T = gridDim.x * blockDim.x;
     const WT n = (WT)ix.n;
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
+    bool searching = false;
+    u32 slo = 0, shi = 0, probe = 0;
+    WT e[RW];
+    if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
+    while (__any_sync(RIG_FULL, left > 1)) {
+        bool emit = false;
+        WT g[D];
+        u32 cnt = 0;
+        WT vn = v;
+        if (left > 1) {
+            if (!searching) {
+                emit = v < e[D];
+                slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+                searching = !emit;
+            } else if (slo == shi) {
+                emit = true;
+            } else if (e[D] <= v) {
+                slo = probe; emit = (slo == shi);
+            } else {
+                shi = probe - 1; emit = false;
+            }
+            if (emit) {
+                searching = false;
+                slo = shi = 0;
+                g[0] = v;
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    WT x = v + e[t];
+                    if ((W32 && x < v) || x >= n) x -= n;
+                    if (t < D - 1) g[t + 1] = x; else vn = x;
+                }
+                cnt = min(left, (u32)D);
+            }
+        }
+        const u32 left_next = left - cnt;
+        probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
+        WT e2[RW];
+        if (left_next > 1)
+            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
+        if (emit) {
+            if (cnt == (u32)D) {
+                store_group<WT, D>(o, g);
+            } else {
+#pragma unroll
+                for (int t = 0; t < D - 1; ++t)
+                    if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+            }
+            o += cnt;
+        }
+        v = vn;
+        left = left_next;
+#pragma unroll
+        for (int t = 0; t < RW; ++t) e[t] = e2[t];
+    }
+    if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+}
+
+// "Window pass", the default form. PERSISTENT: a warp takes 32 consecutive items, walks them in lockstep until its
+// slowest lane is done (window_items_direct), then strides to its next 32.
+// items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first slot, cnt the number of
+// further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v); the lane
+// emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] as one 32-byte sector store and continues from Phi^D(v).
+template <typename WT, int D, bool KEEP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
+                        u64 cap, u64 items_cap, u32 seg_shift) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
+    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);
+    const u32 T = gridDim.x * blockDim.x;
     for (u32 ib = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); ib < n_items; ib += T) {  // warp-uniform
         const u32 i = ib + (threadIdx.x & 31u);
-        u32 left = 0;  // slots of this item still to be written, the seed's included
+        u32 left = 0;
         u64* o = out;
         WT v = 0;
         if (i < n_items) {
@@ -474,61 +567,81 @@ phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u
             o = out + (it.x >> 8);
             v = (WT)it.y;
         }
-        bool searching = false;
-        u32 slo = 0, shi = 0, probe = 0;
-        WT e[RW];
-        if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
-        while (__any_sync(RIG_FULL, left > 1)) {
-            bool emit = false;
-            WT g[D];
-            u32 cnt = 0;
-            WT vn = v;
-            if (left > 1) {
-                if (!searching) {
-                    emit = v < e[D];
-                    slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
-                    searching = !emit;
-                } else if (slo == shi) {
-                    emit = true;
-                } else if (e[D] <= v) {
-                    slo = probe; emit = (slo == shi);
-                } else {
-                    shi = probe - 1; emit = false;
-                }
-                if (emit) {
-                    searching = false;
-                    slo = shi = 0;
-                    g[0] = v;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) {
-                        WT x = v + e[t];
-                        if ((W32 && x < v) || x >= n) x -= n;
-                        if (t < D - 1) g[t + 1] = x; else vn = x;
-                    }
-                    cnt = min(left, (u32)D);
-                }
+        window_items_direct<WT, D, KEEP>(ix, left, o, v);
+    }
+}
+
+// FUSED expansion: seed pass and window pass in ONE persistent kernel. Every warp first PRODUCES — its share of the
+// chains: toeholds, heads, one item per seed-table hop (produce_chains) — and then CONSUMES items, 32 at a time by
+// ticket, as the list fills: the seed pass is a chain of dependent DRAM-latency hops per chain (the longest chain of
+// config C2 takes 31) that leaves the machine idle, the window pass is bound by the SM's request port; fused, the
+// first hides under the second. A consumer accepts an item when both of its words carry this call's epoch tag
+// (produce_chains), and gives up on a ticket only when every warp has finished producing (ctr[RIG_CTR_DONE], a
+// device-scope fence on both sides) and the ticket lies beyond the final item count. No consumer ever waits for a
+// warp that is not running: the grid is sized to be fully resident.
+#define RIG_CTR_DONE 7    // warps that have finished producing
+#define RIG_CTR_TAKEN 8   // items handed out to consumers
+template <typename WT, int D, bool KEEP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+phi_fused_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
+                 const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
+                 const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
+                 u64* __restrict__ items, u64 items_cap, u32 seg_shift, u64 tag, u32 prod_mod) {
+    u64 total, total_chains;
+    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
+    const u32 lane = threadIdx.x & 31u;
+    // Producers: the CTAs with blockIdx % prod_mod == 0 (spread over the SMs); the others consume from the start.
+    // Every warp producing would leave nobody to consume until the longest chains are done.
+    const u32 n_prod_ctas = (gridDim.x + prod_mod - 1) / prod_mod;
+    if (blockIdx.x % prod_mod == 0) {
+        produce_chains<WT, D, KEEP, true>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, tag,
+                                          blockIdx.x / prod_mod, n_prod_ctas);
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicAdd(ctr + RIG_CTR_DONE, 1ull); }
+    }
+    const u64 nwarps = (u64)n_prod_ctas * (blockDim.x >> 5);
+    bool all_done = false;     // every warp has finished producing (warp-uniform)
+    u64 n_final = 0;           // then: the final item count
+    for (;;) {
+        u64 ib = 0;
+        if (lane == 0) ib = atomicAdd(ctr + RIG_CTR_TAKEN, 32ull);
+        ib = __shfl_sync(RIG_FULL, ib, 0);
+        if (ib >= items_cap) break;   // the list never holds more than items_cap entries (expansion_enabled): nothing can appear here
+        const u64 i = ib + lane;
+        bool have = false;
+        u64 w0 = 0, w1 = 0;
+        if (!all_done) n_final = items_cap;   // until the final count is known: the bound of what may still be written
+        for (;;) {
+            if (!have && i < n_final) {
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(items + 2 * i) : "memory");
+                have = ((w0 ^ tag) >> 48) == 0 && ((w1 ^ tag) >> 48) == 0;
             }
-            const u32 left_next = left - cnt;
-            probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
-            WT e2[RW];
-            if (left_next > 1)
-                load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
-            if (emit) {
-                if (cnt == (u32)D) {
-                    store_group<WT, D>(o, g);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < D - 1; ++t)
-                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+            const bool waiting = !have && i < n_final;
+            if (!__any_sync(RIG_FULL, waiting)) break;
+            if (!all_done) {
+                u64 d = 0;
+                if (lane == 0) d = ld_relaxed_gpu(ctr + RIG_CTR_DONE);
+                d = __shfl_sync(RIG_FULL, d, 0);
+                if (d == nwarps) {
+                    __threadfence();
+                    if (lane == 0) n_final = ld_relaxed_gpu(ctr + RIG_CTR_ITEMS);
+                    n_final = __shfl_sync(RIG_FULL, n_final, 0);
+                    all_done = true;
+                    continue;   // every item below n_final is visible now: one more look
                 }
-                o += cnt;
+                __nanosleep(200);
             }
-            v = vn;
-            left = left_next;
-#pragma unroll
-            for (int t = 0; t < RW; ++t) e[t] = e2[t];
         }
-        if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+        if (all_done && ib >= n_final) break;
+        u32 left = 0;
+        u64* o = out;
+        WT v = 0;
+        if (have) {
+            left = (u32)(w0 & 255u) + 1;
+            o = out + ((w0 & RIG_ITEM_MASK) >> 8);
+            v = (WT)(w1 & RIG_ITEM_MASK);
+        }
+        window_items_direct<WT, D, KEEP>(ix, left, o, v);
     }
 }
 
@@ -628,7 +741,7 @@ phi_window_line_kernel(const FlatDev ix, const u64* __restrict__ items, const u6
                     } else if constexpr (std::is_same<ST, WT>::value && D * sizeof(WT) == 32) {
                         reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(x)[0];
                         reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(x)[1];
-                    } else if constexpr (D % 2 == 0) {
+                    } else if constexpr (sizeof(ST) == 8 && D % 2 == 0) {
 #pragma unroll
                         for (int t = 0; t < D; t += 2)
                             reinterpret_cast<ulonglong2*>(dst)[t / 2] = make_ulonglong2((u64)x[t], (u64)x[t + 1]);

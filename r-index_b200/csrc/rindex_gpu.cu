@@ -87,6 +87,10 @@ struct rig_index {
     size_t l2_window_bytes = 0;  // persisting-L2 access policy window over the Phi records (0 = unsupported)
     float l2_hit_ratio = 1.f;
     bool timing_pending = false;
+    size_t arena_bytes = 0;
+    uint64_t digest = 0;           // logical_digest() of the index this handle was made from
+    uint32_t epoch = 0;            // fused expansion: tag of the current call's items (1..65535; the list is zeroed when it wraps)
+    void* items_zeroed = nullptr;  // the item-list allocation that has been zero-filled (a fresh cudaMalloc holds garbage)
     uint64_t last_items_cap = 0;   // item-list capacity the most recent expansion was queued with
     bool last_two_pass = false;
     uint64_t kept_total = 0;       // occurrences of the most recent RIG_LOCATE_DEVICE_ONLY call, still in `occ`
@@ -94,6 +98,44 @@ struct rig_index {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// streams, events, counters of a new handle (the arena is in place)
+static int finish_create(rig_index* ix) {
+    CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ix->ev_scan, cudaEventDisableTiming));
+    for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
+    CU_TRY(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
+    CU_TRY(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
+    CU_TRY(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
+    std::memset(ix->h_counters, 0, 16 * sizeof(ull));
+    CU_TRY(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
+    CU_TRY(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
+    CU_TRY(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
+    return RIG_OK;
+}
+
+// 64-bit digest of an index's logical content (FNV-1a over 8-byte words, four interleaved lanes): ties a file of
+// the flattened form to the logical index it was made from
+static uint64_t logical_digest(const rig_logical_view& v) {
+    uint64_t h[4] = {0xcbf29ce484222325ull, 0x84222325cbf29ce4ull, 0x9e3779b97f4a7c15ull, 0xc2b2ae3d27d4eb4full};
+    auto mix = [&](const void* p, size_t bytes) {
+        const uint8_t* b = (const uint8_t*)p;
+        size_t i = 0, k = 0;
+        for (; i + 8 <= bytes; i += 8, ++k) { uint64_t w; std::memcpy(&w, b + i, 8); h[k & 3] = (h[k & 3] ^ w) * 0x100000001b3ull; }
+        for (; i < bytes; ++i) h[0] = (h[0] ^ b[i]) * 0x100000001b3ull;
+    };
+    mix(&v.n, 8); mix(&v.r, 8); mix(v.F, 257 * 8); mix(v.run_heads, v.r); mix(v.run_lens, v.r * 8);
+    mix(v.samples_last, v.r * 8); mix(v.pred_pos, v.r * 8); mix(v.pred_to_run, v.r * 8);
+    return ((h[0] * 31 + h[1]) * 31 + h[2]) * 31 + h[3];
+}
+
+// every device pointer of a FlatDev, for rebasing between "address" and "offset into the arena"
+template <class Fn>
+static void for_each_pointer(FlatDev& d, Fn fn) {
+    fn((const void*&)d.F); fn((const void*&)d.sid); fn(d.start); fn((const void*&)d.blk); fn(d.last); fn(d.bstart);
+    fn((const void*&)d.bdir); fn(d.samples_last); fn(d.phi.rec); fn(d.phi.pent); fn(d.seed.rec); fn(d.seed.pent);
+}
+
 
 extern "C" {
 
@@ -137,7 +179,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit6 window pass with direct sector stores and warp-level item batches, bit8 the same with per-lane refill (A/B alternatives of the default whole-line window pass), bit11 whole-line window pass whose rows leave through the bulk-copy engine (cp.async.bulk shared -> global) instead of the cooperative vector stores, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit6 window pass with whole-line stores staged in shared memory (lockstep warps), bit8 direct sector stores with per-lane refill (A/B alternatives of the default window pass: direct sector stores, warp-level item batches), bit11 whole-line window pass whose rows leave through the bulk-copy engine (cp.async.bulk shared -> global) instead of the cooperative vector stores, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -248,16 +290,9 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
             }
         }
     }
-    CU_TRY_IX(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CU_TRY_IX(cudaEventCreateWithFlags(&ix->ev_scan, cudaEventDisableTiming));
-    for (auto& ev : ix->ev) CU_TRY_IX(cudaEventCreate(&ev));
-    CU_TRY_IX(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
-    CU_TRY_IX(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
-    CU_TRY_IX(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
-    std::memset(ix->h_counters, 0, 16 * sizeof(ull));
-    CU_TRY_IX(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
-    CU_TRY_IX(cudaMemset(ix->d_post, 0, 8 * sizeof(ull)));
-    CU_TRY_IX(cudaMallocHost((void**)&ix->h_post, 8 * sizeof(ull)));
+    if ((rc = finish_create(ix)) != RIG_OK) { rig_index_destroy(ix); return rc; }
+    ix->arena_bytes = total;
+    ix->digest = logical_digest(*view);
 
     rig_index_info& I = ix->info;
     std::memset(&I, 0, sizeof(I));
@@ -268,6 +303,108 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
     I.reserved = ix->l2_window_bytes ? (uint32_t)(prop.persistingL2CacheMaxSize >> 20) : 0;  // MiB of persisting L2 in use
     I.seed_jump = d.seed.J; I.seed_shift = f.seed.shift; I.seed_pieces = f.seed.pieces(); I.seed_bytes = f.seed.bytes(f.w32);
+    *out = ix;
+    return RIG_OK;
+}
+
+// ---- the flattened index as a file: flatten once, load in seconds ---------------------------------------------
+// Layout: FlatFileHeader | the device arena, byte for byte. The FlatDev in the header holds OFFSETS into the arena
+// instead of addresses. A file is accepted only by the library version that wrote it (magic + struct sizes).
+namespace {
+struct FlatFileHeader {
+    char magic[8];               // "RIGFLAT2"
+    uint32_t header_bytes, flatdev_bytes, info_bytes, reserved;
+    uint64_t arena_bytes, digest, phi_bytes, lf_bytes;
+    rig_options opt;
+    rig_index_info info;
+    FlatDev d;                   // pointers rebased to offsets
+};
+}  // namespace
+
+int rig_index_save_flat(const rig_index* ix, const char* path) {
+    if (!ix || !path) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    FlatFileHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "RIGFLAT2", 8);
+    h.header_bytes = sizeof(FlatFileHeader); h.flatdev_bytes = sizeof(FlatDev); h.info_bytes = sizeof(rig_index_info);
+    h.arena_bytes = ix->arena_bytes; h.digest = ix->digest; h.phi_bytes = ix->phi_bytes; h.lf_bytes = ix->lf_bytes;
+    h.opt = ix->opt; h.info = ix->info; h.d = ix->d;
+    const char* A = (const char*)ix->arena;
+    for_each_pointer(h.d, [&](const void*& p) { p = (const void*)(uintptr_t)((const char*)p - A); });
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return RIG_ERR_ARG;
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
+    const size_t CH = 64u << 20;
+    void* stage = nullptr;
+    if (cudaMallocHost(&stage, CH) != cudaSuccess) { cudaGetLastError(); std::fclose(f); return RIG_ERR_NOMEM; }
+    for (size_t off = 0; ok && off < ix->arena_bytes; off += CH) {
+        const size_t k = std::min(CH, ix->arena_bytes - off);
+        if (cudaMemcpy(stage, A + off, k, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+        ok = std::fwrite(stage, 1, k, f) == k;
+    }
+    cudaFreeHost(stage);
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? RIG_OK : RIG_ERR_CUDA;
+}
+
+int rig_index_load_flat(const char* path, const rig_logical_view* check, int device, rig_index** out) {
+    if (!path || !out) return RIG_ERR_ARG;
+    *out = nullptr;
+    int ndev = rig_device_count();
+    if (device < 0 || device >= ndev) return RIG_ERR_NO_DEVICE;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return RIG_ERR_ARG;
+    FlatFileHeader h;
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "RIGFLAT2", 8) != 0 || h.header_bytes != sizeof(FlatFileHeader) ||
+        h.flatdev_bytes != sizeof(FlatDev) || h.info_bytes != sizeof(rig_index_info) || h.arena_bytes == 0) {
+        std::fclose(f);
+        return RIG_ERR_INDEX;
+    }
+    if (check && (h.d.n != check->n || h.d.r != check->r || h.digest != logical_digest(*check))) { std::fclose(f); return RIG_ERR_INDEX; }
+    // every offset must lie inside the arena
+    bool sane = true;
+    for_each_pointer(h.d, [&](const void*& p) { if ((uintptr_t)p >= h.arena_bytes) sane = false; });
+    if (!sane || h.phi_bytes > h.arena_bytes || h.lf_bytes > h.arena_bytes) { std::fclose(f); return RIG_ERR_INDEX; }
+    CU_TRY(cudaSetDevice(device));
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (h.arena_bytes + (64u << 20) > free_b) { std::fclose(f); return RIG_ERR_NOMEM; }
+    rig_index* ix = new (std::nothrow) rig_index();
+    if (!ix) { std::fclose(f); return RIG_ERR_NOMEM; }
+    ix->device = device; ix->opt = h.opt;
+    if (const char* ev = getenv("RIG_VARIANT")) ix->variant = atoi(ev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); std::fclose(f); delete ix; return RIG_ERR_CUDA; }
+    ix->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc(&ix->arena, h.arena_bytes) != cudaSuccess) { cudaGetLastError(); std::fclose(f); delete ix; return RIG_ERR_NOMEM; }
+    const size_t CH = 64u << 20;
+    void* stage[2] = {nullptr, nullptr};
+    bool ok = cudaMallocHost(&stage[0], CH) == cudaSuccess && cudaMallocHost(&stage[1], CH) == cudaSuccess;
+    cudaStream_t st = nullptr;
+    ok = ok && cudaStreamCreate(&st) == cudaSuccess;
+    cudaEvent_t evs[2] = {nullptr, nullptr};
+    ok = ok && cudaEventCreate(&evs[0]) == cudaSuccess && cudaEventCreate(&evs[1]) == cudaSuccess;
+    int b = 0;
+    for (size_t off = 0; ok && off < h.arena_bytes; off += CH, b ^= 1) {   // read chunk k+1 from the file while chunk k uploads
+        const size_t k = std::min(CH, (size_t)h.arena_bytes - off);
+        ok = cudaEventSynchronize(evs[b]) == cudaSuccess;                  // the buffer's previous upload has drained
+        ok = ok && std::fread(stage[b], 1, k, f) == k;
+        ok = ok && cudaMemcpyAsync((char*)ix->arena + off, stage[b], k, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaEventRecord(evs[b], st) == cudaSuccess;
+    }
+    if (st) { ok = (cudaStreamSynchronize(st) == cudaSuccess) && ok; cudaStreamDestroy(st); }
+    for (auto& e : evs) if (e) cudaEventDestroy(e);
+    for (auto& p : stage) if (p) cudaFreeHost(p);
+    std::fclose(f);
+    if (!ok) { cudaGetLastError(); rig_index_destroy(ix); return RIG_ERR_CUDA; }
+    ix->d = h.d;
+    char* A = (char*)ix->arena;
+    for_each_pointer(ix->d, [&](const void*& p) { p = (const void*)(A + (uintptr_t)p); });
+    ix->info = h.info; ix->info.device = (uint32_t)device; ix->info.sm_count = (uint32_t)ix->sm_count; ix->info.reserved = 0;
+    ix->phi_bytes = h.phi_bytes; ix->lf_bytes = h.lf_bytes; ix->arena_bytes = h.arena_bytes; ix->digest = h.digest;
+    int rc = finish_create(ix);
+    if (rc != RIG_OK) { rig_index_destroy(ix); return rc; }
     *out = ix;
     return RIG_OK;
 }
@@ -304,15 +441,20 @@ namespace {
 // workspace of the search kernel's fused offset scan: ticket + RIG_TILE_WORDS words per tile of 128 patterns
 size_t tile_ws_words(uint64_t N) { return 2 + RIG_TILE_WORDS * ((N + 127) / 128) + 2; }
 
-// Pull the backward-search structures (block records, directories, run starts, samples) into L2 with one streaming
-// pass before the search when they are small enough to stay there (<= 48 MB): the search is a chain of dependent
-// loads, and with 32 lanes in lockstep one cold line per warp-step costs the whole warp a DRAM round trip.
-// RIG_VARIANT bit 12 disables (A/B switch).
-void warm_lf(rig_index* ix, cudaStream_t st) {
-    if ((ix->variant & 4096) || !ix->lf_bytes || ix->lf_bytes > (48u << 20)) return;
-    const uint64_t lines = (ix->lf_bytes + 127) / 128;
-    rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->arena, ix->lf_bytes);
+// Start of a batch call: zero the counters and (locate) the offset-scan workspace, warm the backward-search
+// structures (the head of the arena: F, sid, run starts, block records, directories, samples) into L2 when they are
+// small enough to stay there (<= 48 MB) — one kernel (rigk::prep_kernel). RIG_VARIANT bit 12: no warm-up (A/B switch).
+int prep_call(rig_index* ix, uint64_t N, bool locate, cudaStream_t st) {
+    const bool lane_kernel = ix->d.K == 4 && !(ix->variant & 128);
+    ull* ws = (locate && lane_kernel) ? (ull*)ix->sums.p : nullptr;
+    const uint64_t nws = ws ? tile_ws_words(N) : 0;
+    const uint64_t warm = ((ix->variant & 4096) || ix->lf_bytes > (48u << 20)) ? 0 : ix->lf_bytes;
+    const uint64_t work = std::max<uint64_t>(std::max<uint64_t>(nws, 16), (warm + 127) / 128);
+    const unsigned nb = (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)ix->sm_count * 8);
+    rigk::prep_kernel<<<nb, 256, 0, st>>>(ix->d_counters, 16, ws, nws, (const char*)ix->arena, warm);
+    CU_TRY(cudaGetLastError());
     ix->timing.launches += 1;
+    return RIG_OK;
 }
 
 template <bool LOCATE>
@@ -327,7 +469,6 @@ int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, 
         const uint64_t lb = (N + lt - 1) / lt;
         if (lb > 0x7fffffffull) return RIG_ERR_ARG;
         ull* ws = (ull*)ix->sums.p; ull* choff = (ull*)ix->choff.p; ull* totals = ix->d_counters + RIG_CTR_TOTAL;
-        if (LOCATE) CU_TRY(cudaMemsetAsync(ws, 0, tile_ws_words(N) * sizeof(ull), st));
         if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
         else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
         CU_TRY(cudaGetLastError());
@@ -396,7 +537,6 @@ void begin_call(rig_index* ix) {
     std::memset(&ix->timing, 0, sizeof(ix->timing));
     for (bool& b : ix->ev_valid) b = false;
     ix->timing_pending = true;
-    ix->timing.slices = 1;
 }
 
 int rec(rig_index* ix, int i, cudaStream_t st) {
@@ -408,9 +548,8 @@ int rec(rig_index* ix, int i, cudaStream_t st) {
 // count on device buffers; events 1..2 bracket the kernel
 int count_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, cudaStream_t st) {
     int rc;
-    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 8 * sizeof(ull), st));
+    if ((rc = prep_call(ix, N, false, st))) return rc;
     if ((rc = rec(ix, 1, st))) return rc;
-    if (N) warm_lf(ix, st);
     if (N && (rc = launch_search<false>(ix, d_patt, N, m, d_lo, d_hi, nullptr, st))) return rc;
     if ((rc = rec(ix, 2, st))) return rc;
     CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -465,14 +604,53 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
     const uint64_t max_chains = cap ? cap : 1;
     const uint64_t max_items = items_cap ? items_cap : 1;
     const int wthreads = 256;
+    // Fused expansion (default): one persistent kernel produces the items and consumes them as they appear.
+    // RIG_VARIANT bit 13 keeps the two kernels apart (A/B switch, and the per-pass timings of rig_timing).
+    const bool fused = two_pass && !(ix->variant & 8192) && ix->d.n < (1ull << 48);
+    ull a_tag = 0;
+    bool fused_ok = false;
+    uint32_t a_pmod = 1;   // every CTA produces its share first (measured: dedicating 1/2, 1/4, 1/8 of the CTAs to production is slower; RIG_FUSED_PROD overrides)
+    if (const char* ev = getenv("RIG_FUSED_PROD")) { int v = atoi(ev); if (v >= 1 && v <= 64) a_pmod = (uint32_t)v; }
+    if (fused) {
+        if (ix->items_zeroed != ix->items.p || ((ix->epoch + 1) & 0xFFFFu) == 0) {   // fresh allocation, or the 16-bit tag wraps
+            CU_TRY(cudaMemsetAsync(ix->items.p, 0, ix->items.cap, st));
+            ix->items_zeroed = ix->items.p;
+            ix->epoch = 0;
+        }
+        ix->epoch += 1;
+        a_tag = (ull)ix->epoch << 48;
+    }
 #define RIG_EXPAND2(W, DD, KP)                                                                                  \
     do {                                                                                                        \
-        if (two_pass) {                                                                                         \
+        if (fused) {                                                                                            \
+            auto kf = rigk::phi_fused_kernel<W, DD, KP, (sizeof(W) == 4 ? 5 : 3)>;                              \
+            uint64_t gf = (uint64_t)ix->sm_count * resident_ctas(kf, wthreads);                                 \
+            cudaLaunchConfig_t cfgf = cfg;                                                                      \
+            cfgf.gridDim = dim3((unsigned)gf); cfgf.blockDim = dim3((unsigned)wthreads);                        \
+            /* consumers wait for producers: the grid must be co-resident — a COOPERATIVE launch guarantees it or fails */ \
+            cudaLaunchAttribute fattr[2];                                                                       \
+            unsigned nfa = 0;                                                                                   \
+            if (cfg.numAttrs) fattr[nfa++] = attr[0];                                                           \
+            fattr[nfa].id = cudaLaunchAttributeCooperative; fattr[nfa].val.cooperative = 1; ++nfa;              \
+            cfgf.attrs = fattr; cfgf.numAttrs = nfa;                                                            \
+            if ((rc = rec(ix, 6, st))) return rc;                                                               \
+            cudaError_t fe = cudaLaunchKernelEx(&cfgf, kf, ix->d, a_N, a_choff, d_occoff, d_lo, d_hi, a_toe, a_jl, d_occ, \
+                                                a_ctr, a_cap, a_items, a_icap, seg_shift, a_tag, a_pmod);       \
+            if (fe == cudaSuccess) {                                                                            \
+                ix->timing.launches += 1; ix->timing.slices = 1;                                                \
+                if ((rc = rec(ix, 7, st))) return rc;                                                           \
+                fused_ok = true;                                                                                \
+            } else {                                                                                            \
+                cudaGetLastError();   /* not co-resident on this device right now: the two-kernel form below */ \
+            }                                                                                                   \
+        }                                                                                                       \
+        if (fused_ok) {                                                                                         \
+        } else if (two_pass) {                                                                                  \
             auto k1 = rigk::phi_expand_kernel<W, DD, KP, true>;                                                 \
-            auto k2 = (ix->variant & 64) ? rigk::phi_window_batch_kernel<W, DD, KP>                             \
+            auto k2 = (ix->variant & 64) ? rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), false> \
                       : ((ix->variant & 256) ? rigk::phi_window_kernel<W, DD, KP>                               \
                       : ((ix->variant & 2048) ? rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), true>  \
-                                              : rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), false>)); \
+                                              : rigk::phi_window_batch_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4)>)); \
             uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
             uint64_t g2 = (uint64_t)ix->sm_count * resident_ctas(k2, wthreads);                                 \
             g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
@@ -485,7 +663,7 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
             cfg2.gridDim = dim3((unsigned)g2); cfg2.blockDim = dim3((unsigned)wthreads);                        \
             const ull* c_items = a_items; const ull* c_ctr = a_ctr;                                             \
             CU_TRY(cudaLaunchKernelEx(&cfg2, k2, ix->d, c_items, c_ctr, d_occ, a_cap, a_icap, seg_shift));      \
-            ix->timing.launches += 2;                                                                           \
+            ix->timing.launches += 2; ix->timing.slices = 2;                                                    \
             if ((rc = rec(ix, 7, st))) return rc;                                                               \
         } else {                                                                                                \
             auto k1 = rigk::phi_expand_kernel<W, DD, KP, false>;                                                \
@@ -553,10 +731,9 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
         ix->last_items_cap = items_cap; ix->last_two_pass = two_pass;
         return launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st);
     };
-    CU_TRY(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(ull), st));
+    if ((rc = prep_call(ix, N, true, st))) return rc;
     if ((rc = rec(ix, 1, st))) return rc;
     if (N) {
-        warm_lf(ix, st);
         if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, d_occoff, st))) return rc;
     } else {
         CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
@@ -588,7 +765,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
     if (fits && total && (!queued || (need_items && items_bound(total, chains) > ix->last_items_cap))) {
         // not queued yet (buffer just grown), or the kernels returned at once because the item list was too short
         // (same test on the device): queue the expansion (again) with exact sizes
-        CU_TRY(cudaMemsetAsync(ix->d_counters + RIG_CTR_ITEMS, 0, sizeof(ull), st));
+        CU_TRY(cudaMemsetAsync(ix->d_counters + RIG_CTR_ITEMS, 0, 3 * sizeof(ull), st));  // items, producers done, items taken
         if ((rc = queue_expansion(need_items ? items_bound(total, chains) : 0))) return rc;
     }
     ix->timing.occ_total = total;

@@ -58,8 +58,10 @@ inline void die(int rc, const char* where) {
 // One rig_index per device; shard p covers patterns [N*p/G, N*(p+1)/G).
 class GpuFleet {
 public:
-    // count_only: ri-count never expands occurrences, so the Phi tables are built at their smallest (D = 1, no seed table)
-    explicit GpuFleet(const rib::LogicalIndex& L, int gpus, bool count_only = false) {
+    // count_only: ri-count never expands occurrences, so the Phi tables are built at their smallest (D = 1, no seed table).
+    // flat: file of the FLATTENED index (--flat): loaded instead of flattening when it exists and belongs to L
+    // (rig_index_load_flat), written after the first flatten otherwise; such a file always holds the full tables.
+    explicit GpuFleet(const rib::LogicalIndex& L, int gpus, bool count_only = false, const std::string& flat = std::string()) {
         int have = rig_device_count();
         if (have < 1) { std::cout << "Error: no CUDA device available (this build has no CPU query path)" << std::endl; exit(1); }
         G = gpus <= 0 ? 1 : (gpus > have ? have : gpus);
@@ -68,13 +70,26 @@ public:
         v.n = L.n; v.r = L.r; v.F = L.F;
         v.run_heads = L.run_heads.data(); v.run_lens = L.run_lens.data(); v.samples_last = L.samples_last.data();
         v.pred_pos = L.pred_pos.data(); v.pred_to_run = L.pred_to_run.data();
-        std::vector<int> rcs(G, 0);
+        std::vector<int> rcs(G, 0), loaded(G, 0);
         rig_options opt;
         std::memset(&opt, 0, sizeof(opt));
-        if (count_only) { opt.reserved[0] = 1; opt.reserved[2] = 1; }
-        run([&](int g) { rcs[g] = rig_index_create_ex(&v, g, &opt, &idx[g]); });
+        if (count_only && flat.empty()) { opt.reserved[0] = 1; opt.reserved[2] = 1; }
+        run([&](int g) {
+            if (!flat.empty()) {
+                int rc = rig_index_load_flat(flat.c_str(), &v, g, &idx[g]);
+                if (rc == RIG_OK) { loaded[g] = 1; return; }
+                if (rc != RIG_ERR_INDEX && rc != RIG_ERR_ARG) { rcs[g] = rc; return; }   // absent / another index's file: flatten
+            }
+            rcs[g] = rig_index_create_ex(&v, g, &opt, &idx[g]);
+        });
         for (int g = 0; g < G; ++g) if (rcs[g] != RIG_OK) die(rcs[g], "rig_index_create");
+        if (!flat.empty() && !loaded[0]) {
+            int rc = rig_index_save_flat(idx[0], flat.c_str());
+            if (rc != RIG_OK) std::cout << "Warning: could not write the flattened index to " << flat << std::endl;
+        }
+        from_flat = !flat.empty() && loaded[0];
     }
+    bool from_flat = false;
     ~GpuFleet() { for (auto* p : idx) rig_index_destroy(p); }
     int size() const { return G; }
     void attach_text(const uint8_t* text, uint64_t len) {  // -c: the indexed text goes to every GPU's HBM

@@ -127,6 +127,31 @@ def test_cli_multi_gpu_flag_is_shard_invariant(tmp_path):
     assert open(str(tmp_path / "a"), "rb").read() == open(str(tmp_path / "b"), "rb").read()
 
 
+@pytest.mark.gpu
+def test_cli_flat_file_is_written_once_and_reused(tmp_path):
+    """--flat F: the first run flattens and writes F, later runs (ri-locate and ri-count alike) load it instead of
+    flattening; no printed result changes; a flat file of another index is ignored (the index is flattened)."""
+    tfile, pfile, _, _ = make_inputs(tmp_path, n=60_000, N=300, m=7)
+    assert run([os.path.join(BIN, "ri-build"), tfile]).returncode == 0
+    flat = str(tmp_path / "idx.flat")
+    plain = run([os.path.join(BIN, "ri-locate"), "-c", tfile, "-o", str(tmp_path / "p"), tfile + ".ri", pfile])
+    first = run([os.path.join(BIN, "ri-locate"), "--flat", flat, "-c", tfile, "-o", str(tmp_path / "a"), tfile + ".ri", pfile])
+    assert first.returncode == 0 and os.path.getsize(flat) > 0
+    again = run([os.path.join(BIN, "ri-locate"), "--flat", flat, "-c", tfile, "-o", str(tmp_path / "b"), tfile + ".ri", pfile])
+    assert again.returncode == 0 and "Error" not in again.stdout
+    assert mask(plain.stdout) == mask(first.stdout) == mask(again.stdout)
+    assert open(str(tmp_path / "p"), "rb").read() == open(str(tmp_path / "a"), "rb").read() == open(str(tmp_path / "b"), "rb").read()
+    c0 = run([os.path.join(BIN, "ri-count"), tfile + ".ri", pfile])
+    c1 = run([os.path.join(BIN, "ri-count"), "--flat", flat, tfile + ".ri", pfile])
+    assert c0.returncode == 0 and c1.returncode == 0 and mask(c0.stdout) == mask(c1.stdout)
+    (tmp_path / "other").mkdir()
+    t2, p2, _, _ = make_inputs(tmp_path / "other", n=30_000, N=50, m=5)
+    assert run([os.path.join(BIN, "ri-build"), t2]).returncode == 0
+    o0 = run([os.path.join(BIN, "ri-count"), t2 + ".ri", p2])
+    o1 = run([os.path.join(BIN, "ri-count"), "--flat", flat, t2 + ".ri", p2])   # not this index's file
+    assert o1.returncode == 0 and mask(o0.stdout) == mask(o1.stdout)
+
+
 def test_ri_build_large_text_takes_the_pfp_route_and_equals_sais(tmp_path):
     """From 16 MB up ri-build constructs by prefix-free parsing; the .ri it writes holds exactly
     the arrays the in-memory SA-IS route gives (forced with RIB_BUILDER=sais), and the stdout lines are the same."""

@@ -85,7 +85,7 @@ def test_seed_table_and_two_pass_expansion(seg, wide):
 def test_seed_table_auto_policy():
     t = rib.gen_text("dna_drift", 300_000, 3_000, 3, 5)
     host = rib.HostIndex.from_text(t)
-    assert FlatCheck(host).seed_jump == 64       # small index: the largest window size fits the budget
+    assert FlatCheck(host).seed_jump == 128      # small index: the largest window size fits the budget
     assert FlatCheck(host, seed_jump=1).seed_jump == 0
     assert FlatCheck(host, seed_jump=48).rc == -1
 

@@ -2,6 +2,8 @@
 
 Bar: bit-exact (u64 ranges, offsets and every occurrence position, in locate_all order
 SA[hi], SA[hi-1], ..., SA[lo] — reference internal/r_index.hpp:340-351)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -277,11 +279,12 @@ def test_two_pass_expansion(seg, variant, monkeypatch):
         gpu.close()
 
 
-@pytest.mark.parametrize("variant", ["64", "72", "256", "264", "2048", "2056"])
+@pytest.mark.parametrize("variant", ["8192", "8200", "8256", "8264", "8448", "8456", "10240", "10248"])
 def test_window_pass_alternatives(variant, monkeypatch):
-    """The alternative forms of the window pass kept as A/B switches (RIG_VARIANT bit 6: direct sector stores with
-    warp-level item batches, bit 8: the same with per-lane refill, bit 11: whole lines through the bulk-copy engine), in
-    32- and 64-bit words (bit 3), give the oracle's output like the default whole-line form."""
+    """The expansion as TWO kernels (RIG_VARIANT bit 13: seed pass, then window pass) instead of the default fused
+    producer/consumer kernel, with each form of the window pass kept as an A/B switch (default: direct sector stores,
+    warp-level item batches; bit 6: whole lines staged in shared memory; bit 8: direct stores with per-lane refill;
+    bit 11: whole lines through the bulk-copy engine), in 32- and 64-bit words (bit 3): all give the oracle's output."""
     monkeypatch.setenv("RIG_VARIANT", variant)
     text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 321)
     host = rib.HostIndex.from_text(text)
@@ -395,3 +398,45 @@ def test_item_list_regrows_when_chains_exceed_the_guess():
         patt = mixed_patterns(text, N, m, N, alphabet=np.frombuffer(b"abcd", dtype=np.uint8))
         _check_all(gpu, port, patt, N, m, "many chains N=%d m=%d" % (N, m))
         assert gpu.timing()["chains"] > 2 * N + 1024 or m == 3
+
+
+def test_flat_index_file_round_trip(tmp_path):
+    """rig_index_save_flat / rig_index_load_flat: the flattened index written to a file and loaded back (no flatten step)
+    answers exactly like the index it was saved from, in 32- and 64-bit words; a file that belongs to another index,
+    a truncated file and a file that is not a flat index are refused with RIG_ERR_INDEX / an error, never loaded."""
+    import ctypes
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 77)
+    host = rib.HostIndex.from_text(text)
+    port = ob.PortIndex(text, sa=rib.suffix_array(text))
+    N, m = 900, 7
+    patt = mixed_patterns(text, N, m, 4, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    for variant in ("0", "8"):
+        os.environ["RIG_VARIANT"] = variant
+        try:
+            gpu = rib.GpuIndex(host)
+            path = str(tmp_path / ("idx%s.flat" % variant))
+            gpu.save_flat(path)
+            assert os.path.getsize(path) > gpu.info.device_bytes
+            g2 = rib.GpuIndex(host, flat=path)
+            assert g2.from_flat and g2.info.device_bytes == gpu.info.device_bytes and g2.info.seed_jump == gpu.info.seed_jump
+            _check_all(g2, port, patt, N, m, "flat variant=%s" % variant)
+            g3 = rib.GpuIndex(None, flat=path)     # no logical index at hand: the file is trusted
+            _check_all(g3, port, patt, N, m, "flat (unchecked) variant=%s" % variant)
+            # another index's flat file is refused, and the index is flattened the usual way instead
+            other = rib.HostIndex.from_text(rib.gen_text("dna_drift", 200_000, 2_000, 3, 78))
+            g4 = rib.GpuIndex(other, flat=path)
+            assert not g4.from_flat and g4.n == other.n
+            for g in (gpu, g2, g3, g4):
+                g.close()
+        finally:
+            os.environ.pop("RIG_VARIANT", None)
+    h = ctypes.c_void_p()
+    lib = rib.gpu_lib()
+    junk = tmp_path / "junk.flat"
+    junk.write_bytes(b"not a flat index" * 100)
+    assert lib.rig_index_load_flat(str(junk).encode(), None, 0, ctypes.byref(h)) == -5 and not h.value
+    data = open(path, "rb").read()
+    cut = tmp_path / "cut.flat"
+    cut.write_bytes(data[: len(data) // 2])
+    assert lib.rig_index_load_flat(str(cut).encode(), None, 0, ctypes.byref(h)) != 0 and not h.value
+    assert lib.rig_index_load_flat(str(tmp_path / "absent.flat").encode(), None, 0, ctypes.byref(h)) == -1

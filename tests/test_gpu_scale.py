@@ -91,7 +91,7 @@ def test_config_against_reference_answers(name):
     if name in FULL_SIZE:
         # ri-locate -c on the device over all of the batch's occurrences: brute-force counts from the text (hash join)
         # equal hi-lo+1 for every pattern, text[o, o+m) equals the pattern for every located o, positions distinct
-        assert gpu.info.words32 == (1 if n + 1 < 2**32 - 1 else 0) and gpu.info.seed_jump == 64
+        assert gpu.info.words32 == (1 if n + 1 < 2**32 - 1 else 0) and gpu.info.seed_jump == 128
         gpu.text_attach(text)
         del text
         lo2, hi2, off, occ, rep = gpu.locate_ex(batch, NB, m, rib.LOCATE_SORT | rib.LOCATE_CHECK)

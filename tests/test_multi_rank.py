@@ -50,6 +50,73 @@ def test_two_rank_sharding_equals_single_run(tmp_path):
         assert np.array_equal(g["off"], eoff) and np.array_equal(g["occ"], eocc)
 
 
+def _worker_balanced(rank, world, port, tmpdir):
+    """The strong-scaling flow of bench.py / GpuFleet::locate on CPU: count on equal-count shards, all-gather of the
+    per-pattern counts, contiguous shards re-cut at equal occurrence mass, locate, collation."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest as cf
+    from rindex_b200 import _shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    text = cf.rib.gen_text("dna_drift", 150_000, 1_500, 3, 99)
+    N, m = 403, 4                                    # short patterns: counts spread over three orders of magnitude
+    patt = cf.mixed_patterns(text, N, m, 23, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    engine = cf.FlatCheck(cf.rib.HostIndex.from_text(text), K=4)
+    a, b = _shard.shard_bounds(N, world, rank)
+    per = max(_shard.shard_bounds(N, world, r)[1] - _shard.shard_bounds(N, world, r)[0] for r in range(world))
+    lo, hi = engine.count(patt[a * m: b * m], b - a, m)
+    cnt = torch.zeros(per, dtype=torch.int64)
+    cnt[: b - a] = torch.from_numpy(np.where(hi >= lo, hi - lo + np.uint64(1), np.uint64(0)).astype(np.int64))
+    allc = [torch.zeros(per, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    nocc = np.concatenate([allc[r].numpy()[: _shard.shard_bounds(N, world, r)[1] - _shard.shard_bounds(N, world, r)[0]] for r in range(world)])
+    cuts = _shard.balanced_cuts(nocc, world)
+    c0, c1 = cuts[rank], cuts[rank + 1]
+    lo, hi, off, occ, _ = engine.locate(patt[c0 * m: c1 * m], c1 - c0, m)
+    goff, gocc = _shard.collate_occurrences(off, occ)
+    mass = [int(nocc[cuts[r]: cuts[r + 1]].sum()) for r in range(world)]
+    eq = [int(nocc[_shard.shard_bounds(N, world, r)[0]: _shard.shard_bounds(N, world, r)[1]].sum()) for r in range(world)]
+    np.savez(os.path.join(tmpdir, "bal%d.npz" % rank), off=goff, occ=gocc, cuts=np.array(cuts), mass=np.array(mass), eq=np.array(eq))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_mass_balanced_shards_equal_single_run(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker_balanced, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    text = rib.gen_text("dna_drift", 150_000, 1_500, 3, 99)
+    N, m = 403, 4
+    patt = mixed_patterns(text, N, m, 23, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    elo, ehi, eoff, eocc, _ = ob.PortIndex(text, sa=rib.suffix_array(text)).locate(patt, N, m)
+    for r in range(2):
+        g = np.load(str(tmp_path / ("bal%d.npz" % r)))
+        assert np.array_equal(g["off"], eoff) and np.array_equal(g["occ"], eocc)   # contiguous cuts: concatenation = the single run
+        assert g["cuts"][0] == 0 and g["cuts"][-1] == N
+        assert max(g["mass"]) <= max(g["eq"])                                       # never worse than equal-count shards
+
+
+def test_balanced_cuts_properties():
+    from rindex_b200 import _shard
+    rng = np.random.default_rng(3)
+    for N in (0, 1, 2, 17, 1000):
+        for G in (1, 2, 3, 8):
+            nocc = (rng.pareto(1.1, size=N) * 50).astype(np.uint64)
+            cuts = _shard.balanced_cuts(nocc, G)
+            assert len(cuts) == G + 1 and cuts[0] == 0 and cuts[-1] == N
+            assert all(x <= y for x, y in zip(cuts, cuts[1:]))
+    # a batch whose whole mass sits in one pattern cannot be split: every other shard is (almost) empty
+    nocc = np.zeros(100, dtype=np.uint64); nocc[40] = 10**9
+    cuts = _shard.balanced_cuts(nocc, 4)
+    assert sum(1 for a, b in zip(cuts, cuts[1:]) if a <= 40 < b) == 1
+
+
 def test_shard_bounds_partition():
     from rindex_b200 import _shard
     for N in (0, 1, 7, 100, 1001):
