@@ -484,7 +484,9 @@ def run_ours_count(args):
 
 class LocateJob:
     """One rank's part of a locate job: device-resident step and host-buffer (e2e) step, with the count -> all-gather
-    -> re-cut by occurrence mass -> locate sequence when there is more than one rank (`solo` = the whole job alone)."""
+    -> re-cut by occurrence mass -> locate sequence when there is more than one rank (`solo` = the whole job alone).
+    Equal-count shards are [r * per, (r + 1) * per) with per = ceil(N / world), so the all-gathered count buffer IS
+    the batch's count array (plus padding at its very end)."""
 
     def __init__(self, D, gpu, patt, N, m, stream, solo=False):
         torch = D.torch
@@ -494,46 +496,67 @@ class LocateJob:
         self.shard = _shard
         self.patt = patt
         self.d_patt = torch.from_numpy(patt).to(D.dev)          # the whole batch on every GPU (N x m bytes)
-        self.a, self.b = _shard.shard_bounds(N, self.world, self.rank)
-        self.per = max(_shard.shard_bounds(N, self.world, r)[1] - _shard.shard_bounds(N, self.world, r)[0] for r in range(self.world))
+        self.per = (N + self.world - 1) // self.world
+        self.a, self.b = min(N, self.rank * self.per), min(N, (self.rank + 1) * self.per)
         self.d_lo = torch.empty(N + 1, dtype=torch.int64, device=D.dev)
         self.d_hi = torch.empty(N + 1, dtype=torch.int64, device=D.dev)
         self.d_off = torch.empty(N + 2, dtype=torch.int64, device=D.dev)
         self.d_cnt = torch.zeros(self.per, dtype=torch.int64, device=D.dev)
         self.d_all = torch.zeros(self.world * self.per, dtype=torch.int64, device=D.dev)
+        if self.world > 1:
+            self.d_targets = (torch.arange(1, self.world, dtype=torch.float64, device=D.dev) / self.world)
         self.d_occ = None
         self.cuts = None
-        self.phase_ms = {}
 
     # -- re-balancing: equal-count count phase, all-gather of the counts, cuts of equal occurrence mass --
-    def _cuts_from(self, all_counts):
-        nocc = np.concatenate([all_counts[r * self.per: r * self.per + (self.shard.shard_bounds(self.N, self.world, r)[1] - self.shard.shard_bounds(self.N, self.world, r)[0])]
-                               for r in range(self.world)])
-        return self.shard.balanced_cuts(nocc, self.world), nocc
+    @staticmethod
+    def _refine(cand, c1, c2, targets, N):
+        """_shard.balanced_cuts' rule from the candidate cut points: the pattern that crosses a target goes to the side
+        that leaves the smaller excess. cand[k] = first prefix length whose work reaches target k; c1 / c2 = the
+        cumulative work of cand[k] / cand[k] - 1 patterns."""
+        cuts = [0]
+        for k in range(len(cand)):
+            c = int(cand[k])
+            if 0 < c <= N and (c1[k] - targets[k]) > (targets[k] - c2[k]):
+                c -= 1
+            cuts.append(min(max(c, cuts[-1]), N))
+        cuts.append(N)
+        return cuts
 
     def plan_dev(self):
-        """count phase on the device + NCCL all-gather; returns this rank's [c0, c1) and the per-pattern counts."""
+        """count phase on the device, NCCL all-gather of the counts, cut points computed on the device (prefix sum +
+        binary search); one 3 x (world - 1)-word copy brings them to the host, where the shard bounds are launch
+        parameters. Returns this rank's [c0, c1)."""
         torch, dist = self.D.torch, self.D.dist
         if self.world == 1:
-            return 0, self.N, None
+            return 0, self.N
         n = self.b - self.a
         self.gpu.count_dev(self.d_patt.data_ptr() + self.a * self.m, n, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.stream)
-        self.d_cnt.zero_()
-        self.d_cnt[:n] = (self.d_hi[:n] - self.d_lo[:n] + 1).clamp_(min=0)
+        torch.sub(self.d_hi[:n], self.d_lo[:n], out=self.d_cnt[:n])
+        self.d_cnt[:n].add_(1).clamp_(min=0)
         dist.all_gather_into_tensor(self.d_all, self.d_cnt)
-        cuts, nocc = self._cuts_from(self.d_all.cpu().numpy())      # one small D2H: the cut points are host-side launch parameters
-        self.cuts = cuts
-        return cuts[self.rank], cuts[self.rank + 1], nocc
+        cum = torch.cumsum((self.d_all[: self.N] + 64).to(torch.float64), 0)     # work(p) = n_occ(p) + 64, exact in f64 below 2^53
+        targets = self.d_targets * cum[-1]
+        cand = torch.searchsorted(cum, targets) + 1
+        idx = cand.clamp(max=self.N) - 1
+        c1 = cum[idx]
+        c2 = torch.where(idx > 0, cum[(idx - 1).clamp(min=0)], torch.zeros_like(c1))
+        h = torch.stack([cand.to(torch.float64), c1, c2, targets]).cpu().numpy()   # the only host round trip of the plan
+        self.cuts = self._refine(h[0].astype(np.int64), h[1], h[2], h[3], self.N)
+        return self.cuts[self.rank], self.cuts[self.rank + 1]
+
+    def counts_all(self):
+        return self.d_all[: self.N].cpu().numpy()
 
     def step_dev(self):
-        c0, c1, _ = self.plan_dev()
+        c0, c1 = self.plan_dev()
         return self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
                                    self.d_off.data_ptr(), self.d_occ.data_ptr(), self.d_occ.numel(), self.stream)
 
     def size_output(self):
         """Two-call protocol on this rank's shard; allocates the device occurrence buffer. Returns its occurrences."""
         torch = self.D.torch
-        c0, c1, _ = self.plan_dev()
+        c0, c1 = self.plan_dev()
         try:
             need = self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
                                        self.d_off.data_ptr(), None, 0, self.stream)
@@ -554,7 +577,7 @@ class LocateJob:
         self.h_off = torch.empty(self.N + 2, dtype=torch.int64).pin_memory()
         self.h_occ = torch.empty(max(occ_cap, 1), dtype=torch.int64).pin_memory()
         self.h_cnt = torch.zeros(self.per, dtype=torch.int64)
-        self.h_all = [torch.zeros(self.per, dtype=torch.int64) for _ in range(self.world)]
+        self.h_all = torch.zeros(self.world * self.per, dtype=torch.int64)
 
     def step_host(self):
         torch, dist = self.D.torch, self.D.dist
@@ -562,10 +585,10 @@ class LocateJob:
         if self.world > 1:
             n = self.b - self.a
             self.gpu.count_raw(self.h_patt.data_ptr() + self.a * self.m, n, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr())
-            self.h_cnt.zero_()
-            self.h_cnt[:n] = (self.h_hi[:n] - self.h_lo[:n] + 1).clamp_(min=0)
-            dist.all_gather(self.h_all, self.h_cnt, group=self.D.gloo)
-            cuts, _ = self._cuts_from(torch.cat(self.h_all).numpy())
+            torch.sub(self.h_hi[:n], self.h_lo[:n], out=self.h_cnt[:n])
+            self.h_cnt[:n].add_(1).clamp_(min=0)
+            dist.all_gather_into_tensor(self.h_all, self.h_cnt, group=self.D.gloo)
+            cuts = self.shard.balanced_cuts(self.h_all[: self.N].numpy(), self.world)
             c0, c1 = cuts[self.rank], cuts[self.rank + 1]
         tot = self.gpu.locate_raw(self.h_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr(),
                                   self.h_off.data_ptr(), self.h_occ.data_ptr(), self.h_occ.numel())
@@ -768,8 +791,9 @@ def run_ours(args):
     e2e_sum_ms = D.reduce([M.get("e2e_ms", 0.0)], "SUM")[0]
     eq_occ = None
     if world > 1:   # what equal-count shards would have given each rank (the imbalance the re-cut removes)
-        _, _, nocc_all = job.plan_dev()
-        eq = [float(nocc_all[job.shard.shard_bounds(N, world, r)[0]: job.shard.shard_bounds(N, world, r)[1]].sum()) for r in range(world)]
+        job.plan_dev()
+        nocc_all = job.counts_all()
+        eq = [float(nocc_all[min(N, r * job.per): min(N, (r + 1) * job.per)].sum()) for r in range(world)]
         eq_occ = max(eq) / (sum(eq) / world) if sum(eq) else 1.0
 
     if rank == 0:
