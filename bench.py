@@ -503,46 +503,21 @@ class LocateJob:
         self.d_off = torch.empty(N + 2, dtype=torch.int64, device=D.dev)
         self.d_cnt = torch.zeros(self.per, dtype=torch.int64, device=D.dev)
         self.d_all = torch.zeros(self.world * self.per, dtype=torch.int64, device=D.dev)
-        if self.world > 1:
-            self.d_targets = (torch.arange(1, self.world, dtype=torch.float64, device=D.dev) / self.world)
         self.d_occ = None
         self.cuts = None
 
     # -- re-balancing: equal-count count phase, all-gather of the counts, cuts of equal occurrence mass --
-    @staticmethod
-    def _refine(cand, c1, c2, targets, N):
-        """_shard.balanced_cuts' rule from the candidate cut points: the pattern that crosses a target goes to the side
-        that leaves the smaller excess. cand[k] = first prefix length whose work reaches target k; c1 / c2 = the
-        cumulative work of cand[k] / cand[k] - 1 patterns."""
-        cuts = [0]
-        for k in range(len(cand)):
-            c = int(cand[k])
-            if 0 < c <= N and (c1[k] - targets[k]) > (targets[k] - c2[k]):
-                c -= 1
-            cuts.append(min(max(c, cuts[-1]), N))
-        cuts.append(N)
-        return cuts
-
     def plan_dev(self):
-        """count phase on the device, NCCL all-gather of the counts, cut points computed on the device (prefix sum +
-        binary search); one 3 x (world - 1)-word copy brings them to the host, where the shard bounds are launch
-        parameters. Returns this rank's [c0, c1)."""
-        torch, dist = self.D.torch, self.D.dist
+        """count phase on the device (rig_count_batch_dev + rig_counts_dev), NCCL all-gather of the counts, cut points
+        by the library's device kernel (rig_balanced_cuts_dev: one launch, world + 1 words back to the host, where the
+        shard bounds are launch parameters). Returns this rank's [c0, c1)."""
         if self.world == 1:
             return 0, self.N
         n = self.b - self.a
         self.gpu.count_dev(self.d_patt.data_ptr() + self.a * self.m, n, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.stream)
-        torch.sub(self.d_hi[:n], self.d_lo[:n], out=self.d_cnt[:n])
-        self.d_cnt[:n].add_(1).clamp_(min=0)
-        dist.all_gather_into_tensor(self.d_all, self.d_cnt)
-        cum = torch.cumsum((self.d_all[: self.N] + 64).to(torch.float64), 0)     # work(p) = n_occ(p) + 64, exact in f64 below 2^53
-        targets = self.d_targets * cum[-1]
-        cand = torch.searchsorted(cum, targets) + 1
-        idx = cand.clamp(max=self.N) - 1
-        c1 = cum[idx]
-        c2 = torch.where(idx > 0, cum[(idx - 1).clamp(min=0)], torch.zeros_like(c1))
-        h = torch.stack([cand.to(torch.float64), c1, c2, targets]).cpu().numpy()   # the only host round trip of the plan
-        self.cuts = self._refine(h[0].astype(np.int64), h[1], h[2], h[3], self.N)
+        self.gpu.counts_dev(self.d_lo.data_ptr(), self.d_hi.data_ptr(), n, self.d_cnt.data_ptr(), self.stream)
+        self.D.dist.all_gather_into_tensor(self.d_all, self.d_cnt)
+        self.cuts = self.gpu.balanced_cuts_dev(self.d_all.data_ptr(), self.N, self.world, 64, self.stream)
         return self.cuts[self.rank], self.cuts[self.rank + 1]
 
     def counts_all(self):

@@ -213,6 +213,17 @@ int rig_break_range_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi
  * range's end as in the reference's signature (its value does not enter the result). */
 int rig_closest_run_break_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N, uint64_t* out);
 
+/* ---- multi-GPU fan-out on device buffers ----
+ * The index is replicated, the patterns are sharded; a locate job first COUNTS on equal-count shards, the hosts
+ * all-gather the per-pattern counts (8 bytes per pattern: NCCL), and the batch is re-cut into contiguous shards of
+ * near-equal work, work(p) = n_occ(p) + per_pattern_cost. rig_counts_dev: n_occ from the ranges of a count call
+ * (occ(), r_index.hpp:307-313). rig_balanced_cuts_dev: the shards + 1 ascending cut points (HOST array; synchronises),
+ * cuts[0] = 0, cuts[shards] = N; rank k takes patterns [cuts[k], cuts[k+1]). The rule is integer arithmetic and the
+ * same in r-index_b200/_shard.py and host/cli_common.hpp. */
+int rig_counts_dev(rig_index* idx, const uint64_t* d_lo, const uint64_t* d_hi, uint64_t N, uint64_t* d_nocc, void* stream);
+int rig_balanced_cuts_dev(rig_index* idx, const uint64_t* d_nocc, uint64_t N, uint32_t shards, uint64_t per_pattern_cost,
+                          uint64_t* cuts, void* stream);
+
 int rig_last_timing(const rig_index* idx, rig_timing* t);
 
 #ifdef __cplusplus

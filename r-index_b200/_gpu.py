@@ -20,7 +20,7 @@ DECLARED_SYMBOLS = [
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
     "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_locate_batch32",
     "rig_break_range_batch", "rig_closest_run_break_batch", "rig_fetch_occurrences", "rig_host_alloc", "rig_host_free",
-    "rig_index_save_flat", "rig_index_load_flat",
+    "rig_index_save_flat", "rig_index_load_flat", "rig_counts_dev", "rig_balanced_cuts_dev",
 ]
 
 RIG_ERR_CAPACITY = -4
@@ -110,6 +110,8 @@ def gpu_lib():
         lib.rig_closest_run_break_batch.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
         lib.rig_index_save_flat.argtypes = [_vp, ctypes.c_char_p]
         lib.rig_index_load_flat.argtypes = [ctypes.c_char_p, ctypes.POINTER(LogicalView), ctypes.c_int, ctypes.POINTER(_vp)]
+        lib.rig_counts_dev.argtypes = [_vp, _vp, _vp, _u64, _vp, _vp]
+        lib.rig_balanced_cuts_dev.argtypes = [_vp, _vp, _u64, _u32, _u64, _vp, _vp]
         lib.rig_fetch_occurrences.argtypes = [_vp, _u64, _u64, _vp]
         lib.rig_host_alloc.restype = _vp
         lib.rig_host_alloc.argtypes = [_u64]
@@ -401,6 +403,18 @@ class GpuIndex:
             e.needed = int(tot.value)
             raise e
         return int(tot.value)
+
+    def counts_dev(self, d_lo, d_hi, N, d_nocc, stream=None):
+        rc = self.lib.rig_counts_dev(self.h, d_lo, d_hi, N, d_nocc, stream)
+        if rc != 0:
+            raise RigError(rc, "rig_counts_dev")
+
+    def balanced_cuts_dev(self, d_nocc, N, shards, cost=64, stream=None):
+        cuts = (_u64 * (shards + 1))()
+        rc = self.lib.rig_balanced_cuts_dev(self.h, d_nocc, N, shards, cost, cuts, stream)
+        if rc != 0:
+            raise RigError(rc, "rig_balanced_cuts_dev")
+        return [int(x) for x in cuts]
 
     def digest_dev(self, d_values, count, stream=None):
         out = (_u64 * 2)()

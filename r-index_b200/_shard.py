@@ -18,17 +18,24 @@ def balanced_cuts(nocc, world, per_pattern_cost=64):
     occurrences of expansion). nocc: per-pattern occurrence counts of the WHOLE batch (after the count phase and
     the all-gather of the counts: 8 bytes per pattern). Returns world + 1 ascending cut points, cuts[0] = 0,
     cuts[world] = N; rank k takes [cuts[k], cuts[k+1]). Contiguity keeps the output order = concatenation of the
-    shard outputs."""
-    w = np.asarray(nocc, dtype=np.uint64).astype(np.float64) + float(per_pattern_cost)
-    N = w.size
-    cum = np.cumsum(w)
-    total = float(cum[-1]) if N else 0.0
+    shard outputs. Integer arithmetic only — the same rule, bit for bit, as the device kernel
+    (csrc/post_kernels.cuh: balanced_cuts_kernel) and the C++ fan-out (host/cli_common.hpp):
+      i = the first pattern with cum(i) * world >= total * k;  c = i + 1;
+      if cum(i) * world - total * k > total * k - cum(i-1) * world: c = i      (the crossing pattern goes to the side
+      that leaves the smaller excess);  cuts[k] = clamp(c, cuts[k-1], N)."""
+    w = np.asarray(nocc, dtype=np.uint64) + np.uint64(per_pattern_cost)
+    N = int(w.size)
+    cum = np.cumsum(w, dtype=np.uint64)
+    total = int(cum[-1]) if N else 0
     cuts = [0]
     for k in range(1, world):
-        c = int(np.searchsorted(cum, total * k / world, side="left")) + 1 if N else 0
-        # the pattern that crosses the target goes to the side that leaves the smaller excess
-        if N and c > 0 and c <= N and (cum[c - 1] - total * k / world) > (total * k / world - (cum[c - 2] if c >= 2 else 0.0)):
-            c -= 1
+        c = N
+        if N and total:
+            t = total * k
+            i = int(np.searchsorted(cum, np.uint64(-(-t // world)), side="left"))   # first i with cum[i] >= ceil(t / world)
+            if i < N:
+                ci, cp = int(cum[i]), (int(cum[i - 1]) if i else 0)
+                c = i if (ci * world - t) > (t - cp * world) else i + 1
         cuts.append(min(max(c, cuts[-1]), N))
     cuts.append(N)
     return cuts

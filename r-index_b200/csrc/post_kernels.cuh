@@ -355,4 +355,71 @@ range_nav_kernel(const FlatDev ix, int op, const u64* __restrict__ lo, const u64
     if (op == RANGE_BREAK_COUNT) out_a[t] = cnt;
 }
 
+// ---- multi-GPU fan-out helpers (contiguous shards re-cut at equal occurrence mass) --------------------
+// n_occ(p) = hi - lo + 1, or 0 for the empty range {1,0} (r_index.hpp:307-313)
+__global__ void __launch_bounds__(256) counts_kernel(const u64* __restrict__ lo, const u64* __restrict__ hi, u64 N, u64* __restrict__ nocc) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) { const u64 l = lo[i], h = hi[i]; nocc[i] = h >= l ? h - l + 1 : 0; }
+}
+
+// Cut points of `shards` contiguous shards of near-equal WORK, work(p) = n_occ(p) + cost. One CTA: block-wide running
+// prefix sum over the batch; where the prefix crosses k * total / shards the pattern that crosses goes to the side that
+// leaves the smaller excess. Pure integer arithmetic — the same rule, bit for bit, as r-index_b200/_shard.py
+// (balanced_cuts) and host/cli_common.hpp (GpuFleet::balanced_cuts):
+//   i = the first pattern with cum(i) * shards >= total * k;  c = i + 1;
+//   if (cum(i) * shards - total * k) > (total * k - cum(i - 1) * shards): c = i      (cum(-1) = 0)
+//   cuts[k] = clamp(c, cuts[k-1], N)        (applied on the host: cuts must ascend)
+// cuts_raw[k-1] = c for k = 1 .. shards-1. total * shards must stay below 2^64 (checked by the host: N * 2^40 * shards).
+__global__ void __launch_bounds__(1024) balanced_cuts_kernel(const u64* __restrict__ nocc, u64 N, u32 shards, u64 cost,
+                                                            u64* __restrict__ cuts_raw) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 s_total, s_carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0: total; pass 1: crossings
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (u64 base = 0; base < N; base += blockDim.x) {
+            const u64 i = base + threadIdx.x;
+            const u64 v = i < N ? nocc[i] + cost : 0;
+            u64 inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const u64 t = __shfl_up_sync(RIG_FULL, inc, off);
+                if (lane >= off) inc += t;
+            }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                u64 ws = wsum[lane], wi = ws;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const u64 t = __shfl_up_sync(RIG_FULL, wi, off);
+                    if (lane >= off) wi += t;
+                }
+                wsum[lane] = wi - ws;   // exclusive prefix of the warp sums
+            }
+            __syncthreads();
+            const u64 cum = s_carry + wsum[w] + inc;   // inclusive prefix at i
+            if (pass == 1 && i < N) {
+                const u64 prev = cum - v, total = s_total;
+                for (u32 k = 1; k < shards; ++k) {      // does pattern i cross target k ?  prev * shards < total * k <= cum * shards
+                    const u64 t = total * k;
+                    if (prev * shards < t && cum * shards >= t) {
+                        u64 c = i + 1;
+                        if (cum * shards - t > t - prev * shards) c = i;
+                        cuts_raw[k - 1] = c;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) s_carry = cum;
+            __syncthreads();
+        }
+        if (pass == 0) {
+            if (threadIdx.x == 0) s_total = s_carry;
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace rigk

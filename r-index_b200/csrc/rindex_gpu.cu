@@ -1139,6 +1139,43 @@ int rig_break_range_batch(rig_index* ix, const uint64_t* lo, const uint64_t* hi,
     return RIG_OK;
 }
 
+// ---- multi-GPU fan-out helpers on device buffers ----------------------------------------------------
+int rig_counts_dev(rig_index* ix, const uint64_t* d_lo, const uint64_t* d_hi, uint64_t N, uint64_t* d_nocc, void* stream) {
+    if (!ix || (N && (!d_lo || !d_hi || !d_nocc))) return RIG_ERR_ARG;
+    if (!N) return RIG_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    const uint64_t nb = (N + 255) / 256;
+    if (nb > 0x7fffffffull) return RIG_ERR_ARG;
+    rigk::counts_kernel<<<(unsigned)nb, 256, 0, stream ? (cudaStream_t)stream : ix->stream>>>((const ull*)d_lo, (const ull*)d_hi, N, (ull*)d_nocc);
+    CU_TRY(cudaGetLastError());
+    return RIG_OK;
+}
+
+int rig_balanced_cuts_dev(rig_index* ix, const uint64_t* d_nocc, uint64_t N, uint32_t shards, uint64_t per_pattern_cost,
+                          uint64_t* cuts, void* stream) {
+    if (!ix || !cuts || shards < 1 || shards > 1024 || (N && !d_nocc) || N >= (1ull << 40) / shards) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    cuts[0] = 0;
+    for (uint32_t k = 1; k <= shards; ++k) cuts[k] = N;
+    if (shards == 1 || N == 0) return RIG_OK;
+    int rc;
+    if ((rc = ix->crep.ensure(1024 * 8))) return rc;
+    CU_TRY(cudaMemsetAsync(ix->crep.p, 0xFF, (shards - 1) * 8, st));   // ~0: no pattern crosses this target (empty batch mass)
+    rigk::balanced_cuts_kernel<<<1, 1024, 0, st>>>((const ull*)d_nocc, N, shards, per_pattern_cost, (ull*)ix->crep.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ix->h_post, ix->crep.p, std::min<uint32_t>(shards - 1, 8) * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<ull> big;
+    if (shards - 1 > 8) { big.resize(shards - 1); CU_TRY(cudaMemcpyAsync(big.data(), ix->crep.p, (shards - 1) * 8, cudaMemcpyDeviceToHost, st)); }
+    CU_TRY(cudaStreamSynchronize(st));
+    for (uint32_t k = 1; k < shards; ++k) {
+        ull c = shards - 1 > 8 ? big[k - 1] : ix->h_post[k - 1];
+        if (c == ~0ull) c = N;
+        cuts[k] = std::min<uint64_t>(std::max<uint64_t>(c, cuts[k - 1]), N);
+    }
+    return RIG_OK;
+}
+
 int rig_last_timing(const rig_index* cix, rig_timing* t) {
     if (!cix || !t) return RIG_ERR_ARG;
     rig_index* ix = const_cast<rig_index*>(cix);

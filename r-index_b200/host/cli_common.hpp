@@ -113,14 +113,23 @@ public:
     // SURVEY §8e re-balancing: contiguous shards of near-equal WORK, work(p) = n_occ(p) + 64 (the backward search of a
     // pattern costs about as much as a few dozen occurrences of expansion). Same rule as r-index_b200/_shard.py.
     static std::vector<uint64_t> balanced_cuts(const uint64_t* lo, const uint64_t* hi, uint64_t N, int G) {
-        std::vector<double> cum(N);
-        double acc = 0;
-        for (uint64_t p = 0; p < N; ++p) { acc += (hi[p] >= lo[p] ? double(hi[p] - lo[p] + 1) : 0.0) + 64.0; cum[p] = acc; }
+        // integer arithmetic only: the rule of _shard.py / balanced_cuts_kernel, bit for bit
+        std::vector<uint64_t> cum(N);
+        uint64_t acc = 0;
+        for (uint64_t p = 0; p < N; ++p) { acc += (hi[p] >= lo[p] ? hi[p] - lo[p] + 1 : 0) + 64; cum[p] = acc; }
+        const unsigned __int128 W = (unsigned)G, total = acc;
         std::vector<uint64_t> cuts(1, 0);
         for (int k = 1; k < G; ++k) {
-            const double target = acc * k / G;
-            uint64_t c = N ? uint64_t(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()) + 1 : 0;
-            if (N && c > 0 && c <= N && (cum[c - 1] - target) > (target - (c >= 2 ? cum[c - 2] : 0.0))) --c;
+            uint64_t c = N;
+            if (N && acc) {
+                const unsigned __int128 t = total * (unsigned)k;
+                const uint64_t need = (uint64_t)((t + W - 1) / W);   // first i with cum[i] >= ceil(t / G)
+                const uint64_t i = uint64_t(std::lower_bound(cum.begin(), cum.end(), need) - cum.begin());
+                if (i < N) {
+                    const unsigned __int128 ci = cum[i], cp = i ? cum[i - 1] : 0;
+                    c = (ci * W - t) > (t - cp * W) ? i : i + 1;
+                }
+            }
             cuts.push_back(std::min<uint64_t>(std::max<uint64_t>(c, cuts.back()), N));
         }
         cuts.push_back(N);

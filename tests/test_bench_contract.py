@@ -44,31 +44,6 @@ def test_reference_arm_other_ranks_exit_quietly():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_bench_device_side_cut_points_equal_shard_rule():
-    """bench.py computes the mass-balanced cut points with torch ops on the device (prefix sum + binary search) and
-    finishes them on the host (LocateJob._refine); the result must be _shard.balanced_cuts' — the rule the C++ CLIs
-    (GpuFleet::balanced_cuts) and the gloo test use."""
-    import numpy as np
-    torch = pytest.importorskip("torch")
-    import bench
-    from conftest import rib  # noqa: F401  (registers the package)
-    from rindex_b200 import _shard
-    rng = np.random.default_rng(11)
-    for N in (1, 2, 9, 1000, 20000):
-        for W in (2, 3, 8):
-            nocc = (rng.pareto(1.2, size=N) * 100).astype(np.int64)
-            if N > 5:
-                nocc[rng.integers(0, N, size=3)] = 0
-            cum = torch.cumsum((torch.from_numpy(nocc) + 64).to(torch.float64), 0)
-            targets = (torch.arange(1, W, dtype=torch.float64) / W) * cum[-1]
-            cand = torch.searchsorted(cum, targets) + 1
-            idx = cand.clamp(max=N) - 1
-            c1 = cum[idx]
-            c2 = torch.where(idx > 0, cum[(idx - 1).clamp(min=0)], torch.zeros_like(c1))
-            got = bench.LocateJob._refine(cand.numpy(), c1.numpy(), c2.numpy(), targets.numpy(), N)
-            assert got == _shard.balanced_cuts(nocc.astype(np.uint64), W), (N, W)
-
-
 def test_default_workloads_and_shared_config():
     import bench
     assert bench.job_size("c5", 8) == bench.job_size("c5", 1) == 100_000          # strong: one fixed job

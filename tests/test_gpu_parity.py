@@ -440,3 +440,27 @@ def test_flat_index_file_round_trip(tmp_path):
     cut.write_bytes(data[: len(data) // 2])
     assert lib.rig_index_load_flat(str(cut).encode(), None, 0, ctypes.byref(h)) != 0 and not h.value
     assert lib.rig_index_load_flat(str(tmp_path / "absent.flat").encode(), None, 0, ctypes.byref(h)) == -1
+
+
+def test_device_balanced_cuts_equal_host_rule():
+    """rig_counts_dev + rig_balanced_cuts_dev (the multi-GPU fan-out helpers) give the cut points of
+    _shard.balanced_cuts — the integer rule the C++ CLIs and the gloo test use — on skewed, empty and tiny batches."""
+    torch = pytest.importorskip("torch")
+    from rindex_b200 import _shard
+    text = rib.gen_text("dna_drift", 50_000, 1_000, 3, 3)
+    gpu = rib.GpuIndex(rib.HostIndex.from_text(text))
+    rng = np.random.default_rng(11)
+    dev = torch.device("cuda:0")
+    for N in (1, 2, 9, 1000, 1025, 70_000):
+        for W in (1, 2, 3, 8):
+            nocc = (rng.pareto(1.2, size=N) * 100).astype(np.int64)
+            if N > 5:
+                nocc[rng.integers(0, N, size=3)] = 0
+            d = torch.from_numpy(nocc).to(dev)
+            assert gpu.balanced_cuts_dev(d.data_ptr(), N, W) == _shard.balanced_cuts(nocc.astype(np.uint64), W), (N, W)
+    assert gpu.balanced_cuts_dev(0, 0, 4) == [0, 0, 0, 0, 0]
+    lo = torch.tensor([5, 1, 0, 7], dtype=torch.int64, device=dev); hi = torch.tensor([9, 0, 0, 6], dtype=torch.int64, device=dev)
+    out = torch.zeros(4, dtype=torch.int64, device=dev)
+    gpu.counts_dev(lo.data_ptr(), hi.data_ptr(), 4, out.data_ptr())
+    torch.cuda.synchronize()
+    assert out.tolist() == [5, 0, 1, 0]
