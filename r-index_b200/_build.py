@@ -5,6 +5,7 @@
   cli/ri-build, ri-count, ri-locate       host C++ mains linked against both
 """
 import os
+import platform
 import shutil
 import subprocess
 
@@ -14,6 +15,9 @@ INC = os.path.join(ROOT, "include")
 GPU_SO = os.path.join(PKG, "librindex_gpu.so")
 HOST_SO = os.path.join(PKG, "librindex_host.so")
 CLI_DIR = os.path.join(PKG, "bin")
+
+# host code: AVX2-class x86 (built here, run on the GPU box: not -march=native); other hosts (aarch64 Grace) get the default
+MARCH = ["-march=x86-64-v3"] if platform.machine() in ("x86_64", "AMD64") else []
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -45,7 +49,7 @@ def build_host(force=False):
     srcs = [os.path.join(PKG, "host", f) for f in ("rindex_host.cpp", "logical_index.hpp", "sais.hpp", "textgen.hpp", "pfp_builder.hpp")]
     srcs += [os.path.join(INC, "rindex_host.h"), os.path.join(INC, "rindex_gpu.h")]
     if force or _newer(HOST_SO, srcs):
-        _run(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", INC,
+        _run(["/usr/bin/g++", "-O3"] + MARCH + ["-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", INC,
               "-o", HOST_SO, srcs[0]])
     return HOST_SO
 
@@ -72,7 +76,7 @@ def build_cli(force=False):
             continue
         out = os.path.join(CLI_DIR, name)
         if force or _newer(out, [src, GPU_SO] + hdrs):
-            _run(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-w", "-pthread", "-I", INC, "-I", os.path.join(PKG, "host"),
+            _run(["/usr/bin/g++", "-O3"] + MARCH + ["-std=c++17", "-w", "-pthread", "-I", INC, "-I", os.path.join(PKG, "host"),
                   "-o", out, src, "-L", PKG, "-lrindex_gpu", "-Wl,-rpath,$ORIGIN/..", "-L/usr/local/cuda/lib64"])
         outs.append(out)
     return outs

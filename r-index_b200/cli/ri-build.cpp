@@ -60,16 +60,20 @@ int main(int argc, char** argv) {
     cout << "Building r-index of input file " << input_file << endl;
     cout << "Index will be saved to " << idx_file << endl;
     // The reference copies the file into a string (ri-build.cpp:121-129). Here the file is mapped: the prefix-free
-    // parsing builder reads the text twice, front to back, and keeps only (offset, length) references into it, so the
-    // resident memory of a large build is the dictionary and the parse, not the text.
+    // parsing builder scans the text front to back twice and otherwise touches it at the offsets of its dictionary
+    // phrases (comparisons, sorting, the dictionary fill), keeping only (offset, length) references into it, so the
+    // resident memory of a large build is the dictionary and the parse, not the text. No access-pattern hint is
+    // given: MADV_SEQUENTIAL would drop pages the phrase comparisons come back to. The file must not be truncated
+    // while the build runs (a mapped read past the new end raises SIGBUS, which a private copy would not).
     int fd = open(input_file.c_str(), O_RDONLY);
     struct stat sb;
     const uint8_t* text = nullptr;
     size_t text_len = 0;
     string fallback;
+    void* mapped = nullptr;
     if (fd >= 0 && fstat(fd, &sb) == 0 && sb.st_size > 0) {
         void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m != MAP_FAILED) { text = (const uint8_t*)m; text_len = (size_t)sb.st_size; madvise(m, text_len, MADV_SEQUENTIAL); }
+        if (m != MAP_FAILED) { text = (const uint8_t*)m; text_len = (size_t)sb.st_size; mapped = m; }
     }
     if (!text) {  // empty or unmappable input (a pipe, ...): read it as the reference does
         std::ifstream fs(input_file, std::ios::binary);
@@ -85,6 +89,7 @@ int main(int argc, char** argv) {
         r_index<> idx(text, text_len, sais);
         idx.serialize(out);
     }
+    if (mapped) munmap(mapped, text_len);
     if (fd >= 0) close(fd);
     auto t2 = high_resolution_clock::now();
     uint64_t total = std::chrono::duration_cast<std::chrono::duration<double, std::ratio<1>>>(t2 - t1).count();

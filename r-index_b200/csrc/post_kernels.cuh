@@ -22,21 +22,21 @@ namespace rigk {
 // (i <-> block_end - 1 - i), followed by half-cleaners at distances k/4, k/8, .., 1. Because every
 // compare-exchange puts the smaller key at the lower index, positions >= len behave as +infinity without
 // being stored: a compare-exchange whose upper index is >= len is skipped. No padding to a power of two.
-template <typename KT>
-__device__ __forceinline__ void bitonic_sort_inplace(KT* s, u32 len, u32 tid, u32 nthreads) {
-    u32 P = 1;
+template <typename KT, typename LT>   // LT: index type (u32 for the shared-memory tiers, u64 in global memory: a segment may exceed 2^31 keys)
+__device__ __forceinline__ void bitonic_sort_inplace(KT* s, LT len, LT tid, LT nthreads) {
+    LT P = 1;
     while (P < len) P <<= 1;
-    for (u32 k = 2; k <= P; k <<= 1) {
-        const u32 hk = k >> 1;
-        for (u32 i = tid; i < (P >> 1); i += nthreads) {  // mirror step
-            const u32 blk = i / hk, off = i - blk * hk;
-            const u32 a = blk * k + off, b = blk * k + k - 1 - off;
+    for (LT k = 2; k <= P && k != 0; k <<= 1) {
+        const LT hk = k >> 1;
+        for (LT i = tid; i < (P >> 1); i += nthreads) {  // mirror step
+            const LT blk = i / hk, off = i - blk * hk;
+            const LT a = blk * k + off, b = blk * k + k - 1 - off;
             if (b < len) { const KT x = s[a], y = s[b]; if (x > y) { s[a] = y; s[b] = x; } }
         }
         __syncthreads();
-        for (u32 j = hk >> 1; j >= 1; j >>= 1) {          // half-cleaners
-            for (u32 i = tid; i < (P >> 1); i += nthreads) {
-                const u32 a = ((i / j) * (j << 1)) + (i % j), b = a + j;
+        for (LT j = hk >> 1; j >= 1; j >>= 1) {          // half-cleaners
+            for (LT i = tid; i < (P >> 1); i += nthreads) {
+                const LT a = ((i / j) * (j << 1)) + (i % j), b = a + j;
                 if (b < len) { const KT x = s[a], y = s[b]; if (x > y) { s[a] = y; s[b] = x; } }
             }
             __syncthreads();
@@ -71,20 +71,19 @@ segsort_smem_kernel(const u64* __restrict__ occ_off, u64* __restrict__ occ, u64 
     u64* g = occ + a;
     for (u32 i = threadIdx.x; i < len; i += blockDim.x) s[i] = (KT)g[i];
     __syncthreads();
-    bitonic_sort_inplace<KT>(s, len, threadIdx.x, blockDim.x);
+    bitonic_sort_inplace<KT, u32>(s, len, threadIdx.x, blockDim.x);
     for (u32 i = threadIdx.x; i < len; i += blockDim.x) g[i] = (u64)s[i];
 }
 
 // Last tier: segments of any length, sorted in place in global memory (L2-resident for the sizes that occur)
-// by one CTA each. Lengths >= 2^32 are not supported (a pattern cannot have more than n < 2^63 occurrences,
-// but one CTA would not finish; the host refuses them).
+// by one CTA each, with 64-bit indices (a one-letter pattern on a multi-GB text has more than 2^31 occurrences).
 __global__ void __launch_bounds__(1024)
 segsort_global_kernel(const u64* __restrict__ occ_off, u64* __restrict__ occ, const u32* __restrict__ seg_list,
                       const u64* __restrict__ seg_count) {
     if (blockIdx.x >= __ldcg(seg_count)) return;
     const u64 p = seg_list[blockIdx.x];
     const u64 a = occ_off[p], b = occ_off[p + 1];
-    bitonic_sort_inplace<u64>(occ + a, (u32)(b - a), threadIdx.x, blockDim.x);
+    bitonic_sort_inplace<u64, u64>(occ + a, b - a, (u64)threadIdx.x, (u64)blockDim.x);
 }
 
 // ------------------------------------------------------------------ -c check
@@ -372,52 +371,47 @@ __global__ void __launch_bounds__(256) counts_kernel(const u64* __restrict__ lo,
 // cuts_raw[k-1] = c for k = 1 .. shards-1. total * shards must stay below 2^64 (checked by the host: N * 2^40 * shards).
 __global__ void __launch_bounds__(1024) balanced_cuts_kernel(const u64* __restrict__ nocc, u64 N, u32 shards, u64 cost,
                                                             u64* __restrict__ cuts_raw) {
+    // every thread owns a contiguous chunk: chunk sums -> block-wide exclusive scan -> each thread walks its chunk
+    // again looking for the crossings (two sweeps over 8 * N bytes by one CTA: ~10 us for 1e5 patterns)
     __shared__ u64 wsum[32];
-    __shared__ u64 s_total, s_carry;
+    __shared__ u64 s_total;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int pass = 0; pass < 2; ++pass) {   // pass 0: total; pass 1: crossings
-        if (threadIdx.x == 0) s_carry = 0;
-        __syncthreads();
-        for (u64 base = 0; base < N; base += blockDim.x) {
-            const u64 i = base + threadIdx.x;
-            const u64 v = i < N ? nocc[i] + cost : 0;
-            u64 inc = v;
+    const u64 per = (N + blockDim.x - 1) / blockDim.x;
+    const u64 i0 = min(N, (u64)threadIdx.x * per), i1 = min(N, i0 + per);
+    if (threadIdx.x < shards - 1) cuts_raw[threadIdx.x] = ~0ull;   // no pattern crosses this target (shards <= 1024)
+    u64 mine = 0;
+    for (u64 i = i0; i < i1; ++i) mine += nocc[i] + cost;
+    u64 inc = mine;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const u64 t = __shfl_up_sync(RIG_FULL, inc, off);
-                if (lane >= off) inc += t;
-            }
-            if (lane == 31) wsum[w] = inc;
-            __syncthreads();
-            if (w == 0) {
-                u64 ws = wsum[lane], wi = ws;
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 t = __shfl_up_sync(RIG_FULL, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        u64 ws = wsum[lane], wi = ws;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const u64 t = __shfl_up_sync(RIG_FULL, wi, off);
-                    if (lane >= off) wi += t;
-                }
-                wsum[lane] = wi - ws;   // exclusive prefix of the warp sums
-            }
-            __syncthreads();
-            const u64 cum = s_carry + wsum[w] + inc;   // inclusive prefix at i
-            if (pass == 1 && i < N) {
-                const u64 prev = cum - v, total = s_total;
-                for (u32 k = 1; k < shards; ++k) {      // does pattern i cross target k ?  prev * shards < total * k <= cum * shards
-                    const u64 t = total * k;
-                    if (prev * shards < t && cum * shards >= t) {
-                        u64 c = i + 1;
-                        if (cum * shards - t > t - prev * shards) c = i;
-                        cuts_raw[k - 1] = c;
-                    }
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == blockDim.x - 1) s_carry = cum;
-            __syncthreads();
+        for (int off = 1; off < 32; off <<= 1) {
+            const u64 t = __shfl_up_sync(RIG_FULL, wi, off);
+            if (lane >= off) wi += t;
         }
-        if (pass == 0) {
-            if (threadIdx.x == 0) s_total = s_carry;
-            __syncthreads();
+        wsum[lane] = wi - ws;   // exclusive prefix of the warp sums
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    const u64 total = s_total;
+    u64 cum = wsum[w] + inc - mine;   // work before this thread's chunk
+    for (u64 i = i0; i < i1; ++i) {
+        const u64 prev = cum;
+        cum += nocc[i] + cost;
+        for (u32 k = 1; k < shards; ++k) {      // does pattern i cross target k ?  prev * shards < total * k <= cum * shards
+            const u64 t = total * k;
+            if (prev * shards < t && cum * shards >= t) {
+                u64 c = i + 1;
+                if (cum * shards - t > t - prev * shards) c = i;
+                cuts_raw[k - 1] = c;
+            }
         }
     }
 }

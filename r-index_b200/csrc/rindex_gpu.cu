@@ -1161,7 +1161,6 @@ int rig_balanced_cuts_dev(rig_index* ix, const uint64_t* d_nocc, uint64_t N, uin
     if (shards == 1 || N == 0) return RIG_OK;
     int rc;
     if ((rc = ix->crep.ensure(1024 * 8))) return rc;
-    CU_TRY(cudaMemsetAsync(ix->crep.p, 0xFF, (shards - 1) * 8, st));   // ~0: no pattern crosses this target (empty batch mass)
     rigk::balanced_cuts_kernel<<<1, 1024, 0, st>>>((const ull*)d_nocc, N, shards, per_pattern_cost, (ull*)ix->crep.p);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(ix->h_post, ix->crep.p, std::min<uint32_t>(shards - 1, 8) * 8, cudaMemcpyDeviceToHost, st));

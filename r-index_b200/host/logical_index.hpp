@@ -8,6 +8,7 @@
 //   pred / pred_to_run r_index.hpp:108-146   text positions of the FIRST symbol of every run, sorted, + run ids
 // This header keeps the same information as plain arrays; the GPU library flattens them at load.
 #pragma once
+#include <exception>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -123,8 +124,23 @@ inline bool load(LogicalIndex& L, std::istream& in) {
     in.read((char*)&L.n, 8); in.read((char*)&L.r, 8); in.read((char*)&L.terminator_position, 8);
     in.read((char*)L.F, 257 * 8);
     if (!in) return false;
-    L.run_heads.resize(L.r); L.run_lens.resize(L.r); L.samples_last.resize(L.r);
-    L.pred_pos.resize(L.r); L.pred_to_run.resize(L.r);
+    // sanity before any allocation: a truncated or corrupt file must be refused, not turned into a bad_alloc
+    if (L.n < 1 || L.r < 1 || L.r > L.n || L.terminator_position >= L.n || L.F[0] != 0 || L.F[256] != L.n) return false;
+    {
+        const std::streampos here = in.tellg();
+        if (here != std::streampos(-1)) {   // seekable: the five arrays (33 bytes per run) must all be there
+            in.seekg(0, std::ios::end);
+            const std::streampos end = in.tellg();
+            in.seekg(here);
+            if (end == std::streampos(-1) || (uint64_t)(end - here) / 33 < L.r) return false;
+        }
+    }
+    try {
+        L.run_heads.resize(L.r); L.run_lens.resize(L.r); L.samples_last.resize(L.r);
+        L.pred_pos.resize(L.r); L.pred_to_run.resize(L.r);
+    } catch (const std::exception&) {
+        return false;
+    }
     in.read((char*)L.run_heads.data(), (std::streamsize)L.r);
     in.read((char*)L.run_lens.data(), (std::streamsize)(L.r * 8));
     in.read((char*)L.samples_last.data(), (std::streamsize)(L.r * 8));

@@ -154,3 +154,24 @@ def test_pfp_builder_equals_sais_builder_generators_and_golden():
         rib.HostIndex.from_text_pfp(np.frombuffer(b"ab\x01cd", dtype=np.uint8))
     small = rib.HostIndex.from_text_auto(np.frombuffer(b"abracadabra", dtype=np.uint8))
     assert small.used_pfp is False                                # below 16 MB the SA-IS route is used
+
+
+def test_truncated_or_corrupt_index_file_is_refused(tmp_path):
+    """rib::load checks n, r and the stream length before it allocates: a truncated file or a header with an absurd
+    run count gives RIH_ERR_FORMAT (the CLIs print their error and exit), never a bad_alloc / terminate."""
+    text = rib.gen_text("dna_drift", 50_000, 1_000, 3, 9)
+    good = str(tmp_path / "good.rib")
+    rib.HostIndex.from_text(text).save(good)
+    assert rib.HostIndex.load(good).n == text.size + 1
+    blob = open(good, "rb").read()
+    o = blob.index(b"RIB200v1")      # the `fast` flag byte precedes the container (ri-build.cpp:133)
+    assert int.from_bytes(blob[o + 8: o + 16], "little") == text.size + 1
+    cases = {"cut_arrays": blob[: len(blob) // 2], "cut_header": blob[: o + 40], "empty": b"",
+             "huge_r": blob[: o + 16] + (2**62).to_bytes(8, "little") + blob[o + 24:],
+             "r_gt_n": blob[: o + 8] + (5).to_bytes(8, "little") + (9).to_bytes(8, "little") + blob[o + 24:],
+             "bad_magic": blob[:o] + b"XXXXXXXX" + blob[o + 8:]}
+    for name, data in cases.items():
+        p = str(tmp_path / (name + ".rib"))
+        open(p, "wb").write(data)
+        with pytest.raises(Exception):
+            rib.HostIndex.load(p)
