@@ -67,9 +67,15 @@ struct PhiTable {
     std::vector<u64> delta;   // [pieces * D]
     std::vector<u64> rec;     // [nbkt * RW]
     std::vector<u64> pent;    // [pieces * RW]
+    bool packable = true;     // D = 6: every bucket's (nxt, cnt) fits the shared word
     u64 pieces() const { return start.size(); }
     u64 bytes(bool w32) const { return (rec.size() + pent.size()) * (w32 ? 4 : 8); }
-    static u32 record_words(u32 D) { return D == 1 ? 4 : (D <= 4 ? 8 : 16); }
+    static u32 record_words(u32 D) { return D == 1 ? 4 : (D <= 6 ? 8 : 16); }
+    // D = 6 ("six occurrences per 32-byte entry", 32-bit words only): the 6 deltas and s1 / start fill 7 of the 8 words,
+    // so nxt and cnt share the last one: nxt in the low 24 bits, cnt in the high 8 (the flatten step falls back to
+    // D = 4 when a table has 2^24 pieces or a bucket holds 255 piece starts).
+    static u64 nxt_of(const u64* w, u32 D) { return D == 6 ? (w[7] & 0xFFFFFFull) : w[D + 1]; }
+    static u64 cnt_of(const u64* w, u32 D) { return D == 6 ? ((w[7] >> 24) & 0xFFull) : w[D + 2]; }
     u64 piece_of(u64 i) const { return (u64)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1; }
     // scalar evaluation of Phi^j(i), 1 <= j <= D (host-side construction + tests)
     u64 apply(u64 i, u32 j, u64 n) const {
@@ -89,7 +95,8 @@ struct PhiTable {
         unsigned T = std::thread::hardware_concurrency();
         if (T > 32) T = 32;
         if (T < 1 || nbkt < (1u << 16)) T = 1;
-        auto fill = [&](u64 q0, u64 q1, u64 k0, u64 k1) {
+        packable = true;
+        auto fill = [&](u64 q0, u64 q1, u64 k0, u64 k1) {   // (`packable` is only ever cleared: a benign race between the fill threads)
             for (u64 k = k0; k < k1; ++k) {
                 for (u32 j = 0; j < D; ++j) pent[k * RW + j] = delta[k * D + j];
                 pent[k * RW + D] = start[k];
@@ -104,8 +111,14 @@ struct PhiTable {
                 u64* R = &rec[q * RW];
                 for (u32 j = 0; j < D; ++j) R[j] = delta[a * D + j];
                 R[D] = (e > a + 1) ? start[a + 1] : ~(u64)0;
-                R[D + 1] = (e > a + 1) ? a + 1 : 0;
-                R[D + 2] = e - (a + 1);
+                const u64 nxt = (e > a + 1) ? a + 1 : 0, cnt = e - (a + 1);
+                if (D == 6) {
+                    if (cnt >= 255 || nxt >= (1ull << 24)) packable = false;
+                    R[7] = (nxt & 0xFFFFFFull) | ((cnt & 0xFFull) << 24);
+                } else {
+                    R[D + 1] = nxt;
+                    R[D + 2] = cnt;
+                }
             }
         };
         if (T == 1) { fill(0, nbkt, 0, P); return; }
@@ -493,13 +506,18 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     // table stays in L2: measured on C5s (r = 3.4e5) D=4 at 93 MB 0.44 ms vs D=2 at 50 MB 0.94 ms; beyond L2 a
     // lookup is one random DRAM access (~55 G sectors/s) whatever it yields.
     u32 D = opt.reserved[0];
-    if (D != 0 && D != 1 && D != 2 && D != 4 && D != 8) return RIG_ERR_ARG;
+    if (D != 0 && D != 1 && D != 2 && D != 4 && D != 6 && D != 8) return RIG_ERR_ARG;
+    if (D == 6 && !f.w32) return RIG_ERR_ARG;   // the 32-byte six-delta entry exists for 32-bit words only
+    const bool auto_D = D == 0;
     if (D == 0) {
         u64 budget = 8ull << 30;
         if (max_bytes && max_bytes / 4 < budget) budget = max_bytes / 4;
         const u64 wb = f.w32 ? 4 : 8;
         const bool can_pack = !f.w32 && n < (1ull << 40) - 1 && !(opt.reserved[1] & 4);  // D = 4 entries packed into 32 bytes
         auto cost = [&](u32 d) { return (u64)d * r * (((d == 4 && can_pack) ? 32 : PhiTable::record_words(d) * wb) << fp); };
+        // (D = 6 — six occurrences per 32-byte entry, 32-bit words — is available on request: a third of the lookups go
+        // away, but measured on B200 it is no faster than D = 4 on C2 (0.461 vs 0.453 ms per step) and slower on C5s
+        // (0.547 vs 0.455: the refined table grows by half and its lookups reach DRAM), so it is not the default.)
         D = cost(4) <= budget ? 4 : (cost(2) <= budget ? 2 : 1);
     }
     lap("Phi pieces");
@@ -507,6 +525,13 @@ static inline int flatten(const rig_logical_view& v, const rig_options& opt, Fla
     for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
     lap("Phi^D composition");
     f.phi.build_directory(n, fp);
+    if (D == 6 && (!f.phi.packable || f.phi.pieces() >= (1ull << 24))) {   // a crowded bucket or too many pieces: four per entry
+        if (!auto_D) return RIG_ERR_ARG;
+        D = 4;
+        f.phi = P1;
+        for (u32 j = 1; j < D; ++j) f.phi = extend_by_phi(f.phi, P1, n);
+        f.phi.build_directory(n, fp);
+    }
     f.phi_packed = false;
     if (!f.w32 && D == 4 && n < (1ull << 40) - 1 && !(opt.reserved[1] & 4)) {  // reserved[1] bit2: keep 8-byte words (A/B switch)
         bool fits = true;

@@ -100,6 +100,13 @@ __device__ __forceinline__ void store_group(u64* p, const WT (&e)[D]) {  // p is
     }
 }
 
+// nxt / cnt of a bucket record: words D+1 and D+2, or — D = 6, the six-delta 32-byte entry — one shared word
+// (nxt in the low 24 bits, cnt in the high 8; flat_layout.hpp: PhiTable)
+template <typename WT, int D, int RW>
+__device__ __forceinline__ u32 rec_nxt(const WT (&e)[RW]) { return D == 6 ? ((u32)e[7] & 0xFFFFFFu) : (u32)e[D + 1]; }
+template <typename WT, int D, int RW>
+__device__ __forceinline__ u32 rec_cnt(const WT (&e)[RW]) { return D == 6 ? ((u32)e[7] >> 24) : (u32)e[D + 2]; }
+
 // Pull the Phi tables into L2 with one streaming pass (evict_last) before the walk: a cold table costs
 // every chain a DRAM round trip per first touch, and with 32 lanes in lockstep almost every iteration
 // of every warp would contain one. ~40 MB at HBM speed is a few microseconds.
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(256) prep_kernel(u64* z0, u64 n0, u64* z1, u64
 // and (prev_sample + delta) % n (:219), folded into one delta per piece.
 template <typename WT, int D, bool KEEP>
 __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT remaining) {
-    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
+    constexpr int RW = (D == 1) ? 4 : ((D <= 6) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;  // entry size in bytes (RW words, or 32 when packed)
     const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
@@ -153,7 +160,7 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
         bool emit;
         if (!searching) {
             emit = v < e[D];              // no piece begins inside the bucket at or below v
-            slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+            slo = rec_nxt<WT, D, RW>(e); shi = slo + rec_cnt<WT, D, RW>(e) - 1;
             searching = !emit;
         } else if (slo == shi) {
             emit = true;                  // the entry just loaded is the answer
@@ -187,11 +194,11 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
         // ---- this iteration's occurrences (off the critical path) ----
         if (emit) {
-            if (cnt == (u32)D) {
+            if (D != 6 && cnt == (u32)D) {
                 store_group<WT, D>(o, x);
-            } else {
+            } else {   // partial group, or D = 6 (a group of six is not sector-aligned: the head walk is short, singles do)
 #pragma unroll
-                for (int t = 0; t < D - 1; ++t)
+                for (int t = 0; t < D; ++t)
                     if ((u32)t < cnt) __stcs(o + t, (u64)x[t]);
                 take = D;
             }
@@ -357,128 +364,19 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
                                         blockIdx.x, gridDim.x);
 }
 
-// "Window pass". PERSISTENT, one lane per ITEM AT A TIME: a lane walks the items i = t, t + T, t + 2T, .. (t its
-// global thread index, T the number of threads of the grid) one after the other, switching to its next item inside
-// the trip that ends the current one, so every lane of a warp has a lookup in flight until its own sequence ends —
-// items of different lengths (chain tails, crowded buckets) do not leave lanes idle until the warp's slowest one
-// is done, and the grid drains over one item's time instead of one CTA's. The next item's 16-byte entry is
-// prefetched one item ahead.
-// items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first slot, cnt the number of
-// further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v); the lane
-// emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] as one 32-byte sector store and continues from Phi^D(v).
-// Same per-lane state machine and software pipelining as walk_chain (one table load per lane per trip).
-template <typename WT, int D, bool KEEP>
-__global__ void __launch_bounds__(256)
-phi_window_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
-                  u64 cap, u64 items_cap, u32 seg_shift) {
-    u64 total, total_chains;
-    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
-    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
-    const u32 ESZ = ix.phi.esz;
-    const bool PK = ix.phi.packed != 0;
-    constexpr bool W32 = sizeof(WT) == 4;
-    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);   // the host keeps the item list below 2^31 entries
-    const u32 T = gridDim.x * blockDim.x;
-    const ulonglong2* itp = reinterpret_cast<const ulonglong2*>(items);
-    u32 inext = blockIdx.x * blockDim.x + threadIdx.x;
-    bool have_next = inext < n_items;
-    ulonglong2 nit = make_ulonglong2(0, 0);
-    if (have_next) nit = __ldcs(itp + inext);
-    const WT n = (WT)ix.n;
-    const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
-    const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
-    const u32 shift = ix.phi.shift;
-    u32 left = 0;  // slots of the current item still to be written, the seed's included
-    u64* o = out;
-    WT v = 0;
-    bool searching = false;
-    u32 slo = 0, shi = 0, probe = 0;
-    WT e[RW];
-#pragma unroll
-    for (int t = 0; t < RW; ++t) e[t] = 0;
-#define RIG_TAKE_ITEM(LEFT, O, V)                                          \
-    do {                                                                   \
-        LEFT = (u32)(nit.x & 255u) + 1;                                    \
-        O = out + (nit.x >> 8);                                            \
-        V = (WT)nit.y;                                                     \
-        inext += T;                                                        \
-        have_next = inext < n_items;                                       \
-        if (have_next) nit = __ldcs(itp + inext);                          \
-    } while (0)
-    for (;;) {
-        // lanes without a lookup in flight: one-slot items, the first item, the end of the sequence
-        bool fresh = false;
-        if (left == 1) { __stcs(o, (u64)v); left = 0; }
-        if (left == 0 && have_next) { RIG_TAKE_ITEM(left, o, v); fresh = true; searching = false; slo = shi = 0; }
-        if (!__any_sync(RIG_FULL, left > 0)) break;
-        bool emit = false;
-        WT g[D];          // the group to store: [v, Phi(v), ..]
-        u32 cnt = 0;
-        WT vn = v;
-        if (left > 1 && !fresh) {
-            if (!searching) {
-                emit = v < e[D];
-                slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
-                searching = !emit;
-            } else if (slo == shi) {
-                emit = true;
-            } else if (e[D] <= v) {
-                slo = probe; emit = (slo == shi);
-            } else {
-                shi = probe - 1; emit = false;
-            }
-            if (emit) {
-                searching = false;
-                slo = shi = 0;
-                g[0] = v;
-#pragma unroll
-                for (int t = 0; t < D; ++t) {
-                    WT x = v + e[t];
-                    if ((W32 && x < v) || x >= n) x -= n;
-                    if (t < D - 1) g[t + 1] = x; else vn = x;
-                }
-                cnt = min(left, (u32)D);
-            }
-        }
-        u64* const so = o;           // where this trip's group goes
-        u32 left_next = left - cnt;
-        u64* o_next = o + cnt;
-        if (emit && left_next <= 1) {  // the item ends with this group: switch to the lane's next item in this trip
-            if (left_next == 1) __stcs(o_next, (u64)vn);  // the value carried out of the item's last full group
-            left_next = 0;
-            if (have_next) RIG_TAKE_ITEM(left_next, o_next, vn);
-        }
-        // ---- next load (critical path) ----
-        probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
-        WT e2[RW];
-#pragma unroll
-        for (int t = 0; t < RW; ++t) e2[t] = e[t];
-        if (left_next > 1)
-            load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
-        // ---- this trip's occurrences (off the critical path) ----
-        if (emit) {
-            if (cnt == (u32)D) {
-                store_group<WT, D>(so, g);
-            } else {
-#pragma unroll
-                for (int t = 0; t < D - 1; ++t)
-                    if ((u32)t < cnt) __stcs(so + t, (u64)g[t]);
-            }
-        }
-        v = vn;
-        left = left_next;
-        o = o_next;
-#pragma unroll
-        for (int t = 0; t < RW; ++t) e[t] = e2[t];
-    }
-#undef RIG_TAKE_ITEM
-}
-
 // One item per lane, the warp in lockstep until its slowest lane is done: left = slots of the item still to be written
-// (the seed's included, 0 = no item), o = its first slot, v = the seed. Direct 32-byte sector stores.
+// (the seed's included, 0 = no item), o = its first slot (sector-aligned: items start on a 128-byte line), v = the seed.
+// Direct 32-byte sector stores; per-lane state machine with ONE table load per lane per trip (the bucket record of
+// the next value, or the next probe of a crowded bucket), issued before the trip's stores.
+// D = 6 (on request): a lookup yields six occurrences but a sector holds four, so two values wait in registers every
+// other lookup: lookup A stores [x0..x3] and keeps x4, x5; lookup B stores [x4, x5, y0, y1] and [y2..y5] — three
+// sector stores per two lookups, the same store count per occurrence as D = 4 with two thirds of its lookups.
+// (A leaner form of this loop — full groups only in the main loop, the next entry loaded straight into the registers
+// of the one consumed, 124 M instead of 157 M warp instructions on config C2 — was measured no faster: 0.300 vs
+// 0.285 ms. The pass is not issue-bound; profiles/r2_window_bound.txt.)
 template <typename WT, int D, bool KEEP>
 __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left, u64* o, WT v) {
-    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
+    constexpr int RW = (D == 1) ? 4 : ((D <= 6) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;
     const bool PK = ix.phi.packed != 0;
     constexpr bool W32 = sizeof(WT) == 4;
@@ -488,6 +386,8 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
     const u32 shift = ix.phi.shift;
     bool searching = false;
     u32 slo = 0, shi = 0, probe = 0;
+    u32 pc = 0;          // D = 6: values waiting for their sector (0 or 2), destined for slots o, o + 1
+    WT p0 = 0, p1 = 0;
     WT e[RW];
     if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
     while (__any_sync(RIG_FULL, left > 1)) {
@@ -498,7 +398,7 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
         if (left > 1) {
             if (!searching) {
                 emit = v < e[D];
-                slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
+                slo = rec_nxt<WT, D, RW>(e); shi = slo + rec_cnt<WT, D, RW>(e) - 1;
                 searching = !emit;
             } else if (slo == shi) {
                 emit = true;
@@ -526,20 +426,57 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
         if (left_next > 1)
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
         if (emit) {
-            if (cnt == (u32)D) {
-                store_group<WT, D>(o, g);
-            } else {
+            if constexpr (D == 6) {
+                if (pc == 0) {
+                    if (cnt >= 4) {
+                        stg256_stream(o, (u64)g[0], (u64)g[1], (u64)g[2], (u64)g[3]);
+                        o += 4;
+                        if (cnt == 6) { p0 = g[4]; p1 = g[5]; pc = 2; }
+                        else if (cnt == 5) { __stcs(o, (u64)g[4]); o += 1; }
+                    } else {
 #pragma unroll
-                for (int t = 0; t < D - 1; ++t)
-                    if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                        for (int t = 0; t < 3; ++t)
+                            if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                        o += cnt;
+                    }
+                } else {   // slots o, o + 1 hold p0, p1
+                    if (cnt >= 2) {
+                        stg256_stream(o, (u64)p0, (u64)p1, (u64)g[0], (u64)g[1]);
+                        o += 4; pc = 0;
+                        if (cnt == 6) {
+                            stg256_stream(o, (u64)g[2], (u64)g[3], (u64)g[4], (u64)g[5]);
+                            o += 4;
+                        } else {
+#pragma unroll
+                            for (int t = 2; t < 5; ++t)
+                                if ((u32)t < cnt) __stcs(o + (t - 2), (u64)g[t]);
+                            o += cnt - 2;
+                        }
+                    } else {
+                        __stcs(o, (u64)p0); __stcs(o + 1, (u64)p1);
+                        if (cnt == 1) __stcs(o + 2, (u64)g[0]);
+                        o += 2 + cnt; pc = 0;
+                    }
+                }
+            } else {
+                if (cnt == (u32)D) {
+                    if (ix.pad == 0) store_group<WT, D>(o, g);
+                    else             // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
+                        store_group<WT, D>(ix.dbg + ((reinterpret_cast<unsigned long long>(o) >> 3) & 0x3FFFFCull), g);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < D - 1; ++t)
+                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                }
+                o += cnt;
             }
-            o += cnt;
         }
         v = vn;
         left = left_next;
 #pragma unroll
         for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
+    if (D == 6 && pc) { __stcs(o, (u64)p0); __stcs(o + 1, (u64)p1); o += 2; }
     if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
 }
 
@@ -642,208 +579,6 @@ phi_fused_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const 
             v = (WT)(w1 & RIG_ITEM_MASK);
         }
         window_items_direct<WT, D, KEEP>(ix, left, o, v);
-    }
-}
-
-// ---- lookup of one value: the D deltas of the piece holding v ------------------------------------------------
-// e holds the bucket record of v on entry (already loaded: the caller issued the load when it learned v); on return
-// e[0..D) are the deltas of v's piece. The search inside a crowded bucket runs HERE, inside the trip (its loads are
-// dependent ones and the other lanes of the warp wait), so that every lane of a warp finishes the trip with its
-// group emitted: the warp stays in lockstep and completes whole 128-byte lines together (phi_window_line_kernel).
-template <typename WT, int D, int RW, bool KEEP>
-__device__ __forceinline__ void resolve_piece(const char* pent, u32 ESZ, bool PK, WT v, WT (&e)[RW]) {
-    if (v < e[D]) return;                       // no piece begins inside the bucket at or below v: the record's deltas
-    u32 slo = (u32)e[D + 1], shi = slo + (u32)e[D + 2] - 1;  // invariant: start[slo] <= v
-    bool have = false;                          // e already holds pent[slo]
-    while (slo < shi) {
-        const u32 probe = (slo + shi + 1) >> 1;
-        load_entry<WT, RW, KEEP>(pent + (u64)probe * ESZ, e, PK);
-        if (e[D] <= v) { slo = probe; have = true; } else { shi = probe - 1; have = false; }
-    }
-    if (!have) load_entry<WT, RW, KEEP>(pent + (u64)slo * ESZ, e, PK);
-}
-
-// "Window pass" with WHOLE-LINE stores (the default). PERSISTENT; a warp takes 32 consecutive items and walks them in
-// LOCKSTEP: every trip, every active lane emits one group of D occurrences into its own row of a shared-memory
-// staging tile (as table words: 32-bit when n < 2^32); after 16 / D trips every active lane holds one complete
-// 128-byte output line, and the warp writes the rows out together — 8 lanes x 16 bytes per line, 4 whole lines per
-// store instruction, the 64-bit widening done on the way out. One L2 request per 128-byte line instead of one per
-// 32-byte sector: the direct-store form of this pass ran at the L2 tag-lookup rate (26 M lookups + 26 M sector
-// stores per launch on config C2, lts__t_tag_requests 75-80%), and its stores were half of those requests.
-// What is left of an item below a whole line (< 16 slots) is written by the direct path of the batch kernel.
-template <typename WT, int D, bool KEEP, int MINB, bool TMA>
-__global__ void __launch_bounds__(256, MINB)
-phi_window_line_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
-                       u64 cap, u64 items_cap, u32 seg_shift) {
-    u64 total, total_chains;
-    if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
-    constexpr int RW = (D == 1) ? 4 : ((D <= 4) ? 8 : 16);
-    constexpr int GPL = RIG_LINE / D;                       // trips per line
-    // staged row: one line of table words (of 64-bit output words when the rows leave through the bulk-copy engine,
-    // which moves bytes as they are) + 16 bytes (bank spread)
-    typedef typename std::conditional<TMA, u64, WT>::type ST;
-    constexpr int ROWB = RIG_LINE * (int)sizeof(ST) + 16;
-    __shared__ __align__(128) unsigned char stage[8][32][ROWB];
-    const u32 ESZ = ix.phi.esz;
-    const bool PK = ix.phi.packed != 0;
-    constexpr bool W32 = sizeof(WT) == 4;
-    const u32 n_items = (u32)__ldcg(ctr + RIG_CTR_ITEMS);
-    const u32 T = gridDim.x * blockDim.x;
-    const WT n = (WT)ix.n;
-    const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
-    const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
-    const u32 shift = ix.phi.shift;
-    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    unsigned char* const myrow = &stage[wid][lane][0];
-    for (u32 ib = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); ib < n_items; ib += T) {  // warp-uniform
-        const u32 i = ib + lane;
-        u32 left = 0;  // slots of this item still to be written, the seed's included
-        u64* o = out;
-        WT v = 0;
-        if (i < n_items) {
-            const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
-            left = (u32)(it.x & 255u) + 1;
-            o = out + (it.x >> 8);
-            v = (WT)it.y;
-        }
-        WT e[RW];
-#pragma unroll
-        for (int t = 0; t < RW; ++t) e[t] = 0;
-        if (left > 1) load_entry<WT, RW, KEEP>(rec + (u64)(v >> shift) * ESZ, e, PK);
-        // ---- whole lines, in lockstep ----
-        while (__any_sync(RIG_FULL, left >= (u32)RIG_LINE)) {
-            const bool act = left >= (u32)RIG_LINE;
-#pragma unroll
-            for (int g = 0; g < GPL; ++g) {
-                if (act) {
-                    WT x[D];
-                    x[0] = v;
-                    WT vn = v;
-                    // the group needs a lookup unless its only slot is the item's last one (D = 1, left = 16, g = 15):
-                    // no entry was loaded for it then
-                    if (D > 1 || left - (u32)(g * D) > 1) {
-                        resolve_piece<WT, D, RW, KEEP>(pent, ESZ, PK, v, e);
-#pragma unroll
-                        for (int t = 0; t < D; ++t) {
-                            WT y = v + e[t];
-                            if ((W32 && y < v) || y >= n) y -= n;
-                            if (t < D - 1) x[t + 1] = y; else vn = y;
-                        }
-                    }
-                    if (left - (u32)((g + 1) * D) > 1)   // a further lookup follows (one slot left needs none: it holds vn)
-                        load_entry<WT, RW, KEEP>(rec + (u64)(vn >> shift) * ESZ, e, PK);
-                    ST* dst = reinterpret_cast<ST*>(myrow) + g * D;
-                    if (TMA && g == 0) {   // the row's previous bulk copy must have read it (issued a whole trip ago)
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    if constexpr (std::is_same<ST, WT>::value && D * sizeof(WT) == 16) {
-                        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(x);
-                    } else if constexpr (std::is_same<ST, WT>::value && D * sizeof(WT) == 32) {
-                        reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(x)[0];
-                        reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(x)[1];
-                    } else if constexpr (sizeof(ST) == 8 && D % 2 == 0) {
-#pragma unroll
-                        for (int t = 0; t < D; t += 2)
-                            reinterpret_cast<ulonglong2*>(dst)[t / 2] = make_ulonglong2((u64)x[t], (u64)x[t + 1]);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < D; ++t) dst[t] = (ST)x[t];
-                    }
-                    v = vn;
-                }
-            }
-            if constexpr (TMA) {
-                // every lane hands its own row to the bulk-copy engine: 128 bytes shared -> global, one L2 request per
-                // line and no store payload through the LSU / L1-to-crossbar port (the engine reads shared memory itself)
-                if (act) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const u32 saddr = (u32)__cvta_generic_to_shared(myrow);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" :: "l"(o), "r"(saddr) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            } else {
-            __syncwarp();
-            // write out the completed rows: lane L carries 16 bytes (2 slots) of line 4r + L/8
-            const u32 mask = __ballot_sync(RIG_FULL, act);
-            const u32 c = lane & 7u;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const u32 j = 4u * r + (lane >> 3);
-                const unsigned long long lp = __shfl_sync(RIG_FULL, (unsigned long long)o, j);
-                if ((mask >> j) & 1u) {
-                    const unsigned char* src = &stage[wid][j][0];
-                    u64 a0, a1;
-                    if constexpr (W32) {
-                        const uint2 w2 = reinterpret_cast<const uint2*>(src)[c];
-                        a0 = w2.x; a1 = w2.y;
-                    } else {
-                        const ulonglong2 w2 = reinterpret_cast<const ulonglong2*>(src)[c];
-                        a0 = w2.x; a1 = w2.y;
-                    }
-                    stg128_stream(reinterpret_cast<u64*>(lp) + 2 * c, a0, a1);
-                }
-            }
-            __syncwarp();
-            }
-            if (act) { o += RIG_LINE; left -= RIG_LINE; }
-        }
-        if constexpr (TMA) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        // ---- what is left of the item (< one line): direct stores, per-lane state machine ----
-        bool searching = false;
-        u32 slo = 0, shi = 0, probe = 0;
-        while (__any_sync(RIG_FULL, left > 1)) {
-            bool emit = false;
-            WT g[D];
-            u32 cnt = 0;
-            WT vn = v;
-            if (left > 1) {
-                if (!searching) {
-                    emit = v < e[D];
-                    slo = (u32)e[D + 1]; shi = slo + (u32)e[D + 2] - 1;
-                    searching = !emit;
-                } else if (slo == shi) {
-                    emit = true;
-                } else if (e[D] <= v) {
-                    slo = probe; emit = (slo == shi);
-                } else {
-                    shi = probe - 1; emit = false;
-                }
-                if (emit) {
-                    searching = false;
-                    slo = shi = 0;
-                    g[0] = v;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) {
-                        WT x = v + e[t];
-                        if ((W32 && x < v) || x >= n) x -= n;
-                        if (t < D - 1) g[t + 1] = x; else vn = x;
-                    }
-                    cnt = min(left, (u32)D);
-                }
-            }
-            const u32 left_next = left - cnt;
-            probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
-            WT e2[RW];
-#pragma unroll
-            for (int t = 0; t < RW; ++t) e2[t] = e[t];
-            if (left_next > 1)
-                load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
-            if (emit) {
-                if (cnt == (u32)D) {
-                    store_group<WT, D>(o, g);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < D - 1; ++t)
-                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
-                }
-                o += cnt;
-            }
-            v = vn;
-            left = left_next;
-#pragma unroll
-            for (int t = 0; t < RW; ++t) e[t] = e2[t];
-        }
-        if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
     }
 }
 

@@ -179,7 +179,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit6 window pass with whole-line stores staged in shared memory (lockstep warps), bit8 direct sector stores with per-lane refill (A/B alternatives of the default window pass: direct sector stores, warp-level item batches), bit11 whole-line window pass whose rows leave through the bulk-copy engine (cp.async.bulk shared -> global) instead of the cooperative vector stores, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -269,7 +269,9 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
     ix->lf_bytes = parts[8].off;  // F, sid, start, block records, bstart, last, bdir, samples_last
-    d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
+    d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 32768) ? 1u : 0u;  // diagnostic of the window pass's stores (bit 15)
+    d.dbg = nullptr;
+    if (d.pad) { void* q = nullptr; if (cudaMalloc(&q, 32u << 20) == cudaSuccess) d.dbg = (ull*)q; else d.pad = 0; }
 
     // L2 persistence for the Phi records: reserve the largest carve-out the device allows (device-wide
     // limit; harmless for other users of the context) and size the window / hit ratio to it.
@@ -647,10 +649,7 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
         if (fused_ok) {                                                                                         \
         } else if (two_pass) {                                                                                  \
             auto k1 = rigk::phi_expand_kernel<W, DD, KP, true>;                                                 \
-            auto k2 = (ix->variant & 64) ? rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), false> \
-                      : ((ix->variant & 256) ? rigk::phi_window_kernel<W, DD, KP>                               \
-                      : ((ix->variant & 2048) ? rigk::phi_window_line_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), true>  \
-                                              : rigk::phi_window_batch_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4)>)); \
+            auto k2 = rigk::phi_window_batch_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4)>;                       \
             uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
             uint64_t g2 = (uint64_t)ix->sm_count * resident_ctas(k2, wthreads);                                 \
             g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
@@ -687,6 +686,7 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
         case 5: RIG_EXPAND(uint32_t, 2); break;
         case 8: RIG_EXPAND(ull, 4); break;
         case 9: RIG_EXPAND(uint32_t, 4); break;
+        case 13: RIG_EXPAND(uint32_t, 6); break;
         case 16: RIG_EXPAND(ull, 8); break;
         case 17: RIG_EXPAND(uint32_t, 8); break;
         default: return RIG_ERR_ARG;

@@ -53,7 +53,8 @@ struct FlatDev {
     const void* samples_last; // [r]         PT
     PhiTabDev phi;
     SeedTabDev seed;
-    u32 w32, pad;             // w32: every position-holding array (and the Phi tables) uses 32-bit words
+    u32 w32, pad;             // w32: every position-holding array (and the Phi tables) uses 32-bit words; pad: diagnostics (0 in production)
+    u64* dbg;                 // diagnostics: a 32 MB scratch window (RIG_VARIANT bit 15), else null
 };
 
 #define RIG_FULL 0xffffffffu

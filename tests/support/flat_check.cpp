@@ -90,7 +90,7 @@ void phi_lookup(const FlatHost& f, u64 i, u64* e, u64* loads = nullptr) {
         bool emit;
         if (!searching) {
             emit = i < (w[D] & mask);
-            if (!emit) { slo = w[D + 1] & mask; shi = slo + (w[D + 2] & mask) - 1; searching = true; }
+            if (!emit) { slo = rigf::PhiTable::nxt_of(w, D) & mask; shi = slo + (rigf::PhiTable::cnt_of(w, D) & mask) - 1; searching = true; }
         } else if (slo == shi) emit = true;
         else if ((w[D] & mask) <= i) { slo = probe; emit = (slo == shi); }
         else { shi = probe - 1; emit = false; }

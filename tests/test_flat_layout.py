@@ -64,7 +64,7 @@ def test_seed_table_and_two_pass_expansion(seg, wide):
         n = int(rng.integers(1, 4000))
         t = repetitive_text(n, int(rng.integers(1, 200)), int(rng.integers(0, 4)), 9000 + 17 * seg + it, sigma=int(rng.choice([1, 2, 4, 15])))
         host = rib.HostIndex.from_text(t)
-        jump = int(rng.choice([1, 2, 4, 8]))
+        jump = int(rng.choice([1, 2, 4, 8] if wide else [1, 2, 4, 6, 8]))
         fc = FlatCheck(host, K=4, phi_log2=int(rng.choice([0, 1, 4])), jump=jump, force_wide=wide, seed_jump=seg)
         assert fc.rc == 0 and fc.seed_jump == (seg if seg > 1 else 0)
         if seg > 1:
@@ -93,8 +93,11 @@ def test_seed_table_auto_policy():
 def test_jump_table_auto_policy():
     t = rib.gen_text("dna_drift", 300_000, 3_000, 3, 5)
     fc = FlatCheck(rib.HostIndex.from_text(t))
-    assert fc.jump == 4          # small index: the Phi^4 table is L2-friendly
+    assert fc.jump == 4 and fc.w32       # small index: the Phi^1..4 table is L2-friendly
+    assert FlatCheck(rib.HostIndex.from_text(t), jump=6).jump == 6            # six per 32-byte entry: on request, 32-bit words only
+    assert FlatCheck(rib.HostIndex.from_text(t), force_wide=True).jump == 4
     assert FlatCheck(rib.HostIndex.from_text(t), jump=3).rc == -1
+    assert FlatCheck(rib.HostIndex.from_text(t), jump=6, force_wide=True).rc == -1
 
 
 def test_flat_walk_medium_texts():
