@@ -20,9 +20,11 @@ batch of synthetic patterns.
   value      occurrences/s of the whole job, device-resident inputs and outputs, CUDA-event timed, max over ranks
   e2e        occurrences/s through the host-buffer C-ABI calls (rig_count_batch / rig_locate_batch) with pinned host
              buffers: H2D of the patterns and D2H of ranges, offsets and every occurrence inside the timed region
-  roofline   dominant kernel (phi_window_kernel): bytes that must cross HBM per launch (8 B per occurrence written +
-             one pass over the Phi tables + 16 B per item) / its CUDA-event duration, against the measured HBM copy
-             bandwidth (MEASURED_PEAKS.json)
+  roofline   dominant kernel (phi_fused_kernel: seed hops + window fill in one persistent kernel): bytes that must
+             cross HBM per launch (8 B per occurrence written + one pass over the Phi tables + per item 32 B of list
+             traffic and one 64 B seed record) / its CUDA-event duration, against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json); `traffic` = ncu DRAM bytes of the same (workload, kernel) from
+             profiles/ncu_traffic.json, null when no capture of that pair exists
   cpu_baseline  the reference's own code (oracle/_ref) on the box's host cores, bounded sample (N = 1 only)
 """
 import argparse
@@ -269,6 +271,12 @@ def ncu_traffic(workload, kernel):
         return None
 
 
+def search_kernel_name():
+    """The backward-search kernel the library launches for K = 4 block records (RIG_VARIANT bit 14 / bit 7 select the others)."""
+    v = int(os.environ.get("RIG_VARIANT", "0") or 0)
+    return "search_kernel" if v & 128 else ("search_lane_kernel" if v & 16384 else "search_pair_kernel")
+
+
 def d2h_ceiling(world):
     """Aggregate device->host GB/s this box sustains with `world` GPUs copying at once (profiles/r2_d2h_probe.json,
     measured by tools/d2h_probe.py), or None."""
@@ -443,8 +451,10 @@ def run_ours_count(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         k_ms = statistics.mean(kern_ms)
-        # per rank query this layout touches 4 sectors (bdir, start[], head[], cum[]) = 128 B; 2 queries per LF step
-        alg_bytes = int(lf_steps) * 2 * 128 + Ns * (m + 16)
+        # per rank query this layout touches one directory sector (32 B) and one block record (32/64/96 B); 2 queries per LF step
+        q_bytes = 32 + int(info.lf_record_bytes)
+        alg_bytes = int(lf_steps) * 2 * q_bytes + Ns * (m + 16)
+        skern = search_kernel_name()
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
         line = {
             "metric": "count_patterns_per_s", "value": N_g * args.steps / (total_ms_g * 1e-3), "unit": "patterns/s",
@@ -460,10 +470,12 @@ def run_ours_count(args):
                     "d2h_bytes_per_step": int(16 * N), "api": "rig_count_batch (host buffers, pinned)", "ms_per_step": e2e_ms_g / args.steps},
             "gpu_launches": args.steps * world,
             "lf_steps_per_s": lf_g * args.steps / (total_ms_g * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "search_lane_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(args.workload, "search_lane_kernel"),
+            "roofline": {"bound": "hbm", "kernel": skern, "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(args.workload, skern),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_ms,
-                         "algorithmic_bytes": "per LF step 2 rank queries x 4 sectors x 32 B (bdir, run starts, run heads, symbol directory) + m + 16 B per pattern",
+                         "algorithmic_bytes": "per LF step 2 rank queries x (32 B directory sector + %d B block record) + m + 16 B per pattern; "
+                                              "every touched sector counted as a DRAM fetch: an upper bound when the index fits L2 or reads revisit "
+                                              "the same blocks (then `traffic`, where a capture exists, is the DRAM figure)" % int(info.lf_record_bytes),
                          "regime": regime(info.device_bytes),
                          "survey_touched": {"bytes_per_lf_step": 2 * B_RANK(ell),
                                             "achieved": int(lf_steps) * 2 * B_RANK(ell) / (k_ms * 1e-3) / 1e9}},
@@ -663,7 +675,8 @@ def run_ours(args):
             sm = measure_locate(D, sj, max(3, min(args.steps, 5)), 3, 2, flush, solo=True)
             solo = {"value": sm["occ_rank"] * max(3, min(args.steps, 5)) / (sm["total_ms"] * 1e-3), "ms_per_step": sm["total_ms"] / max(3, min(args.steps, 5)),
                     "e2e": (sm["occ_rank"] / (sm["e2e_ms"] * 1e-3)) if "e2e_ms" in sm else None,
-                    "e2e_ms_per_step": sm.get("e2e_ms"), "occurrences": sm["occ_rank"], "phases_ms": sm["phases"]}
+                    "e2e_ms_per_step": sm.get("e2e_ms"), "occurrences": sm["occ_rank"], "phases_ms": sm["phases"],
+                    "expansion_kernels": sm["expansion_kernels"]}
             del sj
             torch.cuda.empty_cache()
         D.barrier()
@@ -775,9 +788,10 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         phs = M["phases"]
         exp_ms = phs["expand_ms"]
-        # Roofline of the dominant kernel (second expansion pass, phi_window_kernel), HBM-bound. ALGORITHMIC bytes =
-        # what must cross HBM for this launch: 8 B per occurrence written + one pass over the tables it reads (the
-        # flattened index without the seed table, which only pass 1 touches) + 16 B per item read.
+        # Roofline of the dominant kernel (the fused expansion kernel; with RIG_VARIANT bit 13 the window pass of the
+        # two-kernel form), HBM-bound by the contract's definition. ALGORITHMIC bytes = what must cross HBM for this
+        # launch: 8 B per occurrence written + one pass over the tables it reads + the item list (+ one seed-table
+        # record per item when the kernel also produces the items).
         two_pass = int(info.seed_jump) > 1 and phs["window_ms"] > 0
         items = occ_rank // max(1, int(info.seed_jump)) + int(chains)  # upper bound: (L-1)/SEG + 1 items per chain of L
         if two_pass and M["expansion_kernels"] == 1:
@@ -796,6 +810,10 @@ def run_ours(args):
             alg_note = "8 B/occurrence output + one pass over the flattened index"
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         step_ms = M["total_ms"] / args.steps
+        # the whole step (search + expansion): output, one pass over the tables, the item list written and read with one seed
+        # record per item, the patterns and the per-pattern search results (lo, hi, toehold, run, two offsets)
+        step_bytes = (occ_rank * 8 + int(info.device_bytes) - int(info.seed_bytes) + (items * (16 + 16 + 64) if two_pass else 0)
+                      + M["patterns_rank"] * (m + 48))
         ell = max(1, int(np.ceil(np.log2(max(2, info.sigma)))))
         e2e_val = occ_g / (e2e_ms_g * 1e-3) if has_e2e == world and e2e_ms_g > 0 else None
         line = {
@@ -824,11 +842,13 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom_kernel), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "algorithmic_bytes": alg_note,
                          "rank": 0, "regime": regime(info.device_bytes, info.seed_bytes),
-                         "whole_step": {"ms": step_ms, "achieved": (occ_rank * 8 + int(info.device_bytes)) / (step_ms * 1e-3) / 1e9,
-                                        "frac": (occ_rank * 8 + int(info.device_bytes)) / (step_ms * 1e-3) / 1e9 / peak},
+                         "whole_step": {"ms": step_ms, "algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                                        "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
                          "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": occ_rank * B_PHI / (exp_ms * 1e-3) / 1e9,
                                             "note": "SURVEY 8d's touched-bytes figure for the reference's structure / expansion time; L2-served, not an HBM fraction"},
-                         "search_kernel": {"launch_ms": phs["search_ms"], "algorithmic_bytes": int(lf_steps) * 3 * B_RANK(ell)}},
+                         "search_kernel": {"name": search_kernel_name(), "launch_ms": phs["search_ms"], "lf_steps": int(lf_steps),
+                                           "touched_bytes": int(lf_steps) * 2 * (32 + int(info.lf_record_bytes)),
+                                           "note": "per LF step 2 rank queries x (directory sector + block record); L2-served in regime A"}},
         }
         if world > 1:
             ceil = d2h_ceiling(world)

@@ -65,7 +65,8 @@ typedef struct rig_index_info {
     uint32_t runs_per_block, lf_shift, phi_shift, device;
     uint32_t sm_count, phi_jump;  /* phi_jump = D: each Phi record holds the deltas of Phi^1..Phi^D */
     uint64_t phi_jump_pieces;     /* pieces of the refined Phi^1..Phi^D translation (<= D*r) */
-    uint32_t words32, reserved;   /* words32 = 1: n < 2^32-1, Phi directory records are 32-bit */
+    uint32_t words32;             /* 1: n < 2^32-1, position words and Phi entries are 32-bit */
+    uint32_t lf_record_bytes;     /* bytes of one block record of the backward-search structure (what one rank query reads besides its directory sector) */
     uint32_t seed_jump, seed_shift; /* seed table Phi^SEG of the two-pass expansion (0 = none) and its bucket shift */
     uint64_t seed_pieces, seed_bytes;
 } rig_index_info;

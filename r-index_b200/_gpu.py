@@ -35,7 +35,7 @@ class IndexInfo(ctypes.Structure):
     _fields_ = [("n", _u64), ("r", _u64), ("sigma", _u64), ("device_bytes", _u64), ("lf_blocks", _u64),
                 ("lf_buckets", _u64), ("phi_buckets", _u64), ("runs_per_block", _u32), ("lf_shift", _u32),
                 ("phi_shift", _u32), ("device", _u32), ("sm_count", _u32), ("phi_jump", _u32),
-                ("phi_jump_pieces", _u64), ("words32", _u32), ("reserved", _u32), ("seed_jump", _u32),
+                ("phi_jump_pieces", _u64), ("words32", _u32), ("lf_record_bytes", _u32), ("seed_jump", _u32),
                 ("seed_shift", _u32), ("seed_pieces", _u64), ("seed_bytes", _u64)]
 
 

@@ -407,6 +407,7 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
             } else {
                 shi = probe - 1; emit = false;
             }
+            if (ix.pad == 3) emit = true;   // diagnostic: no dependent lookups (WRONG output, timing only)
             if (emit) {
                 searching = false;
                 slo = shi = 0;
@@ -423,7 +424,10 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
         const u32 left_next = left - cnt;
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
-        if (left_next > 1)
+        if (ix.pad == 3) {
+#pragma unroll
+            for (int t = 0; t < RW; ++t) e2[t] = e[t];
+        } else if (left_next > 1)
             load_entry<WT, RW, KEEP>(searching ? (pent + (u64)probe * ESZ) : (rec + (u64)(vn >> shift) * ESZ), e2, PK);
         if (emit) {
             if constexpr (D == 6) {
@@ -460,9 +464,11 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
                 }
             } else {
                 if (cnt == (u32)D) {
-                    if (ix.pad == 0) store_group<WT, D>(o, g);
-                    else             // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
+                    if (ix.pad == 0 || ix.pad == 3) store_group<WT, D>(o, g);
+                    else if (ix.pad == 1)   // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
                         store_group<WT, D>(ix.dbg + ((reinterpret_cast<unsigned long long>(o) >> 3) & 0x3FFFFCull), g);
+                    else if (g[0] == (WT)0xFFFFFFF1u && g[D - 1] == (WT)0xFFFFFFF3u)   // diagnostic (bit 16): no stores (the test keeps the values live)
+                        store_group<WT, D>(o, g);
                 } else {
 #pragma unroll
                     for (int t = 0; t < D - 1; ++t)

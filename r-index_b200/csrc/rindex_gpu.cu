@@ -89,6 +89,7 @@ struct rig_index {
     bool timing_pending = false;
     size_t arena_bytes = 0;
     uint64_t digest = 0;           // logical_digest() of the index this handle was made from
+    bool warned_fused = false;     // the fused kernel's cooperative launch has failed once (reported on stderr)
     uint32_t epoch = 0;            // fused expansion: tag of the current call's items (1..65535; the list is zeroed when it wraps)
     void* items_zeroed = nullptr;  // the item-list allocation that has been zero-filled (a fresh cudaMalloc holds garbage)
     uint64_t last_items_cap = 0;   // item-list capacity the most recent expansion was queued with
@@ -179,7 +180,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel instead of one lane per pattern
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel, bit14 one lane per pattern instead of two (search_lane_kernel), bit15 window-pass store diagnostic
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -269,7 +270,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
     ix->lf_bytes = parts[8].off;  // F, sid, start, block records, bstart, last, bdir, samples_last
-    d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 32768) ? 1u : 0u;  // diagnostic of the window pass's stores (bit 15)
+    d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 32768) ? 1u : ((variant & 65536) ? 2u : ((variant & 131072) ? 3u : 0u));  // window-pass diagnostics (bits 15-17): stores redirected / no stores / no dependent lookups
     d.dbg = nullptr;
     if (d.pad) { void* q = nullptr; if (cudaMalloc(&q, 32u << 20) == cudaSuccess) d.dbg = (ull*)q; else d.pad = 0; }
 
@@ -301,9 +302,8 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     I.n = f.n; I.r = f.r; I.sigma = f.S; I.device_bytes = total;
     I.lf_blocks = f.nblk; I.lf_buckets = f.lf_nbkt; I.phi_buckets = f.phi.nbkt;
     I.runs_per_block = f.K; I.lf_shift = f.lf_shift; I.phi_shift = f.phi.shift;
-    I.phi_jump = f.phi.D; I.phi_jump_pieces = f.phi.pieces(); I.words32 = f.w32 ? 1u : 0u;
+    I.phi_jump = f.phi.D; I.phi_jump_pieces = f.phi.pieces(); I.words32 = f.w32 ? 1u : 0u; I.lf_record_bytes = f.blk_stride;
     I.device = (uint32_t)device; I.sm_count = (uint32_t)ix->sm_count;
-    I.reserved = ix->l2_window_bytes ? (uint32_t)(prop.persistingL2CacheMaxSize >> 20) : 0;  // MiB of persisting L2 in use
     I.seed_jump = d.seed.J; I.seed_shift = f.seed.shift; I.seed_pieces = f.seed.pieces(); I.seed_bytes = f.seed.bytes(f.w32);
     *out = ix;
     return RIG_OK;
@@ -403,7 +403,7 @@ int rig_index_load_flat(const char* path, const rig_logical_view* check, int dev
     ix->d = h.d;
     char* A = (char*)ix->arena;
     for_each_pointer(ix->d, [&](const void*& p) { p = (const void*)(A + (uintptr_t)p); });
-    ix->info = h.info; ix->info.device = (uint32_t)device; ix->info.sm_count = (uint32_t)ix->sm_count; ix->info.reserved = 0;
+    ix->info = h.info; ix->info.device = (uint32_t)device; ix->info.sm_count = (uint32_t)ix->sm_count;
     ix->phi_bytes = h.phi_bytes; ix->lf_bytes = h.lf_bytes; ix->arena_bytes = h.arena_bytes; ix->digest = h.digest;
     int rc = finish_create(ix);
     if (rc != RIG_OK) { rig_index_destroy(ix); return rc; }
@@ -471,8 +471,13 @@ int launch_search(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, 
         const uint64_t lb = (N + lt - 1) / lt;
         if (lb > 0x7fffffffull) return RIG_ERR_ARG;
         ull* ws = (ull*)ix->sums.p; ull* choff = (ull*)ix->choff.p; ull* totals = ix->d_counters + RIG_CTR_TOTAL;
-        if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
-        else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+        if (ix->variant & 16384) {   // one lane per pattern (A/B switch); default: two lanes per pattern, 256-thread CTAs
+            if (n32) rigk::search_lane_kernel<LOCATE, uint32_t><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+            else rigk::search_lane_kernel<LOCATE, ull><<<(unsigned)lb, lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+        } else {
+            if (n32) rigk::search_pair_kernel<LOCATE, uint32_t><<<(unsigned)lb, 2 * lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+            else rigk::search_pair_kernel<LOCATE, ull><<<(unsigned)lb, 2 * lt, 0, st>>>(ix->d, d_patt, N, m, d_lo, d_hi, toe, jl, choff, d_occoff, steps, ws, totals);
+        }
         CU_TRY(cudaGetLastError());
         ix->timing.launches += 1;
         return RIG_OK;
@@ -643,7 +648,14 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
                 if ((rc = rec(ix, 7, st))) return rc;                                                           \
                 fused_ok = true;                                                                                \
             } else {                                                                                            \
-                cudaGetLastError();   /* not co-resident on this device right now: the two-kernel form below */ \
+                /* not co-resident on this device right now: the two-kernel form below */                       \
+                if (!ix->warned_fused) {                                                                        \
+                    fprintf(stderr, "[rindex_gpu] fused expansion kernel not launched (%s, grid %llu x %d); "   \
+                            "falling back to seed pass + window pass\n", cudaGetErrorString(fe),                \
+                            (unsigned long long)gf, wthreads);                                                  \
+                    ix->warned_fused = true;                                                                    \
+                }                                                                                               \
+                cudaGetLastError();                                                                             \
             }                                                                                                   \
         }                                                                                                       \
         if (fused_ok) {                                                                                         \

@@ -104,7 +104,7 @@ __device__ __forceinline__ PT rec_word(const FlatDev& ix, const char* rp, u32 of
 // Dependent memory rounds: bdir -> (bstart, only when the bucket straddles blocks) -> block.
 template <int G, bool WANT_RUN, typename PT>
 __device__ __forceinline__ void block_query(const FlatDev& ix, PT x, uint8_t c, u32 sidc, int gl, u32 gbase,
-                                            PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run) {
+                                            PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run, bool want_run = true) {
     const u32 q = (u32)(x >> ix.lf_shift);
     u32 b0 = __ldg(ix.bdir + q);
     u32 b1 = __ldg(ix.bdir + q + 1);
@@ -263,8 +263,8 @@ __device__ __forceinline__ void st_relaxed_gpu(u64* p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-// Called by every thread of a 128-thread CTA with its pattern's (n_occ, chains); ex_*: the exclusive prefix over
-// all patterns before it; incl_*: the inclusive prefix at the end of this tile (the grand totals in the last tile).
+// Called by every thread of a CTA (NW warps, one tile of 128 patterns) with its (n_occ, chains) contribution;
+// ex_*: the exclusive prefix over everything before the thread; incl_*: the inclusive prefix at the end of this tile (the grand totals in the last tile).
 //
 // In a locate batch every CTA finishes its search at about the same time, so a look-back that waits for a
 // predecessor's PREFIX turns into a chain of rounds (tile t learns its prefix ~t / window rounds after tile 0:
@@ -274,9 +274,10 @@ __device__ __forceinline__ void st_relaxed_gpu(u64* p, u64 v) {
 // an inclusive prefix, which the tiles of the next group add: the chain has one link per 1024 tiles (131072
 // patterns), and batches that large run in waves anyway.
 #define RIG_TILE_GROUP 1024u
+template <int NW>   // warps per CTA
 __device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u64 b, u64& ex_a, u64& ex_b,
                                                     u64& incl_a, u64& incl_b) {
-    __shared__ u64 s_wa[4], s_wb[4], s_ra[4], s_rb[4];
+    __shared__ u64 s_wa[NW], s_wb[NW], s_ra[NW], s_rb[NW];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u64 ia = a, ib = b;
 #pragma unroll
@@ -288,7 +289,7 @@ __device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u6
     __syncthreads();
     u64 pa = 0, pb = 0, ta = 0, tb = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NW; ++j) {
         if (j < w) { pa += s_wa[j]; pb += s_wb[j]; }
         ta += s_wa[j]; tb += s_wb[j];
     }
@@ -317,7 +318,9 @@ __device__ __forceinline__ void tile_exclusive_scan(u64* ws, u32 tile, u64 a, u6
     for (int off = 16; off >= 1; off >>= 1) { va += __shfl_xor_sync(RIG_FULL, va, off); vb += __shfl_xor_sync(RIG_FULL, vb, off); }
     if (lane == 0) { s_ra[w] = va; s_rb[w] = vb; }
     __syncthreads();
-    const u64 sum_a = s_ra[0] + s_ra[1] + s_ra[2] + s_ra[3], sum_b = s_rb[0] + s_rb[1] + s_rb[2] + s_rb[3];
+    u64 sum_a = 0, sum_b = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { sum_a += s_ra[j]; sum_b += s_rb[j]; }
     if (threadIdx.x == 0 && ((tile + 1u) & (RIG_TILE_GROUP - 1u)) == 0) {   // last tile of a group: prefix for the next group
         u64* me = st + (u64)tile * RIG_TILE_WORDS;
         st_relaxed_gpu(me + 3, sum_a + ta); st_relaxed_gpu(me + 4, sum_b + tb);
@@ -383,7 +386,7 @@ __device__ __forceinline__ void lane_load(const FlatDev& ix, u32 b, u32 sidc, La
 // rank / run / head of position x from its block record (same outputs as block_query); all arithmetic in PT
 template <bool WANT_RUN, typename PT>
 __device__ __forceinline__ void lane_eval(const FlatDev& ix, const LaneRec<PT>& r, u32 b, PT x, uint8_t c, u32 sidc,
-                                          PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run) {
+                                          PT& cnt, u32& run, bool& head_is_c, u32& prev_c_run, bool want_run = true) {
     const u32 t = (u32)(r.s1 <= x) + (u32)(r.s2 <= x) + (u32)(r.s3 <= x);  // run of the block holding x
     const u32 cc = (u32)c * 0x01010101u, eq = r.heads ^ cc;                 // byte g is 0 iff head g == c
     const bool m0 = (eq & 0xffu) == 0, m1 = (eq & 0xff00u) == 0, m2 = (eq & 0xff0000u) == 0, m3 = (eq & 0xff000000u) == 0;
@@ -395,7 +398,7 @@ __device__ __forceinline__ void lane_eval(const FlatDev& ix, const LaneRec<PT>& 
     const bool mt = t == 0 ? m0 : (t == 1 ? m1 : (t == 2 ? m2 : m3));
     if (mt) add += x - st + 1;
     cnt = r.before + add;
-    if (WANT_RUN) {
+    if (WANT_RUN && want_run) {
         const u32 mc = (u32)m0 | ((u32)m1 << 1) | ((u32)m2 << 2) | ((u32)m3 << 3);
         head_is_c = mt;
         const u32 below = mc & ((1u << t) - 1u);
@@ -477,7 +480,7 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
         const u64 nocc = ne ? (u64)(hi - lo) + 1 : 0;   // r_index.hpp:338
         const u64 nch = ne ? (u64)(jR - jL + 1) : 0;
         u64 ex_occ, ex_ch, in_occ, in_ch;
-        tile_exclusive_scan(tile_ws, tile, nocc, nch, ex_occ, ex_ch, in_occ, in_ch);
+        tile_exclusive_scan<4>(tile_ws, tile, nocc, nch, ex_occ, ex_ch, in_occ, in_ch);
         if (p < N) {
             toe_out[p] = (u64)k;
             jl_out[p] = jL;
@@ -491,6 +494,98 @@ search_lane_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u6
     }
     if (p < N) { lo_out[p] = (u64)lo; hi_out[p] = (u64)hi; }
     // executed LF steps (for the algorithmic-bytes figure)
+    u32 sum = steps;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(RIG_FULL, sum, off);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(lf_steps, (u64)sum);
+}
+
+// ------------------------------------------------------------------ two lanes per pattern
+// The lane kernel is latency-bound with the machine half empty on batches of ~1e5 patterns (config C2: 782 CTAs of
+// 4 warps, 32% occupancy, ~300 warp instructions per LF step at ~22 cycles each). Here the two rank queries of an
+// LF step sit on ADJACENT lanes — even lane: rank(lo), odd lane: rank(hi + 1) and the toehold — and meet in one
+// shuffle: half the instructions per step on every lane's critical path, twice the warps in flight. Both lanes of a
+// pair keep identical (lo, hi, alive), so the pair leaves the loop together.
+template <bool LOCATE, typename PT>
+__global__ void __launch_bounds__(256)
+search_pair_kernel(const FlatDev ix, const uint8_t* __restrict__ patt, u64 N, u64 m, u64* __restrict__ lo_out,
+                   u64* __restrict__ hi_out, u64* __restrict__ toe_out, u64* __restrict__ jl_out,
+                   u64* __restrict__ choff_out, u64* __restrict__ occoff_out, u64* __restrict__ lf_steps,
+                   u64* __restrict__ tile_ws, u64* __restrict__ totals) {
+    struct SymEnt { PT f0, f1; u32 sid, pad; };
+    __shared__ SymEnt sSym[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sSym[i].f0 = (PT)ix.F[i]; sSym[i].f1 = (PT)ix.F[i + 1]; sSym[i].sid = ix.sid[i]; sSym[i].pad = 0;
+    }
+    __shared__ u32 s_tile;
+    if (LOCATE && threadIdx.x == 0) s_tile = (u32)atomicAdd(tile_ws, 1ull);   // tiles by ticket: see search_lane_kernel
+    __syncthreads();
+    const u32 tile = LOCATE ? s_tile : blockIdx.x;
+    const u32 role = threadIdx.x & 1u;
+    const u64 p = (u64)tile * 128u + (threadIdx.x >> 1);
+    bool alive = p < N;
+    const uint8_t* P = patt + (alive ? p : 0) * m;
+    PT lo = 0, hi = (PT)(ix.n - 1);  // full_range, r_index.hpp:155-160
+    PT k = (PT)ix.toe0;              // SA[n-1], r_index.hpp:489 (kept by the odd lane)
+    u32 steps = 0;
+    for (u64 i = 0; i < m; ++i) {
+        const u32 amask = __ballot_sync(RIG_FULL, alive);
+        if (!amask) break;           // r_index.hpp:297 (early exit on empty range)
+        if (!alive) continue;
+        const uint8_t c = __ldg(P + (m - 1 - i));
+        const SymEnt se = sSym[c];
+        const bool sym = se.f0 < se.f1;            // absent symbol: both counts 0 -> {1,0} below (r_index.hpp:174)
+        const u32 sidc = sym ? se.sid : 0u;
+        steps += (u32)(sym && !role);
+        // even lane: #c in bwt[0, lo); odd lane: #c in bwt[0, hi]  (r_index.hpp:178,181)
+        const bool need = role || lo > 0;
+        const PT x = role ? hi : (lo > 0 ? (PT)(lo - 1) : (PT)0);
+        const u32 q = (u32)(x >> ix.lf_shift);
+        const u32 b = lane_block_of<PT>(ix, x, __ldg(ix.bdir + q), __ldg(ix.bdir + q + 1));
+        LaneRec<PT> r;
+        lane_load<PT>(ix, b, sidc, r);
+        PT cnt = 0;
+        u32 run = 0, prevc = 0;
+        bool hic = false;
+        lane_eval<LOCATE, PT>(ix, r, b, x, c, sidc, cnt, run, hic, prevc, role != 0);
+        if (!need || !sym) cnt = 0;
+        const PT other = __shfl_xor_sync(amask, cnt, 1);
+        const PT A = role ? other : cnt, B = role ? cnt : other;
+        if (B == A) { lo = 1; hi = 0; alive = false; continue; }  // r_index.hpp:175,184
+        if (LOCATE && role) {
+            if (hic) k -= 1;                                   // r_index.hpp:505-509
+            else k = ld_pos<PT>(ix.samples_last, prevc);       // r_index.hpp:516-533
+        }
+        lo = se.f0 + A;        // r_index.hpp:186
+        hi = se.f0 + B - 1;    // r_index.hpp:188
+    }
+    if (LOCATE) {  // even lane: the run holding lo; odd lane: the run holding hi — one Phi chain per overlapped run
+        const bool ne = (p < N) && hi >= lo;
+        u32 j = 0;
+        if (ne) {
+            const PT x = role ? hi : lo;
+            const u32 q = (u32)(x >> ix.lf_shift);
+            const u32 b = lane_block_of<PT>(ix, x, __ldg(ix.bdir + q), __ldg(ix.bdir + q + 1));
+            LaneRec<PT> r;
+            lane_load<PT>(ix, b, 0, r);
+            j = b * 4u + (u32)(r.s1 <= x) + (u32)(r.s2 <= x) + (u32)(r.s3 <= x);
+        }
+        const u32 jo = __shfl_xor_sync(RIG_FULL, j, 1);
+        const u32 jL = role ? jo : j, jR = role ? j : jo;
+        const u64 nocc = (ne && !role) ? (u64)(hi - lo) + 1 : 0;   // r_index.hpp:338
+        const u64 nch = (ne && !role) ? (u64)(jR - jL + 1) : 0;
+        u64 ex_occ, ex_ch, in_occ, in_ch;
+        tile_exclusive_scan<8>(tile_ws, tile, nocc, nch, ex_occ, ex_ch, in_occ, in_ch);
+        if (p < N) {
+            if (role) toe_out[p] = (u64)k;
+            else { jl_out[p] = jL; occoff_out[p] = ex_occ; choff_out[p] = ex_ch; }
+        }
+        if ((u64)(tile + 1) * 128u >= N && threadIdx.x == 0) {  // the last tile closes both arrays
+            occoff_out[N] = in_occ; choff_out[N] = in_ch;
+            totals[0] = in_occ; totals[1] = in_ch;
+        }
+    }
+    if (p < N) { if (role) hi_out[p] = (u64)hi; else lo_out[p] = (u64)lo; }
     u32 sum = steps;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(RIG_FULL, sum, off);
