@@ -384,6 +384,26 @@ class Dist:
             self.dist.destroy_process_group()
 
 
+def open_index(rib, host, args, D, kw):
+    """The device index of this rank. N > 1 (or --flat): one flatten per box, not one per rank — rank 0 flattens and writes
+    the flattened index (rig_index_save_flat) unless the file is already there, every other rank loads that file
+    (rig_index_load_flat: a read + an upload; the library checks it against the logical index's digest)."""
+    if D.world == 1 and not args.flat:
+        return rib.GpuIndex(host, **kw)
+    flat = os.path.join(CACHE, "%s.K%d.D%d.S%d.flat" % (base_of(args.workload), kw.get("runs_per_block", 0), kw.get("phi_jump", 0),
+                                                         kw.get("seed_jump", 0)))
+    gpu = None
+    if D.rank == 0:
+        gpu = rib.GpuIndex(host, flat=flat, **kw)
+        if not gpu.from_flat:
+            gpu.save_flat(flat + ".tmp")
+            os.replace(flat + ".tmp", flat)
+    D.host_barrier()
+    if D.rank != 0:
+        gpu = rib.GpuIndex(host, flat=flat, **kw)
+    return gpu
+
+
 def run_ours_count(args):
     """--mode count: the ri-count configs (C4). A step = one backward-search pass (rig_count_batch_dev) over the job,
     every rank its contiguous equal-count shard (reads of one length cost the same: no re-balancing); value =
@@ -397,8 +417,8 @@ def run_ours_count(args):
     a, b = _shard.shard_bounds(N, world, rank)
     Ns = b - a
     t0 = time.time()
-    gpu = rib.GpuIndex(host, device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
-                       phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1, seed_jump=1)  # count only: smallest locate tables
+    gpu = open_index(rib, host, args, D, dict(device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2,
+                                              phi_bucket_log2=args.phi_log2, phi_jump=args.phi_jump or 1, seed_jump=1))  # count only: smallest locate tables
     load_s = time.time() - t0
     info = gpu.info
     tstream = torch.cuda.Stream(device=dev)
@@ -464,6 +484,7 @@ def run_ours_count(args):
             "config": shared_config(args.workload, world, info.n, info.r),
             "detail": {"sigma": int(info.sigma), "patterns_rank0": Ns, "lf_steps_rank0": int(lf_steps), "total_occurrences": int(occ_g),
                        "index_device_bytes": int(info.device_bytes), "index_load_s": round(load_s, 3),
+                       "index_from_flat_file": bool(getattr(gpu, "from_flat", False)),
                        "runs_per_block": int(info.runs_per_block), "parallelism": "contiguous equal-count shards x%d, index replicated" % world},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": N_g * args.steps / (e2e_ms_g * 1e-3), "unit": "patterns/s", "h2d_bytes_per_step": int(N * m),
@@ -642,21 +663,7 @@ def run_ours(args):
     t0 = time.time()
     kw = dict(device=local, runs_per_block=args.runs_per_block, lf_bucket_log2=args.lf_log2, phi_bucket_log2=args.phi_log2,
               expand_threads=args.expand_threads, phi_jump=args.phi_jump, seed_jump=args.seed_jump)
-    if world > 1:
-        # one flatten per box, not one per rank: rank 0 flattens and writes the flattened index (rig_index_save_flat),
-        # the other ranks load that file (rig_index_load_flat: a read + an upload)
-        flat = os.path.join(CACHE, "%s.K%d.D%d.S%d.flat" % (base_of(args.workload), args.runs_per_block, args.phi_jump, args.seed_jump))
-        gpu = None
-        if rank == 0:
-            gpu = rib.GpuIndex(host, flat=flat, **kw)
-            if not gpu.from_flat:
-                gpu.save_flat(flat + ".tmp")
-                os.replace(flat + ".tmp", flat)
-        D.host_barrier()
-        if rank != 0:
-            gpu = rib.GpuIndex(host, flat=flat, **kw)
-    else:
-        gpu = rib.GpuIndex(host, **kw)
+    gpu = open_index(rib, host, args, D, kw)
     load_s = time.time() - t0
     info = gpu.info
     # the library launches on the stream it is given (NULL would mean its own stream): use a real
@@ -809,6 +816,14 @@ def run_ours(args):
             dom_kernel, dom_ms = "phi_expand_kernel", exp_ms
             alg_note = "8 B/occurrence output + one pass over the flattened index"
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        # the same launch as 32-byte sector requests through the SM->crossbar ports (what ncu shows it is bound by,
+        # profiles/r2_window_bound.txt): one store sector and one table-lookup sector per D occurrences, two sectors
+        # per item; a copy at the HBM peak issues peak/32 sectors per second through the same ports
+        Dj = max(1, int(info.phi_jump))
+        sectors = 2 * (occ_rank // Dj) + 2 * items
+        request_rate = {"sectors_per_launch": sectors, "achieved_Gsectors_per_s": sectors / (dom_ms * 1e-3) / 1e9,
+                        "copy_at_hbm_peak_Gsectors_per_s": peak / 32.0, "frac": sectors / (dom_ms * 1e-3) / 1e9 / (peak / 32.0),
+                        "note": "half of these sectors are L2-served table lookups: the HBM fraction above is structurally <= ~0.5 at this request rate"}
         step_ms = M["total_ms"] / args.steps
         # the whole step (search + expansion): output, one pass over the tables, the item list written and read with one seed
         # record per item, the patterns and the per-pattern search results (lo, hi, toehold, run, two offsets)
@@ -844,6 +859,7 @@ def run_ours(args):
                          "rank": 0, "regime": regime(info.device_bytes, info.seed_bytes),
                          "whole_step": {"ms": step_ms, "algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                                         "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                         "request_rate": request_rate,
                          "survey_touched": {"bytes_per_occurrence": B_PHI, "achieved": occ_rank * B_PHI / (exp_ms * 1e-3) / 1e9,
                                             "note": "SURVEY 8d's touched-bytes figure for the reference's structure / expansion time; L2-served, not an HBM fraction"},
                          "search_kernel": {"name": search_kernel_name(), "launch_ms": phs["search_ms"], "lf_steps": int(lf_steps),
@@ -901,6 +917,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="patterns per step of --impl reference (default: ~1.5e8 occurrences)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-post", action="store_true", help="skip the -o / -c post-processing timing")
+    ap.add_argument("--flat", action="store_true", help="N = 1: keep / reuse the flattened index file in .cache (N > 1 always does)")
     ap.add_argument("--no-solo", action="store_true", help="N > 1: skip rank 0's one-GPU run of the same job")
     ap.add_argument("--no-collate", action="store_true", help="N > 1: skip the NCCL collation of the occurrence buffers")
     ap.add_argument("--runs-per-block", type=int, default=0)

@@ -36,6 +36,15 @@
 
 namespace rigk {
 
+// Timing-only diagnostics of the window pass (profiles/r2_window_bound.txt): compiled in with -DRIG_WINDOW_DIAG, then
+// selected by RIG_VARIANT bits 15-17 (stores redirected into one L2-resident window / no stores / no dependent
+// lookups; all three give WRONG output). The product build folds them away.
+#ifdef RIG_WINDOW_DIAG
+#define RIG_DIAG(ix) ((ix).pad)
+#else
+#define RIG_DIAG(ix) 0u
+#endif
+
 template <bool KEEP>
 __device__ __forceinline__ void ldg256(const void* p, u64& a, u64& b, u64& c, u64& d) {
     if (KEEP)  // ask L2 to evict these lines last: the streamed occurrence output competes for the same sets
@@ -407,7 +416,7 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
             } else {
                 shi = probe - 1; emit = false;
             }
-            if (ix.pad == 3) emit = true;   // diagnostic: no dependent lookups (WRONG output, timing only)
+            if (RIG_DIAG(ix) == 3) emit = true;   // diagnostic: no dependent lookups (WRONG output, timing only)
             if (emit) {
                 searching = false;
                 slo = shi = 0;
@@ -424,7 +433,7 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
         const u32 left_next = left - cnt;
         probe = (slo < shi) ? ((slo + shi + 1) >> 1) : slo;
         WT e2[RW];
-        if (ix.pad == 3) {
+        if (RIG_DIAG(ix) == 3) {
 #pragma unroll
             for (int t = 0; t < RW; ++t) e2[t] = e[t];
         } else if (left_next > 1)
@@ -464,8 +473,8 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
                 }
             } else {
                 if (cnt == (u32)D) {
-                    if (ix.pad == 0 || ix.pad == 3) store_group<WT, D>(o, g);
-                    else if (ix.pad == 1)   // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
+                    if (RIG_DIAG(ix) == 0 || RIG_DIAG(ix) == 3) store_group<WT, D>(o, g);
+                    else if (RIG_DIAG(ix) == 1)   // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
                         store_group<WT, D>(ix.dbg + ((reinterpret_cast<unsigned long long>(o) >> 3) & 0x3FFFFCull), g);
                     else if (g[0] == (WT)0xFFFFFFF1u && g[D - 1] == (WT)0xFFFFFFF3u)   // diagnostic (bit 16): no stores (the test keeps the values live)
                         store_group<WT, D>(o, g);

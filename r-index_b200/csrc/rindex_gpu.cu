@@ -180,7 +180,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel, bit14 one lane per pattern instead of two (search_lane_kernel), bit15 window-pass store diagnostic
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel, bit14 one lane per pattern instead of two (search_lane_kernel), bits 15-17 window-pass timing diagnostics (builds with -DRIG_WINDOW_DIAG only)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -270,7 +270,10 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     d.seed.shift = f.seed.shift; d.seed.J = f.seed.J > 1 ? f.seed.J : 0;
     ix->phi_bytes = (parts[9].off + parts[9].bytes) - parts[8].off;
     ix->lf_bytes = parts[8].off;  // F, sid, start, block records, bstart, last, bdir, samples_last
-    d.w32 = f.w32 ? 1u : 0u; d.pad = (variant & 32768) ? 1u : ((variant & 65536) ? 2u : ((variant & 131072) ? 3u : 0u));  // window-pass diagnostics (bits 15-17): stores redirected / no stores / no dependent lookups
+    d.w32 = f.w32 ? 1u : 0u; d.pad = 0;
+#ifdef RIG_WINDOW_DIAG   // window-pass diagnostics (bits 15-17): stores redirected / no stores / no dependent lookups
+    d.pad = (variant & 32768) ? 1u : ((variant & 65536) ? 2u : ((variant & 131072) ? 3u : 0u));
+#endif
     d.dbg = nullptr;
     if (d.pad) { void* q = nullptr; if (cudaMalloc(&q, 32u << 20) == cudaSuccess) d.dbg = (ull*)q; else d.pad = 0; }
 
