@@ -686,6 +686,9 @@ def run_ours(args):
                     "expansion_kernels": sm["expansion_kernels"]}
             del sj
             torch.cuda.empty_cache()
+        # the other ranks wait on the HOST (gloo): a device-side barrier would leave seven NCCL kernels polling over
+        # NVLink for the whole one-GPU run (measured: it slows rank 0's kernels by 25-75%)
+        D.host_barrier()
         D.barrier()
 
     job = LocateJob(D, gpu, patt, N, m, stream)
@@ -711,6 +714,7 @@ def run_ours(args):
 
     # the same host-buffer call with 32-bit positions (rig_locate_batch32; texts below 4 GiB): half the D2H bytes
     e2e32_ms = None
+    e2e32_dev = None
     if world == 1 and int(info.n) <= 0xFFFFFFFF and "e2e_ms" in M:
         h_occ32 = torch.empty(max(occ_rank, 1), dtype=torch.int32).pin_memory()
         call32 = lambda: gpu.locate32_raw(job.h_patt.data_ptr(), N, m, job.h_lo.data_ptr(), job.h_hi.data_ptr(), job.h_off.data_ptr(),  # noqa: E731
@@ -721,6 +725,8 @@ def run_ours(args):
         for k in range(e2e_steps):
             call32()
         e2e32_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+        t32 = gpu.timing()   # device phases of the last 32-bit call (warm L2: the e2e loop does not flush)
+        e2e32_dev = {k: float(t32[k]) for k in ("search_ms", "expand_ms", "seed_ms", "window_ms", "d2h_ms")}
         assert torch.equal(h_occ32[:4096].to(torch.int64) & 0xFFFFFFFF, job.h_occ[:4096])
         del h_occ32
 
@@ -882,7 +888,7 @@ def run_ours(args):
             line["collate"] = collate
         if e2e32_ms is not None:
             line["e2e_u32"] = {"value": occ_rank / (e2e32_ms * 1e-3), "unit": "occ/s", "ms_per_step": e2e32_ms,
-                               "d2h_bytes_per_step": int(8 * (3 * N + 1) + 4 * occ_rank),
+                               "d2h_bytes_per_step": int(8 * (3 * N + 1) + 4 * occ_rank), "device_phases_ms": e2e32_dev,
                                "api": "rig_locate_batch32 (32-bit positions, n < 2^32; an addition to the reference's 64-bit surface)"}
         if post is not None:
             line["post"] = post

@@ -51,7 +51,8 @@ typedef struct rig_options {
     uint32_t lf_bucket_log2;   /* 0 = auto: log2 of (directory buckets per run block) */
     uint32_t phi_bucket_log2;  /* 0 = auto: log2 of (directory buckets per Phi sample) */
     uint32_t expand_threads;   /* 0 = default block size of the Phi expansion kernel */
-    uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto, 1/2/4/8 = occurrences produced per Phi record lookup;
+    uint32_t reserved[4];      /* reserved[0] = phi_jump D: 0 = auto (4), 1/2/4/8 = occurrences produced per Phi record lookup, 6 = six per
+                                  32-byte entry (n < 2^32-1 only; RIG_ERR_ARG when the entry's next/count fields do not fit 24 + 8 bits);
                                   reserved[1] bit0 = force 64-bit position words (testing the n >= 2^32 paths);
                                   reserved[2] = SEG of the two-pass Phi expansion: 0 = auto, 1 = off (single pass),
                                   16/32/64/128/256 = occurrences per seed-table hop (window size in output slots);

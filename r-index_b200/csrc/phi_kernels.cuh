@@ -98,14 +98,25 @@ __device__ __forceinline__ void load_entry(const void* p, WT (&w)[RW], bool pack
     }
 }
 
-template <typename WT, int D>
-__device__ __forceinline__ void store_group(u64* p, const WT (&e)[D]) {  // p is D*8-byte aligned
-    if constexpr (D == 1) __stcs(p, (u64)e[0]);
-    else if constexpr (D == 2) __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2((u64)e[0], (u64)e[1]));
-    else {
+// OT = output word: u64 (the reference's ulint) or u32 (rig_locate_batch32, n < 2^32: half the store sectors)
+template <typename WT, int D, typename OT>
+__device__ __forceinline__ void store_group(OT* p, const WT (&e)[D]) {  // p is D*sizeof(OT)-byte aligned
+    if constexpr (sizeof(OT) == 8) {
+        if constexpr (D == 1) __stcs(p, (OT)e[0]);
+        else if constexpr (D == 2) __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2((u64)e[0], (u64)e[1]));
+        else {
 #pragma unroll
-        for (int k = 0; k < D / 4; ++k)
-            stg256_stream(p + 4 * k, (u64)e[4 * k], (u64)e[4 * k + 1], (u64)e[4 * k + 2], (u64)e[4 * k + 3]);
+            for (int k = 0; k < D / 4; ++k)
+                stg256_stream(p + 4 * k, (u64)e[4 * k], (u64)e[4 * k + 1], (u64)e[4 * k + 2], (u64)e[4 * k + 3]);
+        }
+    } else {
+        if constexpr (D == 1) __stcs(p, (OT)e[0]);
+        else if constexpr (D == 2) __stcs(reinterpret_cast<uint2*>(p), make_uint2((u32)e[0], (u32)e[1]));
+        else {
+#pragma unroll
+            for (int k = 0; k < D / 4; ++k)
+                __stcs(reinterpret_cast<uint4*>(p) + k, make_uint4((u32)e[4 * k], (u32)e[4 * k + 1], (u32)e[4 * k + 2], (u32)e[4 * k + 3]));
+        }
     }
 }
 
@@ -143,8 +154,9 @@ __global__ void __launch_bounds__(256) prep_kernel(u64* z0, u64 n0, u64* z1, u64
 // deltas are those of the piece holding v. For t = 0 this is r_index::Phi (r_index.hpp:195-221):
 // strict circular predecessor over the sorted run-first samples (sparse_sd_vector.hpp:107-112,153-157)
 // and (prev_sample + delta) % n (:219), folded into one delta per piece.
-template <typename WT, int D, bool KEEP>
-__device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT remaining) {
+template <typename WT, int D, bool KEEP, typename OT>
+__device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, OT* o, WT remaining) {
+    static_assert(D != 6 || sizeof(OT) == 8, "six per entry: 64-bit output only");
     constexpr int RW = (D == 1) ? 4 : ((D <= 6) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;  // entry size in bytes (RW words, or 32 when packed)
     const bool PK = ix.phi.packed != 0;
@@ -153,8 +165,8 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
     const char* rec = reinterpret_cast<const char*>(ix.phi.rec);
     const char* pent = reinterpret_cast<const char*>(ix.phi.pent);
     const u32 shift = ix.phi.shift;
-    // slots up to the next D*8-byte boundary go out singly; afterwards every emit is one aligned group
-    u32 take = D - (u32)((reinterpret_cast<unsigned long long>(o) >> 3) % D);
+    // slots up to the next D-slot boundary go out singly; afterwards every emit is one aligned group
+    u32 take = D - (u32)((reinterpret_cast<unsigned long long>(o) / sizeof(OT)) % D);
     bool searching = false;   // false: next load = bucket record of v; true: next load = piece entry `probe`
     u32 slo = 0, shi = 0;     // search interval of piece indices, invariant start[slo] <= v
     // Software-pipelined: the entry for the CURRENT state is already in flight / in registers when an
@@ -204,11 +216,11 @@ __device__ __forceinline__ WT walk_chain(const FlatDev& ix, WT v, u64* o, WT rem
         // ---- this iteration's occurrences (off the critical path) ----
         if (emit) {
             if (D != 6 && cnt == (u32)D) {
-                store_group<WT, D>(o, x);
+                store_group<WT, D, OT>(o, x);
             } else {   // partial group, or D = 6 (a group of six is not sector-aligned: the head walk is short, singles do)
 #pragma unroll
                 for (int t = 0; t < D; ++t)
-                    if ((u32)t < cnt) __stcs(o + t, (u64)x[t]);
+                    if ((u32)t < cnt) __stcs(o + t, (OT)x[t]);
                 take = D;
             }
             o += cnt;
@@ -253,7 +265,6 @@ __device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
     asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 
-#define RIG_LINE 16  // output slots per 128-byte line
 
 // Device-side view of a locate call's counters (rig_index::d_counters): the expansion kernels read the totals the
 // search produced instead of taking them as launch parameters, so the host can queue the whole call without
@@ -295,13 +306,14 @@ __device__ __forceinline__ bool expansion_enabled(const u64* ctr, u64 cap, u64 i
 // the item list while it is being written; each 16-byte entry then carries the call's epoch in the top 16 bits of
 // BOTH words (slots and positions stay below 2^48) and is written with a device-scope relaxed store, so a reader
 // accepts an entry only when both tags are the current epoch.
-template <typename WT, int D, bool KEEP, bool SEEDED>
+template <typename WT, int D, bool KEEP, bool SEEDED, typename OT>
 __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u64* __restrict__ ch_off,
                                                const u64* __restrict__ occ_off, const u64* __restrict__ lo_in,
                                                const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                                               const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr,
+                                               const u64* __restrict__ jl_in, OT* __restrict__ out, u64* __restrict__ ctr,
                                                u64* __restrict__ items, u32 seg_shift, u64 total_chains, u64 tag,
                                                u32 block, u32 nblocks) {   // this CTA's rank among the nblocks producing CTAs
+    constexpr u64 LINE = 128 / sizeof(OT);   // output slots per 128-byte line
     const int lane = threadIdx.x & 31;
     const u64 stride = (u64)nblocks * blockDim.x;
     for (u64 wb = (u64)block * blockDim.x + (threadIdx.x & ~31u); wb < total_chains; wb += stride) {  // warp-uniform
@@ -323,13 +335,13 @@ __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u
             else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
             g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
             glast = g0 + (top - bot);             // slot of its last (a chain never exceeds n)
-            __stcs(out + g0, v0);
+            __stcs(out + g0, (OT)v0);
         }
         if (!SEEDED) {
-            if (active) walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(glast - g0));
+            if (active) walk_chain<WT, D, KEEP, OT>(ix, (WT)v0, out + g0 + 1, (WT)(glast - g0));
         } else {
             const u64 SEG = 1ull << seg_shift;
-            const u64 a1 = (g0 + RIG_LINE - 1) & ~(u64)(RIG_LINE - 1);  // first line-aligned slot at or after g0
+            const u64 a1 = (g0 + LINE - 1) & ~(LINE - 1);  // first line-aligned slot at or after g0
             const u64 K = (active && a1 <= glast) ? ((glast - a1) >> seg_shift) + 1 : 0;  // items of this chain
             // reserve K entries of items[]: inclusive warp scan, one atomic by the last lane
             u64 incl = K;
@@ -343,7 +355,7 @@ __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u
             wbase = __shfl_sync(RIG_FULL, wbase, 31);
             if (!active) continue;
             const u64 pre_last = min(a1, glast);
-            WT v = walk_chain<WT, D, KEEP>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
+            WT v = walk_chain<WT, D, KEEP, OT>(ix, (WT)v0, out + g0 + 1, (WT)(pre_last - g0));
             if (K) {
                 ulonglong2* it = reinterpret_cast<ulonglong2*>(items) + wbase + (incl - K);
                 u64 s = a1;
@@ -361,15 +373,15 @@ __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u
     }
 }
 
-template <typename WT, int D, bool KEEP, bool SEEDED>
+template <typename WT, int D, bool KEEP, bool SEEDED, typename OT>
 __global__ void __launch_bounds__(256)
 phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
                   const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                  const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
+                  const u64* __restrict__ jl_in, OT* __restrict__ out, u64* __restrict__ ctr, u64 cap,
                   u64* __restrict__ items, u64 items_cap, u32 seg_shift) {
     u64 total, total_chains;
     if (!expansion_enabled(ctr, cap, items_cap, seg_shift, SEEDED, total, total_chains)) return;
-    produce_chains<WT, D, KEEP, SEEDED>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, 0,
+    produce_chains<WT, D, KEEP, SEEDED, OT>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, 0,
                                         blockIdx.x, gridDim.x);
 }
 
@@ -383,8 +395,9 @@ phi_expand_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const
 // (A leaner form of this loop — full groups only in the main loop, the next entry loaded straight into the registers
 // of the one consumed, 124 M instead of 157 M warp instructions on config C2 — was measured no faster: 0.300 vs
 // 0.285 ms. The pass is not issue-bound; profiles/r2_window_bound.txt.)
-template <typename WT, int D, bool KEEP>
-__device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left, u64* o, WT v) {
+template <typename WT, int D, bool KEEP, typename OT>
+__device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left, OT* o, WT v) {
+    static_assert(D != 6 || sizeof(OT) == 8, "six per entry: 64-bit output only");
     constexpr int RW = (D == 1) ? 4 : ((D <= 6) ? 8 : 16);
     const u32 ESZ = ix.phi.esz;
     const bool PK = ix.phi.packed != 0;
@@ -473,15 +486,15 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
                 }
             } else {
                 if (cnt == (u32)D) {
-                    if (RIG_DIAG(ix) == 0 || RIG_DIAG(ix) == 3) store_group<WT, D>(o, g);
+                    if (RIG_DIAG(ix) == 0 || RIG_DIAG(ix) == 3) store_group<WT, D, OT>(o, g);
                     else if (RIG_DIAG(ix) == 1)   // diagnostic (RIG_VARIANT bit 15): every store lands in one 32 MB window — WRONG output, timing only
-                        store_group<WT, D>(ix.dbg + ((reinterpret_cast<unsigned long long>(o) >> 3) & 0x3FFFFCull), g);
+                        store_group<WT, D, OT>(reinterpret_cast<OT*>(ix.dbg) + ((reinterpret_cast<unsigned long long>(o) / sizeof(OT)) & 0x3FFFFCull), g);
                     else if (g[0] == (WT)0xFFFFFFF1u && g[D - 1] == (WT)0xFFFFFFF3u)   // diagnostic (bit 16): no stores (the test keeps the values live)
-                        store_group<WT, D>(o, g);
+                        store_group<WT, D, OT>(o, g);
                 } else {
 #pragma unroll
                     for (int t = 0; t < D - 1; ++t)
-                        if ((u32)t < cnt) __stcs(o + t, (u64)g[t]);
+                        if ((u32)t < cnt) __stcs(o + t, (OT)g[t]);
                 }
                 o += cnt;
             }
@@ -492,7 +505,7 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
         for (int t = 0; t < RW; ++t) e[t] = e2[t];
     }
     if (D == 6 && pc) { __stcs(o, (u64)p0); __stcs(o + 1, (u64)p1); o += 2; }
-    if (left == 1) __stcs(o, (u64)v);  // the value carried out of the last full group
+    if (left == 1) __stcs(o, (OT)v);  // the value carried out of the last full group
 }
 
 // "Window pass", the default form. PERSISTENT: a warp takes 32 consecutive items, walks them in lockstep until its
@@ -500,9 +513,9 @@ __device__ __forceinline__ void window_items_direct(const FlatDev& ix, u32 left,
 // items[i] = (first slot << 8 | cnt, seed): v = seed is the occurrence on the item's first slot, cnt the number of
 // further occurrences of the same chain that the item covers (< SEG). Each lookup yields Phi^1..Phi^D(v); the lane
 // emits the aligned group [v, Phi(v), .., Phi^(D-1)(v)] as one 32-byte sector store and continues from Phi^D(v).
-template <typename WT, int D, bool KEEP, int MINB>
+template <typename WT, int D, bool KEEP, int MINB, typename OT>
 __global__ void __launch_bounds__(256, MINB)
-phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, u64* __restrict__ out,
+phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u64* __restrict__ ctr, OT* __restrict__ out,
                         u64 cap, u64 items_cap, u32 seg_shift) {
     u64 total, total_chains;
     if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
@@ -511,7 +524,7 @@ phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u
     for (u32 ib = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); ib < n_items; ib += T) {  // warp-uniform
         const u32 i = ib + (threadIdx.x & 31u);
         u32 left = 0;
-        u64* o = out;
+        OT* o = out;
         WT v = 0;
         if (i < n_items) {
             const ulonglong2 it = __ldcs(reinterpret_cast<const ulonglong2*>(items) + i);
@@ -519,7 +532,7 @@ phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u
             o = out + (it.x >> 8);
             v = (WT)it.y;
         }
-        window_items_direct<WT, D, KEEP>(ix, left, o, v);
+        window_items_direct<WT, D, KEEP, OT>(ix, left, o, v);
     }
 }
 
@@ -533,11 +546,11 @@ phi_window_batch_kernel(const FlatDev ix, const u64* __restrict__ items, const u
 // warp that is not running: the grid is sized to be fully resident.
 #define RIG_CTR_DONE 7    // warps that have finished producing
 #define RIG_CTR_TAKEN 8   // items handed out to consumers
-template <typename WT, int D, bool KEEP, int MINB>
+template <typename WT, int D, bool KEEP, int MINB, typename OT>
 __global__ void __launch_bounds__(256, MINB)
 phi_fused_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const u64* __restrict__ occ_off,
                  const u64* __restrict__ lo_in, const u64* __restrict__ hi_in, const u64* __restrict__ toe_in,
-                 const u64* __restrict__ jl_in, u64* __restrict__ out, u64* __restrict__ ctr, u64 cap,
+                 const u64* __restrict__ jl_in, OT* __restrict__ out, u64* __restrict__ ctr, u64 cap,
                  u64* __restrict__ items, u64 items_cap, u32 seg_shift, u64 tag, u32 prod_mod) {
     u64 total, total_chains;
     if (!expansion_enabled(ctr, cap, items_cap, seg_shift, true, total, total_chains)) return;
@@ -546,7 +559,7 @@ phi_fused_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const 
     // Every warp producing would leave nobody to consume until the longest chains are done.
     const u32 n_prod_ctas = (gridDim.x + prod_mod - 1) / prod_mod;
     if (blockIdx.x % prod_mod == 0) {
-        produce_chains<WT, D, KEEP, true>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, tag,
+        produce_chains<WT, D, KEEP, true, OT>(ix, N, ch_off, occ_off, lo_in, hi_in, toe_in, jl_in, out, ctr, items, seg_shift, total_chains, tag,
                                           blockIdx.x / prod_mod, n_prod_ctas);
         __syncwarp();
         if (lane == 0) { __threadfence(); atomicAdd(ctr + RIG_CTR_DONE, 1ull); }
@@ -586,14 +599,14 @@ phi_fused_kernel(const FlatDev ix, u64 N, const u64* __restrict__ ch_off, const 
         }
         if (all_done && ib >= n_final) break;
         u32 left = 0;
-        u64* o = out;
+        OT* o = out;
         WT v = 0;
         if (have) {
             left = (u32)(w0 & 255u) + 1;
             o = out + ((w0 & RIG_ITEM_MASK) >> 8);
             v = (WT)(w1 & RIG_ITEM_MASK);
         }
-        window_items_direct<WT, D, KEEP>(ix, left, o, v);
+        window_items_direct<WT, D, KEEP, OT>(ix, left, o, v);
     }
 }
 

@@ -180,7 +180,7 @@ int rig_index_create_ex(const rig_logical_view* view, int device, const rig_opti
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
 
-    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel, bit14 one lane per pattern instead of two (search_lane_kernel), bits 15-17 window-pass timing diagnostics (builds with -DRIG_WINDOW_DIAG only)
+    int variant = 0;  // env RIG_VARIANT: bit0 persisting-L2 experiment, bit1 no evict_last hint, bit2 no L2 warm-up, bit3 forces the 64-bit code paths (as for n >= 2^32), bit5 single-pass expansion, bit12 no L2 warm-up of the search structures, bit13 seed pass and window pass as two kernels instead of the fused producer/consumer kernel, bit7 cooperative (group-per-pattern) search kernel, bit14 one lane per pattern instead of two (search_lane_kernel), bits 15-17 window-pass timing diagnostics (builds with -DRIG_WINDOW_DIAG only), bit18 rig_locate_batch32 through 64-bit positions + narrowing pass (A/B switch)
     if (const char* ev = getenv("RIG_VARIANT")) variant = atoi(ev);
     if (variant & 8) opt.reserved[1] |= 1;
     if (variant & 512) opt.reserved[1] |= 2 | 4;  // bit9: 64-bit words inside the block records even when n < 2^40 (A/B switch)
@@ -581,8 +581,8 @@ int resident_ctas(K kernel, int threads) {
 // Phi expansion of the batch whose offsets and totals the search left on the device: seed pass + window pass, or the
 // single-pass walk. Both kernels are persistent and decide on the device whether to run (expansion_enabled): the
 // host queues them WITHOUT knowing the totals. `items_cap`: entries the item list can hold.
-int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi, const ull* d_occoff, ull* d_occ,
-                     uint64_t cap, bool two_pass, uint64_t items_cap, cudaStream_t st) {
+int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi, const ull* d_occoff, void* d_occ_v,
+                     uint64_t cap, bool two_pass, uint64_t items_cap, cudaStream_t st, bool out32) {
     int rc;
     const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 128;  // measured: 0.445 ms (128) vs 0.463 ms (256) on C2
     if (threads < 32 || threads > 256 || (threads & 31)) return RIG_ERR_ARG;
@@ -630,13 +630,15 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
         ix->epoch += 1;
         a_tag = (ull)ix->epoch << 48;
     }
-#define RIG_EXPAND2(W, DD, KP)                                                                                  \
+#define RIG_EXPAND2(W, DD, KP, OTT)                                                                             \
     do {                                                                                                        \
+        OTT* d_occ = (OTT*)d_occ_v;                                                                             \
         if (fused) {                                                                                            \
-            auto kf = rigk::phi_fused_kernel<W, DD, KP, (sizeof(W) == 4 ? 5 : 3)>;                              \
-            uint64_t gf = (uint64_t)ix->sm_count * resident_ctas(kf, wthreads);                                 \
+            auto kf = rigk::phi_fused_kernel<W, DD, KP, (sizeof(W) == 4 ? 5 : 3), OTT>;                           \
+            const int per_sm = resident_ctas(kf, wthreads);                                                     \
+            uint64_t gf = (uint64_t)ix->sm_count * per_sm;                                                      \
             cudaLaunchConfig_t cfgf = cfg;                                                                      \
-            cfgf.gridDim = dim3((unsigned)gf); cfgf.blockDim = dim3((unsigned)wthreads);                        \
+            cfgf.blockDim = dim3((unsigned)wthreads);                                                           \
             /* consumers wait for producers: the grid must be co-resident — a COOPERATIVE launch guarantees it or fails */ \
             cudaLaunchAttribute fattr[2];                                                                       \
             unsigned nfa = 0;                                                                                   \
@@ -644,8 +646,16 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
             fattr[nfa].id = cudaLaunchAttributeCooperative; fattr[nfa].val.cooperative = 1; ++nfa;              \
             cfgf.attrs = fattr; cfgf.numAttrs = nfa;                                                            \
             if ((rc = rec(ix, 6, st))) return rc;                                                               \
-            cudaError_t fe = cudaLaunchKernelEx(&cfgf, kf, ix->d, a_N, a_choff, d_occoff, d_lo, d_hi, a_toe, a_jl, d_occ, \
-                                                a_ctr, a_cap, a_items, a_icap, seg_shift, a_tag, a_pmod);       \
+            cudaError_t fe = cudaErrorUnknown;                                                                  \
+            /* "too large" can come from resources the occupancy query does not see: retry with one CTA per SM less */ \
+            for (int per = per_sm; per >= 1 && per + 2 >= per_sm; --per) {                                      \
+                gf = (uint64_t)ix->sm_count * per;                                                              \
+                cfgf.gridDim = dim3((unsigned)gf);                                                              \
+                fe = cudaLaunchKernelEx(&cfgf, kf, ix->d, a_N, a_choff, d_occoff, d_lo, d_hi, a_toe, a_jl, d_occ, \
+                                        a_ctr, a_cap, a_items, a_icap, seg_shift, a_tag, a_pmod);               \
+                if (fe != cudaErrorCooperativeLaunchTooLarge) break;                                            \
+                cudaGetLastError();                                                                             \
+            }                                                                                                   \
             if (fe == cudaSuccess) {                                                                            \
                 ix->timing.launches += 1; ix->timing.slices = 1;                                                \
                 if ((rc = rec(ix, 7, st))) return rc;                                                           \
@@ -663,8 +673,8 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
         }                                                                                                       \
         if (fused_ok) {                                                                                         \
         } else if (two_pass) {                                                                                  \
-            auto k1 = rigk::phi_expand_kernel<W, DD, KP, true>;                                                 \
-            auto k2 = rigk::phi_window_batch_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4)>;                       \
+            auto k1 = rigk::phi_expand_kernel<W, DD, KP, true, OTT>;                                             \
+            auto k2 = rigk::phi_window_batch_kernel<W, DD, KP, (sizeof(W) == 4 ? 6 : 4), OTT>;                  \
             uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
             uint64_t g2 = (uint64_t)ix->sm_count * resident_ctas(k2, wthreads);                                 \
             g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
@@ -680,7 +690,7 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
             ix->timing.launches += 2; ix->timing.slices = 2;                                                    \
             if ((rc = rec(ix, 7, st))) return rc;                                                               \
         } else {                                                                                                \
-            auto k1 = rigk::phi_expand_kernel<W, DD, KP, false>;                                                \
+            auto k1 = rigk::phi_expand_kernel<W, DD, KP, false, OTT>;                                            \
             uint64_t g1 = (uint64_t)ix->sm_count * resident_ctas(k1, threads);                                  \
             g1 = std::min<uint64_t>(g1, (max_chains + threads - 1) / threads);                                  \
             cfg.gridDim = dim3((unsigned)g1);                                                                   \
@@ -691,9 +701,14 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
     } while (0)
 #define RIG_EXPAND(W, DD)                                                                                     \
     do {                                                                                                      \
-        if (keep) RIG_EXPAND2(W, DD, true);                                                                   \
-        else RIG_EXPAND2(W, DD, false);                                                                       \
+        if (keep) RIG_EXPAND2(W, DD, true, ull);                                                              \
+        else RIG_EXPAND2(W, DD, false, ull);                                                                  \
     } while (0)
+    if (out32) {   // native 32-bit positions (rig_locate_batch32): the default table form only
+        if (!(ix->d.phi.D == 4 && w32)) return RIG_ERR_ARG;
+        if (keep) RIG_EXPAND2(uint32_t, 4, true, uint32_t);
+        else RIG_EXPAND2(uint32_t, 4, false, uint32_t);
+    } else
     switch (ix->d.phi.D * 2 + (w32 ? 1 : 0)) {
         case 2: RIG_EXPAND(ull, 1); break;
         case 3: RIG_EXPAND(uint32_t, 1); break;
@@ -716,14 +731,15 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
 // out right after the search), while the expansion is already running: events 1..4 on `st`.
 // own_occ (host-buffer entry points with RIG_LOCATE_DEVICE_ONLY): the occurrences go to the library's own buffer,
 // which is grown to the batch total when it is too small — only the expansion is queued again, not the search.
+// out32: d_occ is an array of 32-bit positions (n < 2^32; the default Phi table form), cap counts its elements.
 int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff,
-               ull* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st, DevBuf* own_occ = nullptr) {
+               void* d_occ, uint64_t cap, uint64_t* occ_total, cudaStream_t st, DevBuf* own_occ = nullptr, bool out32 = false) {
     int rc;
     if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
         (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 4) * 8)) ||
         (rc = ix->sums.ensure((std::max<uint64_t>(tile_ws_words(N), 2 * ((N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE) + 8)) * 8)))
         return rc;
-    if (own_occ) { d_occ = (ull*)own_occ->p; cap = own_occ->cap / 8; }
+    if (own_occ) { d_occ = own_occ->p; cap = own_occ->cap / 8; }
     const uint32_t SEG = ix->d.seed.J;
     auto items_bound = [&](uint64_t total, uint64_t chains) { return total / (SEG ? SEG : 1) + chains; };
     // Two passes when the index has a seed table and the output array is line-aligned (the window kernel writes
@@ -744,7 +760,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
             items_cap = ix->items.cap / 16 - 32;
         }
         ix->last_items_cap = items_cap; ix->last_two_pass = two_pass;
-        return launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st);
+        return launch_expansion(ix, N, d_lo, d_hi, d_occoff, d_occ, cap, two_pass, items_cap, st, out32);
     };
     if ((rc = prep_call(ix, N, true, st))) return rc;
     if ((rc = rec(ix, 1, st))) return rc;
@@ -773,7 +789,7 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
     bool fits = !(total > cap || (total && !d_occ));
     if (!fits && own_occ && total) {   // grow the library's buffer to this batch; the search results stay valid on the device
         if ((rc = own_occ->ensure(total * 8 + 128))) return rc;
-        d_occ = (ull*)own_occ->p; cap = own_occ->cap / 8;
+        d_occ = own_occ->p; cap = own_occ->cap / 8;
         fits = true; queued = false;
     }
     const bool need_items = fits && total && ix->d.seed.J > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
@@ -807,14 +823,18 @@ int locate_host(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, 
         (rc = ix->occoff.ensure((N + 2) * 8)))
         return rc;
     const bool want = devonly || (occ && occ_capacity);
-    if (!devonly && want && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
-    if (occ32 && want && (rc = ix->occ32.ensure(occ_capacity * 4 + 16))) return rc;
+    // 32-bit positions are written by the expansion kernels themselves (half the store sectors, no narrowing pass) when the
+    // index has the default table form and no sort is asked for (the sort works on 64-bit keys); otherwise narrowed after
+    const bool native32 = occ32 && ix->d.w32 && ix->d.phi.D == 4 && !(flags & RIG_LOCATE_SORT) && !(ix->variant & 262144);
+    if (!devonly && want && !native32 && (rc = ix->occ.ensure(occ_capacity * 8))) return rc;
+    if (occ32 && want && (rc = ix->occ32.ensure(occ_capacity * 4 + 128))) return rc;
     begin_call(ix);
     if ((rc = rec(ix, 0, st))) return rc;
     if (N * m) CU_TRY(cudaMemcpyAsync(ix->patt.p, patterns, N * m, cudaMemcpyHostToDevice, st));
     uint64_t total = 0;
     int lrc = locate_dev(ix, (const uint8_t*)ix->patt.p, N, m, (ull*)ix->lo.p, (ull*)ix->hi.p, (ull*)ix->occoff.p,
-                         want ? (ull*)ix->occ.p : nullptr, want ? occ_capacity : 0, &total, st, devonly ? &ix->occ : nullptr);
+                         want ? (native32 ? ix->occ32.p : ix->occ.p) : nullptr, want ? occ_capacity : 0, &total, st,
+                         devonly ? &ix->occ : nullptr, native32);
     if (lrc != RIG_OK && lrc != RIG_ERR_CAPACITY) return lrc;
     if (occ_total) *occ_total = total;
     ix->kept_total = (lrc == RIG_OK && devonly) ? total : 0;
@@ -826,7 +846,7 @@ int locate_host(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, 
                             (const ull*)ix->occoff.p, (const ull*)ix->occ.p, total, 1, report, st)))
             return rc;
     }
-    if (lrc == RIG_OK && total && occ32) {
+    if (lrc == RIG_OK && total && occ32 && !native32) {
         const uint64_t nb = ((total + 3) / 4 + 255) / 256;
         if (nb > 0x7fffffffull) return RIG_ERR_ARG;
         rigk::narrow_kernel<<<(unsigned)nb, 256, 0, st>>>((const ull*)ix->occ.p, (uint32_t*)ix->occ32.p, total);

@@ -142,3 +142,13 @@ def test_locate32_equals_locate():
         assert np.array_equal(occ32s.astype(np.uint64), _sorted_per_pattern(off, occ))
     with pytest.raises(rib.RigError):
         gpu.locate32(patt, N, m, rib.LOCATE_CHECK)
+    # native 32-bit output of the expansion kernels (default table form: fused, small windows, single pass) and the
+    # narrowing pass behind the other forms: long ranges, so that chains span many windows and lines
+    for (jump, seg) in [(0, 0), (4, 16), (4, 1), (2, 0), (8, 32)]:
+        g2 = rib.GpuIndex(host, phi_jump=jump, seed_jump=seg)
+        for (N, m, seed) in [(300, 3, 7), (41, 1, 8), (5000, 6, 9)]:
+            patt = mixed_patterns(text, N, m, seed, alphabet=acgt)
+            lo, hi, off, occ = g2.locate(patt, N, m)
+            lo2, hi2, off2, occ32 = g2.locate32(patt, N, m)
+            assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2) and np.array_equal(off, off2)
+            assert np.array_equal(occ32.astype(np.uint64), occ), (jump, seg, N, m)
