@@ -44,17 +44,18 @@ namespace {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    uint64_t generation = 0;   // bumped by every (re)allocation: the new block holds garbage, whatever its address
     int ensure(size_t bytes) {
         if (bytes <= cap) return RIG_OK;
         if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        p = nullptr; cap = 0; ++generation;
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); p = nullptr; return RIG_ERR_NOMEM; }
         cap = want;
         return RIG_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; ++generation; }
 };
 
 }  // namespace
@@ -91,7 +92,9 @@ struct rig_index {
     uint64_t digest = 0;           // logical_digest() of the index this handle was made from
     bool warned_fused = false;     // the fused kernel's cooperative launch has failed once (reported on stderr)
     uint32_t epoch = 0;            // fused expansion: tag of the current call's items (1..65535; the list is zeroed when it wraps)
-    void* items_zeroed = nullptr;  // the item-list allocation that has been zero-filled (a fresh cudaMalloc holds garbage)
+    uint64_t items_zeroed = ~0ull; // generation of the item-list allocation that has been zero-filled. A fresh cudaMalloc holds garbage —
+                                   // possibly another index's items with a matching epoch tag — and can come back at the address of
+                                   // the block just freed, so the pointer does not tell
     uint64_t last_items_cap = 0;   // item-list capacity the most recent expansion was queued with
     bool last_two_pass = false;
     uint64_t kept_total = 0;       // occurrences of the most recent RIG_LOCATE_DEVICE_ONLY call, still in `occ`
@@ -622,9 +625,9 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
     uint32_t a_pmod = 1;   // every CTA produces its share first (measured: dedicating 1/2, 1/4, 1/8 of the CTAs to production is slower; RIG_FUSED_PROD overrides)
     if (const char* ev = getenv("RIG_FUSED_PROD")) { int v = atoi(ev); if (v >= 1 && v <= 64) a_pmod = (uint32_t)v; }
     if (fused) {
-        if (ix->items_zeroed != ix->items.p || ((ix->epoch + 1) & 0xFFFFu) == 0) {   // fresh allocation, or the 16-bit tag wraps
+        if (ix->items_zeroed != ix->items.generation || ((ix->epoch + 1) & 0xFFFFu) == 0) {   // fresh allocation, or the 16-bit tag wraps
             CU_TRY(cudaMemsetAsync(ix->items.p, 0, ix->items.cap, st));
-            ix->items_zeroed = ix->items.p;
+            ix->items_zeroed = ix->items.generation;
             ix->epoch = 0;
         }
         ix->epoch += 1;
