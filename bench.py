@@ -11,10 +11,12 @@ batch of synthetic patterns.
   N > 1   default workload = BASELINE.json configs[4] (C5): ri-locate, 4 GB synthetic DNA, 100k patterns of length 15,
           ~10k occurrences each (~1e9 occurrences per job) — the config BASELINE names for 1 -> 8 GPU scaling. STRONG
           scaling: the job is FIXED, the index replicated in every GPU's HBM, the patterns sharded. Per step every
-          rank (1) counts its equal-count shard, (2) the ranks all-gather the per-pattern counts (8 B per pattern:
-          NCCL for the device-resident number, gloo for the host-buffer one), (3) the batch is re-cut into contiguous
-          shards of equal OCCURRENCE mass, (4) every rank locates its shard. No collective on the
-          search path. In the same run rank 0 also runs the WHOLE job alone (`strong_scaling.n1`), so every line
+          rank (1) learns the per-pattern occurrence counts — `--plan replicate`: it counts the whole batch itself (no
+          collective; the automatic choice up to 8 M LF steps per batch, a count pass then costs less than a
+          collective's latency); `--plan gather`: it counts its equal-count shard and the ranks all-gather the counts
+          (8 B per pattern: NCCL for the device-resident number, gloo for the host-buffer one) —, (2) cuts the batch
+          into contiguous shards of equal OCCURRENCE mass (the same integer rule on every rank), (3)
+          locates its shard. No collective on the search path. In the same run rank 0 also runs the WHOLE job alone (`strong_scaling.n1`), so every line
           carries the one-GPU figure of its own job.
 
   value      occurrences/s of the whole job, device-resident inputs and outputs, CUDA-event timed, max over ranks
@@ -515,16 +517,26 @@ def run_ours_count(args):
     return 0
 
 
+PLAN_REPLICATE_MAX_LF = 8_000_000   # LF steps (patterns x length) up to which every rank counts the whole batch itself
+
+
 class LocateJob:
     """One rank's part of a locate job: device-resident step and host-buffer (e2e) step, with the count -> all-gather
     -> re-cut by occurrence mass -> locate sequence when there is more than one rank (`solo` = the whole job alone).
     Equal-count shards are [r * per, (r + 1) * per) with per = ceil(N / world), so the all-gathered count buffer IS
     the batch's count array (plus padding at its very end)."""
 
-    def __init__(self, D, gpu, patt, N, m, stream, solo=False):
+    def __init__(self, D, gpu, patt, N, m, stream, solo=False, plan="auto"):
         torch = D.torch
         self.D, self.gpu, self.N, self.m, self.stream = D, gpu, N, m, stream
         self.world, self.rank = (1, 0) if solo else (D.world, D.rank)
+        # Planning: "gather" = every rank counts its equal-count shard, the ranks all-gather the counts, every rank then
+        # locates (search + expansion) its re-cut shard; "replicate" = every rank SEARCHES the whole batch itself
+        # (rig_plan_batch_dev: ranges, toeholds, output offsets, and the cut points by binary search in the offsets) and
+        # then only EXPANDS its shard (rig_expand_shard_dev) — no collective at all, and cheaper whenever a search pass
+        # over the batch costs less than a collective's latency (C5: 1.5 M LF steps = 0.06 ms against ~0.3 ms of count
+        # + all-gather + cuts at 8 ranks). auto: replicate up to 8 M LF steps per batch.
+        self.plan = plan if plan != "auto" else ("replicate" if N * m <= PLAN_REPLICATE_MAX_LF else "gather")
         from rindex_b200 import _shard
         self.shard = _shard
         self.patt = patt
@@ -546,18 +558,31 @@ class LocateJob:
         shard bounds are launch parameters). Returns this rank's [c0, c1)."""
         if self.world == 1:
             return 0, self.N
-        n = self.b - self.a
-        self.gpu.count_dev(self.d_patt.data_ptr() + self.a * self.m, n, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.stream)
-        self.gpu.counts_dev(self.d_lo.data_ptr(), self.d_hi.data_ptr(), n, self.d_cnt.data_ptr(), self.stream)
-        self.D.dist.all_gather_into_tensor(self.d_all, self.d_cnt)
+        if self.plan == "replicate":   # search + offsets of the whole batch here, cuts from the offsets (rig_plan_batch_dev)
+            self.cuts, _ = self.gpu.plan_dev(self.d_patt.data_ptr(), self.N, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                                             self.d_off.data_ptr(), self.world, 64, self.stream)
+            return self.cuts[self.rank], self.cuts[self.rank + 1]
+        else:
+            n = self.b - self.a
+            self.gpu.count_dev(self.d_patt.data_ptr() + self.a * self.m, n, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.stream)
+            self.gpu.counts_dev(self.d_lo.data_ptr(), self.d_hi.data_ptr(), n, self.d_cnt.data_ptr(), self.stream)
+            self.D.dist.all_gather_into_tensor(self.d_all, self.d_cnt)
         self.cuts = self.gpu.balanced_cuts_dev(self.d_all.data_ptr(), self.N, self.world, 64, self.stream)
         return self.cuts[self.rank], self.cuts[self.rank + 1]
 
     def counts_all(self):
+        if self.world > 1 and self.plan == "replicate":   # after plan_dev: d_off is the exclusive prefix of the counts
+            off = self.d_off[: self.N + 1].cpu().numpy()
+            return off[1:] - off[:-1]
         return self.d_all[: self.N].cpu().numpy()
 
-    def step_dev(self):
+    def step_dev(self, mark=None):
         c0, c1 = self.plan_dev()
+        if mark is not None:   # end of the planning phase (count, all-gather, cuts: plan_dev ends on a host sync)
+            mark.record()
+        if self.world > 1 and self.plan == "replicate":   # the batch is searched already: expand this rank's shard
+            return self.gpu.expand_shard_dev(self.N, c0, c1, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.d_off.data_ptr(),
+                                             self.d_occ.data_ptr(), self.d_occ.numel(), self.stream)
         return self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
                                    self.d_off.data_ptr(), self.d_occ.data_ptr(), self.d_occ.numel(), self.stream)
 
@@ -566,8 +591,11 @@ class LocateJob:
         torch = self.D.torch
         c0, c1 = self.plan_dev()
         try:
-            need = self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
-                                       self.d_off.data_ptr(), None, 0, self.stream)
+            if self.world > 1 and self.plan == "replicate":
+                need = self.gpu.expand_shard_dev(self.N, c0, c1, self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.d_off.data_ptr(), None, 0, self.stream)
+            else:
+                need = self.gpu.locate_dev(self.d_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                                           self.d_off.data_ptr(), None, 0, self.stream)
         except Exception as e:  # noqa: BLE001
             if getattr(e, "code", 0) != -4:
                 raise
@@ -591,11 +619,17 @@ class LocateJob:
         torch, dist = self.D.torch, self.D.dist
         c0, c1 = 0, self.N
         if self.world > 1:
-            n = self.b - self.a
-            self.gpu.count_raw(self.h_patt.data_ptr() + self.a * self.m, n, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr())
-            torch.sub(self.h_hi[:n], self.h_lo[:n], out=self.h_cnt[:n])
-            self.h_cnt[:n].add_(1).clamp_(min=0)
-            dist.all_gather_into_tensor(self.h_all, self.h_cnt, group=self.D.gloo)
+            if self.plan == "replicate":
+                n = self.N
+                self.gpu.count_raw(self.h_patt.data_ptr(), n, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr())
+                torch.sub(self.h_hi[:n], self.h_lo[:n], out=self.h_all[:n])
+                self.h_all[:n].add_(1).clamp_(min=0)
+            else:
+                n = self.b - self.a
+                self.gpu.count_raw(self.h_patt.data_ptr() + self.a * self.m, n, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr())
+                torch.sub(self.h_hi[:n], self.h_lo[:n], out=self.h_cnt[:n])
+                self.h_cnt[:n].add_(1).clamp_(min=0)
+                dist.all_gather_into_tensor(self.h_all, self.h_cnt, group=self.D.gloo)
             cuts = self.shard.balanced_cuts(self.h_all[: self.N].numpy(), self.world)
             c0, c1 = cuts[self.rank], cuts[self.rank + 1]
         tot = self.gpu.locate_raw(self.h_patt.data_ptr() + c0 * self.m, c1 - c0, self.m, self.h_lo.data_ptr(), self.h_hi.data_ptr(),
@@ -616,23 +650,29 @@ def measure_locate(D, job, steps, warmup, e2e_steps, flush, solo=False):
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ph = {k: [] for k in ("search_ms", "scan_ms", "seed_ms", "window_ms", "expand_ms")}
+    plan = []
     launches = 0
     barrier()
     for k in range(steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
+        mark = torch.cuda.Event(enable_timing=True) if job.world > 1 else None
         ev[k][0].record()
-        tot = job.step_dev()
+        tot = job.step_dev(mark)
         ev[k][1].record()
         torch.cuda.synchronize()
         t = gpu.timing()
         for key in ph:
             ph[key].append(t[key])
+        if mark is not None:
+            plan.append(ev[k][0].elapsed_time(mark))
         launches += t["launches"] + (1 if job.world > 1 else 0)
     barrier()
     assert tot == occ_rank
     total_ms = sum(x.elapsed_time(y) for x, y in ev)
     out = {"occ_rank": occ_rank, "patterns_rank": job.c1 - job.c0, "total_ms": total_ms, "launches": launches, "expansion_kernels": t["slices"],
            "lf_steps": t["lf_steps"], "chains": t["chains"], "phases": {k: statistics.mean(v) for k, v in ph.items()}}
+    if plan:   # N > 1: count on the equal-count shard + all-gather of the counts + cut points, before the locate of the shard
+        out["phases"]["plan_ms"] = statistics.mean(plan)
     # end to end through the host-buffer C-ABI calls, pinned host memory. A shard whose occurrences exceed 16 GB (C3 at
     # full size) is not measured end to end: pinning that much host memory per rank is not what this number is about.
     if e2e_steps and occ_rank * 8 <= (16 << 30):
@@ -648,8 +688,9 @@ def measure_locate(D, job, steps, warmup, e2e_steps, flush, solo=False):
         e2e_t = time.perf_counter() - t1
         barrier()
         assert tot_h == occ_rank and int(job.h_off[pat_h]) == occ_rank   # cheap self-check (parity tests live in tests/)
-        out.update(e2e_ms=e2e_t * 1e3 / e2e_steps, e2e_h2d=int((job.b - job.a if job.world > 1 else 0) * job.m + pat_h * job.m),
-                   e2e_d2h=int(8 * (2 * (job.b - job.a if job.world > 1 else 0) + 3 * pat_h + 1 + occ_rank)))
+        n_cnt = 0 if job.world == 1 else (job.N if job.plan == "replicate" else job.b - job.a)   # patterns of the count call
+        out.update(e2e_ms=e2e_t * 1e3 / e2e_steps, e2e_h2d=int(n_cnt * job.m + pat_h * job.m),
+                   e2e_d2h=int(8 * (2 * n_cnt + 3 * pat_h + 1 + occ_rank)))
     return out
 
 
@@ -676,10 +717,13 @@ def run_ours(args):
 
     # ---- the same job on ONE GPU, measured in this run by rank 0 while the others wait (N > 1 only) ----
     solo = None
+    solo_digest = None
     if world > 1 and not args.no_solo:
+        D.host_barrier()   # every rank has loaded its index: nothing else runs on the host during the one-GPU run
         if rank == 0:
             sj = LocateJob(D, gpu, patt, N, m, stream, solo=True)
             sm = measure_locate(D, sj, max(3, min(args.steps, 5)), 3, 2, flush, solo=True)
+            solo_digest = gpu.digest_dev(sj.d_occ.data_ptr(), sm["occ_rank"], stream)   # of the whole job's output, in order
             solo = {"value": sm["occ_rank"] * max(3, min(args.steps, 5)) / (sm["total_ms"] * 1e-3), "ms_per_step": sm["total_ms"] / max(3, min(args.steps, 5)),
                     "e2e": (sm["occ_rank"] / (sm["e2e_ms"] * 1e-3)) if "e2e_ms" in sm else None,
                     "e2e_ms_per_step": sm.get("e2e_ms"), "occurrences": sm["occ_rank"], "phases_ms": sm["phases"],
@@ -691,7 +735,7 @@ def run_ours(args):
         D.host_barrier()
         D.barrier()
 
-    job = LocateJob(D, gpu, patt, N, m, stream)
+    job = LocateJob(D, gpu, patt, N, m, stream, plan=args.plan)
     sampler = ClockSampler(local)
     sampler.start()
     M = measure_locate(D, job, args.steps, args.warmup, e2e_steps, flush)
@@ -748,6 +792,28 @@ def run_ours(args):
         post = {"sort_ms": s0.elapsed_time(s1), "sort_keys_per_s": occ_rank / (s0.elapsed_time(s1) * 1e-3),
                 "check_ms": check_ms, "check": rep.as_dict(),
                 "note": "rig_sort_occurrences_dev + rig_check_dev on the device-resident output (ri-locate -o / -c)"}
+
+    # the sharded job's output IS the one-GPU run's output: order-sensitive digest of the concatenated shards, combined
+    # from the per-rank digests (sum and index-weighted sum are additive with the shard's base index), against rank 0's
+    # digest of its one-GPU run of the same job
+    same_as_n1 = None
+    if world > 1:
+        job.step_dev(); torch.cuda.synchronize()
+        mine = gpu.digest_dev(job.d_occ.data_ptr(), occ_rank, stream)
+        piece = torch.tensor([mine[0] & 0xFFFFFFFF, mine[0] >> 32, mine[1] & 0xFFFFFFFF, mine[1] >> 32, occ_rank], dtype=torch.int64, device=dev)
+        pieces = torch.zeros(5 * world, dtype=torch.int64, device=dev)
+        D.dist.all_gather_into_tensor(pieces, piece)
+        pieces = pieces.cpu().tolist()
+        if rank == 0 and solo_digest is not None:
+            M64 = (1 << 64) - 1
+            S = W = base = 0
+            for r in range(world):
+                s_r = pieces[5 * r] | (pieces[5 * r + 1] << 32)
+                w_r = pieces[5 * r + 2] | (pieces[5 * r + 3] << 32)
+                S = (S + s_r) & M64
+                W = (W + w_r + base * s_r) & M64
+                base += pieces[5 * r + 4]
+            same_as_n1 = bool(S == solo_digest[0] and W == solo_digest[1])
 
     # optional collation over NVLink (north_star: "an optional NCCL all-gather only to collate occurrence buffers"):
     # every rank ends up with the whole job's occurrences in pattern order; exercised and timed once, not part of `value`
@@ -849,12 +915,15 @@ def run_ours(args):
                        "index_from_flat_file": bool(getattr(gpu, "from_flat", False)),
                        "runs_per_block": int(info.runs_per_block), "phi_jump": int(info.phi_jump),
                        "seed_jump": int(info.seed_jump), "seed_table_bytes": int(info.seed_bytes),
-                       "parallelism": ("index replicated x%d; per step: count on equal-count shards, NCCL all-gather of the counts (8 B/pattern), "
-                                       "contiguous shards re-cut at equal occurrence mass, locate" % world) if world > 1 else "one GPU",
+                       "parallelism": ("index replicated x%d; per step: %s, contiguous shards cut at equal occurrence mass, locate"
+                                       % (world, "every rank searches the whole batch itself (rig_plan_batch_dev: no collective) and expands its shard (rig_expand_shard_dev)" if job.plan == "replicate" else
+                                          "count on equal-count shards, NCCL all-gather of the counts (8 B/pattern)")) if world > 1 else "one GPU",
+                       "plan": job.plan if world > 1 else None,
                        "phases_ms_rank0": phs},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": {"value": e2e_val, "unit": "occ/s", "h2d_bytes_per_step": int(h2d_g), "d2h_bytes_per_step": int(d2h_g),
-                    "api": "rig_locate_batch (host buffers, pinned)" + ("; rig_count_batch + gloo all-gather of the counts before it" if world > 1 else ""),
+                    "api": "rig_locate_batch (host buffers, pinned)" + ("" if world == 1 else ("; rig_count_batch of the whole batch before it" if job.plan == "replicate"
+                                                                     else "; rig_count_batch + gloo all-gather of the counts before it")),
                     "ms_per_step": e2e_ms_g, "steps": e2e_steps},
             "gpu_launches": int(launches_g) + args.steps * world,
             "count": {"metric": "count_patterns_per_s", "value": N * args.steps / (count_ms_g * 1e-3), "unit": "patterns/s",
@@ -877,7 +946,7 @@ def run_ours(args):
             line["balance"] = {"occurrences_max_over_mean": occ_max / (occ_g / world), "equal_count_shards_would_give": eq_occ,
                                "rank_step_ms_max_over_mean": (total_ms_g / args.steps) / rank_ms if rank_ms else None,
                                "rank_e2e_ms_max_over_mean": (e2e_ms_g / (e2e_sum_ms / world)) if e2e_sum_ms else None}
-            line["strong_scaling"] = {"job": WORKLOADS[args.workload][9], "n1": solo,
+            line["strong_scaling"] = {"job": WORKLOADS[args.workload][9], "n1": solo, "output_identical_to_n1": same_as_n1,
                                       "speedup_value": (line["value"] / solo["value"]) if solo else None,
                                       "speedup_e2e": (e2e_val / solo["e2e"]) if solo and solo.get("e2e") and e2e_val else None}
             if ceil and e2e_val:
@@ -924,6 +993,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-post", action="store_true", help="skip the -o / -c post-processing timing")
     ap.add_argument("--flat", action="store_true", help="N = 1: keep / reuse the flattened index file in .cache (N > 1 always does)")
+    ap.add_argument("--plan", default="auto", choices=["auto", "gather", "replicate"],
+                    help="N > 1: how the occurrence counts reach every rank before the shards are cut: all-gather of per-shard "
+                         "counts, or every rank counting the whole batch (auto: replicate up to 8 M LF steps per batch)")
     ap.add_argument("--no-solo", action="store_true", help="N > 1: skip rank 0's one-GPU run of the same job")
     ap.add_argument("--no-collate", action="store_true", help="N > 1: skip the NCCL collation of the occurrence buffers")
     ap.add_argument("--runs-per-block", type=int, default=0)

@@ -181,9 +181,10 @@ void* rig_host_alloc(uint64_t bytes);
 void rig_host_free(void* p);
 
 /* rig_locate_batch with 32-bit positions, for indexes with n <= 2^32 (RIG_ERR_ARG otherwise): the same values as
- * rig_locate_batch narrowed on the device, half the bytes over PCIe (the host-buffer call is PCIe-bound: 8.4 ms
- * instead of 15.7 ms on config C2). flags: 0 or RIG_LOCATE_SORT. The reference's locate_all returns 64-bit ulint;
- * this entry point is an addition for callers that store 32-bit positions anyway. */
+ * rig_locate_batch, written as uint32_t by the expansion kernels themselves (default table form, no sort; otherwise
+ * narrowed on the device afterwards): half the store sectors and half the bytes over PCIe (the host-buffer call is
+ * PCIe-bound: 7.8 ms instead of 15.5 ms on config C2). flags: 0 or RIG_LOCATE_SORT. The reference's locate_all
+ * returns 64-bit ulint; this entry point is an addition for callers that store 32-bit positions anyway. */
 int rig_locate_batch32(rig_index* idx, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
                        uint64_t* occ_offsets, uint32_t* occ, uint64_t occ_capacity, uint64_t* occ_total, uint32_t flags);
 
@@ -214,6 +215,24 @@ int rig_break_range_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi
  * lo's run, otherwise the first position after lo that holds c (~0 if none: the reference asserts). hi is the
  * range's end as in the reference's signature (its value does not enter the result). */
 int rig_closest_run_break_batch(rig_index* idx, const uint64_t* lo, const uint64_t* hi, const uint8_t* c, uint64_t N, uint64_t* out);
+
+/* ---- a job sharded over several GPUs, planned on every device (index replicated) ----
+ * rig_plan_batch_dev: the backward search of the WHOLE batch on this device — ranges, toeholds and the exclusive prefix of
+ * the occurrence counts, i.e. the first half of rig_locate_batch_dev — and, from that prefix, the cut points of `shards`
+ * contiguous shards of equal work (work(p) = n_occ(p) + per_pattern_cost; the integer rule of rig_balanced_cuts_dev).
+ * cuts: HOST array of shards + 1 entries (cuts[0] = 0, cuts[shards] = N). No communication: every device reaches the
+ * same cuts from the same batch, and a count pass over the whole batch costs less than a collective's latency for
+ * batches up to a few million LF steps (beyond that: count shards, exchange the counts, rig_balanced_cuts_dev).
+ * rig_expand_shard_dev: the Phi expansion of patterns [c0, c1) of the batch most recently planned on this index (same N
+ * and device arrays): the occurrences of pattern p go to d_occ[d_occ_offsets[p] - d_occ_offsets[c0] ...], in locate_all
+ * order. RIG_ERR_CAPACITY (and *shard_total) when occ_capacity is too small. Replaces, for a rank's shard, the
+ * per-pattern loop of ri-locate.cpp:126-145. */
+int rig_plan_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo, uint64_t* d_hi,
+                       uint64_t* d_occ_offsets, uint32_t shards, uint64_t per_pattern_cost, uint64_t* cuts,
+                       uint64_t* occ_total, void* stream);
+int rig_expand_shard_dev(rig_index* idx, uint64_t N, uint64_t c0, uint64_t c1, const uint64_t* d_lo, const uint64_t* d_hi,
+                         const uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t occ_capacity, uint64_t* shard_total,
+                         void* stream);
 
 /* ---- multi-GPU fan-out on device buffers ----
  * The index is replicated, the patterns are sharded; a locate job first COUNTS on equal-count shards, the hosts

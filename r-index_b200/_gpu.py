@@ -16,7 +16,7 @@ _vp = ctypes.c_void_p
 DECLARED_SYMBOLS = [
     "rig_device_count", "rig_strerror", "rig_last_cuda_error", "rig_version", "rig_index_create",
     "rig_index_create_ex", "rig_index_destroy", "rig_index_info_get", "rig_count_batch", "rig_locate_batch",
-    "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing",
+    "rig_count_batch_dev", "rig_locate_batch_dev", "rig_digest_dev", "rig_last_timing", "rig_plan_batch_dev", "rig_expand_shard_dev",
     "rig_text_attach", "rig_sort_occurrences_dev", "rig_check_dev", "rig_locate_batch_ex",
     "rig_navigate_batch", "rig_navigate_batch_dev", "rig_get_bwt", "rig_locate_batch32",
     "rig_break_range_batch", "rig_closest_run_break_batch", "rig_fetch_occurrences", "rig_host_alloc", "rig_host_free",
@@ -102,6 +102,10 @@ def gpu_lib():
         lib.rig_locate_batch_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _vp]
         lib.rig_digest_dev.argtypes = [_vp, _vp, _u64, ctypes.POINTER(_u64 * 2), _vp]
         lib.rig_last_timing.argtypes = [_vp, ctypes.POINTER(Timing)]
+        lib.rig_plan_batch_dev.argtypes = [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _u32, _u64, _vp, ctypes.POINTER(_u64), _vp]
+        lib.rig_plan_batch_dev.restype = ctypes.c_int
+        lib.rig_expand_shard_dev.argtypes = [_vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), _vp]
+        lib.rig_expand_shard_dev.restype = ctypes.c_int
         lib.rig_navigate_batch.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp]
         lib.rig_navigate_batch_dev.argtypes = [_vp, ctypes.c_int, _vp, _u64, _vp, _vp]
         lib.rig_get_bwt.argtypes = [_vp, _u64, _u64, _vp]
@@ -422,6 +426,25 @@ class GpuIndex:
         if rc != 0:
             raise RigError(rc, "rig_digest_dev")
         return int(out[0]), int(out[1])
+
+    def plan_dev(self, d_patt, N, m, d_lo, d_hi, d_off, shards, cost=64, stream=None):
+        """rig_plan_batch_dev on raw device pointers: (cuts list of shards + 1 entries, total occurrences of the batch)."""
+        cuts = (_u64 * (shards + 1))()
+        tot = _u64(0)
+        rc = self.lib.rig_plan_batch_dev(self.h, d_patt, N, m, d_lo, d_hi, d_off, shards, cost, ctypes.cast(cuts, _vp), ctypes.byref(tot), stream)
+        if rc != 0:
+            raise RigError(rc, "rig_plan_batch_dev")
+        return [int(c) for c in cuts], int(tot.value)
+
+    def expand_shard_dev(self, N, c0, c1, d_lo, d_hi, d_off, d_occ, cap, stream=None):
+        """rig_expand_shard_dev on raw device pointers: occurrences of the shard (RigError with .needed when cap is short)."""
+        tot = _u64(0)
+        rc = self.lib.rig_expand_shard_dev(self.h, N, c0, c1, d_lo, d_hi, d_off, d_occ, cap, ctypes.byref(tot), stream)
+        if rc != 0:
+            e = RigError(rc, "rig_expand_shard_dev")
+            e.needed = int(tot.value)
+            raise e
+        return int(tot.value)
 
     def timing(self):
         t = Timing()

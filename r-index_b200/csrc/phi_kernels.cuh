@@ -272,6 +272,12 @@ __device__ __forceinline__ void stg128_stream(void* p, u64 a, u64 b) {
 #define RIG_CTR_TOTAL 2    // occurrences of the batch
 #define RIG_CTR_CHAINS 3   // Phi chains of the batch
 #define RIG_CTR_ITEMS 6    // items appended by the seed pass
+// Expansion of a SHARD of a planned batch (rig_expand_shard_dev): the arrays are passed shifted to the shard's first
+// pattern and keep their batch-wide values; a second counter block holds the shard's totals and these two bases (both
+// 0 for a whole batch).
+#define RIG_CTR_OCC_BASE 9   // output offset of the first pattern
+#define RIG_CTR_CH_BASE 10   // chain offset of the first pattern
+#define RIG_CTR_BLOCK 16     // words per counter block
 
 // Both kernels return at once when the host will not want the output (total > capacity) or when the item list
 // could overflow (the host re-launches with a larger list: it evaluates the same two conditions from the same
@@ -316,6 +322,7 @@ __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u
     constexpr u64 LINE = 128 / sizeof(OT);   // output slots per 128-byte line
     const int lane = threadIdx.x & 31;
     const u64 stride = (u64)nblocks * blockDim.x;
+    const u64 occ_base = __ldcg(ctr + RIG_CTR_OCC_BASE), ch_base = __ldcg(ctr + RIG_CTR_CH_BASE);
     for (u64 wb = (u64)block * blockDim.x + (threadIdx.x & ~31u); wb < total_chains; wb += stride) {  // warp-uniform
         const u64 w = wb + lane;
         const bool active = w < total_chains;
@@ -324,16 +331,16 @@ __device__ __forceinline__ void produce_chains(const FlatDev& ix, u64 N, const u
             u64 a = 0, b = N;  // largest p with ch_off[p] <= w
             while (b - a > 1) {
                 const u64 mid = (a + b) >> 1;
-                if (__ldg(ch_off + mid) <= w) a = mid; else b = mid;
+                if (__ldg(ch_off + mid) - ch_base <= w) a = mid; else b = mid;
             }
             const u64 p = a;
             const u64 L = __ldg(lo_in + p), H = __ldg(hi_in + p);
-            const u64 j = __ldg(jl_in + p) + (w - __ldg(ch_off + p));
+            const u64 j = __ldg(jl_in + p) + (w - (__ldg(ch_off + p) - ch_base));
             const u64 sj = ld_pos<WT>(ix.start, j), ej = (u64)ld_pos<WT>(ix.start, j + 1) - 1;
             const u64 top = min(H, ej), bot = max(L, sj);
             if (top == H) v0 = __ldg(toe_in + p);  // toehold carried by the backward search (r_index.hpp:482-545)
             else { v0 = (u64)ld_pos<WT>(ix.samples_last, j) + 1; if (v0 >= ix.n) v0 -= ix.n; }  // run end: SA = sample + 1
-            g0 = __ldg(occ_off + p) + (H - top);  // slot of the chain's first occurrence
+            g0 = __ldg(occ_off + p) - occ_base + (H - top);  // slot of the chain's first occurrence
             glast = g0 + (top - bot);             // slot of its last (a chain never exceeds n)
             __stcs(out + g0, (OT)v0);
         }

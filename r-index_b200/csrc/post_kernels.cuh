@@ -416,4 +416,58 @@ __global__ void __launch_bounds__(1024) balanced_cuts_kernel(const u64* __restri
     }
 }
 
+// The same cut points from the EXCLUSIVE PREFIX of the occurrence counts that the locate-mode search leaves behind
+// (occ_off[0..N], occ_off[N] = total): cum(i) = occ_off[i + 1] + cost * (i + 1) is monotone, so each target is a binary
+// search — no pass over the batch. out[0..S]: the clamped cuts; out[S+1..2S+1], out[2S+2..3S+2]: occ_off and ch_off at
+// the cuts (what the host needs to size a shard's expansion). One warp; thread k searches target k.
+__global__ void __launch_bounds__(32) cuts_from_offsets_kernel(const u64* __restrict__ occ_off, const u64* __restrict__ ch_off, u64 N,
+                                                               u32 shards, u64 cost, u64* __restrict__ out) {
+    __shared__ u64 s_c[1025];
+    const u64 total = N ? occ_off[N] + cost * N : 0;
+    for (u32 k = threadIdx.x; k <= shards; k += 32) {
+        u64 c = N;
+        if (k == 0) c = 0;
+        else if (k < shards && N && total) {
+            const u64 t = total * k;
+            u64 lo = 0, hi = N;      // first i in [0, N) with cum(i) * shards >= t (cum(N-1) * shards = total * shards >= t)
+            while (lo < hi) {
+                const u64 mid = (lo + hi) >> 1;
+                if ((occ_off[mid + 1] + cost * (mid + 1)) * shards >= t) hi = mid; else lo = mid + 1;
+            }
+            const u64 i = lo;
+            if (i < N) {
+                const u64 cum = occ_off[i + 1] + cost * (i + 1), prev = occ_off[i] + cost * i;
+                c = (cum * shards - t > t - prev * shards) ? i : i + 1;
+            }
+        }
+        s_c[k] = c;
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        u64 last = 0;
+        for (u32 k = 0; k <= shards; ++k) {     // cuts must ascend
+            u64 c = s_c[k];
+            if (c < last) c = last;
+            if (c > N) c = N;
+            if (k == shards) c = N;
+            last = c;
+            out[k] = c;
+            out[shards + 1 + k] = occ_off[c];
+            out[2 * (shards + 1) + k] = ch_off[c];
+        }
+    }
+}
+
+// Counter block of a shard's expansion (phi_kernels.cuh: RIG_CTR_*): totals and bases from the batch-wide arrays.
+__global__ void shard_setup_kernel(u64* __restrict__ ctr, const u64* __restrict__ occ_off, const u64* __restrict__ ch_off, u64 c0, u64 c1) {
+    if (threadIdx.x < 16) ctr[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctr[2] = occ_off[c1] - occ_off[c0];   // RIG_CTR_TOTAL
+        ctr[3] = ch_off[c1] - ch_off[c0];     // RIG_CTR_CHAINS
+        ctr[9] = occ_off[c0];                 // RIG_CTR_OCC_BASE
+        ctr[10] = ch_off[c0];                 // RIG_CTR_CH_BASE
+    }
+}
+
 }  // namespace rigk

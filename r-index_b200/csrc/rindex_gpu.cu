@@ -90,6 +90,11 @@ struct rig_index {
     bool timing_pending = false;
     size_t arena_bytes = 0;
     uint64_t digest = 0;           // logical_digest() of the index this handle was made from
+    // the batch most recently planned on this index (rig_plan_batch_dev): cut points and the offsets at them
+    uint64_t plan_N = 0;
+    std::vector<uint64_t> plan_cuts, plan_occ, plan_ch;
+    DevBuf d_plan;
+    ull* h_plan = nullptr;         // pinned, 3 * 1025 words
     bool warned_fused = false;     // the fused kernel's cooperative launch has failed once (reported on stderr)
     uint32_t epoch = 0;            // fused expansion: tag of the current call's items (1..65535; the list is zeroed when it wraps)
     uint64_t items_zeroed = ~0ull; // generation of the item-list allocation that has been zero-filled. A fresh cudaMalloc holds garbage —
@@ -108,8 +113,8 @@ static int finish_create(rig_index* ix) {
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&ix->ev_scan, cudaEventDisableTiming));
     for (auto& ev : ix->ev) CU_TRY(cudaEventCreate(&ev));
-    CU_TRY(cudaMalloc((void**)&ix->d_counters, 16 * sizeof(ull)));
-    CU_TRY(cudaMemset(ix->d_counters, 0, 16 * sizeof(ull)));
+    CU_TRY(cudaMalloc((void**)&ix->d_counters, 2 * RIG_CTR_BLOCK * sizeof(ull)));   // the call's block + a shard's block (rig_expand_shard_dev)
+    CU_TRY(cudaMemset(ix->d_counters, 0, 2 * RIG_CTR_BLOCK * sizeof(ull)));
     CU_TRY(cudaMallocHost((void**)&ix->h_counters, 16 * sizeof(ull)));
     std::memset(ix->h_counters, 0, 16 * sizeof(ull));
     CU_TRY(cudaMalloc((void**)&ix->d_post, 8 * sizeof(ull)));
@@ -427,6 +432,8 @@ void rig_index_destroy(rig_index* ix) {
     if (ix->arena) cudaFree(ix->arena);
     if (ix->d_counters) cudaFree(ix->d_counters);
     if (ix->h_counters) cudaFreeHost(ix->h_counters);
+    if (ix->h_plan) cudaFreeHost(ix->h_plan);
+    ix->d_plan.release();
     if (ix->d_post) cudaFree(ix->d_post);
     if (ix->h_post) cudaFreeHost(ix->h_post);
     for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
@@ -585,7 +592,8 @@ int resident_ctas(K kernel, int threads) {
 // single-pass walk. Both kernels are persistent and decide on the device whether to run (expansion_enabled): the
 // host queues them WITHOUT knowing the totals. `items_cap`: entries the item list can hold.
 int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi, const ull* d_occoff, void* d_occ_v,
-                     uint64_t cap, bool two_pass, uint64_t items_cap, cudaStream_t st, bool out32) {
+                     uint64_t cap, bool two_pass, uint64_t items_cap, cudaStream_t st, bool out32, uint64_t p0 = 0,
+                     ull* ctr = nullptr) {   // p0, ctr: a shard of a planned batch (d_lo / d_hi / d_occoff already point at pattern p0)
     int rc;
     const int threads = ix->opt.expand_threads ? (int)ix->opt.expand_threads : 128;  // measured: 0.445 ms (128) vs 0.463 ms (256) on C2
     if (threads < 32 || threads > 256 || (threads & 31)) return RIG_ERR_ARG;
@@ -603,9 +611,9 @@ int launch_expansion(rig_index* ix, uint64_t N, const ull* d_lo, const ull* d_hi
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-    const ull* a_choff = (const ull*)ix->choff.p;
-    const ull* a_toe = (const ull*)ix->toe.p; const ull* a_jl = (const ull*)ix->jl.p;
-    ull* a_ctr = ix->d_counters;
+    const ull* a_choff = (const ull*)ix->choff.p + p0;
+    const ull* a_toe = (const ull*)ix->toe.p + p0; const ull* a_jl = (const ull*)ix->jl.p + p0;
+    ull* a_ctr = ctr ? ctr : ix->d_counters;
     ull a_N = N, a_cap = cap, a_icap = items_cap;
     ull* a_items = (ull*)ix->items.p;
     const bool keep = (ix->variant & 2) == 0;  // L2::evict_last on the Phi entry loads (bit1 disables: A/B switch)
@@ -809,6 +817,96 @@ int locate_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull
     return fits ? RIG_OK : RIG_ERR_CAPACITY;
 }
 
+// Replicated planning of a job sharded over several GPUs: search + offsets of the WHOLE batch here, cut points of equal
+// work from the offsets (a binary search per cut), one small D2H. The search results stay in the index's buffers.
+int plan_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* d_lo, ull* d_hi, ull* d_occoff, uint32_t shards,
+             uint64_t cost, uint64_t* cuts, uint64_t* occ_total, cudaStream_t st) {
+    int rc;
+    if ((rc = ix->toe.ensure((N + 1) * 8)) || (rc = ix->jl.ensure((N + 1) * 8)) || (rc = ix->nch.ensure((N + 1) * 8)) ||
+        (rc = ix->nocc.ensure((N + 1) * 8)) || (rc = ix->choff.ensure((N + 4) * 8)) ||
+        (rc = ix->sums.ensure((std::max<uint64_t>(tile_ws_words(N), 2 * ((N + RIG_SCAN_TILE - 1) / RIG_SCAN_TILE) + 8)) * 8)) ||
+        (rc = ix->d_plan.ensure(3 * 1025 * 8)))
+        return rc;
+    if (!ix->h_plan) CU_TRY(cudaMallocHost((void**)&ix->h_plan, 3 * 1025 * sizeof(ull)));
+    if ((rc = prep_call(ix, N, true, st))) return rc;
+    if ((rc = rec(ix, 1, st))) return rc;
+    if (N) {
+        if ((rc = launch_search<true>(ix, d_patt, N, m, d_lo, d_hi, d_occoff, st))) return rc;
+    } else {
+        CU_TRY(cudaMemsetAsync(d_occoff, 0, 8, st));
+        CU_TRY(cudaMemsetAsync(ix->choff.p, 0, 8, st));
+    }
+    if ((rc = rec(ix, 2, st))) return rc;
+    rigk::cuts_from_offsets_kernel<<<1, 32, 0, st>>>(d_occoff, (const ull*)ix->choff.p, N, shards, cost, (ull*)ix->d_plan.p);
+    CU_TRY(cudaGetLastError());
+    ix->timing.launches += 1;
+    CU_TRY(cudaMemcpyAsync(ix->h_counters, ix->d_counters, 8 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(ix->h_plan, ix->d_plan.p, 3 * (shards + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if ((rc = rec(ix, 3, st)) || (rc = rec(ix, 4, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    ix->plan_N = N;
+    ix->plan_cuts.assign(ix->h_plan, ix->h_plan + shards + 1);
+    ix->plan_occ.assign(ix->h_plan + shards + 1, ix->h_plan + 2 * (shards + 1));
+    ix->plan_ch.assign(ix->h_plan + 2 * (shards + 1), ix->h_plan + 3 * (shards + 1));
+    for (uint32_t k = 0; k <= shards; ++k) cuts[k] = ix->plan_cuts[k];
+    ix->timing.occ_total = N ? ix->h_counters[RIG_CTR_TOTAL] : 0;
+    ix->timing.chains = N ? ix->h_counters[RIG_CTR_CHAINS] : 0;
+    if (occ_total) *occ_total = ix->timing.occ_total;
+    return RIG_OK;
+}
+
+// Expansion of patterns [c0, c1) of the planned batch into d_occ (the shard's occurrences from slot 0).
+int expand_shard_dev(rig_index* ix, uint64_t N, uint64_t c0, uint64_t c1, const ull* d_lo, const ull* d_hi, const ull* d_occoff,
+                     ull* d_occ, uint64_t cap, uint64_t* shard_total, cudaStream_t st) {
+    int rc;
+    if (N != ix->plan_N || c0 > c1 || c1 > N) return RIG_ERR_ARG;
+    uint64_t o0 = 0, o1 = 0, h0 = 0, h1 = 0;
+    bool known0 = false, known1 = false;
+    for (size_t k = 0; k < ix->plan_cuts.size(); ++k) {
+        if (ix->plan_cuts[k] == c0 && !known0) { o0 = ix->plan_occ[k]; h0 = ix->plan_ch[k]; known0 = true; }
+        if (ix->plan_cuts[k] == c1) { o1 = ix->plan_occ[k]; h1 = ix->plan_ch[k]; known1 = true; }
+    }
+    if (!known0 || !known1) {   // not cut points of the plan: fetch the four offsets
+        ull v[4];
+        CU_TRY(cudaMemcpyAsync(&v[0], d_occoff + c0, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&v[1], d_occoff + c1, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&v[2], (const ull*)ix->choff.p + c0, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&v[3], (const ull*)ix->choff.p + c1, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        o0 = v[0]; o1 = v[1]; h0 = v[2]; h1 = v[3];
+    }
+    const uint64_t total = o1 - o0, chains = h1 - h0;
+    if (shard_total) *shard_total = total;
+    ix->timing.occ_total = total; ix->timing.chains = chains;
+    if ((rc = rec(ix, 3, st))) return rc;
+    if (total > cap || (total && !d_occ)) { if ((rc = rec(ix, 4, st))) return rc; return RIG_ERR_CAPACITY; }
+    if (total) {
+        ull* ctr = ix->d_counters + RIG_CTR_BLOCK;
+        rigk::shard_setup_kernel<<<1, 32, 0, st>>>(ctr, d_occoff, (const ull*)ix->choff.p, c0, c1);
+        CU_TRY(cudaGetLastError());
+        ix->timing.launches += 1;
+        if (!(ix->variant & 4) && ix->phi_bytes) {
+            const uint64_t lines = (ix->phi_bytes + 127) / 128;
+            rigk::l2_warm_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>((const char*)ix->d.phi.rec, ix->phi_bytes);
+            ix->timing.launches += 1;
+        }
+        const uint32_t SEG = ix->d.seed.J;
+        const bool two_pass = SEG > 1 && !(ix->variant & 32) && ((reinterpret_cast<uintptr_t>(d_occ) & 127) == 0);
+        uint64_t items_cap = 0;
+        if (two_pass) {
+            const uint64_t want_items = total / SEG + chains + 64;
+            if (want_items >= (1ull << 31)) return RIG_ERR_ARG;
+            if (ix->items.cap < (want_items + 32) * 16 && (rc = ix->items.ensure((want_items + 32) * 16))) return rc;
+            items_cap = ix->items.cap / 16 - 32;
+        }
+        ix->last_items_cap = items_cap; ix->last_two_pass = two_pass;
+        if ((rc = launch_expansion(ix, c1 - c0, d_lo + c0, d_hi + c0, d_occoff + c0, d_occ, cap, two_pass, items_cap, st, false, c0, ctr)))
+            return rc;
+    }
+    if ((rc = rec(ix, 4, st))) return rc;
+    return RIG_OK;
+}
+
 // The host-buffer locate calls: upload the patterns, locate, optional -o / -c post-processing on the device, download.
 // occ32: narrow the positions to 32 bits on the device before the download (rig_locate_batch32).
 int locate_host(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi,
@@ -890,6 +988,28 @@ int rig_locate_batch_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, u
     begin_call(ix);
     return locate_dev(ix, d_patterns, N, m, (ull*)d_lo, (ull*)d_hi, (ull*)d_occ_offsets, (ull*)d_occ, occ_capacity,
                       occ_total, st);
+}
+
+int rig_plan_batch_dev(rig_index* ix, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo, uint64_t* d_hi,
+                       uint64_t* d_occ_offsets, uint32_t shards, uint64_t per_pattern_cost, uint64_t* cuts, uint64_t* occ_total,
+                       void* stream) {
+    if (!ix || !cuts || !d_occ_offsets || shards < 1 || shards > 1024 || (N && (!d_patterns && m)) || (N && (!d_lo || !d_hi)))
+        return RIG_ERR_ARG;
+    if (N >= (1ull << 32) || per_pattern_cost > (1ull << 20)) return RIG_ERR_ARG;   // total * shards must stay below 2^64
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    begin_call(ix);
+    return plan_dev(ix, d_patterns, N, m, (ull*)d_lo, (ull*)d_hi, (ull*)d_occ_offsets, shards, per_pattern_cost, cuts, occ_total, st);
+}
+
+int rig_expand_shard_dev(rig_index* ix, uint64_t N, uint64_t c0, uint64_t c1, const uint64_t* d_lo, const uint64_t* d_hi,
+                         const uint64_t* d_occ_offsets, uint64_t* d_occ, uint64_t occ_capacity, uint64_t* shard_total, void* stream) {
+    if (!ix || !d_occ_offsets || !d_lo || !d_hi) return RIG_ERR_ARG;
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    begin_call(ix);
+    return expand_shard_dev(ix, N, c0, c1, (const ull*)d_lo, (const ull*)d_hi, (const ull*)d_occ_offsets, (ull*)d_occ, occ_capacity,
+                            shard_total, st);
 }
 
 int rig_count_batch(rig_index* ix, const uint8_t* patterns, uint64_t N, uint64_t m, uint64_t* lo, uint64_t* hi) {

@@ -462,3 +462,73 @@ def test_device_balanced_cuts_equal_host_rule():
     gpu.counts_dev(lo.data_ptr(), hi.data_ptr(), 4, out.data_ptr())
     torch.cuda.synchronize()
     assert out.tolist() == [5, 0, 1, 0]
+
+
+def test_plan_and_shard_expansion_equal_the_whole_batch(monkeypatch):
+    """rig_plan_batch_dev + rig_expand_shard_dev (a job sharded over several GPUs, planned on every device): the cuts
+    are the integer rule's, the ranges and offsets are the whole batch's, and the shards' occurrences, concatenated,
+    are the whole batch's occurrences in locate_all order — for cut points of the plan and for arbitrary [c0, c1),
+    over 32- and 64-bit words, fused / two-kernel / single-pass expansion."""
+    torch = pytest.importorskip("torch")
+    from rindex_b200 import _shard
+    dev = torch.device("cuda:0")
+    text = rib.gen_text("dna_drift", 300_000, 3_000, 3, 23)
+    host = rib.HostIndex.from_text(text)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for kw in (dict(), dict(seed_jump=16), dict(seed_jump=1), dict(phi_jump=2), dict(phi_jump=6)):
+        gpu = rib.GpuIndex(host, **kw)
+        for (N, m, seed) in [(900, 7, 1), (37, 1, 2), (1, 3, 3), (6000, 4, 4)]:
+            patt = mixed_patterns(text, N, m, seed, alphabet=acgt)
+            elo, ehi, eoff, eocc = gpu.locate(patt, N, m)
+            nocc = np.diff(eoff.astype(np.int64)).astype(np.uint64)
+            d_patt = torch.from_numpy(patt).to(dev)
+            d_lo = torch.empty(N + 1, dtype=torch.int64, device=dev)
+            d_hi = torch.empty(N + 1, dtype=torch.int64, device=dev)
+            d_off = torch.empty(N + 2, dtype=torch.int64, device=dev)
+            for W in (1, 2, 3, 8):
+                cuts, total = gpu.plan_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), W)
+                assert cuts == _shard.balanced_cuts(nocc, W), (kw, N, m, W)
+                assert total == eocc.size
+                assert np.array_equal(d_lo[:N].cpu().numpy().astype(np.uint64), elo) and np.array_equal(d_hi[:N].cpu().numpy().astype(np.uint64), ehi)
+                assert np.array_equal(d_off[: N + 1].cpu().numpy().astype(np.uint64), eoff)
+                bounds = list(zip(cuts, cuts[1:]))
+                if W == 3 and N > 4:
+                    bounds = [(0, 1), (1, N // 2), (N // 2, N // 2), (N // 2, N)]   # not cut points of the plan
+                got = []
+                for (c0, c1) in bounds:
+                    with pytest.raises(rib.RigError) if eoff[c1] > eoff[c0] else _null():
+                        gpu.expand_shard_dev(N, c0, c1, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), None, 0)
+                    need = int(eoff[c1] - eoff[c0])
+                    d_occ = torch.full((need + 16,), -1, dtype=torch.int64, device=dev)
+                    assert gpu.expand_shard_dev(N, c0, c1, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(), need) == need
+                    torch.cuda.synchronize()
+                    assert (d_occ[need:] == -1).all()
+                    got.append(d_occ[:need].cpu().numpy().astype(np.uint64))
+                assert np.array_equal(np.concatenate(got) if got else np.zeros(0, np.uint64), eocc), (kw, N, m, W)
+    monkeypatch.setenv("RIG_VARIANT", "8")   # 64-bit position words, as for n >= 2^32
+    g64 = rib.GpuIndex(host)
+    assert g64.info.words32 == 0
+    if True:
+        N, m = 500, 5
+        patt = mixed_patterns(text, N, m, 9, alphabet=acgt)
+        _, _, eoff, eocc = g64.locate(patt, N, m)
+        d_patt = torch.from_numpy(patt).to(dev)
+        d_lo = torch.empty(N + 1, dtype=torch.int64, device=dev); d_hi = torch.empty(N + 1, dtype=torch.int64, device=dev)
+        d_off = torch.empty(N + 2, dtype=torch.int64, device=dev)
+        cuts, _ = g64.plan_dev(d_patt.data_ptr(), N, m, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), 4)
+        got = []
+        for c0, c1 in zip(cuts, cuts[1:]):
+            need = int(eoff[c1] - eoff[c0])
+            d_occ = torch.empty(need + 16, dtype=torch.int64, device=dev)
+            g64.expand_shard_dev(N, c0, c1, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), d_occ.data_ptr(), need)
+            torch.cuda.synchronize()
+            got.append(d_occ[:need].cpu().numpy().astype(np.uint64))
+        assert np.array_equal(np.concatenate(got), eocc)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
