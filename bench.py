@@ -550,6 +550,7 @@ class LocateJob:
         self.d_all = torch.zeros(self.world * self.per, dtype=torch.int64, device=D.dev)
         self.d_occ = None
         self.cuts = None
+        self.plan_launches = 0
 
     # -- re-balancing: equal-count count phase, all-gather of the counts, cuts of equal occurrence mass --
     def plan_dev(self):
@@ -561,6 +562,7 @@ class LocateJob:
         if self.plan == "replicate":   # search + offsets of the whole batch here, cuts from the offsets (rig_plan_batch_dev)
             self.cuts, _ = self.gpu.plan_dev(self.d_patt.data_ptr(), self.N, self.m, self.d_lo.data_ptr(), self.d_hi.data_ptr(),
                                              self.d_off.data_ptr(), self.world, 64, self.stream)
+            self.plan_launches = 3   # prep_kernel, search_pair_kernel, cuts_from_offsets_kernel
             return self.cuts[self.rank], self.cuts[self.rank + 1]
         else:
             n = self.b - self.a
@@ -568,6 +570,7 @@ class LocateJob:
             self.gpu.counts_dev(self.d_lo.data_ptr(), self.d_hi.data_ptr(), n, self.d_cnt.data_ptr(), self.stream)
             self.D.dist.all_gather_into_tensor(self.d_all, self.d_cnt)
         self.cuts = self.gpu.balanced_cuts_dev(self.d_all.data_ptr(), self.N, self.world, 64, self.stream)
+        self.plan_launches = 4   # prep, search (count), counts, cuts — the all-gather is NCCL's kernel, not counted
         return self.cuts[self.rank], self.cuts[self.rank + 1]
 
     def counts_all(self):
@@ -665,7 +668,7 @@ def measure_locate(D, job, steps, warmup, e2e_steps, flush, solo=False):
             ph[key].append(t[key])
         if mark is not None:
             plan.append(ev[k][0].elapsed_time(mark))
-        launches += t["launches"] + (1 if job.world > 1 else 0)
+        launches += t["launches"] + (job.plan_launches if job.world > 1 else 0)
     barrier()
     assert tot == occ_rank
     total_ms = sum(x.elapsed_time(y) for x, y in ev)
