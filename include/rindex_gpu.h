@@ -224,8 +224,9 @@ int rig_closest_run_break_batch(rig_index* idx, const uint64_t* lo, const uint64
  * same cuts from the same batch, and a count pass over the whole batch costs less than a collective's latency for
  * batches up to a few million LF steps (beyond that: count shards, exchange the counts, rig_balanced_cuts_dev).
  * rig_expand_shard_dev: the Phi expansion of patterns [c0, c1) of the batch most recently planned on this index (same N
- * and device arrays): the occurrences of pattern p go to d_occ[d_occ_offsets[p] - d_occ_offsets[c0] ...], in locate_all
- * order. RIG_ERR_CAPACITY (and *shard_total) when occ_capacity is too small. Replaces, for a rank's shard, the
+ * and device arrays; any other count / locate / plan call on the index in between invalidates the plan: RIG_ERR_ARG):
+ * the occurrences of pattern p go to d_occ[d_occ_offsets[p] - d_occ_offsets[c0] ...], in locate_all order.
+ * RIG_ERR_CAPACITY (and *shard_total) when occ_capacity is too small; several shards may be expanded after one plan. Replaces, for a rank's shard, the
  * per-pattern loop of ri-locate.cpp:126-145. */
 int rig_plan_batch_dev(rig_index* idx, const uint8_t* d_patterns, uint64_t N, uint64_t m, uint64_t* d_lo, uint64_t* d_hi,
                        uint64_t* d_occ_offsets, uint32_t shards, uint64_t per_pattern_cost, uint64_t* cuts,

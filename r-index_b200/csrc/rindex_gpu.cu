@@ -92,6 +92,7 @@ struct rig_index {
     uint64_t digest = 0;           // logical_digest() of the index this handle was made from
     // the batch most recently planned on this index (rig_plan_batch_dev): cut points and the offsets at them
     uint64_t plan_N = 0;
+    bool plan_valid = false;
     std::vector<uint64_t> plan_cuts, plan_occ, plan_ch;
     DevBuf d_plan;
     ull* h_plan = nullptr;         // pinned, 3 * 1025 words
@@ -553,7 +554,8 @@ int finish_timing(rig_index* ix) {
     return RIG_OK;
 }
 
-void begin_call(rig_index* ix) {
+void begin_call(rig_index* ix, bool keep_plan = false) {
+    if (!keep_plan) ix->plan_valid = false;   // any other batch call reuses the buffers a planned batch lives in
     std::memset(&ix->timing, 0, sizeof(ix->timing));
     for (bool& b : ix->ev_valid) b = false;
     ix->timing_pending = true;
@@ -844,7 +846,7 @@ int plan_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* 
     CU_TRY(cudaMemcpyAsync(ix->h_plan, ix->d_plan.p, 3 * (shards + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     if ((rc = rec(ix, 3, st)) || (rc = rec(ix, 4, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
-    ix->plan_N = N;
+    ix->plan_N = N; ix->plan_valid = true;
     ix->plan_cuts.assign(ix->h_plan, ix->h_plan + shards + 1);
     ix->plan_occ.assign(ix->h_plan + shards + 1, ix->h_plan + 2 * (shards + 1));
     ix->plan_ch.assign(ix->h_plan + 2 * (shards + 1), ix->h_plan + 3 * (shards + 1));
@@ -859,7 +861,7 @@ int plan_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* 
 int expand_shard_dev(rig_index* ix, uint64_t N, uint64_t c0, uint64_t c1, const ull* d_lo, const ull* d_hi, const ull* d_occoff,
                      ull* d_occ, uint64_t cap, uint64_t* shard_total, cudaStream_t st) {
     int rc;
-    if (N != ix->plan_N || c0 > c1 || c1 > N) return RIG_ERR_ARG;
+    if (!ix->plan_valid || N != ix->plan_N || c0 > c1 || c1 > N) return RIG_ERR_ARG;   // no planned batch (or another call since)
     uint64_t o0 = 0, o1 = 0, h0 = 0, h1 = 0;
     bool known0 = false, known1 = false;
     for (size_t k = 0; k < ix->plan_cuts.size(); ++k) {
@@ -1007,7 +1009,7 @@ int rig_expand_shard_dev(rig_index* ix, uint64_t N, uint64_t c0, uint64_t c1, co
     if (!ix || !d_occ_offsets || !d_lo || !d_hi) return RIG_ERR_ARG;
     CU_TRY(cudaSetDevice(ix->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
-    begin_call(ix);
+    begin_call(ix, true);
     return expand_shard_dev(ix, N, c0, c1, (const ull*)d_lo, (const ull*)d_hi, (const ull*)d_occ_offsets, (ull*)d_occ, occ_capacity,
                             shard_total, st);
 }

@@ -505,6 +505,10 @@ def test_plan_and_shard_expansion_equal_the_whole_batch(monkeypatch):
                     assert (d_occ[need:] == -1).all()
                     got.append(d_occ[:need].cpu().numpy().astype(np.uint64))
                 assert np.array_equal(np.concatenate(got) if got else np.zeros(0, np.uint64), eocc), (kw, N, m, W)
+    gpu.count(patt, N, m)                    # any other batch call invalidates the plan
+    with pytest.raises(rib.RigError) as e:
+        gpu.expand_shard_dev(N, 0, N, d_lo.data_ptr(), d_hi.data_ptr(), d_off.data_ptr(), None, 0)
+    assert e.value.code == -1
     monkeypatch.setenv("RIG_VARIANT", "8")   # 64-bit position words, as for n >= 2^32
     g64 = rib.GpuIndex(host)
     assert g64.info.words32 == 0

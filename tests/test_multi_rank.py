@@ -102,6 +102,50 @@ def test_two_rank_mass_balanced_shards_equal_single_run(tmp_path):
         assert max(g["mass"]) <= max(g["eq"])                                       # never worse than equal-count shards
 
 
+def _worker_replicated(rank, world, port, tmpdir):
+    """Replicated planning (rig_plan_batch_dev + rig_expand_shard_dev; bench.py --plan replicate) on CPU: every rank
+    searches the WHOLE batch, derives the same cuts from the offsets it computed, and expands only its shard. No
+    collective on the data path (the barrier below only keeps the processes together)."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest as cf
+    from rindex_b200 import _shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    text = cf.rib.gen_text("dna_drift", 150_000, 1_500, 3, 99)
+    N, m = 403, 4
+    patt = cf.mixed_patterns(text, N, m, 23, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    engine = cf.FlatCheck(cf.rib.HostIndex.from_text(text), K=4)
+    lo, hi = engine.count(patt, N, m)                       # the whole batch, on every rank
+    nocc = np.where(hi >= lo, hi - lo + np.uint64(1), np.uint64(0))
+    off = np.concatenate([[0], np.cumsum(nocc)]).astype(np.uint64)
+    cuts = _shard.balanced_cuts(np.diff(off.astype(np.int64)).astype(np.uint64), world)   # from the offsets, as the device does
+    c0, c1 = cuts[rank], cuts[rank + 1]
+    _, _, soff, socc, _ = engine.locate(patt[c0 * m: c1 * m], c1 - c0, m)
+    assert int(soff[-1]) == int(off[c1] - off[c0])          # the shard's slots are the batch's, rebased
+    np.savez(os.path.join(tmpdir, "rep%d.npz" % rank), occ=socc, cuts=np.array(cuts), base=np.array([int(off[c0])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_replicated_planning_equals_single_run(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker_replicated, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    text = rib.gen_text("dna_drift", 150_000, 1_500, 3, 99)
+    N, m = 403, 4
+    patt = mixed_patterns(text, N, m, 23, alphabet=np.frombuffer(b"ACGT", dtype=np.uint8))
+    _, _, eoff, eocc, _ = ob.PortIndex(text, sa=rib.suffix_array(text)).locate(patt, N, m)
+    g = [np.load(str(tmp_path / ("rep%d.npz" % r))) for r in range(2)]
+    assert np.array_equal(g[0]["cuts"], g[1]["cuts"])                          # same cuts without talking
+    assert int(g[0]["base"][0]) == 0 and int(g[1]["base"][0]) == g[0]["occ"].size
+    assert np.array_equal(np.concatenate([g[0]["occ"], g[1]["occ"]]), eocc)    # shard outputs concatenate to the single run
+
+
 def test_balanced_cuts_properties():
     from rindex_b200 import _shard
     rng = np.random.default_rng(3)
