@@ -41,6 +41,43 @@ def balanced_cuts(nocc, world, per_pattern_cost=64):
     return cuts
 
 
+def balanced_cuts_from_offsets(off, world, per_pattern_cost=64):
+    """The same cut points from the EXCLUSIVE PREFIX of the occurrence counts (off[0..N], off[N] = total) that a
+    locate-mode search leaves behind — the arithmetic of csrc/post_kernels.cuh: cuts_from_offsets_kernel
+    (rig_plan_batch_dev), restated for the CPU tests: cum(i) = off[i + 1] + cost * (i + 1) is monotone, so every
+    target is a binary search instead of a pass over the batch."""
+    off = [int(x) for x in off]
+    N = len(off) - 1
+    total = off[N] + per_pattern_cost * N if N else 0
+    raw = []
+    for k in range(world + 1):
+        c = N
+        if k == 0:
+            c = 0
+        elif k < world and N and total:
+            t = total * k
+            lo, hi = 0, N
+            while lo < hi:
+                mid = (lo + hi) >> 1
+                if (off[mid + 1] + per_pattern_cost * (mid + 1)) * world >= t:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            i = lo
+            if i < N:
+                cum, prev = off[i + 1] + per_pattern_cost * (i + 1), off[i] + per_pattern_cost * i
+                c = i if (cum * world - t) > (t - prev * world) else i + 1
+        raw.append(c)
+    cuts, last = [], 0
+    for k, c in enumerate(raw):
+        c = min(max(c, last), N)
+        if k == world:
+            c = N
+        cuts.append(c)
+        last = c
+    return cuts
+
+
 def _torch():
     import torch
     import torch.distributed as dist

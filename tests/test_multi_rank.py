@@ -161,6 +161,31 @@ def test_balanced_cuts_properties():
     assert sum(1 for a, b in zip(cuts, cuts[1:]) if a <= 40 < b) == 1
 
 
+def test_cuts_from_offsets_equal_cuts_from_counts():
+    """rig_plan_batch_dev finds the cuts by binary search in the offset array, rig_balanced_cuts_dev / GpuFleet by a
+    running sum over the counts: one rule, two formulations — equal on skewed, sparse, all-zero and tiny batches."""
+    from rindex_b200 import _shard
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        N = int(rng.choice([0, 1, 2, 3, 7, 64, 1000]))
+        kind = trial % 4
+        if kind == 0:
+            nocc = (rng.pareto(1.1, size=N) * 50).astype(np.uint64)
+        elif kind == 1:
+            nocc = np.zeros(N, dtype=np.uint64)
+            if N:
+                nocc[rng.integers(0, N, size=min(N, 3))] = rng.integers(1, 10**9, size=min(N, 3)).astype(np.uint64)
+        elif kind == 2:
+            nocc = np.zeros(N, dtype=np.uint64)
+        else:
+            nocc = rng.integers(0, 5, size=N).astype(np.uint64)
+        off = np.concatenate([[0], np.cumsum(nocc)]).astype(np.uint64)
+        for G in (1, 2, 3, 8, 64):
+            for cost in (64, 1, 0):
+                want = _shard.balanced_cuts(nocc, G, cost)
+                assert _shard.balanced_cuts_from_offsets(off, G, cost) == want, (trial, N, G, cost)
+
+
 def test_shard_bounds_partition():
     from rindex_b200 import _shard
     for N in (0, 1, 7, 100, 1001):
