@@ -105,11 +105,12 @@ def shared_config(workload, world, n, r):
             "notes": CONFIG_NOTE}
 
 
-def job_inputs(workload, world, rank, need_text=False, barrier=None):
+def job_inputs(workload, world, rank, need_text=False, barrier=None, need_index=True):
     """The job's pattern array (the same on every rank) and this repo's logical index. Rank 0 builds what .cache/
     lacks (text -> prefix-free-parsing builder; patterns drawn from the text) and the others load it after the
-    barrier: one build per box, not one per rank. Returns (text or None, patt, N, m, host)."""
-    rib = ge.load_package()
+    barrier: one build per box, not one per rank. Returns (text or None, patt, N, m, host). need_index=False (the
+    reference arm with its own cached index): nothing of this repo is loaded when the cached files exist."""
+    rib = None
     kind, n, p0, p1, tseed, _, m, pseed, limit, desc = WORKLOADS[workload]
     N = job_size(workload, world)
     os.makedirs(CACHE, exist_ok=True)
@@ -119,6 +120,7 @@ def job_inputs(workload, world, rank, need_text=False, barrier=None):
     t0 = time.time()
     if rank == 0:
         if need_text or not (os.path.exists(rpath) and os.path.exists(ppath)):
+            rib = ge.load_package()
             text = rib.gen_text(kind, n, p0, p1, tseed)
         if not os.path.exists(ppath):
             patt = rib.gen_patterns(text, N, m, pseed, limit)
@@ -133,8 +135,11 @@ def job_inputs(workload, world, rank, need_text=False, barrier=None):
     if barrier is not None:
         barrier()
     patt = np.load(ppath)
-    host = rib.HostIndex.load(rpath)
-    if rank == 0:
+    host = None
+    if need_index:
+        rib = rib or ge.load_package()
+        host = rib.HostIndex.load(rpath)
+    if rank == 0 and host is not None:
         log("[bench] inputs of %s ready in %.1fs: n=%d r=%d n/r=%.1f, %d patterns" % (workload, time.time() - t0, host.n, host.r, host.n / host.r, N))
     return text, patt, N, m, host
 
@@ -142,7 +147,6 @@ def job_inputs(workload, world, rank, need_text=False, barrier=None):
 def reference_index(workload, host=None):
     """The reference's r_index<> for the workload (oracle/_ref), or the plain-C port when _ref did not travel."""
     ob = ge.load_oracle()
-    rib = ge.load_package()
     if ob.have_ref():
         rpath = os.path.join(CACHE, "%s.ref.ri" % base_of(workload))
         if os.path.exists(rpath):
@@ -154,6 +158,7 @@ def reference_index(workload, host=None):
     if not ob.have_port():
         ob.build()
     log("[bench] oracle/_ref missing: CPU baseline falls back to the plain-C port")
+    rib = ge.load_package()
     kind, n, p0, p1, tseed = WORKLOADS[workload][:5]
     text = rib.gen_text(kind, n, p0, p1, tseed)
     return ob.PortIndex(text, sa=rib.suffix_array(text)), "plain-C port over a suffix array"
@@ -316,8 +321,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    _, patt, N, m, _ = job_inputs(args.workload, world, 0)   # patterns only (the logical index is not used when a .ref.ri exists)
-    ref, how = reference_index(args.workload)
+    ob = ge.load_oracle()
+    own_index = ob.have_ref() and os.path.exists(os.path.join(CACHE, "%s.ref.ri" % base_of(args.workload)))
+    _, patt, N, m, host = job_inputs(args.workload, world, 0, need_index=not own_index)   # patterns only when the reference has its own index
+    ref, how = reference_index(args.workload, host)
     threads = cores if ref.kind == "reference" else 1
     count_mode = args.mode == "count"
     metric, unit = ("count_patterns_per_s", "patterns/s") if count_mode else ("locate_occurrences_per_s", "occ/s")
@@ -344,8 +351,18 @@ def run_reference(args):
         "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": shared_config(args.workload, world, ref.n, ref.r),
         "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": ref.kind, "sample": sample, "index": how},
-        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        "repo_libraries_loaded": repo_libraries_loaded()}), flush=True)
     return 0
+
+
+def repo_libraries_loaded():
+    """This repo's native libraries mapped into the process (the reference arm must not need any once its inputs are cached)."""
+    try:
+        with open("/proc/self/maps") as f:
+            return sorted({os.path.basename(l.split()[-1]) for l in f if "librindex_" in l})
+    except OSError:
+        return None
 
 
 class Dist:

@@ -37,6 +37,8 @@ def test_reference_arm_prints_one_json_line(mode):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if cb["kind"] == "reference" and "cached .ri" in cb["index"]:
+        assert d["repo_libraries_loaded"] == []      # the reference arm runs without any of this repo's native code
 
 
 def test_reference_arm_other_ranks_exit_quietly():
