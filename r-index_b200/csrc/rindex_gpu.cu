@@ -846,6 +846,10 @@ int plan_dev(rig_index* ix, const uint8_t* d_patt, uint64_t N, uint64_t m, ull* 
     CU_TRY(cudaMemcpyAsync(ix->h_plan, ix->d_plan.p, 3 * (shards + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     if ((rc = rec(ix, 3, st)) || (rc = rec(ix, 4, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
+    {   // the cut rule multiplies the batch's work by the shard count in 64 bits
+        const unsigned __int128 work = (unsigned __int128)(N ? ix->h_counters[RIG_CTR_TOTAL] : 0) + (unsigned __int128)cost * N;
+        if (work * shards > (unsigned __int128)~0ull) return RIG_ERR_ARG;
+    }
     ix->plan_N = N; ix->plan_valid = true;
     ix->plan_cuts.assign(ix->h_plan, ix->h_plan + shards + 1);
     ix->plan_occ.assign(ix->h_plan + shards + 1, ix->h_plan + 2 * (shards + 1));
